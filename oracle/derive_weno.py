@@ -1,0 +1,167 @@
+#!/usr/bin/env python3
+"""Derive the WENO-N (N = 2..5, order 2N-1) tables symbolically and emit C headers.
+
+TEST INFRASTRUCTURE + build-time generator.  The arithmetic that the reference
+benchmark runs lives in Oceananigans.jl v0.90.1 (Manifest.toml:643-649), whose
+source is NOT available in this container; SURVEY.md Appendix A10 records the
+tables from recollection.  This script re-derives every table from first
+principles (cell-average reconstruction polynomials on a uniform grid) with
+sympy rationals, checks them against the recalled decimal literals, and writes
+
+  oracle/weno_tables.h                               (used by the CPU oracle)
+  oceanscalingtests.jl_b200/csrc/weno_tables.cuh     (used by the CUDA kernels)
+
+Conventions:
+  * left-biased value at face i (between cells i-1 and i); stencil s (0 = most
+    downwind) covers cells (i-1-s) .. (i-1-s+N-1); values listed in increasing
+    cell index;
+  * smoothness beta_s = sum_{a<=b} C[s][ab] psi_a psi_b, upper-triangular
+    row-major, scaled by 1 (N=2), 3 (N=3), 0.24 (N=4), 0.0504 (N=5) relative to
+    sum_l int (d^l p_s/dx^l)^2 dx over the cell upwind of the face (dx = 1);
+  * optimal weights C*_s such that sum_s C*_s p_s = the (2N-1)-order
+    upwind-biased reconstruction.
+"""
+import os
+import sys
+import sympy as sp
+
+x = sp.Symbol("x")
+
+SCALE = {2: sp.Integer(1), 3: sp.Integer(3), 4: sp.Rational(24, 100), 5: sp.Rational(504, 10000)}
+
+
+def recon_poly(cells, vals):
+    """Polynomial p(x) of degree len(cells)-1 whose cell averages over
+    [c, c+1] equal vals (cells are integer left edges)."""
+    n = len(cells)
+    a = sp.symbols("a0:%d" % n)
+    p = sum(a[m] * x**m for m in range(n))
+    eqs = [sp.integrate(p, (x, c, c + 1)) - v for c, v in zip(cells, vals)]
+    sol = sp.solve(eqs, a, dict=True)[0]
+    return sp.expand(p.subs(sol))
+
+
+def derive(N):
+    """Tables for the left-biased reconstruction at the face x = 0
+    (cell -1 is [-1,0], cell 0 is [0,1])."""
+    coeffs, smooth = [], []
+    for s in range(N):
+        cells = list(range(-1 - s, -1 - s + N))
+        psi = sp.symbols("psi0:%d" % N)
+        p = recon_poly(cells, psi)
+        face = sp.expand(p.subs(x, 0))
+        coeffs.append([sp.Rational(face.coeff(psi[a])) for a in range(N)])
+        beta = 0
+        for l in range(1, N):
+            beta += sp.integrate(sp.diff(p, x, l) ** 2, (x, -1, 0))
+        beta = sp.expand(beta * SCALE[N])
+        row = []
+        for a in range(N):
+            for b in range(a, N):
+                row.append(sp.Rational(beta.coeff(psi[a], 1).coeff(psi[b], 1)) if a != b
+                           else sp.Rational(beta.coeff(psi[a], 2)))
+        smooth.append(row)
+    # optimal weights: match the full (2N-1)-cell reconstruction
+    cells = list(range(-N, N - 1))
+    q = sp.symbols("q0:%d" % (2 * N - 1))
+    full = sp.expand(recon_poly(cells, q).subs(x, 0))
+    g = sp.symbols("g0:%d" % N)
+    combo = 0
+    for s in range(N):
+        for a in range(N):
+            cell = -1 - s + a
+            combo += g[s] * coeffs[s][a] * q[cell + N]
+    eqs = [sp.expand(combo - full).coeff(q[m]) for m in range(2 * N - 1)]
+    sol = sp.solve(eqs, g, dict=True)[0]
+    opt = [sp.Rational(sol[g[s]]) for s in range(N)]
+    return coeffs, opt, smooth
+
+
+# decimal literals recalled in SURVEY.md A10 (the scale factors rest on these)
+RECALLED_SMOOTH = {
+    2: [[1, -2, 1], [1, -2, 1]],
+    3: [[10, -31, 11, 25, -19, 4], [4, -13, 5, 13, -13, 4], [4, -19, 11, 25, -31, 10]],
+    4: [[2.107, -9.402, 7.042, -1.854, 11.003, -17.246, 4.642, 7.043, -3.882, 0.547],
+        [0.547, -2.522, 1.922, -0.494, 3.443, -5.966, 1.602, 2.843, -1.642, 0.267],
+        [0.267, -1.642, 1.602, -0.494, 2.843, -5.966, 1.922, 3.443, -2.522, 0.547],
+        [0.547, -3.882, 4.642, -1.854, 7.043, -17.246, 7.042, 11.003, -9.402, 2.107]],
+    5: [[1.07918, -6.49501, 7.58823, -4.11487, 0.86329, 10.20563, -24.62076, 13.58458, -2.88007,
+         15.21393, -17.04396, 3.64863, 4.82963, -2.08501, 0.22658],
+        [0.22658, -1.40251, 1.65153, -0.88297, 0.18079, 2.42723, -6.11976, 3.37018, -0.70237,
+         4.06293, -4.64976, 0.99213, 1.38563, -0.60871, 0.06908],
+        [0.06908, -0.51001, 0.67923, -0.38947, 0.08209, 1.04963, -2.99076, 1.79098, -0.38947,
+         2.31153, -2.99076, 0.67923, 1.04963, -0.51001, 0.06908],
+        [0.06908, -0.60871, 0.99213, -0.70237, 0.18079, 1.38563, -4.64976, 3.37018, -0.88297,
+         4.06293, -6.11976, 1.65153, 2.42723, -1.40251, 0.22658],
+        [0.22658, -2.08501, 3.64863, -2.88007, 0.86329, 4.82963, -17.04396, 13.58458, -4.11487,
+         15.21393, -24.62076, 7.58823, 10.20563, -6.49501, 1.07918]],
+}
+RECALLED_OPT = {
+    2: [sp.Rational(2, 3), sp.Rational(1, 3)],
+    3: [sp.Rational(3, 10), sp.Rational(3, 5), sp.Rational(1, 10)],
+    4: [sp.Rational(4, 35), sp.Rational(18, 35), sp.Rational(12, 35), sp.Rational(1, 35)],
+    5: [sp.Rational(5, 126), sp.Rational(20, 63), sp.Rational(10, 21), sp.Rational(10, 63), sp.Rational(1, 126)],
+}
+
+
+def lit(r):
+    return repr(float(r))
+
+
+def emit(tables, path, cuda):
+    q = "__device__ __constant__ const" if cuda else "static const"
+    guard = "OB200_WENO_TABLES_%s" % ("CUH" if cuda else "H")
+    out = ["// GENERATED by oracle/derive_weno.py -- do not edit.",
+           "// WENO-N tables, N = 2..5 (index [N][s][...], rows for N < 2 unused).",
+           "#ifndef %s" % guard, "#define %s" % guard, ""]
+    def arr3(name, key, width):
+        out.append("%s double %s[6][5][%d] = {" % (q, name, width))
+        for N in range(6):
+            out.append("  {")
+            for s in range(5):
+                vals = ["0.0"] * width
+                if N in tables and s < N:
+                    src = tables[N][key][s]
+                    for m, v in enumerate(src):
+                        vals[m] = lit(v)
+                out.append("    {" + ", ".join(vals) + "},")
+            out.append("  },")
+        out.append("};")
+    arr3("WENO_COEFF", 0, 5)
+    out.append("%s double WENO_OPT[6][5] = {" % q)
+    for N in range(6):
+        vals = ["0.0"] * 5
+        if N in tables:
+            for s in range(N):
+                vals[s] = lit(tables[N][1][s])
+        out.append("  {" + ", ".join(vals) + "},")
+    out.append("};")
+    arr3("WENO_SMOOTH", 2, 15)
+    out += ["", "#endif", ""]
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        f.write("\n".join(out))
+
+
+def main():
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    tables = {}
+    for N in (2, 3, 4, 5):
+        c, o, b = derive(N)
+        tables[N] = (c, o, b)
+        assert o == RECALLED_OPT[N], (N, o)
+        for s in range(N):
+            for got, want in zip(b[s], RECALLED_SMOOTH[N][s]):
+                assert abs(float(got) - want) < 1e-9, (N, s, float(got), want)
+            assert sum(c[s]) == 1
+    # spot checks of the classic coefficients
+    assert tables[3][0][0] == [sp.Rational(1, 3), sp.Rational(5, 6), sp.Rational(-1, 6)]
+    assert tables[3][0][2] == [sp.Rational(1, 3), sp.Rational(-7, 6), sp.Rational(11, 6)]
+    emit(tables, os.path.join(here, "weno_tables.h"), cuda=False)
+    emit(tables, os.path.join(root, "oceanscalingtests.jl_b200", "csrc", "weno_tables.cuh"), cuda=True)
+    print("weno tables derived and verified against SURVEY A10 literals")
+
+
+if __name__ == "__main__":
+    sys.exit(main())

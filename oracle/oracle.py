@@ -1,0 +1,150 @@
+"""ctypes wrapper of the CPU oracle (oracle/libocean_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+May be imported from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs -- never from the product package.  `OracleBackend` offers the
+same methods as the product's `B200Backend`, so a `HydrostaticFreeSurfaceModel` can be
+built on either and the parity tests read the same for both.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libocean_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(HERE, f) for f in ("ocean_oracle.cpp", "weno_tables.h", "Makefile")]
+    src.append(os.path.join(HERE, "..", "include", "ocean_b200.h"))
+    stale = (not os.path.exists(LIB)) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in src if os.path.exists(s))
+    if force or stale:
+        subprocess.check_call(["make", "-C", HERE, "libocean_oracle.so"], stdout=subprocess.DEVNULL)
+    return LIB
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB):
+        build()
+    lib = C.CDLL(LIB)
+    H, dp = C.c_void_p, C.c_void_p
+    lib.oracle_create.argtypes = [C.c_void_p]
+    lib.oracle_create.restype = H
+    lib.oracle_destroy.argtypes = [H]
+    lib.oracle_destroy.restype = None
+    for f in (lib.oracle_set_field, lib.oracle_get_field):
+        f.argtypes = [H, C.c_int, dp, C.c_int, C.c_int, C.c_int]
+        f.restype = C.c_int
+    for f in (lib.oracle_get_strip, lib.oracle_set_strip):
+        f.argtypes = [H, C.c_int, dp, C.c_int, C.c_int, C.c_int]
+        f.restype = C.c_int
+    lib.oracle_set_forcing.argtypes = [H, C.c_int, dp]
+    lib.oracle_set_forcing.restype = C.c_int
+    lib.oracle_update_state.argtypes = [H]
+    lib.oracle_time_step.argtypes = [H, C.c_double]
+    lib.oracle_run_stage.argtypes = [H, C.c_int, C.c_double, C.c_int]
+    lib.oracle_get_clock.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    lib.oracle_set_clock.argtypes = [H, C.c_double, C.c_int64, C.c_double]
+    lib.oracle_tick.argtypes = [H, C.c_double]
+    lib.oracle_zero_prev_tendencies.argtypes = [H]
+    lib.oracle_weno.argtypes = [C.c_int, dp, dp, dp]
+    lib.oracle_weno.restype = C.c_double
+    lib.oracle_teos10_rprime.argtypes = [C.c_double] * 3
+    lib.oracle_teos10_rprime.restype = C.c_double
+    _lib = lib
+    return lib
+
+
+class OracleBackend:
+    name = "oracle"
+
+    def __init__(self, cfg):
+        self.lib = load()
+        self.h = self.lib.oracle_create(C.byref(cfg))
+        if not self.h:
+            raise RuntimeError("oracle_create failed")
+        self.Nx, self.Ny, self.Nz = cfg.Nx, cfg.Ny, cfg.Nz
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"oracle error {rc}")
+
+    def set_field(self, fid, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        self._check(self.lib.oracle_set_field(self.h, fid, arr.ctypes.data, 0, 0, 0))
+
+    def get_field(self, fid, shape):
+        out = np.empty(shape, dtype=np.float64)
+        self._check(self.lib.oracle_get_field(self.h, fid, out.ctypes.data, 0, 0, 0))
+        return out
+
+    def get_strip(self, fid, n, side, width, interior_edge):
+        out = np.empty(n, dtype=np.float64)
+        self._check(self.lib.oracle_get_strip(self.h, fid, out.ctypes.data, side, width, int(interior_edge)))
+        return out
+
+    def set_strip(self, fid, arr, side, width, interior_edge):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        self._check(self.lib.oracle_set_strip(self.h, fid, arr.ctypes.data, side, width, int(interior_edge)))
+
+    def set_forcing(self, which, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        self._check(self.lib.oracle_set_forcing(self.h, which, arr.ctypes.data))
+
+    def update_state(self):
+        self._check(self.lib.oracle_update_state(self.h))
+
+    def time_step(self, dt):
+        self._check(self.lib.oracle_time_step(self.h, float(dt)))
+
+    def time_steps(self, dt, n):
+        for _ in range(n):
+            self.time_step(dt)
+
+    def run_stage(self, stage, dt=0.0, arg=0):
+        self._check(self.lib.oracle_run_stage(self.h, stage, float(dt), int(arg)))
+
+    def sync(self):
+        pass
+
+    def clock(self):
+        t, it, ldt = C.c_double(), C.c_int64(), C.c_double()
+        self.lib.oracle_get_clock(self.h, C.byref(t), C.byref(it), C.byref(ldt))
+        return t.value, it.value, ldt.value
+
+    def set_clock(self, time, iteration, last_dt):
+        self.lib.oracle_set_clock(self.h, float(time), int(iteration), float(last_dt))
+
+    def tick(self, dt):
+        self.lib.oracle_tick(self.h, float(dt))
+
+    def zero_prev_tendencies(self):
+        self.lib.oracle_zero_prev_tendencies(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def weno(N, q, sa=None, sb=None) -> float:
+    lib = load()
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    sa = q if sa is None else np.ascontiguousarray(sa, dtype=np.float64)
+    sbp = None if sb is None else np.ascontiguousarray(sb, dtype=np.float64).ctypes.data
+    return lib.oracle_weno(N, q.ctypes.data, sa.ctypes.data, sbp)

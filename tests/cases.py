@@ -1,0 +1,109 @@
+"""Shared problem definitions for tests, smoke() and bench.py (closed-form, no RNG).
+
+A case = grid size + experiment + time step + a deterministic initial state that exercises
+every term of the step: the reference's DoubleDrake initial condition
+(boundary_and_initial_conditions.jl:9-18) plus smooth closed-form perturbations of u, v, eta
+and of T, S (so that WENO weights, Coriolis, pressure gradient and the barotropic solver all
+see non-trivial inputs).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class Case:
+    name: str
+    Nx: int
+    Ny: int
+    Nz: int
+    experiment: str = "DoubleDrake"
+    dt: float = 1200.0
+    perturb: bool = True
+    depth: float = 3000.0
+    qgleith: bool = False
+    bathymetry: str = "experiment"    # "experiment" | "bumpy" (k-dependent masks)
+    ranks: int = 1
+
+    def grid(self, pkg, rank=0, ranks=None):
+        ranks = ranks or self.ranks
+        zf = pkg.exponential_z_faces(self.Nz, self.depth)
+        g0 = pkg.LatitudeLongitudeGrid(self.Nx, self.Ny, self.Nz, zf)
+        lam, phi = g0.lam_c()[None, :], g0.phi_c()[:, None]
+        if self.experiment == "Quiescent" and self.bathymetry == "experiment":
+            bottom = None
+        elif self.bathymetry == "bumpy":
+            # smooth seamounts + a continent: exercises k-dependent immersed masks
+            bottom = -self.depth * (1.0 - 0.85 * np.exp(-((lam - 40.0) / 25.0) ** 2 - ((phi - 10.0) / 18.0) ** 2)
+                                    - 0.6 * np.exp(-((lam + 100.0) / 30.0) ** 2 - ((phi + 30.0) / 15.0) ** 2))
+            bottom = np.where((np.abs(lam + 20.0) < 12.0) & (np.abs(phi - 35.0) < 14.0), 100.0, bottom)
+            bottom = bottom + 0 * lam
+        else:
+            bottom = pkg.double_drake_bathymetry(lam, phi)
+        part = pkg.Partition.equal(self.Nx, ranks)
+        return pkg.LatitudeLongitudeGrid(self.Nx, self.Ny, self.Nz, zf, rank=rank, partition=part,
+                                         bottom_height_global=bottom)
+
+    def make_model(self, pkg, backend_factory, rank=0, ranks=None, device=0, initialize=True):
+        grid = self.grid(pkg, rank, ranks)
+        res = self.Nx / 360.0
+        max_dt = 3240.0 / res
+        nsub = pkg.barotropic_substeps(max_dt, grid)
+        fs = pkg.SplitExplicitFreeSurface(substeps=nsub)
+        bcs = pkg.set_boundary_conditions("DoubleDrake" if self.experiment == "DoubleDrake" else "Quiescent", grid)
+        closure = (pkg.VerticalScalarDiffusivity(), pkg.RiBasedVerticalDiffusivity())
+        if self.qgleith:
+            closure = closure + (pkg.QGLeith(),)
+        eos = "linear" if self.experiment == "DoubleDrake" else "teos10"
+        model = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=fs, eos=eos, closure=closure,
+                                                boundary_conditions=bcs, device=device,
+                                                backend_factory=backend_factory)
+        if initialize:
+            self.initialize(pkg, model)
+        return model
+
+    def initialize(self, pkg, model):
+        if self.experiment == "DoubleDrake":
+            pkg.initialize_model(model, "DoubleDrake")
+        if not self.perturb:
+            return
+        D = self.depth
+        r = math.pi / 180.0
+
+        def Tf(lam, phi, z):
+            base = pkg.exponential_profile(z, Lz=D, h=D / 15.0) * np.maximum(pkg.T_reference(phi), 2.0)
+            return base + 0.5 * np.sin(3 * lam * r) * np.cos(2 * phi * r) * np.exp(z / 500.0)
+
+        def Sf(lam, phi, z):
+            return 35.0 + 0.2 * np.cos(2 * lam * r + 0.3) * np.sin(3 * phi * r) * np.exp(z / 800.0)
+
+        def uf(lam, phi, z):
+            return 0.1 * np.sin(2 * lam * r) * np.cos(phi * r) * (1.0 + z / D) + 0 * z
+
+        def vf(lam, phi, z):
+            return 0.05 * np.cos(3 * lam * r) * np.sin(2 * phi * r) * np.exp(z / 1000.0)
+
+        def ef(lam, phi):
+            return 0.1 * np.cos(phi * r) * np.sin(2 * lam * r)
+
+        pkg.set_model(model, T=Tf, S=Sf, u=uf, v=vf, eta=ef)
+
+
+CASES = {
+    # the reference's own test size (test/runtests.jl:11-13: resolution 1/5 -> 72 x 30, Nz = 10)
+    "ref_test": Case("ref_test", 72, 30, 10, dt=600.0),
+    "dd_small": Case("dd_small", 90, 40, 8, dt=1200.0),
+    "dd_mid": Case("dd_mid", 180, 75, 12, dt=1200.0),
+    "dd_leith": Case("dd_leith", 90, 40, 8, dt=1200.0, qgleith=True),
+    "bumpy": Case("bumpy", 96, 48, 12, dt=900.0, bathymetry="bumpy"),
+    "quiescent": Case("quiescent", 90, 40, 8, experiment="Quiescent", dt=3240.0, perturb=False),
+    # C1: BASELINE.json configs[0]
+    "c1": Case("c1", 360, 150, 10, experiment="Quiescent", dt=3240.0, perturb=False),
+}
+
+
+def build_case(name: str) -> Case:
+    return CASES[name]
