@@ -1,15 +1,15 @@
 #!/usr/bin/env python3
 """Derive the WENO-N (N = 2..5, order 2N-1) tables symbolically and emit C headers.
 
-TEST INFRASTRUCTURE + build-time generator.  The arithmetic that the reference
+Build-time generator (its outputs are committed, so a normal build does not need sympy).  The arithmetic that the reference
 benchmark runs lives in Oceananigans.jl v0.90.1 (Manifest.toml:643-649), whose
 source is NOT available in this container; SURVEY.md Appendix A10 records the
 tables from recollection.  This script re-derives every table from first
 principles (cell-average reconstruction polynomials on a uniform grid) with
 sympy rationals, checks them against the recalled decimal literals, and writes
 
-  oracle/weno_tables.h                               (used by the CPU oracle)
-  oceanscalingtests.jl_b200/csrc/weno_tables.cuh     (used by the CUDA kernels)
+  oceanscalingtests.jl_b200/csrc/weno_gen.cuh   straight-line device code, constants folded (CUDA kernels)
+  oracle/weno_tables.h                          plain tables for the CPU oracle's runtime-order loops
 
 Conventions:
   * left-biased value at face i (between cells i-1 and i); stencil s (0 = most
@@ -143,9 +143,57 @@ def emit(tables, path, cuda):
         f.write("\n".join(out))
 
 
+def emit_device_code(tables, path):
+    """Straight-line __device__ code per order N: q[0..2N-2] are the stencil values ordered from the
+    most upwind-ward cell (q[0]) to the most downwind (q[2N-2]); stencil s uses q[N-1-s .. 2N-2-s].
+    weno_beta<N>(q, b) fills the N smoothness indicators; weno_combine<N>(q, b) applies Z-weights."""
+    out = ["// GENERATED by csrc/derive_weno.py -- do not edit.",
+           "#pragma once", "",
+           "template <int N> struct Weno;", ""]
+    taus = {2: "fabs(b[0] - b[1])", 3: "fabs(b[0] - b[2])",
+            4: "fabs(b[0] + 3.0 * b[1] - 3.0 * b[2] - b[3])",
+            5: "fabs(b[0] + 2.0 * b[1] - 6.0 * b[2] + 2.0 * b[3] + b[4])"}
+    for N in (2, 3, 4, 5):
+        c, o, b = tables[N]
+        out.append("template <> struct Weno<%d> {" % N)
+        out.append("  static constexpr int NQ = %d;" % (2 * N - 1))
+        out.append("  __device__ __forceinline__ static void beta(const double* __restrict__ q, double* __restrict__ b) {")
+        for s in range(N):
+            off = N - 1 - s
+            terms, m = [], 0
+            for a in range(N):
+                inner = []
+                for bb in range(a, N):
+                    inner.append("%s * q[%d]" % (lit(b[s][m]), off + bb))
+                    m += 1
+                terms.append("q[%d] * (%s)" % (off + a, " + ".join(inner)))
+            out.append("    b[%d] = %s;" % (s, " + ".join(terms)))
+        out.append("  }")
+        out.append("  __device__ __forceinline__ static double combine(const double* __restrict__ q, const double* __restrict__ b) {")
+        out.append("    const double tau = %s;" % taus[N])
+        out.append("    double asum = 0.0, r = 0.0;")
+        for s in range(N):
+            off = N - 1 - s
+            poly = " + ".join("%s * q[%d]" % (lit(c[s][a]), off + a) for a in range(N))
+            out.append("    { const double t = tau / (b[%d] + 1e-8); const double al = %s * (1.0 + t * t);" % (s, lit(o[s])))
+            out.append("      asum += al; r += al * (%s); }" % poly)
+        out.append("    return r / asum;")
+        out.append("  }")
+        out.append("};")
+        out.append("")
+    out.append("template <> struct Weno<1> {")
+    out.append("  static constexpr int NQ = 1;")
+    out.append("  __device__ __forceinline__ static void beta(const double*, double*) {}")
+    out.append("  __device__ __forceinline__ static double combine(const double* q, const double*) { return q[0]; }")
+    out.append("};")
+    out.append("")
+    with open(path, "w") as f:
+        f.write("\n".join(out))
+
+
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
-    root = os.path.dirname(here)
+    root = os.path.dirname(os.path.dirname(here))
     tables = {}
     for N in (2, 3, 4, 5):
         c, o, b = derive(N)
@@ -158,8 +206,8 @@ def main():
     # spot checks of the classic coefficients
     assert tables[3][0][0] == [sp.Rational(1, 3), sp.Rational(5, 6), sp.Rational(-1, 6)]
     assert tables[3][0][2] == [sp.Rational(1, 3), sp.Rational(-7, 6), sp.Rational(11, 6)]
-    emit(tables, os.path.join(here, "weno_tables.h"), cuda=False)
-    emit(tables, os.path.join(root, "oceanscalingtests.jl_b200", "csrc", "weno_tables.cuh"), cuda=True)
+    emit(tables, os.path.join(root, "oracle", "weno_tables.h"), cuda=False)
+    emit_device_code(tables, os.path.join(here, "weno_gen.cuh"))
     print("weno tables derived and verified against SURVEY A10 literals")
 
 

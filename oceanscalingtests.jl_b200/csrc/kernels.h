@@ -1,0 +1,46 @@
+// Host-callable launchers of the CUDA kernels (one translation unit per kernel family).
+#pragma once
+#include "ob_common.cuh"
+
+struct Fields {
+    // 3-D (Nz+1 planes)
+    double *u, *v, *w, *T, *S, *p, *kc, *ku, *Ri, *scratch;
+    double *Gu, *Gv, *GT, *GS, *Gu0, *Gv0, *GT0, *GS0;
+    double *nuL, *qx, *qy;
+    // 2-D
+    double *eta, *U, *V, *etab, *Ub, *Vb, *GU, *GV, *Hfc, *Hcf, *Ld;
+    // RealisticOcean forcing (Nx x Ny(+1) x 6, compact), may be null
+    double* forcing[6];
+};
+
+// kernels_halo.cu
+void launch_fill_halos(const Geom& G, const Fields& F, bool periodic_x, cudaStream_t st);
+void launch_mask_fields(const Geom& G, const Fields& F, cudaStream_t st);
+void launch_copy_field(const Geom& G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, bool three_d,
+                       bool to_field, cudaStream_t st);
+void launch_column_depths(const Geom& G, const Fields& F, cudaStream_t st);
+void launch_pack_x(const Geom& G, const Fields& F, double* sendW, double* sendE, cudaStream_t st);
+void launch_unpack_x(const Geom& G, const Fields& F, const double* recvW, const double* recvE, cudaStream_t st);
+size_t pack_x_count(const Geom& G);
+void launch_diagnostics(const Geom& G, const Fields& F, double* out8, cudaStream_t st);
+
+// kernels_column.cu
+void launch_w_p(const Geom& G, const Fields& F, cudaStream_t st);
+void launch_ri_kappa(const Geom& G, const Fields& F, double time, cudaStream_t st);
+void launch_barotropic_forcing(const Geom& G, const Fields& F, double chi, cudaStream_t st);
+void launch_ab2_implicit(const Geom& G, const Fields& F, double dt, double chi, cudaStream_t st);
+void launch_correct(const Geom& G, const Fields& F, cudaStream_t st);
+
+// kernels_baro.cu
+void launch_baro_init(const Geom& G, const Fields& F, bool periodic_x, cudaStream_t st);
+void launch_baro_eta(const Geom& G, const Fields& F, double dtau, bool periodic_x, cudaStream_t st);
+void launch_baro_vel(const Geom& G, const Fields& F, double dtau, double wgt, bool periodic_x, cudaStream_t st);
+void launch_baro_finish(const Geom& G, const Fields& F, cudaStream_t st);
+int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const double* weights_dev, int M, bool periodic_x,
+                           cudaStream_t st);
+
+// kernels_tend.cu
+void launch_tendencies(const Geom& G, const Fields& F, int ord_vort, int ord_div, int ord_tracer, double time,
+                       cudaStream_t st);
+// kernels_leith.cu
+void launch_leith(const Geom& G, const Fields& F, cudaStream_t st);

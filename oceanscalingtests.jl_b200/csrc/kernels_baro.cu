@@ -1,0 +1,121 @@
+// Split-explicit free surface: barotropic substeps (forward-backward scheme).
+//   eta -= dtau * div(U, V) / Az ;  U, V += dtau * (-g H d(eta) + G^{U,V}) ; averages += w_m * (eta, U, V)
+// Round-1 variant: two small 2-D launches per substep; the producing kernel also maintains the periodic
+// x-halo column the consumer needs (eta at i = -1, U at i = Nx), so no halo launches inside the loop.
+// launch_baro_persistent: one cooperative launch for all M substeps (grid-wide barrier between half steps).
+#include <cooperative_groups.h>
+
+#include "kernels.h"
+namespace cg = cooperative_groups;
+
+__global__ void k_baro_init(Geom G, Fields F, bool periodic) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;  // 0..Ny
+    if (i >= G.Nx) return;
+    const int c = idx2(G, i, j);
+    const double a = F.Ub[c], b = F.Vb[c];
+    F.U[c] = a;
+    F.V[c] = b;
+    if (periodic) {   // the first eta substep reads U at the east halo column
+        if (i < OB_H) { F.U[c + G.Nx] = a; F.V[c + G.Nx] = b; }
+        if (i >= G.Nx - OB_H) { F.U[c - G.Nx] = a; F.V[c - G.Nx] = b; }
+    }
+    F.etab[c] = 0.0; F.Ub[c] = 0.0; F.Vb[c] = 0.0;
+}
+
+__device__ __forceinline__ void eta_update(const Geom& G, const Fields& F, int i, int j, double dtau, bool periodic) {
+    const int c = idx2(G, i, j);
+    const double Vn = (j + 1 == G.Ny) ? 0.0 : F.V[c + G.pitch];
+    const double Vs = (j == 0) ? 0.0 : F.V[c];
+    const double e = F.eta[c] - dtau * ((G.dy * F.U[c + 1] - G.dy * F.U[c]) + (G.dxcf[j + 1] * Vn - G.dxcf[j] * Vs)) / G.azcc[j];
+    F.eta[c] = e;
+    if (periodic) {
+        if (i == G.Nx - 1) F.eta[c - G.Nx] = e;   // west halo column i = -1
+        if (i == 0) F.eta[c + G.Nx] = e;          // east halo column i = Nx
+    }
+}
+
+__device__ __forceinline__ void vel_update(const Geom& G, const Fields& F, int i, int j, double dtau, double wgt,
+                                           bool periodic) {
+    const int c = idx2(G, i, j);
+    const double e = F.eta[c];
+    const double detax = (e - F.eta[c - 1]) / G.dxfc[j];
+    const double detay = (j == 0) ? 0.0 : (e - F.eta[c - G.pitch]) / G.dy;
+    const double Un = F.U[c] + dtau * (-G.g * F.Hfc[c] * detax + F.GU[c]);
+    const double Vn = F.V[c] + dtau * (-G.g * F.Hcf[c] * detay + F.GV[c]);
+    F.U[c] = Un; F.V[c] = Vn;
+    F.etab[c] += wgt * e;
+    F.Ub[c] += wgt * Un;
+    F.Vb[c] += wgt * Vn;
+    if (periodic) {
+        if (i == 0) { F.U[c + G.Nx] = Un; F.V[c + G.Nx] = Vn; }
+        if (i == G.Nx - 1) { F.U[c - G.Nx] = Un; F.V[c - G.Nx] = Vn; }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_baro_eta(Geom G, Fields F, double dtau, bool periodic) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.Nx) return;
+    eta_update(G, F, i, blockIdx.y, dtau, periodic);
+}
+__global__ void __launch_bounds__(128) k_baro_vel(Geom G, Fields F, double dtau, double wgt, bool periodic) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.Nx) return;
+    vel_update(G, F, i, blockIdx.y, dtau, wgt, periodic);
+}
+__global__ void k_baro_finish(Geom G, Fields F) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= G.Nx) return;
+    const int c = idx2(G, i, j);
+    F.eta[c] = F.etab[c];
+}
+
+void launch_baro_init(const Geom& G, const Fields& F, bool periodic, cudaStream_t st) {
+    dim3 b(128), g((G.Nx + 127) / 128, G.Ny + 1);
+    k_baro_init<<<g, b, 0, st>>>(G, F, periodic);
+}
+void launch_baro_eta(const Geom& G, const Fields& F, double dtau, bool periodic, cudaStream_t st) {
+    dim3 b(128), g((G.Nx + 127) / 128, G.Ny);
+    k_baro_eta<<<g, b, 0, st>>>(G, F, dtau, periodic);
+}
+void launch_baro_vel(const Geom& G, const Fields& F, double dtau, double wgt, bool periodic, cudaStream_t st) {
+    dim3 b(128), g((G.Nx + 127) / 128, G.Ny);
+    k_baro_vel<<<g, b, 0, st>>>(G, F, dtau, wgt, periodic);
+}
+void launch_baro_finish(const Geom& G, const Fields& F, cudaStream_t st) {
+    dim3 b(128), g((G.Nx + 127) / 128, G.Ny);
+    k_baro_finish<<<g, b, 0, st>>>(G, F);
+}
+
+// ---- persistent variant: all substeps in one cooperative launch --------------------------------------
+__global__ void __launch_bounds__(256) k_baro_persistent(Geom G, Fields F, double dtau, const double* __restrict__ wts,
+                                                          int M, bool periodic) {
+    cg::grid_group grid = cg::this_grid();
+    const long long n = (long long)G.Nx * G.Ny;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    for (int m = 0; m < M; m++) {
+        for (long long t = tid; t < n; t += nth) eta_update(G, F, (int)(t % G.Nx), (int)(t / G.Nx), dtau, periodic);
+        grid.sync();
+        const double wgt = wts[m];
+        for (long long t = tid; t < n; t += nth) vel_update(G, F, (int)(t % G.Nx), (int)(t / G.Nx), dtau, wgt, periodic);
+        grid.sync();
+    }
+}
+
+int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const double* wts, int M, bool periodic,
+                           cudaStream_t st) {
+    static int nblk = 0;
+    if (nblk == 0) {
+        int dev = 0, sms = 0, per = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_baro_persistent, 256, 0);
+        nblk = sms * (per > 4 ? 4 : per);
+    }
+    Geom g = G; Fields f = F;
+    void* args[] = {&g, &f, &dtau, &wts, &M, &periodic};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_baro_persistent, dim3(nblk), dim3(256), args, 0, st);
+    return e == cudaSuccess ? 0 : -1;
+}

@@ -1,0 +1,175 @@
+// Halo fills, immersed masking, field transfer, x-slab pack/unpack, diagnostics.
+#include "kernels.h"
+
+// x: periodic copy of OB_H columns (single rank).  Threads over (h, row j, plane k).
+__global__ void k_fill_x(Geom G, Fields F) {
+    const int h = threadIdx.x;                        // 0..OB_H-1
+    const int j = blockIdx.x * blockDim.y + threadIdx.y;   // 0..Ny (interior rows, plus the v wall row)
+    const int k = blockIdx.y;
+    if (h >= OB_H || j > G.Ny) return;
+    double* fs[4] = {F.u, F.v, F.T, F.S};
+    const long long c = idx3(G, 0, j, k);
+    if (k < G.Nz) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            double* f = fs[q];
+            f[c - 1 - h] = f[c + G.Nx - 1 - h];
+            f[c + G.Nx + h] = f[c + h];
+        }
+    } else {  // 2-D eta rides along as "plane Nz"
+        const int c2 = idx2(G, 0, j);
+        F.eta[c2 - 1 - h] = F.eta[c2 + G.Nx - 1 - h];
+        F.eta[c2 + G.Nx + h] = F.eta[c2 + h];
+    }
+}
+
+// y: centre-located fields get zero-gradient copies of the boundary row in every halo row; v is zero on and
+// beyond the wall faces.  Threads over all columns incl. x-halos.
+__global__ void k_fill_y(Geom G, Fields F) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - OB_H;
+    const int k = blockIdx.y;
+    if (i >= G.Nx + OB_H) return;
+    if (k < G.Nz) {
+        double* fs[3] = {F.u, F.T, F.S};
+        const long long s0 = idx3(G, i, 0, k), s1 = idx3(G, i, G.Ny - 1, k);
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            double* f = fs[q];
+            const double a = f[s0], b = f[s1];
+            for (int h = 1; h <= OB_H; h++) { f[s0 - (long long)h * G.pitch] = a; f[s1 + (long long)h * G.pitch] = b; }
+        }
+        const long long v0 = idx3(G, i, 0, k), v1 = idx3(G, i, G.Ny, k);
+        for (int h = 0; h <= OB_H; h++) { F.v[v0 - (long long)h * G.pitch] = 0.0; F.v[v1 + (long long)h * G.pitch] = 0.0; }
+    } else {
+        const int s0 = idx2(G, i, 0), s1 = idx2(G, i, G.Ny - 1);
+        const double a = F.eta[s0], b = F.eta[s1];
+        for (int h = 1; h <= OB_H; h++) { F.eta[s0 - h * G.pitch] = a; F.eta[s1 + h * G.pitch] = b; }
+    }
+}
+
+void launch_fill_halos(const Geom& G, const Fields& F, bool periodic_x, cudaStream_t st) {
+    if (periodic_x) {
+        dim3 b(8, 16), g((G.Ny + 1 + 15) / 16, G.Nz + 1);
+        k_fill_x<<<g, b, 0, st>>>(G, F);
+    }
+    dim3 b2(128), g2((G.Nx + 2 * OB_H + 127) / 128, G.Nz + 1);
+    k_fill_y<<<g2, b2, 0, st>>>(G, F);
+}
+
+// mask_immersed_field! for u, v, T, S and eta; needed after set_field only: the step never
+// writes a masked node.
+__global__ void k_mask(Geom G, Fields F) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, k = blockIdx.z;
+    if (i >= G.Nx) return;
+    const long long c = idx3(G, i, j, k);
+    if (j < G.Ny) {
+        if (peripheral_fcc(G, i, j, k)) F.u[c] = 0.0;
+        if (!active(G, i, j, k)) { F.T[c] = 0.0; F.S[c] = 0.0; }
+        if (k == G.Nz - 1 && !active(G, i, j, k)) F.eta[idx2(G, i, j)] = 0.0;
+    }
+    if (peripheral_cfc(G, i, j, k)) F.v[c] = 0.0;
+}
+void launch_mask_fields(const Geom& G, const Fields& F, cudaStream_t st) {
+    dim3 b(128), g((G.Nx + 127) / 128, G.Ny + 1, G.Nz);
+    k_mask<<<g, b, 0, st>>>(G, F);
+}
+
+// wet column depth at u / v points: sum of dz over non-peripheral nodes
+__global__ void k_column_depths(Geom G, Fields F) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - OB_H + 1;
+    const int j = blockIdx.y;  // 0..Ny
+    if (i >= G.Nx + OB_H) return;
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < G.Nz; k++) {
+        if (!peripheral_fcc(G, i, j, k)) a += G.dzc[k];
+        if (!peripheral_cfc(G, i, j, k)) b += G.dzc[k];
+    }
+    F.Hfc[idx2(G, i, j)] = a;
+    F.Hcf[idx2(G, i, j)] = b;
+}
+void launch_column_depths(const Geom& G, const Fields& F, cudaStream_t st) {
+    dim3 b(128), g((G.Nx + 2 * OB_H + 127) / 128, G.Ny + 1);
+    k_column_depths<<<g, b, 0, st>>>(G, F);
+}
+
+// interior <-> user buffer laid out like an Oceananigans parent array with halos (hx, hy, hz)
+__global__ void k_copy_field(Geom G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, bool three_d,
+                             bool to_field) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, k = blockIdx.z;
+    if (i >= G.Nx) return;
+    const size_t sx = G.Nx + 2 * hx, sy = ny + 2 * hy;
+    const size_t b = ((size_t)(k + (three_d ? hz : 0)) * sy + (j + hy)) * sx + (i + hx);
+    const long long c = three_d ? idx3(G, i, j, k) : (long long)idx2(G, i, j);
+    if (to_field) field[c] = buf[b]; else buf[b] = field[c];
+}
+void launch_copy_field(const Geom& G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, bool three_d,
+                       bool to_field, cudaStream_t st) {
+    dim3 b(128), g((G.Nx + 127) / 128, ny, nz);
+    k_copy_field<<<g, b, 0, st>>>(G, field, buf, ny, nz, hx, hy, hz, three_d, to_field);
+}
+
+// ---- x-slab exchange buffers: [u | v | T | S] x (Nz planes x (Ny+1) rows x OB_H cols) + eta ((Ny+1) x OB_H)
+size_t pack_x_count(const Geom& G) { return (size_t)OB_H * (G.Ny + 1) * (4 * (size_t)G.Nz + 1); }
+
+__global__ void k_pack_x(Geom G, Fields F, double* sendW, double* sendE, bool unpack) {
+    const int h = threadIdx.x;
+    const int j = blockIdx.x * blockDim.y + threadIdx.y;
+    const int k = blockIdx.y;   // 0..Nz (Nz = eta)
+    if (h >= OB_H || j > G.Ny) return;
+    const size_t per = (size_t)OB_H * (G.Ny + 1);
+    const size_t o = (size_t)j * OB_H + h;
+    if (k < G.Nz) {
+        double* fs[4] = {F.u, F.v, F.T, F.S};
+        const long long c = idx3(G, 0, j, k);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const size_t b = ((size_t)q * G.Nz + k) * per + o;
+            if (!unpack) { sendW[b] = fs[q][c + h]; sendE[b] = fs[q][c + G.Nx - OB_H + h]; }
+            else { fs[q][c - OB_H + h] = sendW[b]; fs[q][c + G.Nx + h] = sendE[b]; }
+        }
+    } else {
+        const size_t b = (size_t)4 * G.Nz * per + o;
+        const int c = idx2(G, 0, j);
+        if (!unpack) { sendW[b] = F.eta[c + h]; sendE[b] = F.eta[c + G.Nx - OB_H + h]; }
+        else { F.eta[c - OB_H + h] = sendW[b]; F.eta[c + G.Nx + h] = sendE[b]; }
+    }
+}
+void launch_pack_x(const Geom& G, const Fields& F, double* sendW, double* sendE, cudaStream_t st) {
+    dim3 b(8, 16), g((G.Ny + 1 + 15) / 16, G.Nz + 1);
+    k_pack_x<<<g, b, 0, st>>>(G, F, sendW, sendE, false);
+}
+// recvW = data for the west halo (from the west neighbour's east edge), recvE likewise
+void launch_unpack_x(const Geom& G, const Fields& F, const double* recvW, const double* recvE, cudaStream_t st) {
+    dim3 b(8, 16), g((G.Ny + 1 + 15) / 16, G.Nz + 1);
+    k_pack_x<<<g, b, 0, st>>>(G, F, const_cast<double*>(recvW), const_cast<double*>(recvE), true);
+}
+
+// ---- diagnostics: max |u|,|v|,|w|,|eta|,|T|,|S| and the advective CFL time scale (TimeStepWizard) ----------
+__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {   // v >= 0
+    atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
+}
+__global__ void k_diag(Geom G, Fields F, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, k = blockIdx.z;
+    double m[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (i < G.Nx) {
+        const long long c = idx3(G, i, j, k);
+        m[0] = fabs(F.u[c]); m[1] = fabs(F.v[c]); m[2] = fmax(fabs(F.w[c]), k == G.Nz - 1 ? fabs(F.w[c + G.sz]) : 0.0);
+        m[3] = (k == 0) ? fabs(F.eta[idx2(G, i, j)]) : 0.0;
+        m[4] = fabs(F.T[c]); m[5] = fabs(F.S[c]);
+        // 1 / cell advection time scale: |u|/dx + |v|/dy + |w|/dz
+        m[6] = m[0] / G.dxfc[j] + m[1] / G.dy + fabs(F.w[c]) / G.dzc[k];
+    }
+    for (int q = 0; q < 7; q++) {
+        double v = m[q];
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((threadIdx.x & 31) == 0 && v > 0.0) atomic_max_pos(out + q, v);
+    }
+}
+void launch_diagnostics(const Geom& G, const Fields& F, double* out8, cudaStream_t st) {
+    cudaMemsetAsync(out8, 0, 8 * sizeof(double), st);
+    dim3 b(128), g((G.Nx + 127) / 128, G.Ny, G.Nz);
+    k_diag<<<g, b, 0, st>>>(G, F, out8);
+}

@@ -1,0 +1,132 @@
+// Shared device-side definitions of libocean_b200: geometry, indexing, node predicates,
+// equation of state, WENO wrappers.  sm_100a only; Float64 throughout.
+//
+// HBM layout (DESIGN.md "Data layout"): every 3-D field is one array of (Nz+1) planes x NyP rows x
+// `pitch` doubles, i (longitude) contiguous.  Interior column 0 sits at element X0 = 16 of a row (128-byte
+// aligned since pitch % 16 == 0 and the base is 256-byte aligned); 7 halo columns on each side are used
+// (periodic copy on one GPU, NCCL-exchanged neighbour columns on several).  Rows j = -7 .. Ny+7 (v has the
+// extra face row Ny).  No vertical halos are stored: vertical stencils are 2-point and clamp.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/ocean_b200.h"
+
+#define OB_H 7     // horizontal halo used by stencils
+#define OB_X0 16   // element offset of interior column 0 inside a row
+
+struct Geom {
+    int Nx, Ny, Nz;
+    int pitch, NyP;          // row pitch (elements), number of rows
+    long long sz;            // plane stride = pitch * NyP
+    // per-latitude metrics, indexable for j = -OB_H-1 .. Ny+OB_H+1 (pointers pre-offset so [j] works)
+    const double *dxfc, *dxcf, *azcc, *azcf, *fff, *taux, *sflux, *tref;
+    // vertical metrics: dzc[k], zc[k] for k = -1..Nz (pre-offset), dzf[k] for k = 0..Nz
+    const double *dzc, *dzf, *zc;
+    const int* kb;           // first active level per column (2-D, field layout); Nz = no active cell
+    const int* kfast;        // level from which the full-order, mask-free stencils are valid (2-D)
+    double dy;
+    double g, alpha, beta_s, rho0;
+    int eos;
+    double nu_z, kappa_z;
+    int ri_enabled;
+    double ri_nu0, ri_kappa0, ri_kappa_ca, ri_Cen, ri_Cav, ri_Ri0, ri_Ridelta;
+    int bc_kind;
+    double lambda_T, mu_drag;
+    int qgleith;
+    double leith_C, leith_minN2, leith_Vscale;
+};
+
+__device__ __forceinline__ long long idx3(const Geom& G, int i, int j, int k) {
+    return (long long)k * G.sz + (long long)(j + OB_H) * G.pitch + (i + OB_X0);
+}
+__device__ __forceinline__ int idx2(const Geom& G, int i, int j) { return (j + OB_H) * G.pitch + (i + OB_X0); }
+
+// ---- node predicates.  kb rows outside the y-domain hold Nz, so the j-range test is implicit.
+__device__ __forceinline__ bool active(const Geom& G, int i, int j, int k) {
+    return (unsigned)k < (unsigned)G.Nz && k >= __ldg(&G.kb[idx2(G, i, j)]);
+}
+__device__ __forceinline__ bool in_domain(const Geom& G, int j, int k) {
+    return (unsigned)j < (unsigned)G.Ny && (unsigned)k < (unsigned)G.Nz;
+}
+__device__ __forceinline__ bool inactive_fcc(const Geom& G, int i, int j, int k) { return !active(G, i - 1, j, k) && !active(G, i, j, k); }
+__device__ __forceinline__ bool inactive_cfc(const Geom& G, int i, int j, int k) { return !active(G, i, j - 1, k) && !active(G, i, j, k); }
+__device__ __forceinline__ bool peripheral_fcc(const Geom& G, int i, int j, int k) { return !active(G, i - 1, j, k) || !active(G, i, j, k); }
+__device__ __forceinline__ bool peripheral_cfc(const Geom& G, int i, int j, int k) { return !active(G, i, j - 1, k) || !active(G, i, j, k); }
+__device__ __forceinline__ bool peripheral_ccf(const Geom& G, int i, int j, int k) { return !active(G, i, j, k - 1) || !active(G, i, j, k); }
+__device__ __forceinline__ bool peripheral_fcf(const Geom& G, int i, int j, int k) {
+    return !active(G, i - 1, j, k - 1) || !active(G, i, j, k - 1) || !active(G, i - 1, j, k) || !active(G, i, j, k);
+}
+__device__ __forceinline__ bool peripheral_cff(const Geom& G, int i, int j, int k) {
+    return !active(G, i, j - 1, k - 1) || !active(G, i, j, k - 1) || !active(G, i, j - 1, k) || !active(G, i, j, k);
+}
+
+// ---- TEOS-10 55-term polynomial (Roquet et al. 2015; SeawaterPolynomials 0.3.2) [OCN-recall coefficients].
+// Stored as R[k][j][i] (powers of zeta, tau, s); evaluated by nested Horner over the triangular support.
+static __device__ __constant__ double TEOS_R[4][7][7] = {
+    {{8.0189615746e+02, 8.6672408165e+02, -1.7864682637e+03, 2.0375295546e+03, -1.2849161071e+03, 4.3227585684e+02, -6.0579916612e+01},
+     {2.6010145068e+01, -6.5281885265e+01, 8.1770425108e+01, -5.6888046321e+01, 1.7681814114e+01, -1.9193502195e+00, 0},
+     {-3.7074170417e+01, 6.1548258127e+01, -6.0362551501e+01, 2.9130021253e+01, -5.4723692739e+00, 0, 0},
+     {2.1661789529e+01, -3.3449108469e+01, 1.9717078466e+01, -3.1742946532e+00, 0, 0, 0},
+     {-8.3627885467e+00, 1.1311538584e+01, -5.3563304045e+00, 0, 0, 0, 0},
+     {5.4048723791e-01, 4.8169980163e-01, 0, 0, 0, 0, 0},
+     {-1.9083568888e-01, 0, 0, 0, 0, 0, 0}},
+    {{1.9681925209e+01, -4.2549998214e+01, 5.0774768218e+01, -3.0938076334e+01, 6.6051753097e+00, 0, 0},
+     {-1.3336301113e+01, -4.4870114575e+00, 5.0042598061e+00, -6.5399043664e-01, 0, 0, 0},
+     {6.7080479603e+00, 3.5063081279e+00, -1.8795372996e+00, 0, 0, 0, 0},
+     {-2.4649669534e+00, -5.5077101279e-01, 0, 0, 0, 0, 0},
+     {5.5927935970e-01, 0, 0, 0, 0, 0, 0},
+     {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}},
+    {{2.0660924175e+00, -4.9527603989e+00, 2.5019633244e+00, 0, 0, 0, 0},
+     {2.0564311499e+00, -2.1311365518e-01, 0, 0, 0, 0, 0},
+     {-1.2419983026e+00, 0, 0, 0, 0, 0, 0},
+     {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}},
+    {{-2.3342758797e-02, -1.8507636718e-02, 0, 0, 0, 0, 0},
+     {3.7969820455e-01, 0, 0, 0, 0, 0, 0},
+     {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}}};
+
+// r'(tau, s, zeta) and optionally its derivatives w.r.t. Theta and S_A
+template <bool DERIV>
+__device__ __forceinline__ double teos_rprime(double Th, double SA, double Z, double* dTh, double* dSA) {
+    const double Sau = 40.0 * 35.16504 / 35.0, Thu = 40.0, Zu = 1e4, dS = 32.0;
+    const double tau = Th / Thu, s = sqrt((SA + dS) / Sau), ze = -Z / Zu;
+    const int deg[4] = {6, 4, 2, 1};
+    double r = 0.0, rt = 0.0, rs = 0.0;
+#pragma unroll
+    for (int k = 3; k >= 0; k--) {
+        double pj = 0.0, pjt = 0.0, pjs = 0.0;
+#pragma unroll
+        for (int j = 6; j >= 0; j--) {
+            if (j > deg[k]) continue;
+            double pi = 0.0, pis = 0.0;
+#pragma unroll
+            for (int i = 6; i >= 0; i--) {
+                if (i + j > deg[k]) continue;
+                if (DERIV) pis = pis * s + pi;
+                pi = pi * s + TEOS_R[k][j][i];
+            }
+            if (DERIV) { pjt = pjt * tau + pj; pjs = pjs * tau + pis; }
+            pj = pj * tau + pi;
+        }
+        r = r * ze + pj;
+        if (DERIV) { rt = rt * ze + pjt; rs = rs * ze + pjs; }
+    }
+    if (DERIV) { *dTh = rt / Thu; *dSA = rs / (2.0 * s * Sau); }
+    return r;
+}
+
+__device__ __forceinline__ double buoyancy_of(const Geom& G, double T, double S, int k) {
+    if (G.eos == OB200_EOS_LINEAR) return G.g * (G.alpha * T - G.beta_s * S);
+    return -G.g * teos_rprime<false>(T, S, G.zc[k], nullptr, nullptr) / G.rho0;
+}
+
+__device__ __forceinline__ double upwind_flux(double vel, double L, double R) {
+    const double a = fabs(vel);
+    return 0.5 * ((vel + a) * L + (vel - a) * R);
+}
+
+#define OB_CUDA_CHECK(h, expr)                                                         \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) return (h)->fail(OB200_ECUDA, #expr, cudaGetErrorString(_e)); \
+    } while (0)

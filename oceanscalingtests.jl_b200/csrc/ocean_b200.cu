@@ -1,0 +1,570 @@
+// libocean_b200.so -- C ABI (include/ocean_b200.h): handle, HBM allocation, sequencing of one
+// HydrostaticFreeSurfaceModel time step, x-slab halo exchange over NCCL.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
+
+#include "kernels.h"
+
+static thread_local std::string g_last_error;
+
+struct ob200_handle {
+    ob200_config cfg;
+    int device = 0;
+    Geom G;
+    Fields F;
+    bool periodic_local = true;
+    bool own_stream = true;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev[20];
+    cudaEvent_t ev_comm[2];
+    bool timing = false, use_graph = false, persistent_baro = false;
+    float last_ms[16];
+    int n_timed = 0;
+    std::vector<void*> allocs;
+    std::vector<double> weights;
+    double* d_weights = nullptr;
+    double* d_diag = nullptr;
+    double* G_swap[8];
+    // clock
+    double time = 0.0, last_dt = INFINITY;
+    int64_t iteration = 0;
+    bool fields_dirty = true;   // set_field since the last mask
+    // NCCL ring
+    ncclComm_t comm = nullptr;
+    double *sendW = nullptr, *sendE = nullptr, *recvW = nullptr, *recvE = nullptr;
+    size_t xcount = 0;
+    // CUDA graph of a full step at fixed dt
+    cudaGraphExec_t graph_exec = nullptr;
+    double graph_dt = NAN;
+    bool graph_euler = false;
+    std::string err;
+
+    int fail(int code, const char* what, const char* detail) {
+        err = std::string(what) + ": " + (detail ? detail : "");
+        g_last_error = err;
+        return code;
+    }
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(ob200_handle* h, T** p, size_t n, bool zero = true) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) return h->fail(OB200_ENOMEM, "cudaMalloc", cudaGetErrorString(e));
+    if (zero) cudaMemset(q, 0, n * sizeof(T));
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return OB200_OK;
+}
+
+double wind_stress(const ob200_config& c, double phi) {   // bathymetry_and_forcings.jl:110-119
+    const double* q = phi < -45 ? c.wind_coeffs : phi < -15 ? c.wind_coeffs + 4 : phi < 0 ? c.wind_coeffs + 8
+                    : phi < 15 ? c.wind_coeffs + 12 : phi < 45 ? c.wind_coeffs + 16 : c.wind_coeffs + 20;
+    return q[0] * phi * phi * phi + q[1] * phi * phi + q[2] * phi + q[3];
+}
+double salinity_flux(const ob200_config& c, double phi) {   // :121-128
+    const double* q = phi < -20 ? c.salt_coeffs : phi < 0 ? c.salt_coeffs + 4 : phi < 20 ? c.salt_coeffs + 8 : c.salt_coeffs + 12;
+    return q[0] * phi * phi * phi + q[1] * phi * phi + q[2] * phi + q[3];
+}
+
+int setup_geometry(ob200_handle* h) {
+    const ob200_config& c = h->cfg;
+    Geom& G = h->G;
+    std::memset(&G, 0, sizeof(G));
+    G.Nx = c.Nx; G.Ny = c.Ny; G.Nz = c.Nz;
+    G.pitch = OB_X0 + ((c.Nx + OB_H + 15) / 16) * 16;
+    G.NyP = c.Ny + 1 + 2 * OB_H;
+    G.sz = (long long)G.pitch * G.NyP;
+    const double pi = M_PI;
+    const double dlam = (c.lon_east - c.lon_west) / c.Nx_global;
+    const double dphi = (c.lat_north - c.lat_south) / c.Ny;
+    const double dlam_rad = dlam * pi / 180.0;
+    G.dy = c.radius * (dphi * pi / 180.0);
+    // per-latitude metrics for j = -(H+1) .. Ny+H+1
+    const int jo = OB_H + 1, nj = c.Ny + 2 * jo + 1;
+    std::vector<double> m[8];
+    for (auto& v : m) v.assign(nj, 0.0);
+    auto pf = [&](int j) { return (double)((long double)c.lat_south + (long double)j * (long double)dphi); };
+    auto pc = [&](int j) { return (double)((long double)c.lat_south + ((long double)j + 0.5L) * (long double)dphi); };
+    auto cosd = [&](double x) { return std::cos(pi * x / 180.0); };
+    auto sind = [&](double x) { return std::sin(pi * x / 180.0); };
+    for (int jj = 0; jj < nj; jj++) {
+        const int j = jj - jo;
+        m[0][jj] = c.radius * cosd(pc(j)) * dlam_rad;                                        // dxfc = dxcc
+        m[1][jj] = c.radius * cosd(pf(j)) * dlam_rad;                                        // dxcf = dxff
+        m[2][jj] = c.radius * c.radius * dlam_rad * (sind(pf(j + 1)) - sind(pf(j)));         // azcc = azfc
+        m[3][jj] = c.radius * c.radius * dlam_rad * (sind(pc(j)) - sind(pc(j - 1)));         // azcf = azff
+        m[4][jj] = 2.0 * c.rotation_rate * sind(pf(j));                                      // f at (f,f)
+        m[5][jj] = wind_stress(c, pc(j));
+        m[6][jj] = salinity_flux(c, pc(j));
+        m[7][jj] = std::fmax(0.0, 30.0 * std::cos(1.2 * pi * pc(j) / 180.0));                // T_reference (:154)
+    }
+    const double** dst[8] = {&G.dxfc, &G.dxcf, &G.azcc, &G.azcf, &G.fff, &G.taux, &G.sflux, &G.tref};
+    for (int q = 0; q < 8; q++) {
+        double* d = nullptr;
+        if (int rc = dev_alloc(h, &d, nj, false)) return rc;
+        cudaMemcpy(d, m[q].data(), nj * sizeof(double), cudaMemcpyHostToDevice);
+        *dst[q] = d + jo;
+    }
+    // vertical metrics
+    const int Nz = c.Nz;
+    std::vector<double> zc(Nz + 2), dzc(Nz + 2), dzf(Nz + 1);
+    for (int k = 0; k < Nz; k++) { dzc[k + 1] = c.z_faces[k + 1] - c.z_faces[k]; zc[k + 1] = 0.5 * (c.z_faces[k + 1] + c.z_faces[k]); }
+    dzc[0] = dzc[1]; dzc[Nz + 1] = dzc[Nz];
+    zc[0] = c.z_faces[0] - 0.5 * dzc[0]; zc[Nz + 1] = c.z_faces[Nz] + 0.5 * dzc[Nz + 1];
+    for (int k = 0; k <= Nz; k++) dzf[k] = zc[k + 1] - zc[k];
+    double *dzc_d, *zc_d, *dzf_d;
+    if (int rc = dev_alloc(h, &dzc_d, Nz + 2, false)) return rc;
+    if (int rc = dev_alloc(h, &zc_d, Nz + 2, false)) return rc;
+    if (int rc = dev_alloc(h, &dzf_d, Nz + 1, false)) return rc;
+    cudaMemcpy(dzc_d, dzc.data(), (Nz + 2) * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(zc_d, zc.data(), (Nz + 2) * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(dzf_d, dzf.data(), (Nz + 1) * sizeof(double), cudaMemcpyHostToDevice);
+    G.dzc = dzc_d + 1; G.zc = zc_d + 1; G.dzf = dzf_d;
+    // bathymetry -> first active level per column; rows outside the y-domain are fully inactive
+    const size_t n2 = (size_t)G.pitch * G.NyP;
+    std::vector<int> kb(n2, Nz), kfast(n2, Nz);
+    const int nxh = c.Nx + 2 * OB_H;
+    for (int j = 0; j < c.Ny; j++)
+        for (int ii = 0; ii < nxh; ii++) {
+            const double hgt = c.bottom_height[(size_t)j * nxh + ii];
+            int k0 = 0;
+            while (k0 < Nz && zc[k0 + 1] <= hgt) k0++;
+            kb[(size_t)(j + OB_H) * G.pitch + (ii - OB_H + OB_X0)] = k0;
+        }
+    // first level from which the mask-free full-order stencils are valid: every cell within 5 columns / rows
+    // wet and in the domain; the level just above a neighbour's sea floor still needs the conditional
+    // vertical flux, hence K + 1 unless K == 0.  Only when the configured orders are the defaults (9, 5, 7).
+    const bool default_orders = c.order_vorticity == 9 && c.order_divergence == 5 && c.order_tracer == 7;
+    if (default_orders)
+        for (int j = 0; j < c.Ny; j++)
+            for (int i = 0; i < c.Nx; i++) {
+                int K = 0;
+                for (int b = -5; b <= 5; b++)
+                    for (int a = -5; a <= 5; a++) {
+                        const int jj = j + b;
+                        const int v = (jj < 0 || jj >= c.Ny) ? Nz : kb[(size_t)(jj + OB_H) * G.pitch + (i + a + OB_X0)];
+                        K = v > K ? v : K;
+                    }
+                kfast[(size_t)(j + OB_H) * G.pitch + (i + OB_X0)] = (K == 0) ? 0 : (K >= Nz ? Nz : K + 1);
+            }
+    int *kb_d, *kf_d;
+    if (int rc = dev_alloc(h, &kb_d, n2, false)) return rc;
+    if (int rc = dev_alloc(h, &kf_d, n2, false)) return rc;
+    cudaMemcpy(kb_d, kb.data(), n2 * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(kf_d, kfast.data(), n2 * sizeof(int), cudaMemcpyHostToDevice);
+    G.kb = kb_d; G.kfast = kf_d;
+    // parameters
+    G.g = c.gravity; G.alpha = c.eos_alpha; G.beta_s = c.eos_beta; G.rho0 = c.eos_rho0; G.eos = c.eos_kind;
+    G.nu_z = c.nu_z; G.kappa_z = c.kappa_z; G.ri_enabled = c.ri_enabled;
+    G.ri_nu0 = c.ri_nu0; G.ri_kappa0 = c.ri_kappa0; G.ri_kappa_ca = c.ri_kappa_ca; G.ri_Cen = c.ri_Cen;
+    G.ri_Cav = c.ri_Cav; G.ri_Ri0 = c.ri_Ri0; G.ri_Ridelta = c.ri_Ridelta;
+    G.bc_kind = c.bc_kind; G.lambda_T = c.T_restoring_lambda; G.mu_drag = c.drag_mu;
+    G.qgleith = c.qgleith_enabled; G.leith_C = c.leith_C; G.leith_minN2 = c.leith_min_N2; G.leith_Vscale = c.leith_Vscale;
+    return OB200_OK;
+}
+
+int alloc_fields(ob200_handle* h) {
+    const Geom& G = h->G;
+    Fields& F = h->F;
+    std::memset(&F, 0, sizeof(F));
+    const size_t n3 = (size_t)G.sz * (G.Nz + 1), n2 = (size_t)G.sz;
+    double** f3[] = {&F.u, &F.v, &F.w, &F.T, &F.S, &F.p, &F.kc, &F.ku, &F.Ri, &F.scratch,
+                     &F.Gu, &F.Gv, &F.GT, &F.GS, &F.Gu0, &F.Gv0, &F.GT0, &F.GS0};
+    for (double** p : f3)
+        if (int rc = dev_alloc(h, p, n3)) return rc;
+    if (G.qgleith)
+        for (double** p : {&F.nuL, &F.qx, &F.qy})
+            if (int rc = dev_alloc(h, p, n3)) return rc;
+    double** f2[] = {&F.eta, &F.U, &F.V, &F.etab, &F.Ub, &F.Vb, &F.GU, &F.GV, &F.Hfc, &F.Hcf, &F.Ld};
+    for (double** p : f2)
+        if (int rc = dev_alloc(h, p, n2)) return rc;
+    return OB200_OK;
+}
+
+struct FieldRef { double* p; int ny, nz; bool three_d; };
+FieldRef field_ref(ob200_handle* h, int id) {
+    const Geom& G = h->G;
+    Fields& F = h->F;
+    const int Ny = G.Ny, Nz = G.Nz;
+    switch (id) {
+        case OB200_F_U: return {F.u, Ny, Nz, true};
+        case OB200_F_V: return {F.v, Ny + 1, Nz, true};
+        case OB200_F_W: return {F.w, Ny, Nz + 1, true};
+        case OB200_F_T: return {F.T, Ny, Nz, true};
+        case OB200_F_S: return {F.S, Ny, Nz, true};
+        case OB200_F_P: return {F.p, Ny, Nz, true};
+        case OB200_F_KAPPA_C: return {F.kc, Ny, Nz + 1, true};
+        case OB200_F_KAPPA_U: return {F.ku, Ny, Nz + 1, true};
+        case OB200_F_GU: return {F.Gu, Ny, Nz, true};
+        case OB200_F_GV: return {F.Gv, Ny + 1, Nz, true};
+        case OB200_F_GT: return {F.GT, Ny, Nz, true};
+        case OB200_F_GS: return {F.GS, Ny, Nz, true};
+        case OB200_F_GU_PREV: return {F.Gu0, Ny, Nz, true};
+        case OB200_F_GV_PREV: return {F.Gv0, Ny + 1, Nz, true};
+        case OB200_F_GT_PREV: return {F.GT0, Ny, Nz, true};
+        case OB200_F_GS_PREV: return {F.GS0, Ny, Nz, true};
+        case OB200_F_ETA: return {F.eta, Ny, 1, false};
+        case OB200_F_UBAR: return {F.Ub, Ny, 1, false};
+        case OB200_F_VBAR: return {F.Vb, Ny + 1, 1, false};
+        case OB200_F_UTRANS: return {F.U, Ny, 1, false};
+        case OB200_F_VTRANS: return {F.V, Ny + 1, 1, false};
+        case OB200_F_GUBT: return {F.GU, Ny, 1, false};
+        case OB200_F_GVBT: return {F.GV, Ny + 1, 1, false};
+        case OB200_F_NU_LEITH: return {F.nuL, Ny, Nz, true};
+        case OB200_F_QX: return {F.qx, Ny, Nz + 1, true};
+        case OB200_F_QY: return {F.qy, Ny, Nz + 1, true};
+        case OB200_F_LD: return {F.Ld, Ny, 1, false};
+        default: return {nullptr, 0, 0, false};
+    }
+}
+
+// ---- stages ------------------------------------------------------------------------------------------
+int exchange_halos(ob200_handle* h) {
+    if (h->periodic_local) return OB200_OK;
+    if (!h->comm) return h->fail(OB200_ESTATE, "exchange_halos", "nranks > 1 but ob200_comm_init was not called");
+    const int r = h->cfg.rank, n = h->cfg.nranks;
+    const int west = (r + n - 1) % n, east = (r + 1) % n;
+    launch_pack_x(h->G, h->F, h->sendW, h->sendE, h->stream);
+    ncclGroupStart();
+    ncclSend(h->sendW, h->xcount, ncclDouble, west, h->comm, h->stream);
+    ncclSend(h->sendE, h->xcount, ncclDouble, east, h->comm, h->stream);
+    ncclRecv(h->recvW, h->xcount, ncclDouble, west, h->comm, h->stream);
+    ncclRecv(h->recvE, h->xcount, ncclDouble, east, h->comm, h->stream);
+    ncclResult_t rc = ncclGroupEnd();
+    if (rc != ncclSuccess) return h->fail(OB200_ENCCL, "halo exchange", ncclGetErrorString(rc));
+    launch_unpack_x(h->G, h->F, h->recvW, h->recvE, h->stream);
+    return OB200_OK;
+}
+
+int barotropic_loop(ob200_handle* h, double dt);
+
+int mask_and_halos(ob200_handle* h) {
+    if (h->fields_dirty) { launch_mask_fields(h->G, h->F, h->stream); h->fields_dirty = false; }
+    if (int rc = exchange_halos(h)) return rc;
+    launch_fill_halos(h->G, h->F, h->periodic_local, h->stream);
+    return OB200_OK;
+}
+void auxiliaries(ob200_handle* h) {
+    launch_w_p(h->G, h->F, h->stream);
+    launch_ri_kappa(h->G, h->F, h->time, h->stream);
+    if (h->G.qgleith) launch_leith(h->G, h->F, h->stream);
+}
+void tendencies(ob200_handle* h) {
+    launch_tendencies(h->G, h->F, h->cfg.order_vorticity, h->cfg.order_divergence, h->cfg.order_tracer, h->time, h->stream);
+}
+int update_state(ob200_handle* h) {
+    if (int rc = mask_and_halos(h)) return rc;
+    auxiliaries(h);
+    tendencies(h);
+    return OB200_OK;
+}
+void swap_tendencies(ob200_handle* h) {   // store_tendencies!: G^- <- G^n by pointer swap
+    Fields& F = h->F;
+    std::swap(F.Gu, F.Gu0); std::swap(F.Gv, F.Gv0); std::swap(F.GT, F.GT0); std::swap(F.GS, F.GS0);
+}
+
+int barotropic_loop(ob200_handle* h, double dt) {
+    const double dtau = h->cfg.frac_dtau * dt;
+    launch_baro_init(h->G, h->F, h->periodic_local, h->stream);
+    if (!h->periodic_local) return h->fail(OB200_ESTATE, "barotropic_loop", "distributed barotropic solver not initialised");
+    if (h->persistent_baro) {
+        if (launch_baro_persistent(h->G, h->F, dtau, h->d_weights, h->cfg.n_substeps, true, h->stream) != 0)
+            return h->fail(OB200_ECUDA, "cooperative launch", cudaGetErrorString(cudaGetLastError()));
+    } else {
+        for (int m = 0; m < h->cfg.n_substeps; m++) {
+            launch_baro_eta(h->G, h->F, dtau, true, h->stream);
+            launch_baro_vel(h->G, h->F, dtau, h->weights[m], true, h->stream);
+        }
+    }
+    launch_baro_finish(h->G, h->F, h->stream);
+    return OB200_OK;
+}
+
+int step_body(ob200_handle* h, double dt, bool euler) {
+    const double chi = euler ? -0.5 : h->cfg.ab2_chi;
+    const Geom& G = h->G;
+    if (euler) {
+        const size_t n3 = (size_t)G.sz * (G.Nz + 1) * sizeof(double);
+        for (double* g : {h->F.Gu0, h->F.Gv0, h->F.GT0, h->F.GS0}) cudaMemsetAsync(g, 0, n3, h->stream);
+    }
+    int e = 0;
+    auto mark = [&]() { if (h->timing) cudaEventRecord(h->ev[e++], h->stream); };
+    mark();
+    launch_barotropic_forcing(G, h->F, chi, h->stream);
+    launch_ab2_implicit(G, h->F, dt, chi, h->stream);
+    mark();
+    if (int rc = barotropic_loop(h, dt)) return rc;
+    mark();
+    launch_correct(G, h->F, h->stream);
+    swap_tendencies(h);
+    mark();
+    h->time += dt; h->iteration += 1; h->last_dt = dt;
+    if (int rc = mask_and_halos(h)) return rc;
+    mark();
+    launch_w_p(G, h->F, h->stream);
+    mark();
+    launch_ri_kappa(G, h->F, h->time, h->stream);
+    if (G.qgleith) launch_leith(G, h->F, h->stream);
+    mark();
+    tendencies(h);
+    mark();
+    h->n_timed = e - 1;
+    return OB200_OK;
+}
+
+}  // namespace
+
+// ==========================================================================================================
+extern "C" {
+
+const char* ob200_version(void) { return "ocean_b200 0.1 (sm_100a, f64)"; }
+const char* ob200_last_error(const ob200_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out) {
+    if (!cfg || !out) { g_last_error = "null argument"; return OB200_EINVAL; }
+    if (cfg->struct_bytes != (int32_t)sizeof(ob200_config)) { g_last_error = "ob200_config size mismatch (ABI)"; return OB200_EINVAL; }
+    if (cfg->Nx < 2 * OB_H || cfg->Ny < 2 || cfg->Nz < 2 || cfg->n_substeps < 1 || cfg->n_substeps > OB200_MAX_SUBSTEPS ||
+        !cfg->z_faces || !cfg->bottom_height || !cfg->averaging_weights || cfg->nranks < 1) {
+        g_last_error = "invalid ob200_config (sizes / null arrays; Nx must be >= 14)";
+        return OB200_EINVAL;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_last_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libocean_b200 has no CPU fallback)";
+        return OB200_ECUDA;
+    }
+    if (device < 0 || device >= ndev) { g_last_error = "bad device ordinal"; return OB200_EINVAL; }
+    ob200_handle* h = new ob200_handle();
+    h->cfg = *cfg;
+    h->device = device;
+    cudaSetDevice(device);
+    h->weights.assign(cfg->averaging_weights, cfg->averaging_weights + cfg->n_substeps);
+    h->periodic_local = cfg->nranks <= 1;
+    int rc = setup_geometry(h);
+    if (!rc) rc = alloc_fields(h);
+    if (!rc) rc = dev_alloc(h, &h->d_weights, cfg->n_substeps, false);
+    if (!rc) rc = dev_alloc(h, &h->d_diag, 8);
+    if (rc) { g_last_error = h->err; ob200_destroy(h); return rc; }
+    cudaMemcpy(h->d_weights, h->weights.data(), cfg->n_substeps * sizeof(double), cudaMemcpyHostToDevice);
+    h->cfg.z_faces = nullptr; h->cfg.bottom_height = nullptr; h->cfg.averaging_weights = nullptr;  // borrowed only during create
+    cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    for (auto& ev : h->ev) cudaEventCreate(&ev);
+    launch_column_depths(h->G, h->F, h->stream);
+    e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { g_last_error = std::string("setup kernels: ") + cudaGetErrorString(e); ob200_destroy(h); return OB200_ECUDA; }
+    *out = h;
+    return OB200_OK;
+}
+
+void ob200_destroy(ob200_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->comm) ncclCommDestroy(h->comm);
+    for (void* p : h->allocs) cudaFree(p);
+    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static int copy_common(ob200_handle* h, int32_t field, double* buf, int on_device, int hx, int hy, int hz, bool to_field) {
+    if (!h || !buf) return OB200_EINVAL;
+    cudaSetDevice(h->device);
+    FieldRef r = field_ref(h, field);
+    if (!r.p) return h->fail(OB200_EINVAL, "field", "unknown or unallocated field id");
+    if (hx < 0 || hy < 0 || hz < 0) return h->fail(OB200_EINVAL, "halo", "negative halo");
+    const Geom& G = h->G;
+    const size_t n = (size_t)(G.Nx + 2 * hx) * (r.ny + 2 * hy) * (r.three_d ? (r.nz + 2 * hz) : 1);
+    double* d = buf;
+    if (!on_device) {
+        OB_CUDA_CHECK(h, cudaMalloc((void**)&d, n * sizeof(double)));
+        if (to_field) OB_CUDA_CHECK(h, cudaMemcpyAsync(d, buf, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        else if (hx | hy | hz) OB_CUDA_CHECK(h, cudaMemsetAsync(d, 0, n * sizeof(double), h->stream));
+    }
+    launch_copy_field(G, r.p, d, r.ny, r.nz, hx, hy, hz, r.three_d, to_field, h->stream);
+    if (!on_device) {
+        if (!to_field) OB_CUDA_CHECK(h, cudaMemcpyAsync(buf, d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+        cudaFree(d);
+    }
+    OB_CUDA_CHECK(h, cudaGetLastError());
+    if (to_field) h->fields_dirty = true;
+    return OB200_OK;
+}
+int ob200_set_field(ob200_handle* h, int32_t field, const double* buf, int32_t on_device, int32_t hx, int32_t hy, int32_t hz) {
+    return copy_common(h, field, const_cast<double*>(buf), on_device, hx, hy, hz, true);
+}
+int ob200_get_field(ob200_handle* h, int32_t field, double* buf, int32_t on_device, int32_t hx, int32_t hy, int32_t hz) {
+    return copy_common(h, field, buf, on_device, hx, hy, hz, false);
+}
+
+int ob200_set_forcing(ob200_handle* h, int32_t which, const double* buf, int32_t on_device) {
+    if (!h || !buf || which < 0 || which > 5) return OB200_EINVAL;
+    cudaSetDevice(h->device);
+    const size_t n = (size_t)h->G.Nx * (which == 1 ? h->G.Ny + 1 : h->G.Ny) * 6;
+    if (!h->F.forcing[which])
+        if (int rc = dev_alloc(h, &h->F.forcing[which], n, false)) return rc;
+    OB_CUDA_CHECK(h, cudaMemcpyAsync(h->F.forcing[which], buf, n * sizeof(double),
+                                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    return OB200_OK;
+}
+
+int ob200_update_state(ob200_handle* h) {
+    if (!h) return OB200_EINVAL;
+    cudaSetDevice(h->device);
+    if (int rc = update_state(h)) return rc;
+    OB_CUDA_CHECK(h, cudaGetLastError());
+    return OB200_OK;
+}
+
+int ob200_time_step(ob200_handle* h, double dt) {
+    if (!h) return OB200_EINVAL;
+    cudaSetDevice(h->device);
+    nvtxRangePushA("one time step");   // same range name as near_global_simulation.jl:195
+    int rc = OB200_OK;
+    if (h->iteration == 0) rc = update_state(h);
+    const bool euler = (dt != h->last_dt);
+    if (!rc) rc = step_body(h, dt, euler);
+    nvtxRangePop();
+    if (rc) return rc;
+    OB_CUDA_CHECK(h, cudaGetLastError());
+    return OB200_OK;
+}
+
+int ob200_time_steps(ob200_handle* h, double dt, int32_t n) {
+    for (int s = 0; s < n; s++)
+        if (int rc = ob200_time_step(h, dt)) return rc;
+    return OB200_OK;
+}
+
+int ob200_run_stage(ob200_handle* h, int32_t stage, double dt, int32_t arg) {
+    if (!h) return OB200_EINVAL;
+    cudaSetDevice(h->device);
+    const double chi = (dt != h->last_dt) ? -0.5 : h->cfg.ab2_chi;
+    const double dtau = h->cfg.frac_dtau * dt;
+    int rc = OB200_OK;
+    switch (stage) {
+        case OB200_ST_BAROTROPIC_FORCING: launch_barotropic_forcing(h->G, h->F, chi, h->stream); break;
+        case OB200_ST_AB2_IMPLICIT: launch_ab2_implicit(h->G, h->F, dt, chi, h->stream); break;
+        case OB200_ST_BAROTROPIC_INIT: launch_baro_init(h->G, h->F, h->periodic_local, h->stream); break;
+        case OB200_ST_BAROTROPIC_ETA: launch_baro_eta(h->G, h->F, dtau, h->periodic_local, h->stream); break;
+        case OB200_ST_BAROTROPIC_VEL:
+            if (arg < 0 || arg >= h->cfg.n_substeps) return h->fail(OB200_EINVAL, "substep", "index out of range");
+            launch_baro_vel(h->G, h->F, dtau, h->weights[arg], h->periodic_local, h->stream);
+            break;
+        case OB200_ST_BAROTROPIC_FINISH: launch_baro_finish(h->G, h->F, h->stream); break;
+        case OB200_ST_CORRECT_AND_STORE: launch_correct(h->G, h->F, h->stream); swap_tendencies(h); break;
+        case OB200_ST_MASK_AND_LOCAL_HALOS:
+            if (h->fields_dirty) { launch_mask_fields(h->G, h->F, h->stream); h->fields_dirty = false; }
+            launch_fill_halos(h->G, h->F, h->periodic_local, h->stream);
+            break;
+        case OB200_ST_AUXILIARIES: auxiliaries(h); break;
+        case OB200_ST_TENDENCIES: tendencies(h); break;
+        case OB200_ST_BAROTROPIC_LOOP: rc = barotropic_loop(h, dt); break;
+        case OB200_ST_EXCHANGE_HALOS: rc = exchange_halos(h); break;
+        default: return h->fail(OB200_EINVAL, "stage", "unknown stage id");
+    }
+    if (rc) return rc;
+    OB_CUDA_CHECK(h, cudaGetLastError());
+    return OB200_OK;
+}
+
+int ob200_sync(ob200_handle* h) {
+    if (!h) return OB200_EINVAL;
+    cudaSetDevice(h->device);
+    OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    return OB200_OK;
+}
+
+int ob200_get_clock(ob200_handle* h, double* time, int64_t* iteration, double* last_dt) {
+    if (!h) return OB200_EINVAL;
+    if (time) *time = h->time;
+    if (iteration) *iteration = h->iteration;
+    if (last_dt) *last_dt = h->last_dt;
+    return OB200_OK;
+}
+int ob200_set_clock(ob200_handle* h, double time, int64_t iteration, double last_dt) {
+    if (!h) return OB200_EINVAL;
+    h->time = time; h->iteration = iteration; h->last_dt = last_dt;
+    return OB200_OK;
+}
+
+int ob200_diagnostics(ob200_handle* h, double maxabs[6], double* cfl_dt) {
+    if (!h) return OB200_EINVAL;
+    cudaSetDevice(h->device);
+    launch_diagnostics(h->G, h->F, h->d_diag, h->stream);
+    double out[8];
+    OB_CUDA_CHECK(h, cudaMemcpyAsync(out, h->d_diag, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    if (maxabs) for (int q = 0; q < 6; q++) maxabs[q] = out[q];
+    if (cfl_dt) *cfl_dt = out[6] > 0.0 ? 1.0 / out[6] : INFINITY;
+    return OB200_OK;
+}
+
+int ob200_get_timing(ob200_handle* h, ob200_timing* t) {
+    if (!h || !t) return OB200_EINVAL;
+    cudaSetDevice(h->device);
+    t->n = 0;
+    if (!h->timing || h->n_timed <= 0) return OB200_OK;
+    OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < h->n_timed && q < 16; q++) cudaEventElapsedTime(&t->ms[q], h->ev[q], h->ev[q + 1]);
+    t->n = h->n_timed;
+    return OB200_OK;
+}
+
+int ob200_set_stream(ob200_handle* h, void* cuda_stream) {
+    if (!h) return OB200_EINVAL;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+    return OB200_OK;
+}
+
+int ob200_set_option(ob200_handle* h, const char* name, int32_t value) {
+    if (!h || !name) return OB200_EINVAL;
+    if (!std::strcmp(name, "timing")) h->timing = value != 0;
+    else if (!std::strcmp(name, "persistent_barotropic")) h->persistent_baro = value != 0;
+    else return h->fail(OB200_EINVAL, "option", name);
+    return OB200_OK;
+}
+
+int ob200_comm_unique_id(void* id128) {
+    if (!id128) return OB200_EINVAL;
+    static_assert(sizeof(ncclUniqueId) <= 128, "unique id size");
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) { g_last_error = "ncclGetUniqueId failed"; return OB200_ENCCL; }
+    std::memset(id128, 0, 128);
+    std::memcpy(id128, &id, sizeof(id));
+    return OB200_OK;
+}
+
+int ob200_comm_init(ob200_handle* h, const void* id128) {
+    if (!h || !id128) return OB200_EINVAL;
+    cudaSetDevice(h->device);
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    ncclResult_t rc = ncclCommInitRank(&h->comm, h->cfg.nranks, id, h->cfg.rank);
+    if (rc != ncclSuccess) return h->fail(OB200_ENCCL, "ncclCommInitRank", ncclGetErrorString(rc));
+    h->xcount = pack_x_count(h->G);
+    for (double** p : {&h->sendW, &h->sendE, &h->recvW, &h->recvE})
+        if (int r2 = dev_alloc(h, p, h->xcount)) return r2;
+    return OB200_OK;
+}
+
+}  // extern "C"
