@@ -146,7 +146,11 @@ def emit(tables, path, cuda):
 def emit_device_code(tables, path):
     """Straight-line __device__ code per order N: q[0..2N-2] are the stencil values ordered from the
     most upwind-ward cell (q[0]) to the most downwind (q[2N-2]); stencil s uses q[N-1-s .. 2N-2-s].
-    weno_beta<N>(q, b) fills the N smoothness indicators; weno_combine<N>(q, b) applies Z-weights."""
+    Weno<N>::beta(q, b) fills the N smoothness indicators; Weno<N>::combine(q, b) applies Z-weights.
+    Every multiply-add is an EXPLICIT fma() in a fixed order, identical to the oracle's loops: the quadratic
+    forms cancel catastrophically on fields with a large mean (S ~ 35), so beta is only reproducible to
+    ~1e-8 relative between two evaluation orders; pinning the order keeps CUDA and oracle bit-compatible
+    while the library is compiled with -fmad=false (no implicit contraction anywhere else)."""
     out = ["// GENERATED by csrc/derive_weno.py -- do not edit.",
            "#pragma once", "",
            "template <int N> struct Weno;", ""]
@@ -160,23 +164,29 @@ def emit_device_code(tables, path):
         out.append("  __device__ __forceinline__ static void beta(const double* __restrict__ q, double* __restrict__ b) {")
         for s in range(N):
             off = N - 1 - s
-            terms, m = [], 0
+            m = 0
+            acc = None
             for a in range(N):
-                inner = []
+                inner = None
                 for bb in range(a, N):
-                    inner.append("%s * q[%d]" % (lit(b[s][m]), off + bb))
+                    term = "%s * q[%d]" % (lit(b[s][m]), off + bb) if inner is None else \
+                        "fma(%s, q[%d], %s)" % (lit(b[s][m]), off + bb, inner)
+                    inner = term
                     m += 1
-                terms.append("q[%d] * (%s)" % (off + a, " + ".join(inner)))
-            out.append("    b[%d] = %s;" % (s, " + ".join(terms)))
+                acc = "q[%d] * (%s)" % (off + a, inner) if acc is None else "fma(q[%d], %s, %s)" % (off + a, inner, acc)
+            out.append("    b[%d] = %s;" % (s, acc))
         out.append("  }")
         out.append("  __device__ __forceinline__ static double combine(const double* __restrict__ q, const double* __restrict__ b) {")
         out.append("    const double tau = %s;" % taus[N])
         out.append("    double asum = 0.0, r = 0.0;")
         for s in range(N):
             off = N - 1 - s
-            poly = " + ".join("%s * q[%d]" % (lit(c[s][a]), off + a) for a in range(N))
-            out.append("    { const double t = tau / (b[%d] + 1e-8); const double al = %s * (1.0 + t * t);" % (s, lit(o[s])))
-            out.append("      asum += al; r += al * (%s); }" % poly)
+            poly = None
+            for a in range(N):
+                poly = "%s * q[%d]" % (lit(c[s][a]), off + a) if poly is None else \
+                    "fma(%s, q[%d], %s)" % (lit(c[s][a]), off + a, poly)
+            out.append("    { const double t = tau / (b[%d] + 1e-8); const double al = %s * fma(t, t, 1.0);" % (s, lit(o[s])))
+            out.append("      asum += al; r = fma(al, %s, r); }" % poly)
         out.append("    return r / asum;")
         out.append("  }")
         out.append("};")

@@ -120,6 +120,27 @@ __device__ __forceinline__ double buoyancy_of(const Geom& G, double T, double S,
     return -G.g * teos_rprime<false>(T, S, G.zc[k], nullptr, nullptr) / G.rho0;
 }
 
+// Deterministic tanh from +,-,*,/ only (the library is compiled with -fmad=false): the same operation
+// sequence as the CPU oracle, so kappa agrees bit for bit; |error| < 3e-16 absolute.
+__device__ __forceinline__ double det_exp_neg(double y) {   // exp(y), y <= 0
+    const double LOG2E = 1.4426950408889634, LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double n = rint(y * LOG2E);
+    const double r = (y - n * LN2_HI) - n * LN2_LO;
+    double p = 1.0 / 6227020800.0;
+    const double inv_fact[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+                                 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+#pragma unroll
+    for (int m = 0; m < 13; m++) p = p * r + inv_fact[m];
+    return ldexp(p, (int)n);
+}
+__device__ __forceinline__ double det_tanh(double x) {
+    const double a = fabs(x);
+    if (a > 20.0) return x > 0 ? 1.0 : -1.0;
+    const double t = det_exp_neg(-2.0 * a);
+    const double r = (1.0 - t) / (1.0 + t);
+    return x < 0 ? -r : r;
+}
+
 __device__ __forceinline__ double upwind_flux(double vel, double L, double R) {
     const double a = fabs(vel);
     return 0.5 * ((vel + a) * L + (vel - a) * R);

@@ -38,6 +38,27 @@ constexpr int H = OB200_HALO;  // horizontal halo (grid_load_balance.jl:25)
 constexpr int HZ = 1;          // vertical halo kept by the oracle (2nd-order vertical ops only)
 constexpr double WENO_EPS = 1e-8;  // SURVEY A8 (Oceananigans `const eps = 1e-8`) [OCN-recall]
 
+// Deterministic tanh built from +,-,*,/ only (no libm), so that CPU and GPU agree bit for bit: the Ri-based
+// diffusivity switches (N2 < 0 ...) amplify one-ulp differences of tanh into O(1e-9) differences of kappa
+// within 100 steps.  |error| < 3e-16 absolute; Oceananigans itself calls libm tanh (DESIGN.md "Arithmetic contract").
+static inline double det_exp_neg(double y) {  // exp(y) for y <= 0
+    const double LOG2E = 1.4426950408889634, LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double n = std::nearbyint(y * LOG2E);
+    const double r = (y - n * LN2_HI) - n * LN2_LO;
+    double p = 1.0 / 6227020800.0;  // 1/13!
+    const double inv_fact[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+                                 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+    for (int m = 0; m < 13; m++) p = p * r + inv_fact[m];
+    return std::ldexp(p, (int)n);
+}
+static inline double det_tanh(double x) {
+    const double a = std::fabs(x);
+    if (a > 20.0) return x > 0 ? 1.0 : -1.0;
+    const double t = det_exp_neg(-2.0 * a);
+    const double r = (1.0 - t) / (1.0 + t);
+    return x < 0 ? -r : r;
+}
+
 struct F3 {  // 3-D array with halos; (i,j,k) -> i fastest
     int NxP = 0, NyP = 0, NzP = 0;
     std::vector<double> a;
@@ -87,20 +108,26 @@ struct Teos {
         R[0][0][3] = -2.3342758797e-02; R[1][0][3] = -1.8507636718e-02; R[0][1][3] = 3.7969820455e-01;
     }
     static constexpr double Sau = 40.0 * 35.16504 / 35.0, Thu = 40.0, Zu = 1e4, dS = 32.0;
-    // returns r'(tau,s,zeta); optionally d/dTheta and d/dSA
+    // returns r'(tau,s,zeta); optionally d/dTheta and d/dSA.  Nested Horner over the triangular support
+    // (powers of zeta outermost), the same evaluation order as the product so the two agree bit for bit.
     double rprime(double Th, double SA, double Z, double* dTh = nullptr, double* dSA = nullptr) const {
-        double tau = Th / Thu, s = std::sqrt((SA + dS) / Sau), ze = -Z / Zu;
-        double r = 0, rt = 0, rs = 0;
-        for (int i = 0; i < 7; i++)
-            for (int j = 0; j < 7; j++)
-                for (int k = 0; k < 4; k++) {
-                    double c = R[i][j][k];
-                    if (c == 0.0) continue;
-                    double zk = std::pow(ze, k);
-                    r += c * std::pow(s, i) * std::pow(tau, j) * zk;
-                    if (j > 0) rt += c * std::pow(s, i) * j * std::pow(tau, j - 1) * zk;
-                    if (i > 0) rs += c * i * std::pow(s, i - 1) * std::pow(tau, j) * zk;
+        const double tau = Th / Thu, s = std::sqrt((SA + dS) / Sau), ze = -Z / Zu;
+        const int deg[4] = {6, 4, 2, 1};
+        double r = 0.0, rt = 0.0, rs = 0.0;
+        for (int k = 3; k >= 0; k--) {
+            double pj = 0.0, pjt = 0.0, pjs = 0.0;
+            for (int j = deg[k]; j >= 0; j--) {
+                double pi = 0.0, pis = 0.0;
+                for (int i = deg[k] - j; i >= 0; i--) {
+                    pis = pis * s + pi;
+                    pi = pi * s + R[i][j][k];
                 }
+                pjt = pjt * tau + pj; pjs = pjs * tau + pis;
+                pj = pj * tau + pi;
+            }
+            r = r * ze + pj;
+            rt = rt * ze + pjt; rs = rs * ze + pjs;
+        }
         if (dTh) *dTh = rt / Thu;
         if (dSA) *dSA = rs / (2.0 * s * Sau);
         return r;
@@ -258,7 +285,7 @@ struct Oracle {
     static inline double T_reference(double phi) { return std::max(0.0, 30.0 * std::cos(1.2 * M_PI * phi / 180.0)); }
     // flux_from_interpolated_array (bathymetry_and_forcings.jl:162-169)
     inline double interp_flux(const std::vector<double>& F, int i, int j, int nyf, double period_days, bool div3) const {
-        if (F.empty()) return 0.0;
+        if (F.empty() || i < 0 || i >= Nx) return 0.0;
         double days = time / 86400.0;
         double n;
         if (!div3) n = std::fmod(days, period_days) + 1;
@@ -423,7 +450,7 @@ struct Oracle {
                             return 0.25 * (Ri(a - 1, b - 1, k) + Ri(a, b - 1, k) + Ri(a - 1, b, k) + Ri(a, b, k));
                         };
                         double Rif = 0.25 * (ff(i, j) + ff(i + 1, j) + ff(i, j + 1) + ff(i + 1, j + 1));
-                        double tau = 0.5 * (1.0 - std::tanh((Rif - c.ri_Ri0) / c.ri_Ridelta));
+                        double tau = 0.5 * (1.0 - det_tanh((Rif - c.ri_Ri0) / c.ri_Ridelta));
                         kcp = c.ri_kappa0 * tau + kca + ken;
                         kup = c.ri_nu0 * tau;
                     }
@@ -439,11 +466,13 @@ struct Oracle {
     // measured on (VelocityStencil: two fields averaged; otherwise sb == nullptr).
     static double beta_of(int N, int s, const double* ps) {
         const double* C = WENO_SMOOTH[N][s];
+        // explicit fma in a fixed order (see DESIGN.md "Arithmetic contract"): the quadratic form cancels
+        // catastrophically on fields with a large mean, so the evaluation order is part of the contract
         double b = 0.0; int m = 0;
         for (int a = 0; a < N; a++) {
             double inner = 0.0;
-            for (int bb = a; bb < N; bb++) inner += C[m++] * ps[bb];
-            b += ps[a] * inner;
+            for (int bb = a; bb < N; bb++) inner = std::fma(C[m++], ps[bb], inner);
+            b = std::fma(ps[a], inner, b);
         }
         return b;
     }
@@ -464,16 +493,14 @@ struct Oracle {
         }
         for (int s = 0; s < N; s++) {
             double t = tau / (beta[s] + WENO_EPS);
-            alpha[s] = WENO_OPT[N][s] * (1.0 + t * t);
+            alpha[s] = WENO_OPT[N][s] * std::fma(t, t, 1.0);
             asum += alpha[s];
-        }
-        for (int s = 0; s < N; s++) {
             int off = N - 1 - s;
             double ps = 0.0;
-            for (int a = 0; a < N; a++) ps += WENO_COEFF[N][s][a] * q[off + a];
-            r += (alpha[s] / asum) * ps;
+            for (int a = 0; a < N; a++) ps = std::fma(WENO_COEFF[N][s][a], q[off + a], ps);
+            r = std::fma(alpha[s], ps, r);
         }
-        return r;
+        return r / asum;
     }
     static inline double upwind(double vel, double L, double R) {
         return 0.5 * ((vel + std::fabs(vel)) * L + (vel - std::fabs(vel)) * R);
@@ -1084,4 +1111,5 @@ int oracle_zero_prev_tendencies(void* h) {
 // standalone WENO entry point for unit tests: biased reconstruction from 2N-1 values
 double oracle_weno(int N, const double* q, const double* sa, const double* sb) { return Oracle::weno(N, q, sa, sb); }
 double oracle_teos10_rprime(double Th, double SA, double Z) { static Teos t; return t.rprime(Th, SA, Z); }
+double oracle_det_tanh(double x) { return det_tanh(x); }
 }

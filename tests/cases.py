@@ -107,3 +107,32 @@ CASES = {
 
 def build_case(name: str) -> Case:
     return CASES[name]
+
+
+def signature(fields: dict) -> dict:
+    """Compact fingerprint of a set of fields: bottom / middle / top horizontal slices plus global statistics."""
+    out = {}
+    for n, a in fields.items():
+        if a.ndim == 3:
+            ks = sorted(set([0, a.shape[0] // 2, a.shape[0] - 1]))
+            out[n + "_slices"] = np.ascontiguousarray(a[ks])
+        else:
+            out[n + "_slices"] = np.ascontiguousarray(a)
+        out[n + "_stats"] = np.array([np.sum(a), np.sum(a * a), np.max(np.abs(a))])
+    return out
+
+
+def check_signature(fields: dict, gold, tol: float) -> list:
+    """Compare fields against a stored signature; returns a list of mismatch descriptions."""
+    bad = []
+    sig = signature(fields)
+    for key, val in sig.items():
+        ref = gold[key]
+        scale = max(1.0, float(np.max(np.abs(ref))))
+        err = float(np.max(np.abs(val - ref)))
+        if key.endswith("_stats"):
+            # sums of O(1e5) terms: compare relative to the sum of absolute values' scale
+            scale = max(scale, float(np.abs(ref[1])) ** 0.5 * 10)
+        if not err <= tol * scale:
+            bad.append(f"{key}: err {err:.3e} (scale {scale:.3e})")
+    return bad

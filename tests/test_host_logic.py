@@ -1,0 +1,136 @@
+"""CPU tests of the host-side mirror of the reference's Julia configuration code."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+
+def test_exponential_z_faces_matches_reference_formula(pkg):
+    # bathymetry_and_forcings.jl:47-58, Nz = 120, Depth = 3000 (BASELINE configs 2, 3)
+    zf = pkg.exponential_z_faces(120, 3000)
+    assert zf.shape == (121,)
+    assert abs(zf[0] + 3000.0) < 1e-9 and zf[-1] == 0.0
+    dz = np.diff(zf)
+    assert np.all(dz > 0)
+    # dz from 1.29 m at the top to 111.7 m at the bottom
+    assert abs(dz[-1] - 1.29) < 0.01 and abs(dz[0] - 111.7) < 0.1
+
+
+def test_linear_z_faces(pkg):
+    zf = pkg.linear_z_faces(10, 1000.0)
+    assert abs(zf[0] + 1000.0) < 1e-9 and zf[-1] == 0.0
+    assert abs((zf[-1] - zf[-2]) - 5.0) < 1e-12
+
+
+def test_double_drake_bathymetry(pkg):
+    f = pkg.double_drake_bathymetry
+    assert f(0.5, 0.0) == 0.0 and f(90.5, 10.0) == 0.0
+    assert f(0.5, -40.0) == -10000.0 and f(1.0, 0.0) == -10000.0 and f(45.0, 0.0) == -10000.0
+    # C3: 7 920 of 1 944 000 columns solid
+    g = pkg.LatitudeLongitudeGrid(2160, 900, 2, np.array([-1.0, -0.5, 0.0]))
+    solid = f(g.lam_c()[None, :], g.phi_c()[:, None]) == 0.0
+    assert int(solid.sum()) == 7920
+
+
+def test_cubic_profiles_hit_their_knots(pkg):
+    wc = pkg.wind_stress_coefficients(75.0)
+    sc = pkg.salinity_flux_coefficients(75.0, 35.0)
+    knots = [(-75, 0.0), (-45, 0.2), (-15, -0.1), (0, -0.02), (15, -0.1), (45, 0.1), (75, 0.0)]
+    for phi, val in knots:
+        for eps in (-1e-9, 1e-9):
+            if abs(phi + eps) <= 75:
+                assert abs(pkg.wind_stress(phi + eps, wc) - val / 1000) < 1e-9
+    for phi, val in [(-75, -2e-8), (-20, 2e-8), (0, -4e-8), (20, 2e-8), (75, -2e-8)]:
+        assert abs(pkg.salinity_flux(phi - 1e-9 if phi > 0 else phi + 1e-9, sc) - val * 35.0) < 1e-12
+
+
+def test_barotropic_substeps_match_survey_appendix_b(pkg):
+    # C3 (1/6 deg, 3000 m, dt = 540 s) -> N = 53..54 -> M = 38
+    zf = pkg.exponential_z_faces(120, 3000)
+    g = pkg.LatitudeLongitudeGrid(2160, 900, 120, zf)
+    N = pkg.barotropic_substeps(540.0, g)
+    assert N in (53, 54)
+    fs = pkg.SplitExplicitFreeSurface(substeps=N)
+    assert pkg.substeps(fs) == 38
+    assert abs(np.sum(fs.averaging_weights) - 1.0) < 1e-14
+    assert fs.averaging_weights[-1] > 0 and abs(fs.fractional_step_size - 2.0 / N) < 1e-15
+    # minimum of 10 (near_global_simulation.jl:18)
+    assert pkg.barotropic_substeps(1.0, g) == 10
+
+
+def test_calculate_local_N_reference_algorithm(pkg):
+    # uniform load: greedy `<=` advance takes one more column than the mean per rank (grid_load_balance.jl:102-109)
+    load = np.full(100, 10)
+    assert pkg.calculate_local_N(load, 100, 4) == [26, 26, 26, 22]
+    # ragged load with land
+    load = np.array([0] * 10 + [5] * 20 + [1] * 30 + [8] * 40)
+    ln = pkg.calculate_local_N(load, 100, 3)
+    assert sum(ln) == 100 and all(n > 0 for n in ln)
+    total = load.sum() / 3
+    assert load[:ln[0]].sum() > total >= load[:ln[0] - 1].sum()
+    # single rank
+    assert pkg.calculate_local_N(load, 100, 1) == [100]
+
+
+def test_redistribute_size(pkg):
+    l = [1200, 1100, 900, 1120]
+    pkg.redistribute_size_to_fulfill_memory_limitation(l, 1150)
+    assert sum(l) == 4320 and max(l) <= 1150
+    l = [10, 300, 300, 300]
+    pkg.redistribute_size_to_fulfill_memory_limitation(l, 1150)
+    assert sum(l) == 910 and min(l) >= 20
+    l = [19, 300, 300]
+    pkg.redistribute_size_to_fulfill_memory_limitation(l, 1150)
+    assert l == [20, 299, 300]
+
+
+def test_load_balanced_grid_partitions(pkg):
+    zf = pkg.exponential_z_faces(10, 3000)
+    grids = [pkg.load_balanced_grid(r, 4, (360, 150, 10), (-75, 75), zf, 1, False, "DoubleDrake") for r in range(4)]
+    assert [g.Nx for g in grids] == [90] * 4 and [g.i_offset for g in grids] == [0, 90, 180, 270]
+    # bottom height with halo columns wraps periodically and matches the neighbours' interiors
+    b0, b3 = grids[0].bottom_height_local(), grids[3].bottom_height_local()
+    assert b0.shape == (150, 90 + 14)
+    assert np.array_equal(b0[:, :7], b3[:, -14:-7])
+
+    def bathy(Nx, Ny):   # synthetic continents: land in the western half
+        lam = -180 + (np.arange(Nx) + 0.5) * 360 / Nx
+        return np.where(lam[None, :] < -60, 100.0, -4000.0) * np.ones((Ny, 1))
+    gb = [pkg.load_balanced_grid(r, 4, (360, 150, 10), (-75, 75), zf, 1, True, "RealisticOcean",
+                                 realistic_bathymetry=bathy) for r in range(4)]
+    sizes = [g.Nx for g in gb]
+    assert sum(sizes) == 360 and sizes[0] > sizes[1]     # the land-heavy slab is wider
+    wet = [int((~g.immersed_cell_mask()[:, :, g.i_offset:g.i_offset + g.Nx]).sum()) for g in gb]
+    assert max(wet[:3]) - min(wet[:3]) <= 2 * 150 * 10   # balanced to within ~one column each way
+
+
+def test_abi_library_exports_every_declared_symbol(pkg):
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "ocean_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(ob200_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared == sorted(pkg._abi.EXPORTED_SYMBOLS)
+    lib = pkg._abi.LIB_PATH
+    assert os.path.exists(lib), "libocean_b200.so not built (run __graft_entry__.build())"
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+    exported = set(line.split()[-1] for line in out.splitlines() if line.strip())
+    missing = [s for s in declared if s not in exported]
+    assert not missing, missing
+    # the struct the host passes has the size the header's C compiler sees
+    src = '#include "ocean_b200.h"\n#include <stdio.h>\nint main(){printf("%zu", sizeof(ob200_config));return 0;}\n'
+    exe = "/tmp/ob200_sizeof"
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(root, "include"), "-o", exe], input=src, text=True, check=True)
+    size = int(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)
+    assert size == C.sizeof(pkg._abi.ob200_config)
+
+
+def test_product_fails_loudly_without_gpu(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import cases
+    with pytest.raises(RuntimeError, match="no CUDA device|ob200_create failed"):
+        cases.build_case("dd_small").make_model(pkg, None)

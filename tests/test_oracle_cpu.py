@@ -1,0 +1,189 @@
+"""CPU tests of the oracle (test infrastructure): WENO machinery against independent numpy restatements,
+physical invariants that hold regardless of recollection (SURVEY 7 "hard parts"), and the committed golden
+vectors.  The reference's own tests pin no numbers (test/runtests.jl:33-34): parity with Oceananigans is UNPINNED."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ---- WENO ---------------------------------------------------------------------------------------------
+def numpy_weno_js(N, q):
+    """Independent restatement: Z-weighted WENO from Lagrange-type cell-average polynomials fitted with numpy."""
+    q = np.asarray(q, dtype=np.float64)
+    optimal = {2: [2 / 3, 1 / 3], 3: [3 / 10, 3 / 5, 1 / 10], 4: [4 / 35, 18 / 35, 12 / 35, 1 / 35],
+               5: [5 / 126, 20 / 63, 10 / 21, 10 / 63, 1 / 126]}[N]
+    scale = {2: 1.0, 3: 3.0, 4: 0.24, 5: 0.0504}[N]
+    from numpy.polynomial import polynomial as P
+    cand, beta = [], []
+    for s in range(N):
+        cells = np.arange(-1 - s, -1 - s + N)          # left edges; face at x = 0
+        vals = q[N - 1 - s: 2 * N - 1 - s]
+        A = np.array([[((c + 1) ** (m + 1) - c ** (m + 1)) / (m + 1) for m in range(N)] for c in cells])
+        a = np.linalg.solve(A, vals)                   # polynomial with the given cell averages
+        cand.append(a[0])                              # value at x = 0
+        b = 0.0
+        for l in range(1, N):
+            d = P.polyder(a, l)
+            d2 = P.polymul(d, d)
+            I = P.polyint(d2)
+            b += P.polyval(0.0, I) - P.polyval(-1.0, I)
+        beta.append(scale * b)
+    beta = np.array(beta)
+    tau_w = {2: [1, -1], 3: [1, 0, -1], 4: [1, 3, -3, -1], 5: [1, 2, -6, 2, 1]}[N]
+    tau = abs(float(np.dot(tau_w, beta)))
+    alpha = np.array(optimal) * (1 + (tau / (beta + 1e-8)) ** 2)
+    return float(np.sum(alpha / alpha.sum() * np.array(cand)))
+
+
+@pytest.mark.parametrize("N", [2, 3, 4, 5])
+def test_weno_matches_independent_numpy_restatement(orc, N):
+    for trial, f in enumerate([np.sin, np.exp, lambda x: np.tanh(5 * x), lambda x: np.where(x > 0.1, 1.0, 0.0)]):
+        x = (np.arange(2 * N - 1) - N + 0.5) * 0.3 + 0.05 * trial
+        q = f(x)
+        got = orc.weno(N, q)
+        want = numpy_weno_js(N, q)
+        assert abs(got - want) <= 5e-12 * max(1.0, abs(want)), (N, trial, got, want)
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 5])
+def test_weno_exact_on_constants_and_high_order_on_smooth_data(orc, N):
+    q = np.full(2 * N - 1, 35.0)
+    assert abs(orc.weno(N, q) - 35.0) < 1e-13
+    if N == 1:
+        return
+    # cell averages of a degree-(N-1) polynomial are reconstructed exactly by every candidate stencil
+    rng = np.random.default_rng(20240611)
+    coef = rng.standard_normal(N)
+    from numpy.polynomial import polynomial as P
+    I = P.polyint(coef)
+    edges = np.arange(-N, N)
+    q = np.array([P.polyval(e + 1, I) - P.polyval(e, I) for e in edges[:2 * N - 1]])
+    assert abs(orc.weno(N, q) - P.polyval(0.0, coef)) < 1e-11
+    # velocity-stencil smoothness: with smooth u, v stencils the weights tend to the optimal ones (order 2N-1)
+    h = 0.05
+    xs = (np.arange(2 * N - 1) - N) * h
+    Iq = lambda a, b: (np.cos(a) - np.cos(b)) / (b - a)       # cell average of sin
+    q = np.array([Iq(a, a + h) for a in xs])
+    got = orc.weno(N, q, sa=np.cos(xs), sb=np.sin(2 * xs))
+    assert abs(got - np.sin(0.0)) < 10 * h ** (2 * N - 1)
+
+
+def test_deterministic_tanh_and_teos10_known_values(orc):
+    lib = orc.load()
+    xs = np.concatenate([np.linspace(-25, 25, 2001), [1e-9, -1e-9, 0.0, 0.25, -0.25]])
+    err = max(abs(lib.oracle_det_tanh(float(x)) - np.tanh(x)) for x in xs)
+    assert err < 3e-16
+    # TEOS-10 polynomial: fresh water at 0 C, 0 dbar -> 999.843 kg/m3 (known value); sea water is denser
+    assert abs(lib.oracle_teos10_rprime(0.0, 0.0, 0.0) - 999.843) < 1e-3
+    assert 1026.0 < lib.oracle_teos10_rprime(10.0, 35.0, 0.0) < 1028.0
+    assert lib.oracle_teos10_rprime(10.0, 35.0, 0.0) > lib.oracle_teos10_rprime(20.0, 35.0, 0.0)
+
+
+# ---- physical invariants -----------------------------------------------------------------------------------
+def test_quiescent_stays_at_rest(pkg, orc):
+    c = cases.build_case("quiescent")
+    m = c.make_model(pkg, orc.OracleBackend)
+    for _ in range(5):
+        pkg.time_step(m, c.dt)
+    for n in ("U", "V", "W", "ETA", "T", "S"):
+        assert np.max(np.abs(m.get(n))) == 0.0
+
+
+def test_stratified_rest_state_has_no_spurious_flow(pkg, orc):
+    """Horizontally uniform T(z), S on the DoubleDrake bathymetry with the surface forcing switched off:
+    pressure gradients vanish identically, so the ocean stays at rest (vertical diffusion only)."""
+    c = cases.Case("rest", 90, 40, 8, experiment="DoubleDrake", perturb=False)
+    grid = c.grid(pkg)
+    fs = pkg.SplitExplicitFreeSurface(substeps=30)
+    m = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=fs, eos="linear",
+                                        boundary_conditions=pkg.set_boundary_conditions("Quiescent", grid),
+                                        backend_factory=orc.OracleBackend)
+    pkg.set_model(m, T=lambda lam, phi, z: 20.0 * np.exp(z / 400.0) + 0 * lam + 0 * phi, S=35.0)
+    for _ in range(10):
+        pkg.time_step(m, 1200.0)
+    assert np.max(np.abs(m.get("U"))) < 1e-14 and np.max(np.abs(m.get("V"))) < 1e-14
+    assert np.max(np.abs(m.get("ETA"))) < 1e-12
+
+
+def volume_integral(pkg, model, name):
+    g = model.grid
+    dz = np.diff(g.z_faces)[:, None, None]
+    phif = g.phi_f()
+    az = (np.sin(np.pi * phif[1:] / 180) - np.sin(np.pi * phif[:-1] / 180))[None, :, None]
+    return float(np.sum(model.get(name) * dz * az))
+
+
+def test_tracer_content_changes_only_through_surface_fluxes(pkg, orc):
+    """Flux-form advection + no-flux walls: with zero surface fluxes the volume integral of S is conserved up
+    to the free-surface term (w at the top face carries tracer through the linearised surface)."""
+    c = cases.Case("cons", 90, 40, 8, experiment="DoubleDrake", perturb=True)
+    grid = c.grid(pkg)
+    fs = pkg.SplitExplicitFreeSurface(substeps=30)
+    m = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=fs, eos="linear",
+                                        boundary_conditions=pkg.set_boundary_conditions("Quiescent", grid),
+                                        backend_factory=orc.OracleBackend)
+    c.initialize(pkg, m) if False else None
+    r = np.pi / 180
+    pkg.set_model(m, T=lambda lam, phi, z: 10.0 + 5 * np.exp(z / 500.0) * np.cos(phi * r) + 0 * lam,
+                  S=lambda lam, phi, z: 35.0 + 0.3 * np.sin(2 * lam * r) * np.cos(phi * r) * np.exp(z / 800.0),
+                  u=lambda lam, phi, z: 0.1 * np.sin(2 * lam * r) * np.cos(phi * r) + 0 * z)
+    s0 = volume_integral(pkg, m, "S")
+    for _ in range(10):
+        pkg.time_step(m, 600.0)
+    s1 = volume_integral(pkg, m, "S")
+    # surface term: int S w_top dt dA / int S dV ~ eta / depth ~ 1e-4; everything else telescopes exactly
+    assert abs(s1 - s0) / abs(s0) < 5e-5
+    # uniform salinity is preserved to rounding whatever the flow (constancy preservation of div(U c))
+    pkg.set_model(m, S=35.0)
+    for _ in range(5):
+        pkg.time_step(m, 600.0)
+    S = m.get("S")
+    wet = S != 0
+    assert np.max(np.abs(S[wet] - 35.0)) < 2e-4   # w_top * S / dz free-surface term only
+
+
+def test_zonally_symmetric_setup_stays_zonally_symmetric(pkg, orc):
+    """No bathymetry + zonally symmetric forcing and state => every field independent of longitude."""
+    c = cases.Case("zonal", 48, 40, 8, experiment="Quiescent", perturb=False)
+    grid = c.grid(pkg)
+    fs = pkg.SplitExplicitFreeSurface(substeps=30)
+    bcs = pkg.set_boundary_conditions("DoubleDrake", grid)
+    m = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=fs, eos="linear", boundary_conditions=bcs,
+                                        backend_factory=orc.OracleBackend)
+    pkg.initialize_model(m, "DoubleDrake")
+    for _ in range(20):
+        pkg.time_step(m, 1200.0)
+    for n in ("U", "V", "T", "S", "ETA"):
+        a = m.get(n)
+        assert np.max(np.abs(a - a[..., :1])) <= 1e-13 * max(1.0, np.max(np.abs(a))), n
+    assert np.max(np.abs(m.get("U"))) > 1e-4      # the wind does spin the ocean up
+
+
+def test_masked_nodes_stay_zero(pkg, orc):
+    c = cases.build_case("bumpy")
+    m = c.make_model(pkg, orc.OracleBackend)
+    for _ in range(5):
+        pkg.time_step(m, c.dt)
+    imm = m.grid.immersed_cell_mask()
+    assert np.all(m.get("T")[imm] == 0) and np.all(m.get("S")[imm] == 0)
+    u = m.get("U")
+    assert np.all(u[imm] == 0) and np.all(u[np.roll(imm, 1, axis=2)] == 0)
+    assert np.all(np.isfinite(u)) and np.max(np.abs(u)) < 5.0
+
+
+# ---- golden vectors (generated by tests/golden/make_golden.py from this oracle; regression pins) ---------------
+@pytest.mark.parametrize("name", ["ref_test", "dd_small", "bumpy"])
+def test_oracle_reproduces_golden_vectors(pkg, orc, name):
+    path = os.path.join(GOLDEN, f"{name}.npz")
+    gold = np.load(path)
+    c = cases.build_case(name)
+    m = c.make_model(pkg, orc.OracleBackend)
+    for _ in range(int(gold["steps"])):
+        pkg.time_step(m, c.dt)
+    bad = cases.check_signature({n: m.get(n) for n in ("U", "V", "W", "ETA", "T", "S")}, gold, 1e-11)
+    assert not bad, bad
