@@ -1,0 +1,338 @@
+#!/usr/bin/env python3
+"""bench.py -- grid-cell-steps/s (and SYPD) of the hydrostatic `time_step!` on B200.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`; for N > 1 the driver
+launches it under torch.distributed.run, one rank per GPU.  Rank 0 prints ONE JSON line.
+
+Workload (BASELINE.json metric): DoubleDrake 1/6 deg, NZ = 120 (2160 x 900 x 120 = 233.28 M cells, dt = 540 s),
+initialised state + closed-form perturbation (tests/cases.py), strong scaling over x-slabs.
+  value : whole-job cell-steps/s, state resident in HBM, K steps between CUDA-synchronised barriers.
+  e2e   : the same metric through the public API with HOST buffers: pinned host initial state -> set! (H2D)
+          -> K x time_step! -> prognostic fields read back (D2H), all inside the timed region.
+  roofline : the dominant kernel (momentum tendencies), algorithmic bytes / CUDA-event duration vs the measured
+          HBM copy bandwidth of MEASURED_PEAKS.json.
+  cpu_baseline : the CPU oracle (port of the reference's algorithm) on a bounded sample of the same workload.
+`--impl reference` times that CPU oracle alone (all host threads) and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import __graft_entry__ as ge  # noqa: E402
+import cases  # noqa: E402
+
+WORKLOADS = {
+    # name: (Nx, Ny, Nz, dt)  -- dt = 3240 / RESOLUTION (experiments/run.jl:44)
+    "c3": (2160, 900, 120, 540.0),    # DoubleDrake 1/6 deg NZ=120: the configuration the metric is quoted on
+    "c2": (1080, 450, 120, 1080.0),   # DoubleDrake 1/3 deg NZ=120
+    "small": (360, 150, 24, 3240.0),
+}
+# algorithmic bytes per cell (SURVEY 8d / DESIGN.md): momentum kernel reads u,v,w,p and writes Gu,Gv
+MOMENTUM_BYTES_PER_CELL = 48.0
+GROUP_NAMES = ["ab2_implicit+baro_forcing", "barotropic_substeps", "corrector", "halos", "w_p", "ri_kappa",
+               "momentum_tendencies", "tracer_tendencies"]
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[q] for r in self.rows if len(r) >= 7 for q in range(4) if r[3 + q].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_case(workload: str, ranks: int) -> cases.Case:
+    Nx, Ny, Nz, dt = WORKLOADS[workload]
+    return cases.Case(workload, Nx, Ny, Nz, experiment="DoubleDrake", dt=dt, perturb=True, ranks=ranks)
+
+
+def initial_state(pkg, case, grid):
+    """Closed-form initial state as host arrays (the same formulas as tests/cases.py)."""
+    D, r = case.depth, np.pi / 180.0
+    lam, lamf = grid.lam_c()[None, None, :], (grid.lam_c() - 0.5 * grid.dlam)[None, None, :]
+    phi, phif = grid.phi_c()[None, :, None], grid.phi_f()[None, :, None]
+    z = grid.z_c()[:, None, None]
+    T = (pkg.exponential_profile(z, Lz=D, h=D / 15.0) * np.maximum(pkg.T_reference(phi), 2.0)
+         + 0.5 * np.sin(3 * lam * r) * np.cos(2 * phi * r) * np.exp(z / 500.0))
+    S = 35.0 + 0.2 * np.cos(2 * lam * r + 0.3) * np.sin(3 * phi * r) * np.exp(z / 800.0)
+    u = 0.1 * np.sin(2 * lamf * r) * np.cos(phi * r) * (1.0 + z / D)
+    v = 0.05 * np.cos(3 * lam * r) * np.sin(2 * phif * r) * np.exp(z / 1000.0)
+    eta = 0.1 * np.cos(phi[0] * r) * np.sin(2 * lam[0] * r)
+    return {"T": T, "S": S, "U": u, "V": v, "ETA": eta}
+
+
+def run_reference(args, rank, world):
+    """The reference arm: the CPU oracle (port of the reference's algorithm; Julia/Oceananigans cannot run here)
+    on a bounded sample of the workload -- a 12-degree periodic sector of the same grid (same spacing, levels,
+    bathymetry rule, forcing), all host threads."""
+    if rank != 0:
+        return
+    pkg, orc = ge.package(), ge.oracle_module()
+    orc.build()
+    Nx, Ny, Nz, dt = WORKLOADS[args.workload]
+    # bounded sample: shrink the sector when many steps are requested so the run ends within a few minutes
+    sector = max(16, min(args.cpu_columns, Nx, int(args.cpu_columns * 13 / max(13, args.steps + args.warmup))))
+    zf = pkg.exponential_z_faces(Nz, 3000.0)
+    g0 = pkg.LatitudeLongitudeGrid(Nx, Ny, Nz, zf)
+    bottom = pkg.double_drake_bathymetry(g0.lam_c()[None, :], g0.phi_c()[:, None])[:, Nx // 2 - 8: Nx // 2 - 8 + sector]
+    # sector grid: same dlam / dphi / z as the full workload, periodic over `sector` columns (contains one ridge)
+    grid = pkg.LatitudeLongitudeGrid(sector, Ny, Nz, zf, longitude=(-180.0, -180.0 + 360.0 * sector / Nx),
+                                     bottom_height_global=np.ascontiguousarray(bottom))
+    nsub = pkg.barotropic_substeps(dt, g0)
+    model = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=pkg.SplitExplicitFreeSurface(substeps=nsub),
+                                            eos="linear", boundary_conditions=pkg.set_boundary_conditions("DoubleDrake", grid),
+                                            backend_factory=orc.OracleBackend)
+    case = make_case(args.workload, 1)
+    case.initialize(pkg, model)
+    for _ in range(args.warmup):
+        pkg.time_step(model, dt)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pkg.time_step(model, dt)
+    el = time.perf_counter() - t0
+    cells = sector * Ny * Nz
+    value = cells * args.steps / el
+    cores = os.cpu_count()
+    sample = f"{sector}x{Ny}x{Nz} periodic sector ({cells / 1e6:.2f} M cells, {100.0 * sector / Nx:.1f}% of the workload), {args.steps} steps"
+    out = {"impl": "reference", "metric": "grid-cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps * (Nx / sector),
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"DoubleDrake {Nx}x{Ny}x{Nz} dt={dt:g}s (CPU: bounded sample, ms_per_step extrapolated to the full grid)"},
+           "sypd": dt / (el / args.steps * (Nx / sector)) / 365.0,
+           "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline_sample(pkg, args, budget_s=20.0):
+    """Bounded CPU-oracle sample for the main arm's `cpu_baseline` object (rank 0, N = 1 only)."""
+    orc = ge.oracle_module()
+    orc.build()
+    Nx, Ny, Nz, dt = WORKLOADS[args.workload]
+    sector = 32
+    zf = pkg.exponential_z_faces(Nz, 3000.0)
+    g0 = pkg.LatitudeLongitudeGrid(Nx, Ny, Nz, zf)
+    bottom = pkg.double_drake_bathymetry(g0.lam_c()[None, :], g0.phi_c()[:, None])[:, Nx // 2 - 8: Nx // 2 - 8 + sector]
+    grid = pkg.LatitudeLongitudeGrid(sector, Ny, Nz, zf, longitude=(-180.0, -180.0 + 360.0 * sector / Nx),
+                                     bottom_height_global=np.ascontiguousarray(bottom))
+    model = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=pkg.SplitExplicitFreeSurface(substeps=pkg.barotropic_substeps(dt, g0)),
+                                            eos="linear", boundary_conditions=pkg.set_boundary_conditions("DoubleDrake", grid),
+                                            backend_factory=orc.OracleBackend)
+    make_case(args.workload, 1).initialize(pkg, model)
+    pkg.time_step(model, dt)
+    n, t0 = 0, time.perf_counter()
+    while n < 2 or (time.perf_counter() - t0 < budget_s and n < 8):
+        pkg.time_step(model, dt)
+        n += 1
+    el = time.perf_counter() - t0
+    cells = sector * Ny * Nz
+    return {"value": cells * n / el, "unit": "cell-steps/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{sector}x{Ny}x{Nz} periodic sector ({cells / 1e6:.2f} M cells), {n} steps, OpenMP all cores"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("OB200_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-columns", type=int, default=72)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--persistent-barotropic", type=int, default=int(os.environ.get("OB200_PERSISTENT_BARO", "0")))
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pkg = ge.package()
+    case = make_case(args.workload, world)
+    Nx, Ny, Nz, dt = WORKLOADS[args.workload]
+    grid = case.grid(pkg, rank, world)
+    g0 = case.grid(pkg, 0, 1)
+    fs = pkg.SplitExplicitFreeSurface(substeps=pkg.barotropic_substeps(dt, g0))
+    model = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=fs, eos="linear",
+                                            boundary_conditions=pkg.set_boundary_conditions("DoubleDrake", grid),
+                                            device=local_rank)
+    if world > 1:
+        uid = [model.backend.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        model.backend.comm_init(uid[0])
+    if args.persistent_barotropic:
+        model.backend.set_option("persistent_barotropic", 1)
+    state = initial_state(pkg, case, grid)
+    # pinned host copies of the initial state (what a host application owns)
+    pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in state.items()}
+
+    def upload():
+        for k, t in pinned.items():
+            model.backend.lib.ob200_set_field(model.backend.h, pkg._abi.FIELD_ID[k], t.data_ptr(), 0, 0, 0, 0)
+        model.backend.update_state()
+
+    out_names = ("U", "V", "W", "ETA", "T", "S")
+    out_pinned = {k: torch.empty(pkg._abi.field_shape(k, *grid.size()), dtype=torch.float64).pin_memory() for k in out_names}
+
+    def download():
+        for k, t in out_pinned.items():
+            model.backend.lib.ob200_get_field(model.backend.h, pkg._abi.FIELD_ID[k], t.data_ptr(), 0, 0, 0, 0)
+
+    def barrier():
+        model.backend.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    upload()
+    for _ in range(args.warmup):
+        pkg.time_step(model, dt)
+    barrier()
+
+    # ---- timed region: K steps, state resident in HBM -------------------------------------------------
+    model.backend.set_option("timing", 1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    groups = np.zeros(len(GROUP_NAMES))
+    _, launches0 = model.backend.timing()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pkg.time_step(model, dt)
+        # per-stage CUDA-event times of this step, read after the step's last event (stream-ordered; the next
+        # step is enqueued only after this read, which costs one sync per step -- included in the timing)
+        ms, _ = model.backend.timing()
+        groups[:len(ms)] += ms
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.stop()
+    _, launches1 = model.backend.timing()
+    model.backend.set_option("timing", 0)
+    if world > 1:
+        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    mx, _ = model.backend.diagnostics()
+    if not all(np.isfinite(mx)) or mx[0] > 10.0:
+        raise SystemExit(f"bench.py: the run blew up (max-abs {mx})")
+
+    cells = Nx * Ny * Nz
+    value = cells * args.steps / elapsed
+    ms_per_step = 1e3 * elapsed / args.steps
+
+    # ---- e2e: host buffers, H2D + K steps + D2H inside the timed region ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        upload()
+        for _ in range(args.steps):
+            pkg.time_step(model, dt)
+        download()
+        barrier()
+        e2e_el = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_el], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_el = float(t.item())
+        h2d = sum(t.numel() * 8 for t in pinned.values())
+        d2h = sum(t.numel() * 8 for t in out_pinned.values())
+        e2e = {"value": cells * args.steps / e2e_el, "unit": "cell-steps/s",
+               "h2d_bytes_per_step": int(h2d * world / args.steps), "d2h_bytes_per_step": int(d2h * world / args.steps),
+               "what": "pinned host initial state -> set! -> K x time_step! -> prognostic fields to pinned host"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    local_cells = grid.Nx * Ny * Nz
+    mom_ms = groups[6] / args.steps
+    achieved = MOMENTUM_BYTES_PER_CELL * local_cells / (mom_ms * 1e-3) / 1e9 if mom_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "k_momentum (fused Gu,Gv tendencies)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_cell": MOMENTUM_BYTES_PER_CELL,
+                "ms_per_launch": mom_ms, "note": "FP64-ALU-bound WENO stencil (SURVEY F10); HBM fraction reported as the contract asks"}
+    out = {"metric": "grid-cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"DoubleDrake {Nx}x{Ny}x{Nz} dt={dt:g}s, {fs.substeps}->{len(fs.averaging_weights)} barotropic substeps",
+                      "partition": f"x-slabs {list(grid.partition.sizes)}",
+                      "l2": "inputs (44 GB of fields per step at 1 GPU) exceed the 126 MB L2; no flush needed"},
+           "sypd": dt / (elapsed / args.steps) / 365.0,
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches1 - launches0),
+           "stage_ms": {n: float(g / args.steps) for n, g in zip(GROUP_NAMES, groups)},
+           "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_sample(pkg, args)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

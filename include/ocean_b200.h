@@ -127,9 +127,14 @@ typedef struct ob200_config {
 
 typedef struct ob200_handle ob200_handle;
 
+/* Stage groups timed with CUDA events on the handle's stream when option "timing" = 1:
+ * 0 barotropic forcing + AB2/implicit x4, 1 barotropic substeps, 2 corrector, 3 halos/exchange,
+ * 4 w + pHY', 5 Ri + kappa (+ QG-Leith), 6 momentum tendencies, 7 tracer tendencies.              */
+#define OB200_TIMED_GROUPS 8
 typedef struct ob200_timing {
-    int32_t n;                 /* number of timed stage groups                  */
-    float   ms[16];            /* last step: per stage group, CUDA-event ms     */
+    int32_t n;                 /* number of timed stage groups (OB200_TIMED_GROUPS) */
+    float   ms[16];            /* last step: per stage group, CUDA-event ms          */
+    int64_t launches;          /* kernels launched by this library since create      */
 } ob200_timing;
 
 /* --- lifecycle ---------------------------------------------------------- */

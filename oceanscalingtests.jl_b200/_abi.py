@@ -71,7 +71,7 @@ class ob200_config(C.Structure):
 
 
 class ob200_timing(C.Structure):
-    _fields_ = [("n", C.c_int32), ("ms", C.c_float * 16)]
+    _fields_ = [("n", C.c_int32), ("ms", C.c_float * 16), ("launches", C.c_int64)]
 
 
 def as_double_ptr(a: np.ndarray):

@@ -2,6 +2,9 @@
 #pragma once
 #include "ob_common.cuh"
 
+extern long long ob_launch_count;   // kernels launched by this library (bench.py reports it as gpu_launches)
+#define OB_COUNT_LAUNCH(n) (ob_launch_count += (n))
+
 struct Fields {
     // 3-D (Nz+1 planes)
     double *u, *v, *w, *T, *S, *p, *kc, *ku, *Ri, *scratch;
@@ -40,7 +43,7 @@ int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const do
                            cudaStream_t st);
 
 // kernels_tend.cu
-void launch_tendencies(const Geom& G, const Fields& F, int ord_vort, int ord_div, int ord_tracer, double time,
-                       cudaStream_t st);
+void launch_momentum(const Geom& G, const Fields& F, int ord_vort, int ord_div, double time, cudaStream_t st);
+void launch_tracers(const Geom& G, const Fields& F, int ord_tracer, double time, cudaStream_t st);
 // kernels_leith.cu
 void launch_leith(const Geom& G, const Fields& F, cudaStream_t st);

@@ -74,18 +74,22 @@ __global__ void k_baro_finish(Geom G, Fields F) {
 void launch_baro_init(const Geom& G, const Fields& F, bool periodic, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 127) / 128, G.Ny + 1);
     k_baro_init<<<g, b, 0, st>>>(G, F, periodic);
+    OB_COUNT_LAUNCH(1);
 }
 void launch_baro_eta(const Geom& G, const Fields& F, double dtau, bool periodic, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 127) / 128, G.Ny);
     k_baro_eta<<<g, b, 0, st>>>(G, F, dtau, periodic);
+    OB_COUNT_LAUNCH(1);
 }
 void launch_baro_vel(const Geom& G, const Fields& F, double dtau, double wgt, bool periodic, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 127) / 128, G.Ny);
     k_baro_vel<<<g, b, 0, st>>>(G, F, dtau, wgt, periodic);
+    OB_COUNT_LAUNCH(1);
 }
 void launch_baro_finish(const Geom& G, const Fields& F, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 127) / 128, G.Ny);
     k_baro_finish<<<g, b, 0, st>>>(G, F);
+    OB_COUNT_LAUNCH(1);
 }
 
 // ---- persistent variant: all substeps in one cooperative launch --------------------------------------
@@ -117,5 +121,6 @@ int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const do
     Geom g = G; Fields f = F;
     void* args[] = {&g, &f, &dtau, &wts, &M, &periodic};
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k_baro_persistent, dim3(nblk), dim3(256), args, 0, st);
+    OB_COUNT_LAUNCH(1);
     return e == cudaSuccess ? 0 : -1;
 }

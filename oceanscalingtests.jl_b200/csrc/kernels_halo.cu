@@ -51,9 +51,11 @@ void launch_fill_halos(const Geom& G, const Fields& F, bool periodic_x, cudaStre
     if (periodic_x) {
         dim3 b(8, 16), g((G.Ny + 1 + 15) / 16, G.Nz + 1);
         k_fill_x<<<g, b, 0, st>>>(G, F);
+        OB_COUNT_LAUNCH(1);
     }
     dim3 b2(128), g2((G.Nx + 2 * OB_H + 127) / 128, G.Nz + 1);
     k_fill_y<<<g2, b2, 0, st>>>(G, F);
+    OB_COUNT_LAUNCH(1);
 }
 
 // mask_immersed_field! for u, v, T, S and eta; needed after set_field only: the step never
@@ -73,6 +75,7 @@ __global__ void k_mask(Geom G, Fields F) {
 void launch_mask_fields(const Geom& G, const Fields& F, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 127) / 128, G.Ny + 1, G.Nz);
     k_mask<<<g, b, 0, st>>>(G, F);
+    OB_COUNT_LAUNCH(1);
 }
 
 // wet column depth at u / v points: sum of dz over non-peripheral nodes
@@ -91,6 +94,7 @@ __global__ void k_column_depths(Geom G, Fields F) {
 void launch_column_depths(const Geom& G, const Fields& F, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 2 * OB_H + 127) / 128, G.Ny + 1);
     k_column_depths<<<g, b, 0, st>>>(G, F);
+    OB_COUNT_LAUNCH(1);
 }
 
 // interior <-> user buffer laid out like an Oceananigans parent array with halos (hx, hy, hz)
@@ -108,6 +112,7 @@ void launch_copy_field(const Geom& G, double* field, double* buf, int ny, int nz
                        bool to_field, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 127) / 128, ny, nz);
     k_copy_field<<<g, b, 0, st>>>(G, field, buf, ny, nz, hx, hy, hz, three_d, to_field);
+    OB_COUNT_LAUNCH(1);
 }
 
 // ---- x-slab exchange buffers: [u | v | T | S] x (Nz planes x (Ny+1) rows x OB_H cols) + eta ((Ny+1) x OB_H)
@@ -139,11 +144,13 @@ __global__ void k_pack_x(Geom G, Fields F, double* sendW, double* sendE, bool un
 void launch_pack_x(const Geom& G, const Fields& F, double* sendW, double* sendE, cudaStream_t st) {
     dim3 b(8, 16), g((G.Ny + 1 + 15) / 16, G.Nz + 1);
     k_pack_x<<<g, b, 0, st>>>(G, F, sendW, sendE, false);
+    OB_COUNT_LAUNCH(1);
 }
 // recvW = data for the west halo (from the west neighbour's east edge), recvE likewise
 void launch_unpack_x(const Geom& G, const Fields& F, const double* recvW, const double* recvE, cudaStream_t st) {
     dim3 b(8, 16), g((G.Ny + 1 + 15) / 16, G.Nz + 1);
     k_pack_x<<<g, b, 0, st>>>(G, F, const_cast<double*>(recvW), const_cast<double*>(recvE), true);
+    OB_COUNT_LAUNCH(1);
 }
 
 // ---- diagnostics: max |u|,|v|,|w|,|eta|,|T|,|S| and the advective CFL time scale (TimeStepWizard) ----------
@@ -172,4 +179,5 @@ void launch_diagnostics(const Geom& G, const Fields& F, double* out8, cudaStream
     cudaMemsetAsync(out8, 0, 8 * sizeof(double), st);
     dim3 b(128), g((G.Nx + 127) / 128, G.Ny, G.Nz);
     k_diag<<<g, b, 0, st>>>(G, F, out8);
+    OB_COUNT_LAUNCH(1);
 }

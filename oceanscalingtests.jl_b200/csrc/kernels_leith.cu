@@ -101,8 +101,11 @@ void launch_leith(const Geom& G, const Fields& F, cudaStream_t st) {
     dim3 b(128);
     dim3 g2((G.Nx + 2 * LEITH_E + 127) / 128, G.Ny + 2 * LEITH_E);
     k_leith_ld<<<g2, b, 0, st>>>(G, F);
+    OB_COUNT_LAUNCH(1);
     dim3 g3((G.Nx + 2 * LEITH_E + 127) / 128, G.Ny + 2 * LEITH_E, G.Nz + 1);
     k_leith_q<<<g3, b, 0, st>>>(G, F);
+    OB_COUNT_LAUNCH(1);
     dim3 g4((G.Nx + 2 * LEITH_E + 127) / 128, G.Ny + 2 * LEITH_E, G.Nz);
     k_leith_nu<<<g4, b, 0, st>>>(G, F);
+    OB_COUNT_LAUNCH(1);
 }

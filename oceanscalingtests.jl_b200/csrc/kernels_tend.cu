@@ -435,9 +435,13 @@ __global__ void __launch_bounds__(128) k_tracers(Geom G, Fields F, int NT, doubl
     F.GS[c] = gS;
 }
 
-void launch_tendencies(const Geom& G, const Fields& F, int ord_vort, int ord_div, int ord_tracer, double time,
-                       cudaStream_t st) {
+void launch_momentum(const Geom& G, const Fields& F, int ord_vort, int ord_div, double time, cudaStream_t st) {
     dim3 b(32, 4), g((G.Nx + 31) / 32, (G.Ny + 3) / 4, G.Nz);
     k_momentum<<<g, b, 0, st>>>(G, F, (ord_vort + 1) / 2, (ord_div + 1) / 2, time);
+    OB_COUNT_LAUNCH(1);
+}
+void launch_tracers(const Geom& G, const Fields& F, int ord_tracer, double time, cudaStream_t st) {
+    dim3 b(32, 4), g((G.Nx + 31) / 32, (G.Ny + 3) / 4, G.Nz);
     k_tracers<<<g, b, 0, st>>>(G, F, (ord_tracer + 1) / 2, time);
+    OB_COUNT_LAUNCH(1);
 }

@@ -13,6 +13,7 @@
 #include "kernels.h"
 
 static thread_local std::string g_last_error;
+long long ob_launch_count = 0;
 
 struct ob200_handle {
     ob200_config cfg;
@@ -260,7 +261,8 @@ void auxiliaries(ob200_handle* h) {
     if (h->G.qgleith) launch_leith(h->G, h->F, h->stream);
 }
 void tendencies(ob200_handle* h) {
-    launch_tendencies(h->G, h->F, h->cfg.order_vorticity, h->cfg.order_divergence, h->cfg.order_tracer, h->time, h->stream);
+    launch_momentum(h->G, h->F, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, h->stream);
+    launch_tracers(h->G, h->F, h->cfg.order_tracer, h->time, h->stream);
 }
 int update_state(ob200_handle* h) {
     if (int rc = mask_and_halos(h)) return rc;
@@ -316,7 +318,9 @@ int step_body(ob200_handle* h, double dt, bool euler) {
     launch_ri_kappa(G, h->F, h->time, h->stream);
     if (G.qgleith) launch_leith(G, h->F, h->stream);
     mark();
-    tendencies(h);
+    launch_momentum(G, h->F, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, h->stream);
+    mark();
+    launch_tracers(G, h->F, h->cfg.order_tracer, h->time, h->stream);
     mark();
     h->n_timed = e - 1;
     return OB200_OK;
@@ -519,6 +523,7 @@ int ob200_get_timing(ob200_handle* h, ob200_timing* t) {
     if (!h || !t) return OB200_EINVAL;
     cudaSetDevice(h->device);
     t->n = 0;
+    t->launches = ob_launch_count;
     if (!h->timing || h->n_timed <= 0) return OB200_OK;
     OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
     for (int q = 0; q < h->n_timed && q < 16; q++) cudaEventElapsedTime(&t->ms[q], h->ev[q], h->ev[q + 1]);

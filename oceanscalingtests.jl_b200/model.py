@@ -245,7 +245,7 @@ class B200Backend:
     def timing(self):
         t = _abi.ob200_timing()
         self._check(self.lib.ob200_get_timing(self.h, C.byref(t)))
-        return [t.ms[i] for i in range(t.n)]
+        return [t.ms[i] for i in range(t.n)], int(t.launches)
 
     def set_option(self, name: str, value: int):
         self._check(self.lib.ob200_set_option(self.h, name.encode(), int(value)))
