@@ -43,7 +43,17 @@ int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const do
                            cudaStream_t st);
 
 // kernels_tend.cu
-void launch_momentum(const Geom& G, const Fields& F, int ord_vort, int ord_div, double time, cudaStream_t st);
-void launch_tracers(const Geom& G, const Fields& F, int ord_tracer, double time, cudaStream_t st);
+// Per-tile plan of the momentum kernels: tile_kfast[t] = first level the shared-memory fast kernel may take for
+// tile t (max of kfast over the tile's columns; Nz = never); slow_tiles = (tile, kfast) pairs with kfast > 0,
+// handled below that level by the general masked kernel.
+struct MomPlan {
+    int ntx = 0, nty = 0, nslow = 0;
+    bool any_fast = false;
+    int* tile_kfast = nullptr;   // device, ntx * nty
+    int* slow_tiles = nullptr;   // device, 2 * nslow
+};
+void mom_plan_tile_shape(int* tx, int* ty);
+void launch_momentum(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st);
+void launch_tracers(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st);
 // kernels_leith.cu
 void launch_leith(const Geom& G, const Fields& F, cudaStream_t st);

@@ -12,12 +12,16 @@
 #include "ob_bc.cuh"
 #include "weno_gen.cuh"
 
-struct Mom {
+// ---- accessors: the same operators read either straight from HBM/L1 (MomG) or from a shared-memory tile
+// in which zeta, the tangential-velocity stencils, the divergence pieces and K were computed once (MomS).
+struct MomG {
     const Geom& G;
     const double* __restrict__ u;
     const double* __restrict__ v;
     __device__ __forceinline__ double U(int i, int j, int k) const { return u[idx3(G, i, j, k)]; }
     __device__ __forceinline__ double V(int i, int j, int k) const { return v[idx3(G, i, j, k)]; }
+    __device__ __forceinline__ double usm(int i, int j, int k) const { return 0.5 * (U(i, j - 1, k) + U(i, j, k)); }
+    __device__ __forceinline__ double vsm(int i, int j, int k) const { return 0.5 * (V(i - 1, j, k) + V(i, j, k)); }
     // vertical vorticity at (f,f,c); GEN applies the immersed conditional differences
     template <bool GEN>
     __device__ __forceinline__ double zeta(int i, int j, int k) const {
@@ -46,17 +50,47 @@ struct Mom {
     }
 };
 
+// shared-memory tile geometry for the fast path (TX x TY cells per block)
+template <int TX, int TY>
+struct TileDims {
+    static constexpr int HU = 5;                         // halo of the u, v tiles
+    static constexpr int PU = TX + 2 * HU + 1, RU = TY + 2 * HU + 1;   // i in [i0-5, i0+TX+5], j in [j0-5, j0+TY+5]
+    static constexpr int HZ = 4;                         // zeta / us / vs: i in [i0-4, i0+TX+4], j likewise
+    static constexpr int PZ = TX + 2 * HZ + 1, RZ = TY + 2 * HZ + 1;
+    static constexpr int HD = 3;                         // dxU, dyV: [i0-3, i0+TX+2]
+    static constexpr int PD = TX + 2 * HD, RD = TY + 2 * HD;
+    static constexpr int PK = TX + 1, RK = TY + 1;       // K: [i0-1, i0+TX-1]
+    static constexpr int NU = PU * RU, NZ = PZ * RZ, ND = PD * RD, NK = PK * RK;
+    static constexpr int TOTAL = 2 * NU + 3 * NZ + 2 * ND + NK;   // doubles
+};
+
+template <int TX, int TY>
+struct MomS {
+    using D = TileDims<TX, TY>;
+    const double *su, *sv, *sz, *sus, *svs, *sdx, *sdy, *sK;
+    int i0, j0;
+    __device__ __forceinline__ double U(int i, int j, int) const { return su[(j - j0 + D::HU) * D::PU + (i - i0 + D::HU)]; }
+    __device__ __forceinline__ double V(int i, int j, int) const { return sv[(j - j0 + D::HU) * D::PU + (i - i0 + D::HU)]; }
+    __device__ __forceinline__ double usm(int i, int j, int) const { return sus[(j - j0 + D::HZ) * D::PZ + (i - i0 + D::HZ)]; }
+    __device__ __forceinline__ double vsm(int i, int j, int) const { return svs[(j - j0 + D::HZ) * D::PZ + (i - i0 + D::HZ)]; }
+    template <bool GEN>
+    __device__ __forceinline__ double zeta(int i, int j, int) const { return sz[(j - j0 + D::HZ) * D::PZ + (i - i0 + D::HZ)]; }
+    __device__ __forceinline__ double dxU(int i, int j, int) const { return sdx[(j - j0 + D::HD) * D::PD + (i - i0 + D::HD)]; }
+    __device__ __forceinline__ double dyV(int i, int j, int) const { return sdy[(j - j0 + D::HD) * D::PD + (i - i0 + D::HD)]; }
+    __device__ __forceinline__ double Kh(int i, int j, int) const { return sK[(j - j0 + 1) * D::PK + (i - i0 + 1)]; }
+};
+
 // ---- biased reconstructions along a line; `base + sgn*m` walks from the most upwind-ward point -------------
-template <int N, bool GEN>
-__device__ __forceinline__ double recon_vort_y(const Mom& M, int i, int j, int k, bool left) {
+template <int N, bool GEN, class A>
+__device__ __forceinline__ double recon_vort_y(const A& M, int i, int j, int k, bool left) {
     const int base = left ? j - N + 1 : j + N, sgn = left ? 1 : -1;
     double zq[2 * N - 1], us[2 * N - 1], vs[2 * N - 1];
 #pragma unroll
     for (int m = 0; m < 2 * N - 1; m++) {
         const int jj = base + sgn * m;
         zq[m] = M.template zeta<GEN>(i, jj, k);
-        us[m] = 0.5 * (M.U(i, jj - 1, k) + M.U(i, jj, k));
-        vs[m] = 0.5 * (M.V(i - 1, jj, k) + M.V(i, jj, k));
+        us[m] = M.usm(i, jj, k);
+        vs[m] = M.vsm(i, jj, k);
     }
     if (N == 1) return zq[0];
     double bu[N], bv[N];
@@ -66,16 +100,16 @@ __device__ __forceinline__ double recon_vort_y(const Mom& M, int i, int j, int k
     for (int s = 0; s < N; s++) bu[s] = 0.5 * (bu[s] + bv[s]);
     return Weno<N>::combine(zq, bu);
 }
-template <int N, bool GEN>
-__device__ __forceinline__ double recon_vort_x(const Mom& M, int i, int j, int k, bool left) {
+template <int N, bool GEN, class A>
+__device__ __forceinline__ double recon_vort_x(const A& M, int i, int j, int k, bool left) {
     const int base = left ? i - N + 1 : i + N, sgn = left ? 1 : -1;
     double zq[2 * N - 1], us[2 * N - 1], vs[2 * N - 1];
 #pragma unroll
     for (int m = 0; m < 2 * N - 1; m++) {
         const int ii = base + sgn * m;
         zq[m] = M.template zeta<GEN>(ii, j, k);
-        us[m] = 0.5 * (M.U(ii, j - 1, k) + M.U(ii, j, k));
-        vs[m] = 0.5 * (M.V(ii - 1, j, k) + M.V(ii, j, k));
+        us[m] = M.usm(ii, j, k);
+        vs[m] = M.vsm(ii, j, k);
     }
     if (N == 1) return zq[0];
     double bu[N], bv[N];
@@ -85,8 +119,8 @@ __device__ __forceinline__ double recon_vort_x(const Mom& M, int i, int j, int k
     for (int s = 0; s < N; s++) bu[s] = 0.5 * (bu[s] + bv[s]);
     return Weno<N>::combine(zq, bu);
 }
-template <int N>
-__device__ __forceinline__ double recon_div_x(const Mom& M, int i, int j, int k, bool left) {
+template <int N, class A>
+__device__ __forceinline__ double recon_div_x(const A& M, int i, int j, int k, bool left) {
     const int base = left ? i - N : i + N - 1, sgn = left ? 1 : -1;
     double q[2 * N - 1], s[2 * N - 1];
 #pragma unroll
@@ -100,8 +134,8 @@ __device__ __forceinline__ double recon_div_x(const Mom& M, int i, int j, int k,
     Weno<N>::beta(s, b);
     return Weno<N>::combine(q, b);
 }
-template <int N>
-__device__ __forceinline__ double recon_div_y(const Mom& M, int i, int j, int k, bool left) {
+template <int N, class A>
+__device__ __forceinline__ double recon_div_y(const A& M, int i, int j, int k, bool left) {
     const int base = left ? j - N : j + N - 1, sgn = left ? 1 : -1;
     double q[2 * N - 1], s[2 * N - 1];
 #pragma unroll
@@ -150,13 +184,13 @@ __device__ __forceinline__ int order_faces(const Geom& G, int i, int j, int k, i
 // ================================================================================================
 // momentum tendencies
 // ================================================================================================
-template <bool GEN>
-__device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, int i, int j, int k, int NV, int ND, double time) {
-    const Mom M{G, F.u, F.v};
+template <bool GEN, class A>
+__device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A& M, int i, int j, int k, int NV, int ND,
+                                         double time) {
     const long long c = idx3(G, i, j, k);
     // (1) vorticity flux
-    const double q00 = G.dxcf[j] * F.v[c - 1], q01 = G.dxcf[j + 1] * F.v[c - 1 + G.pitch];
-    const double q10 = G.dxcf[j] * F.v[c], q11 = G.dxcf[j + 1] * F.v[c + G.pitch];
+    const double q00 = G.dxcf[j] * M.V(i - 1, j, k), q01 = G.dxcf[j + 1] * M.V(i - 1, j + 1, k);
+    const double q10 = G.dxcf[j] * M.V(i, j, k), q11 = G.dxcf[j + 1] * M.V(i, j + 1, k);
     const double vavg = 0.5 * (0.5 * (q00 + q01) + 0.5 * (q10 + q11));
     const double vhat = vavg / G.dxfc[j];
     double Gt = 0.0;
@@ -173,7 +207,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, int i, 
         Gt = vhat * z;
     }
     // (2) divergence flux + vertical advection
-    const double uh = F.u[c];
+    const double uh = M.U(i, j, k);
     double Phi = 0.0;
     if (uh != 0.0) {
         const bool left = uh > 0.0;
@@ -216,14 +250,15 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, int i, 
     Gt -= (F.p[c] - F.p[c - 1]) / G.dxfc[j];
     // (6) QG-Leith stress divergence
     if (G.qgleith) {
+        const MomG Mg{G, F.u, F.v};
         const double ax = G.dy * G.dzc[k];
-        auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * ((M.dxU(a, b, k) / G.dzc[k] + M.dyV(a, b, k) / G.dzc[k]) / G.azcc[b]) : 0.0; };
+        auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * ((Mg.dxU(a, b, k) / G.dzc[k] + Mg.dyV(a, b, k) / G.dzc[k]) / G.azcc[b]) : 0.0; };
         auto fffc = [&](int a, int b) {
             const bool per = !active(G, a - 1, b - 1, k) || !active(G, a, b - 1, k) || !active(G, a - 1, b, k) || !active(G, a, b, k);
             if (per && in_domain(G, b - 1, k) && in_domain(G, b, k)) return 0.0;
             const long long q = idx3(G, a, b, k);
             const double nu = 0.25 * (F.nuL[q - 1 - G.pitch] + F.nuL[q - G.pitch] + F.nuL[q - 1] + F.nuL[q]);
-            return nu * M.zeta<true>(a, b, k);
+            return nu * Mg.zeta<true>(a, b, k);
         };
         const double t = ax * fccc(i, j) - ax * fccc(i - 1, j) +
                          (G.dxcf[j + 1] * G.dzc[k] * fffc(i, j + 1) - G.dxcf[j] * G.dzc[k] * fffc(i, j));
@@ -240,7 +275,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, int i, 
         double J = 0.0;
         if (G.bc_kind == OB200_BC_DOUBLEDRAKE) J = -G.mu_drag * uh;
         else if (G.bc_kind == OB200_BC_REALISTIC) {
-            const double v0 = F.v[c - 1], v1 = F.v[c - 1 + G.pitch], v2 = F.v[c], v3 = F.v[c + G.pitch];
+            const double v0 = M.V(i - 1, j, k), v1 = M.V(i - 1, j + 1, k), v2 = M.V(i, j, k), v3 = M.V(i, j + 1, k);
             J = -G.mu_drag * uh * sqrt(uh * uh + 0.25 * (v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3));
         }
         Gt += J / G.dzc[k];
@@ -248,13 +283,13 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, int i, 
     return Gt;
 }
 
-template <bool GEN>
-__device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, int i, int j, int k, int NV, int ND, double time) {
-    const Mom M{G, F.u, F.v};
+template <bool GEN, class A>
+__device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A& M, int i, int j, int k, int NV, int ND,
+                                         double time) {
     const long long c = idx3(G, i, j, k);
     const double dy = G.dy;
-    const double q00 = dy * F.u[c - G.pitch], q10 = dy * F.u[c + 1 - G.pitch];
-    const double q01 = dy * F.u[c], q11 = dy * F.u[c + 1];
+    const double q00 = dy * M.U(i, j - 1, k), q10 = dy * M.U(i + 1, j - 1, k);
+    const double q01 = dy * M.U(i, j, k), q11 = dy * M.U(i + 1, j, k);
     const double uavg = 0.5 * (0.5 * (q00 + q10) + 0.5 * (q01 + q11));
     const double uhat = uavg / dy;
     double Gt = 0.0;
@@ -270,7 +305,7 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, int i, 
         }
         Gt = -(uhat * z);
     }
-    const double vh = F.v[c];
+    const double vh = M.V(i, j, k);
     double Phi = 0.0;
     if (vh != 0.0) {
         const bool left = vh > 0.0;
@@ -305,14 +340,15 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, int i, 
     Gt -= fbar * cor / dy;
     Gt -= (F.p[c] - F.p[c - G.pitch]) / dy;
     if (G.qgleith) {
+        const MomG Mg{G, F.u, F.v};
         const double ax = dy * G.dzc[k];
-        auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * ((M.dxU(a, b, k) / G.dzc[k] + M.dyV(a, b, k) / G.dzc[k]) / G.azcc[b]) : 0.0; };
+        auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * ((Mg.dxU(a, b, k) / G.dzc[k] + Mg.dyV(a, b, k) / G.dzc[k]) / G.azcc[b]) : 0.0; };
         auto fffc = [&](int a, int b) {
             const bool per = !active(G, a - 1, b - 1, k) || !active(G, a, b - 1, k) || !active(G, a - 1, b, k) || !active(G, a, b, k);
             if (per && in_domain(G, b - 1, k) && in_domain(G, b, k)) return 0.0;
             const long long q = idx3(G, a, b, k);
             const double nu = 0.25 * (F.nuL[q - 1 - G.pitch] + F.nuL[q - G.pitch] + F.nuL[q - 1] + F.nuL[q]);
-            return nu * M.zeta<true>(a, b, k);
+            return nu * Mg.zeta<true>(a, b, k);
         };
         const double t = ax * (-fffc(i + 1, j)) - ax * (-fffc(i, j)) +
                          (G.dxfc[j] * G.dzc[k] * fccc(i, j) - G.dxfc[j - 1] * G.dzc[k] * fccc(i, j - 1));
@@ -323,7 +359,7 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, int i, 
         double J = 0.0;
         if (G.bc_kind == OB200_BC_DOUBLEDRAKE) J = -G.mu_drag * vh;
         else if (G.bc_kind == OB200_BC_REALISTIC) {
-            const double u0 = F.u[c - G.pitch], u1 = F.u[c + 1 - G.pitch], u2 = F.u[c], u3 = F.u[c + 1];
+            const double u0 = M.U(i, j - 1, k), u1 = M.U(i + 1, j - 1, k), u2 = M.U(i, j, k), u3 = M.U(i + 1, j, k);
             J = -G.mu_drag * vh * sqrt(vh * vh + 0.25 * (u0 * u0 + u2 * u2 + u1 * u1 + u3 * u3));
         }
         Gt += J / G.dzc[k];
@@ -331,24 +367,96 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, int i, 
     return Gt;
 }
 
-__global__ void __launch_bounds__(128) k_momentum(Geom G, Fields F, int NV, int ND, double time) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = blockIdx.z;
+// ---- general (masked, order-reducing) path, one thread per cell straight from global memory ----------------
+// Runs on the tiles listed in `slow_tiles` (near ridges, walls, sea floor) for the levels the tiled kernel skips.
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX * TY) k_momentum_general(Geom G, Fields F, int NV, int ND, double time,
+                                                               const int* __restrict__ slow_tiles, int ntx) {
+    const int t = slow_tiles[2 * blockIdx.x], kf = slow_tiles[2 * blockIdx.x + 1];
+    const int k = blockIdx.y;
+    if (k >= kf) return;   // the tiled fast kernel owns levels k >= kf of this tile
+    const int i = (t % ntx) * TX + threadIdx.x, j = (t / ntx) * TY + threadIdx.y;
     if (i >= G.Nx || j >= G.Ny) return;
     const long long c = idx3(G, i, j, k);
-    const int c2 = idx2(G, i, j);
-    const bool fast = k >= __ldg(&G.kfast[c2]);
+    const MomG M{G, F.u, F.v};
+    const bool fast = k >= __ldg(&G.kfast[idx2(G, i, j)]);
     double gu, gv;
     if (fast) {
-        gu = tend_u<false>(G, F, i, j, k, NV, ND, time);
-        gv = tend_v<false>(G, F, i, j, k, NV, ND, time);
+        gu = tend_u<false>(G, F, M, i, j, k, NV, ND, time);
+        gv = tend_v<false>(G, F, M, i, j, k, NV, ND, time);
     } else {
-        gu = peripheral_fcc(G, i, j, k) ? 0.0 : tend_u<true>(G, F, i, j, k, NV, ND, time);
-        gv = peripheral_cfc(G, i, j, k) ? 0.0 : tend_v<true>(G, F, i, j, k, NV, ND, time);
+        gu = peripheral_fcc(G, i, j, k) ? 0.0 : tend_u<true>(G, F, M, i, j, k, NV, ND, time);
+        gv = peripheral_cfc(G, i, j, k) ? 0.0 : tend_v<true>(G, F, M, i, j, k, NV, ND, time);
     }
     F.Gu[c] = gu;
     F.Gv[c] = gv;
+}
+
+// ---- fast path: shared-memory tile, all stencils full order, no masks ----------------------------------------
+// Block = TX x TY cells of one level; zeta, I_y(u), I_x(v), dxU, dyV, K are computed once per tile point
+// (instead of once per stencil point per thread) and every thread then reads its 9/9/5-point stencils from smem.
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX * TY) k_momentum_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
+                                                             int klevels) {
+    using D = TileDims<TX, TY>;
+    extern __shared__ double sm[];
+    double* su = sm;
+    double* sv = su + D::NU;
+    double* sz = sv + D::NU;
+    double* sus = sz + D::NZ;
+    double* svs = sus + D::NZ;
+    double* sdx = svs + D::NZ;
+    double* sdy = sdx + D::ND;
+    double* sK = sdy + D::ND;
+    const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
+    const int kf = tile_kfast[blockIdx.y * gridDim.x + blockIdx.x];
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    const int k_begin = max((int)blockIdx.z * klevels, kf), k_end = min(((int)blockIdx.z + 1) * klevels, G.Nz);
+    const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
+    const MomS<TX, TY> M{su, sv, sz, sus, svs, sdx, sdy, sK, i0, j0};
+    for (int k = k_begin; k < k_end; k++) {
+        // stage u, v (indices clamped to the allocated halo; clamped values only feed discarded threads)
+        for (int e = tid; e < D::NU; e += TX * TY) {
+            const int a = e % D::PU, b = e / D::PU;
+            const int ii = min(i0 - D::HU + a, G.Nx + OB_H - 1), jj = min(j0 - D::HU + b, G.Ny + OB_H);
+            const long long c = idx3(G, ii, jj, k);
+            su[e] = F.u[c];
+            sv[e] = F.v[c];
+        }
+        __syncthreads();
+        const double dzk = G.dzc[k];
+        for (int e = tid; e < D::NZ; e += TX * TY) {
+            const int a = e % D::PZ, b = e / D::PZ;
+            const int jj = j0 - D::HZ + b;
+            const int q = (b + D::HU - D::HZ) * D::PU + (a + D::HU - D::HZ);   // same point in the u/v tiles
+            const double dxv = G.dy * sv[q] - G.dy * sv[q - 1];
+            const double dyu = G.dxfc[jj] * su[q] - G.dxfc[jj - 1] * su[q - D::PU];
+            sz[e] = (dxv - dyu) / G.azcf[jj];
+            sus[e] = 0.5 * (su[q - D::PU] + su[q]);
+            svs[e] = 0.5 * (sv[q - 1] + sv[q]);
+        }
+        for (int e = tid; e < D::ND; e += TX * TY) {
+            const int a = e % D::PD, b = e / D::PD;
+            const int jj = j0 - D::HD + b;
+            const int q = (b + D::HU - D::HD) * D::PU + (a + D::HU - D::HD);
+            const double ax = G.dy * dzk;
+            sdx[e] = ax * su[q + 1] - ax * su[q];
+            sdy[e] = G.dxcf[jj + 1] * dzk * sv[q + D::PU] - G.dxcf[jj] * dzk * sv[q];
+        }
+        for (int e = tid; e < D::NK; e += TX * TY) {
+            const int a = e % D::PK, b = e / D::PK;
+            const int q = (b + D::HU - 1) * D::PU + (a + D::HU - 1);
+            const double ua = su[q], ub = su[q + 1], va = sv[q], vb = sv[q + D::PU];
+            sK[e] = (0.5 * (ua * ua + ub * ub) + 0.5 * (va * va + vb * vb)) / 2.0;
+        }
+        __syncthreads();
+        if (i < G.Nx && j < G.Ny) {
+            const long long c = idx3(G, i, j, k);
+            F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time);
+            F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time);
+        }
+        __syncthreads();
+    }
 }
 
 // ================================================================================================
@@ -410,14 +518,17 @@ __device__ __forceinline__ double tend_c(const Geom& G, const Fields& F, const d
     return Gt;
 }
 
-__global__ void __launch_bounds__(128) k_tracers(Geom G, Fields F, int NT, double time) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = blockIdx.z;
+// ---- general path: one thread per cell from global memory, on the slow tiles only ---------------------------
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX * TY) k_tracers_general(Geom G, Fields F, int NT, double time,
+                                                              const int* __restrict__ slow_tiles, int ntx) {
+    const int t = slow_tiles[2 * blockIdx.x], kf = slow_tiles[2 * blockIdx.x + 1];
+    const int k = blockIdx.y;
+    if (k >= kf) return;
+    const int i = (t % ntx) * TX + threadIdx.x, j = (t / ntx) * TY + threadIdx.y;
     if (i >= G.Nx || j >= G.Ny) return;
     const long long c = idx3(G, i, j, k);
-    const int c2 = idx2(G, i, j);
-    const bool fast = k >= __ldg(&G.kfast[c2]);
+    const bool fast = k >= __ldg(&G.kfast[idx2(G, i, j)]);
     double jT = 0.0, jS = 0.0;
     if (k == G.Nz - 1) {
         jT = top_flux_T(G, F, i, j, F.T[c], time);
@@ -435,13 +546,135 @@ __global__ void __launch_bounds__(128) k_tracers(Geom G, Fields F, int NT, doubl
     F.GS[c] = gS;
 }
 
-void launch_momentum(const Geom& G, const Fields& F, int ord_vort, int ord_div, double time, cudaStream_t st) {
-    dim3 b(32, 4), g((G.Nx + 31) / 32, (G.Ny + 3) / 4, G.Nz);
-    k_momentum<<<g, b, 0, st>>>(G, F, (ord_vort + 1) / 2, (ord_div + 1) / 2, time);
-    OB_COUNT_LAUNCH(1);
+// ---- fast path: T and S tiles in shared memory, every face flux computed ONCE (the reference computes each
+// face twice, once per adjacent cell), upwind side only, then each thread differences the fluxes of its cell.
+template <int TX, int TY>
+struct TracerTile {
+    static constexpr int HC = 4;                                   // WENO-7 halo
+    static constexpr int PC = TX + 2 * HC, RC = TY + 2 * HC;       // cells [i0-4, i0+TX+3] x [j0-4, j0+TY+3]
+    static constexpr int NC = PC * RC;
+    static constexpr int NFX = (TX + 1) * TY, NFY = TX * (TY + 1); // faces per tracer
+    static constexpr int TOTAL = 2 * NC + 2 * (NFX + NFY);
+};
+
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX * TY) k_tracers_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
+                                                            int klevels) {
+    using D = TracerTile<TX, TY>;
+    extern __shared__ double sm[];
+    double* sc = sm;                       // [2][RC][PC]
+    double* sfx = sc + 2 * D::NC;          // [2][TY][TX+1]
+    double* sfy = sfx + 2 * D::NFX;        // [2][TY+1][TX]
+    const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
+    const int kf = tile_kfast[blockIdx.y * gridDim.x + blockIdx.x];
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    const int k_begin = max((int)blockIdx.z * klevels, kf), k_end = min(((int)blockIdx.z + 1) * klevels, G.Nz);
+    const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
+    const bool mine = i < G.Nx && j < G.Ny;
+    for (int k = k_begin; k < k_end; k++) {
+        for (int e = tid; e < D::NC; e += TX * TY) {
+            const int a = e % D::PC, b = e / D::PC;
+            const int ii = min(i0 - D::HC + a, G.Nx + OB_H - 1), jj = min(j0 - D::HC + b, G.Ny + OB_H);
+            const long long c = idx3(G, ii, jj, k);
+            sc[e] = F.T[c];
+            sc[D::NC + e] = F.S[c];
+        }
+        __syncthreads();
+        const double dzk = G.dzc[k];
+        // flat work list over (tracer, direction, face)
+        for (int e = tid; e < 2 * (D::NFX + D::NFY); e += TX * TY) {
+            const int tr = e / (D::NFX + D::NFY);
+            int f = e - tr * (D::NFX + D::NFY);
+            const double* cc = sc + tr * D::NC;
+            double flux = 0.0;
+            if (f < D::NFX) {   // x-face between cells a-1 and a of row b
+                const int a = f % (TX + 1), b = f / (TX + 1);
+                const int ii = min(i0 + a, G.Nx + OB_H - 1), jj = min(j0 + b, G.Ny - 1);
+                const double vel = F.u[idx3(G, ii, jj, k)];
+                if (vel != 0.0) {
+                    const bool left = vel > 0.0;
+                    const int q = (b + D::HC) * D::PC + (a + D::HC);   // cell a in the tile
+                    const double r = recon_cell<4>(cc, left ? q - 4 : q + 3, left ? 1 : -1);
+                    flux = G.dy * dzk * (vel * r);
+                }
+                sfx[tr * D::NFX + f] = flux;
+            } else {            // y-face between cells b-1 and b of column a
+                f -= D::NFX;
+                const int a = f % TX, b = f / TX;
+                const int ii = min(i0 + a, G.Nx + OB_H - 1), jj = min(j0 + b, G.Ny);
+                const double vel = F.v[idx3(G, ii, jj, k)];
+                if (vel != 0.0) {
+                    const bool left = vel > 0.0;
+                    const int q = (b + D::HC) * D::PC + (a + D::HC);
+                    const double r = recon_cell<4>(cc, left ? q - 4 * D::PC : q + 3 * D::PC, left ? D::PC : -D::PC);
+                    flux = G.dxcf[jj] * dzk * (vel * r);
+                }
+                sfy[tr * D::NFY + f] = flux;
+            }
+        }
+        __syncthreads();
+        if (mine) {
+            const long long c = idx3(G, i, j, k);
+            const int km = max(k - 1, 0), kp = min(k + 1, G.Nz - 1);
+            const long long cm = idx3(G, i, j, km), cp = idx3(G, i, j, kp);
+            const double wlo = F.w[c], whi = F.w[c + G.sz], az = G.azcc[j];
+            const int fxi = threadIdx.y * (TX + 1) + threadIdx.x, fyi = threadIdx.y * TX + threadIdx.x;
+            const int q = (threadIdx.y + D::HC) * D::PC + (threadIdx.x + D::HC);
+#pragma unroll
+            for (int tr = 0; tr < 2; tr++) {
+                const double* cf = tr == 0 ? F.T : F.S;
+                const double ck = sc[tr * D::NC + q];
+                const double fzl = az * wlo * 0.5 * (cf[cm] + ck);
+                const double fzh = az * whi * 0.5 * (ck + cf[cp]);
+                const double fxw = sfx[tr * D::NFX + fxi], fxe = sfx[tr * D::NFX + fxi + 1];
+                const double fys = sfy[tr * D::NFY + fyi], fyn = sfy[tr * D::NFY + fyi + TX];
+                double Gt = -((fxe - fxw) + (fyn - fys) + (fzh - fzl)) / (az * dzk);
+                if (k == G.Nz - 1) {
+                    const double J = tr == 0 ? top_flux_T(G, F, i, j, ck, time) : top_flux_S(G, F, i, j, ck, time);
+                    Gt -= J / dzk;
+                }
+                (tr == 0 ? F.GT : F.GS)[c] = Gt;
+            }
+        }
+        __syncthreads();
+    }
 }
-void launch_tracers(const Geom& G, const Fields& F, int ord_tracer, double time, cudaStream_t st) {
-    dim3 b(32, 4), g((G.Nx + 31) / 32, (G.Ny + 3) / 4, G.Nz);
-    k_tracers<<<g, b, 0, st>>>(G, F, (ord_tracer + 1) / 2, time);
-    OB_COUNT_LAUNCH(1);
+
+#define MOM_TX 32
+#define MOM_TY 8
+void launch_momentum(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st) {
+    using D = TileDims<MOM_TX, MOM_TY>;
+    static bool attr_set = false;
+    const size_t smem = D::TOTAL * sizeof(double);
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_momentum_tiled<MOM_TX, MOM_TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    if (P.any_fast) {
+        const int klev = 8;
+        dim3 b(MOM_TX, MOM_TY), g(P.ntx, P.nty, (G.Nz + klev - 1) / klev);
+        k_momentum_tiled<MOM_TX, MOM_TY><<<g, b, smem, st>>>(G, F, time, P.tile_kfast, klev);
+        OB_COUNT_LAUNCH(1);
+    }
+    if (P.nslow > 0) {
+        dim3 b(MOM_TX, MOM_TY), g(P.nslow, G.Nz);
+        k_momentum_general<MOM_TX, MOM_TY><<<g, b, 0, st>>>(G, F, (ord_vort + 1) / 2, (ord_div + 1) / 2, time, P.slow_tiles, P.ntx);
+        OB_COUNT_LAUNCH(1);
+    }
+}
+void mom_plan_tile_shape(int* tx, int* ty) { *tx = MOM_TX; *ty = MOM_TY; }
+void launch_tracers(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st) {
+    using D = TracerTile<MOM_TX, MOM_TY>;
+    const size_t smem = D::TOTAL * sizeof(double);
+    if (P.any_fast) {
+        const int klev = 8;
+        dim3 b(MOM_TX, MOM_TY), g(P.ntx, P.nty, (G.Nz + klev - 1) / klev);
+        k_tracers_tiled<MOM_TX, MOM_TY><<<g, b, smem, st>>>(G, F, time, P.tile_kfast, klev);
+        OB_COUNT_LAUNCH(1);
+    }
+    if (P.nslow > 0) {
+        dim3 b(MOM_TX, MOM_TY), g(P.nslow, G.Nz);
+        k_tracers_general<MOM_TX, MOM_TY><<<g, b, 0, st>>>(G, F, (ord_tracer + 1) / 2, time, P.slow_tiles, P.ntx);
+        OB_COUNT_LAUNCH(1);
+    }
 }

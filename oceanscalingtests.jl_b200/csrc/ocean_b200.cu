@@ -1,5 +1,6 @@
 // libocean_b200.so -- C ABI (include/ocean_b200.h): handle, HBM allocation, sequencing of one
 // HydrostaticFreeSurfaceModel time step, x-slab halo exchange over NCCL.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -20,6 +21,7 @@ struct ob200_handle {
     int device = 0;
     Geom G;
     Fields F;
+    MomPlan mom_plan;
     bool periodic_local = true;
     bool own_stream = true;
     cudaStream_t stream = nullptr, comm_stream = nullptr;
@@ -164,6 +166,30 @@ int setup_geometry(ob200_handle* h) {
     cudaMemcpy(kb_d, kb.data(), n2 * sizeof(int), cudaMemcpyHostToDevice);
     cudaMemcpy(kf_d, kfast.data(), n2 * sizeof(int), cudaMemcpyHostToDevice);
     G.kb = kb_d; G.kfast = kf_d;
+    {   // per-tile plan for the momentum kernels (kernels.h MomPlan)
+        int tx, ty;
+        mom_plan_tile_shape(&tx, &ty);
+        MomPlan& P = h->mom_plan;
+        P.ntx = (c.Nx + tx - 1) / tx; P.nty = (c.Ny + ty - 1) / ty;
+        std::vector<int> tk((size_t)P.ntx * P.nty, 0), slow;
+        for (int b = 0; b < P.nty; b++)
+            for (int a = 0; a < P.ntx; a++) {
+                int K = 0;
+                for (int j = b * ty; j < std::min((b + 1) * ty, c.Ny); j++)
+                    for (int i = a * tx; i < std::min((a + 1) * tx, c.Nx); i++)
+                        K = std::max(K, kfast[(size_t)(j + OB_H) * G.pitch + (i + OB_X0)]);
+                tk[(size_t)b * P.ntx + a] = K;
+                if (K < Nz) P.any_fast = true;
+                if (K > 0) { slow.push_back(b * P.ntx + a); slow.push_back(K); }
+            }
+        P.nslow = (int)slow.size() / 2;
+        if (int rc = dev_alloc(h, &P.tile_kfast, tk.size(), false)) return rc;
+        cudaMemcpy(P.tile_kfast, tk.data(), tk.size() * sizeof(int), cudaMemcpyHostToDevice);
+        if (P.nslow) {
+            if (int rc = dev_alloc(h, &P.slow_tiles, slow.size(), false)) return rc;
+            cudaMemcpy(P.slow_tiles, slow.data(), slow.size() * sizeof(int), cudaMemcpyHostToDevice);
+        }
+    }
     // parameters
     G.g = c.gravity; G.alpha = c.eos_alpha; G.beta_s = c.eos_beta; G.rho0 = c.eos_rho0; G.eos = c.eos_kind;
     G.nu_z = c.nu_z; G.kappa_z = c.kappa_z; G.ri_enabled = c.ri_enabled;
@@ -261,8 +287,8 @@ void auxiliaries(ob200_handle* h) {
     if (h->G.qgleith) launch_leith(h->G, h->F, h->stream);
 }
 void tendencies(ob200_handle* h) {
-    launch_momentum(h->G, h->F, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, h->stream);
-    launch_tracers(h->G, h->F, h->cfg.order_tracer, h->time, h->stream);
+    launch_momentum(h->G, h->F, h->mom_plan, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, h->stream);
+    launch_tracers(h->G, h->F, h->mom_plan, h->cfg.order_tracer, h->time, h->stream);
 }
 int update_state(ob200_handle* h) {
     if (int rc = mask_and_halos(h)) return rc;
@@ -318,9 +344,9 @@ int step_body(ob200_handle* h, double dt, bool euler) {
     launch_ri_kappa(G, h->F, h->time, h->stream);
     if (G.qgleith) launch_leith(G, h->F, h->stream);
     mark();
-    launch_momentum(G, h->F, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, h->stream);
+    launch_momentum(G, h->F, h->mom_plan, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, h->stream);
     mark();
-    launch_tracers(G, h->F, h->cfg.order_tracer, h->time, h->stream);
+    launch_tracers(G, h->F, h->mom_plan, h->cfg.order_tracer, h->time, h->stream);
     mark();
     h->n_timed = e - 1;
     return OB200_OK;
