@@ -217,11 +217,7 @@ def main():
     fs = pkg.SplitExplicitFreeSurface(substeps=pkg.barotropic_substeps(dt, g0))
     model = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=fs, eos="linear",
                                             boundary_conditions=pkg.set_boundary_conditions("DoubleDrake", grid),
-                                            device=local_rank)
-    if world > 1:
-        uid = [model.backend.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        model.backend.comm_init(uid[0])
+                                            device=local_rank, comm=pkg.Comm())
     if args.persistent_barotropic:
         model.backend.set_option("persistent_barotropic", 1)
     state = initial_state(pkg, case, grid)

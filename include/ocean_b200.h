@@ -120,8 +120,10 @@ typedef struct ob200_config {
     int32_t qgleith_enabled;
     double  leith_C, leith_min_N2, leith_Vscale;
     /* host arrays, copied during ob200_create */
+    int32_t bottom_halo_columns;     /* x-halo columns carried by bottom_height: >= OB200_HALO, and
+                                        >= n_substeps + 1 when nranks > 1 (wide barotropic halo) */
     const double* z_faces;           /* Nz+1, bottom to top (bathymetry_and_forcings.jl:47-58) */
-    const double* bottom_height;     /* Ny rows x (Nx + 2*OB200_HALO) columns incl. x-halos    */
+    const double* bottom_height;     /* Ny rows x (Nx + 2*bottom_halo_columns) columns incl. x-halos */
     const double* averaging_weights; /* n_substeps                                             */
 } ob200_config;
 

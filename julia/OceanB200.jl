@@ -30,6 +30,7 @@ Base.@kwdef mutable struct Config
     salt_coeffs::NTuple{16, Float64} = ntuple(_ -> 0.0, 16)
     T_restoring_lambda::Float64 = 0; drag_mu::Float64 = 0
     qgleith_enabled::Int32 = 0; leith_C::Float64 = 2; leith_min_N2::Float64 = 1e-20; leith_Vscale::Float64 = 1
+    bottom_halo_columns::Int32 = 7
     z_faces::Ptr{Float64} = C_NULL; bottom_height::Ptr{Float64} = C_NULL; averaging_weights::Ptr{Float64} = C_NULL
 end
 

@@ -15,7 +15,7 @@ from .grid_load_balance import (LatitudeLongitudeGrid, Partition, assess_x_load,
 from .model import (B200Backend, BoundaryConditions, HydrostaticFreeSurfaceModel, QGLeith,
                     RiBasedVerticalDiffusivity, SplitExplicitFreeSurface, VerticalScalarDiffusivity,
                     barotropic_substeps, build_config, set_model, substeps, time_step, weights_from_substeps)
-from .near_global_simulation import (Simulation, equation_of_state, experiment_depth, profiled_time_steps, run,
+from .near_global_simulation import (Comm, Simulation, equation_of_state, experiment_depth, profiled_time_steps, run,
                                      scaling_test_simulation)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

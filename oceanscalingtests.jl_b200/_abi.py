@@ -64,6 +64,7 @@ class ob200_config(C.Structure):
         ("T_restoring_lambda", C.c_double), ("drag_mu", C.c_double),
         ("qgleith_enabled", C.c_int32),
         ("leith_C", C.c_double), ("leith_min_N2", C.c_double), ("leith_Vscale", C.c_double),
+        ("bottom_halo_columns", C.c_int32),
         ("z_faces", C.POINTER(C.c_double)),
         ("bottom_height", C.POINTER(C.c_double)),
         ("averaging_weights", C.POINTER(C.c_double)),

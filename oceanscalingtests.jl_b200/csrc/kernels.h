@@ -19,9 +19,9 @@ struct Fields {
 // kernels_halo.cu
 void launch_fill_halos(const Geom& G, const Fields& F, bool periodic_x, cudaStream_t st);
 void launch_mask_fields(const Geom& G, const Fields& F, cudaStream_t st);
-void launch_copy_field(const Geom& G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, bool three_d,
+// layout: 0 = 3-D field, 1 = 2-D in the 3-D plane layout (Ld), 2 = 2-D barotropic layout
+void launch_copy_field(const Geom& G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, int layout,
                        bool to_field, cudaStream_t st);
-void launch_column_depths(const Geom& G, const Fields& F, cudaStream_t st);
 void launch_pack_x(const Geom& G, const Fields& F, double* sendW, double* sendE, cudaStream_t st);
 void launch_unpack_x(const Geom& G, const Fields& F, const double* recvW, const double* recvE, cudaStream_t st);
 size_t pack_x_count(const Geom& G);
@@ -35,12 +35,15 @@ void launch_ab2_implicit(const Geom& G, const Fields& F, double dt, double chi, 
 void launch_correct(const Geom& G, const Fields& F, cudaStream_t st);
 
 // kernels_baro.cu
-void launch_baro_init(const Geom& G, const Fields& F, bool periodic_x, cudaStream_t st);
-void launch_baro_eta(const Geom& G, const Fields& F, double dtau, bool periodic_x, cudaStream_t st);
-void launch_baro_vel(const Geom& G, const Fields& F, double dtau, double wgt, bool periodic_x, cudaStream_t st);
+// `ex` = columns beyond the interior computed on each side (0 on one GPU, Wb - 1 on x-slabs)
+void launch_baro_init(const Geom& G, const Fields& F, bool periodic_x, int ex, cudaStream_t st);
+void launch_baro_eta(const Geom& G, const Fields& F, double dtau, bool periodic_x, int ex, cudaStream_t st);
+void launch_baro_vel(const Geom& G, const Fields& F, double dtau, double wgt, bool periodic_x, int ex, cudaStream_t st);
 void launch_baro_finish(const Geom& G, const Fields& F, cudaStream_t st);
 int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const double* weights_dev, int M, bool periodic_x,
-                           cudaStream_t st);
+                           int ex, cudaStream_t st);
+size_t pack_baro_count(const Geom& G, int W);
+void launch_pack_baro(const Geom& G, const Fields& F, double* bufW, double* bufE, int W, bool unpack, cudaStream_t st);
 
 // kernels_tend.cu
 // Per-tile plan of the momentum kernels: tile_kfast[t] = first level the shared-memory fast kernel may take for

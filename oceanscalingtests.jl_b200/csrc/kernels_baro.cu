@@ -1,18 +1,21 @@
 // Split-explicit free surface: barotropic substeps (forward-backward scheme).
 //   eta -= dtau * div(U, V) / Az ;  U, V += dtau * (-g H d(eta) + G^{U,V}) ; averages += w_m * (eta, U, V)
-// Round-1 variant: two small 2-D launches per substep; the producing kernel also maintains the periodic
-// x-halo column the consumer needs (eta at i = -1, U at i = Nx), so no halo launches inside the loop.
+// One GPU: the producing kernel also maintains the periodic x-halo column its consumer needs (eta at i = -1,
+// U at i = Nx), so there are no halo launches inside the loop.  Several GPUs: the barotropic arrays carry a
+// halo of Wb = M + 1 columns that is exchanged ONCE before the loop (as Oceananigans' distributed solver does,
+// SURVEY F9); every substep is computed over [-ex, Nx + ex) and the invalid fringe, which grows by one column
+// per substep, never reaches the interior.
 // launch_baro_persistent: one cooperative launch for all M substeps (grid-wide barrier between half steps).
 #include <cooperative_groups.h>
 
 #include "kernels.h"
 namespace cg = cooperative_groups;
 
-__global__ void k_baro_init(Geom G, Fields F, bool periodic) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_baro_init(Geom G, Fields F, bool periodic, int ex) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - ex;
     const int j = blockIdx.y;  // 0..Ny
-    if (i >= G.Nx) return;
-    const int c = idx2(G, i, j);
+    if (i >= G.Nx + ex) return;
+    const int c = idx2b(G, i, j);
     const double a = F.Ub[c], b = F.Vb[c];
     F.U[c] = a;
     F.V[c] = b;
@@ -24,8 +27,8 @@ __global__ void k_baro_init(Geom G, Fields F, bool periodic) {
 }
 
 __device__ __forceinline__ void eta_update(const Geom& G, const Fields& F, int i, int j, double dtau, bool periodic) {
-    const int c = idx2(G, i, j);
-    const double Vn = (j + 1 == G.Ny) ? 0.0 : F.V[c + G.pitch];
+    const int c = idx2b(G, i, j);
+    const double Vn = (j + 1 == G.Ny) ? 0.0 : F.V[c + G.pitch2];
     const double Vs = (j == 0) ? 0.0 : F.V[c];
     const double e = F.eta[c] - dtau * ((G.dy * F.U[c + 1] - G.dy * F.U[c]) + (G.dxcf[j + 1] * Vn - G.dxcf[j] * Vs)) / G.azcc[j];
     F.eta[c] = e;
@@ -37,10 +40,10 @@ __device__ __forceinline__ void eta_update(const Geom& G, const Fields& F, int i
 
 __device__ __forceinline__ void vel_update(const Geom& G, const Fields& F, int i, int j, double dtau, double wgt,
                                            bool periodic) {
-    const int c = idx2(G, i, j);
+    const int c = idx2b(G, i, j);
     const double e = F.eta[c];
     const double detax = (e - F.eta[c - 1]) / G.dxfc[j];
-    const double detay = (j == 0) ? 0.0 : (e - F.eta[c - G.pitch]) / G.dy;
+    const double detay = (j == 0) ? 0.0 : (e - F.eta[c - G.pitch2]) / G.dy;
     const double Un = F.U[c] + dtau * (-G.g * F.Hfc[c] * detax + F.GU[c]);
     const double Vn = F.V[c] + dtau * (-G.g * F.Hcf[c] * detay + F.GV[c]);
     F.U[c] = Un; F.V[c] = Vn;
@@ -53,37 +56,37 @@ __device__ __forceinline__ void vel_update(const Geom& G, const Fields& F, int i
     }
 }
 
-__global__ void __launch_bounds__(128) k_baro_eta(Geom G, Fields F, double dtau, bool periodic) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G.Nx) return;
+__global__ void __launch_bounds__(128) k_baro_eta(Geom G, Fields F, double dtau, bool periodic, int ex) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - ex;
+    if (i >= G.Nx + ex) return;
     eta_update(G, F, i, blockIdx.y, dtau, periodic);
 }
-__global__ void __launch_bounds__(128) k_baro_vel(Geom G, Fields F, double dtau, double wgt, bool periodic) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G.Nx) return;
+__global__ void __launch_bounds__(128) k_baro_vel(Geom G, Fields F, double dtau, double wgt, bool periodic, int ex) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - ex;
+    if (i >= G.Nx + ex) return;
     vel_update(G, F, i, blockIdx.y, dtau, wgt, periodic);
 }
 __global__ void k_baro_finish(Geom G, Fields F) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (i >= G.Nx) return;
-    const int c = idx2(G, i, j);
+    const int c = idx2b(G, i, j);
     F.eta[c] = F.etab[c];
 }
 
-void launch_baro_init(const Geom& G, const Fields& F, bool periodic, cudaStream_t st) {
-    dim3 b(128), g((G.Nx + 127) / 128, G.Ny + 1);
-    k_baro_init<<<g, b, 0, st>>>(G, F, periodic);
+void launch_baro_init(const Geom& G, const Fields& F, bool periodic, int ex, cudaStream_t st) {
+    dim3 b(128), g((G.Nx + 2 * ex + 127) / 128, G.Ny + 1);
+    k_baro_init<<<g, b, 0, st>>>(G, F, periodic, ex);
     OB_COUNT_LAUNCH(1);
 }
-void launch_baro_eta(const Geom& G, const Fields& F, double dtau, bool periodic, cudaStream_t st) {
-    dim3 b(128), g((G.Nx + 127) / 128, G.Ny);
-    k_baro_eta<<<g, b, 0, st>>>(G, F, dtau, periodic);
+void launch_baro_eta(const Geom& G, const Fields& F, double dtau, bool periodic, int ex, cudaStream_t st) {
+    dim3 b(128), g((G.Nx + 2 * ex + 127) / 128, G.Ny);
+    k_baro_eta<<<g, b, 0, st>>>(G, F, dtau, periodic, ex);
     OB_COUNT_LAUNCH(1);
 }
-void launch_baro_vel(const Geom& G, const Fields& F, double dtau, double wgt, bool periodic, cudaStream_t st) {
-    dim3 b(128), g((G.Nx + 127) / 128, G.Ny);
-    k_baro_vel<<<g, b, 0, st>>>(G, F, dtau, wgt, periodic);
+void launch_baro_vel(const Geom& G, const Fields& F, double dtau, double wgt, bool periodic, int ex, cudaStream_t st) {
+    dim3 b(128), g((G.Nx + 2 * ex + 127) / 128, G.Ny);
+    k_baro_vel<<<g, b, 0, st>>>(G, F, dtau, wgt, periodic, ex);
     OB_COUNT_LAUNCH(1);
 }
 void launch_baro_finish(const Geom& G, const Fields& F, cudaStream_t st) {
@@ -94,21 +97,22 @@ void launch_baro_finish(const Geom& G, const Fields& F, cudaStream_t st) {
 
 // ---- persistent variant: all substeps in one cooperative launch --------------------------------------
 __global__ void __launch_bounds__(256) k_baro_persistent(Geom G, Fields F, double dtau, const double* __restrict__ wts,
-                                                          int M, bool periodic) {
+                                                          int M, bool periodic, int ex) {
     cg::grid_group grid = cg::this_grid();
-    const long long n = (long long)G.Nx * G.Ny;
+    const int nxe = G.Nx + 2 * ex;
+    const long long n = (long long)nxe * G.Ny;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
     for (int m = 0; m < M; m++) {
-        for (long long t = tid; t < n; t += nth) eta_update(G, F, (int)(t % G.Nx), (int)(t / G.Nx), dtau, periodic);
+        for (long long t = tid; t < n; t += nth) eta_update(G, F, (int)(t % nxe) - ex, (int)(t / nxe), dtau, periodic);
         grid.sync();
         const double wgt = wts[m];
-        for (long long t = tid; t < n; t += nth) vel_update(G, F, (int)(t % G.Nx), (int)(t / G.Nx), dtau, wgt, periodic);
+        for (long long t = tid; t < n; t += nth) vel_update(G, F, (int)(t % nxe) - ex, (int)(t / nxe), dtau, wgt, periodic);
         grid.sync();
     }
 }
 
-int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const double* wts, int M, bool periodic,
+int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const double* wts, int M, bool periodic, int ex,
                            cudaStream_t st) {
     static int nblk = 0;
     if (nblk == 0) {
@@ -119,8 +123,27 @@ int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const do
         nblk = sms * (per > 4 ? 4 : per);
     }
     Geom g = G; Fields f = F;
-    void* args[] = {&g, &f, &dtau, &wts, &M, &periodic};
+    void* args[] = {&g, &f, &dtau, &wts, &M, &periodic, &ex};
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k_baro_persistent, dim3(nblk), dim3(256), args, 0, st);
     OB_COUNT_LAUNCH(1);
     return e == cudaSuccess ? 0 : -1;
+}
+
+// ---- wide-halo exchange buffers: [Ubar | Vbar | eta | GU | GV] x (Ny + 1) rows x W columns --------------------
+__global__ void k_pack_baro(Geom G, Fields F, double* bufW, double* bufE, int W, bool unpack) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, q = blockIdx.z;
+    if (h >= W) return;
+    double* fs[5] = {F.Ub, F.Vb, F.eta, F.GU, F.GV};
+    double* f = fs[q];
+    const size_t b = ((size_t)q * (G.Ny + 1) + j) * W + h;
+    const int c = idx2b(G, 0, j);
+    if (!unpack) { bufW[b] = f[c + h]; bufE[b] = f[c + G.Nx - W + h]; }
+    else { f[c - W + h] = bufW[b]; f[c + G.Nx + h] = bufE[b]; }
+}
+size_t pack_baro_count(const Geom& G, int W) { return (size_t)5 * (G.Ny + 1) * W; }
+void launch_pack_baro(const Geom& G, const Fields& F, double* bufW, double* bufE, int W, bool unpack, cudaStream_t st) {
+    dim3 b(64), g((W + 63) / 64, G.Ny + 1, 5);
+    k_pack_baro<<<g, b, 0, st>>>(G, F, bufW, bufE, W, unpack);
+    OB_COUNT_LAUNCH(1);
 }

@@ -17,7 +17,7 @@ __global__ void k_fill_x(Geom G, Fields F) {
             f[c + G.Nx + h] = f[c + h];
         }
     } else {  // 2-D eta rides along as "plane Nz"
-        const int c2 = idx2(G, 0, j);
+        const int c2 = idx2b(G, 0, j);
         F.eta[c2 - 1 - h] = F.eta[c2 + G.Nx - 1 - h];
         F.eta[c2 + G.Nx + h] = F.eta[c2 + h];
     }
@@ -41,9 +41,9 @@ __global__ void k_fill_y(Geom G, Fields F) {
         const long long v0 = idx3(G, i, 0, k), v1 = idx3(G, i, G.Ny, k);
         for (int h = 0; h <= OB_H; h++) { F.v[v0 - (long long)h * G.pitch] = 0.0; F.v[v1 + (long long)h * G.pitch] = 0.0; }
     } else {
-        const int s0 = idx2(G, i, 0), s1 = idx2(G, i, G.Ny - 1);
+        const int s0 = idx2b(G, i, 0), s1 = idx2b(G, i, G.Ny - 1);
         const double a = F.eta[s0], b = F.eta[s1];
-        for (int h = 1; h <= OB_H; h++) { F.eta[s0 - h * G.pitch] = a; F.eta[s1 + h * G.pitch] = b; }
+        for (int h = 1; h <= OB_H; h++) { F.eta[s0 - h * G.pitch2] = a; F.eta[s1 + h * G.pitch2] = b; }
     }
 }
 
@@ -68,7 +68,7 @@ __global__ void k_mask(Geom G, Fields F) {
     if (j < G.Ny) {
         if (peripheral_fcc(G, i, j, k)) F.u[c] = 0.0;
         if (!active(G, i, j, k)) { F.T[c] = 0.0; F.S[c] = 0.0; }
-        if (k == G.Nz - 1 && !active(G, i, j, k)) F.eta[idx2(G, i, j)] = 0.0;
+        if (k == G.Nz - 1 && !active(G, i, j, k)) F.eta[idx2b(G, i, j)] = 0.0;
     }
     if (peripheral_cfc(G, i, j, k)) F.v[c] = 0.0;
 }
@@ -78,40 +78,21 @@ void launch_mask_fields(const Geom& G, const Fields& F, cudaStream_t st) {
     OB_COUNT_LAUNCH(1);
 }
 
-// wet column depth at u / v points: sum of dz over non-peripheral nodes
-__global__ void k_column_depths(Geom G, Fields F) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x - OB_H + 1;
-    const int j = blockIdx.y;  // 0..Ny
-    if (i >= G.Nx + OB_H) return;
-    double a = 0.0, b = 0.0;
-    for (int k = 0; k < G.Nz; k++) {
-        if (!peripheral_fcc(G, i, j, k)) a += G.dzc[k];
-        if (!peripheral_cfc(G, i, j, k)) b += G.dzc[k];
-    }
-    F.Hfc[idx2(G, i, j)] = a;
-    F.Hcf[idx2(G, i, j)] = b;
-}
-void launch_column_depths(const Geom& G, const Fields& F, cudaStream_t st) {
-    dim3 b(128), g((G.Nx + 2 * OB_H + 127) / 128, G.Ny + 1);
-    k_column_depths<<<g, b, 0, st>>>(G, F);
-    OB_COUNT_LAUNCH(1);
-}
-
 // interior <-> user buffer laid out like an Oceananigans parent array with halos (hx, hy, hz)
-__global__ void k_copy_field(Geom G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, bool three_d,
+__global__ void k_copy_field(Geom G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, int layout,
                              bool to_field) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y, k = blockIdx.z;
     if (i >= G.Nx) return;
     const size_t sx = G.Nx + 2 * hx, sy = ny + 2 * hy;
-    const size_t b = ((size_t)(k + (three_d ? hz : 0)) * sy + (j + hy)) * sx + (i + hx);
-    const long long c = three_d ? idx3(G, i, j, k) : (long long)idx2(G, i, j);
+    const size_t b = ((size_t)(k + (layout == 0 ? hz : 0)) * sy + (j + hy)) * sx + (i + hx);
+    const long long c = layout == 0 ? idx3(G, i, j, k) : layout == 1 ? (long long)idx2(G, i, j) : (long long)idx2b(G, i, j);
     if (to_field) field[c] = buf[b]; else buf[b] = field[c];
 }
-void launch_copy_field(const Geom& G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, bool three_d,
+void launch_copy_field(const Geom& G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, int layout,
                        bool to_field, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 127) / 128, ny, nz);
-    k_copy_field<<<g, b, 0, st>>>(G, field, buf, ny, nz, hx, hy, hz, three_d, to_field);
+    k_copy_field<<<g, b, 0, st>>>(G, field, buf, ny, nz, hx, hy, hz, layout, to_field);
     OB_COUNT_LAUNCH(1);
 }
 
@@ -136,7 +117,7 @@ __global__ void k_pack_x(Geom G, Fields F, double* sendW, double* sendE, bool un
         }
     } else {
         const size_t b = (size_t)4 * G.Nz * per + o;
-        const int c = idx2(G, 0, j);
+        const int c = idx2b(G, 0, j);
         if (!unpack) { sendW[b] = F.eta[c + h]; sendE[b] = F.eta[c + G.Nx - OB_H + h]; }
         else { F.eta[c - OB_H + h] = sendW[b]; F.eta[c + G.Nx + h] = sendE[b]; }
     }
@@ -164,7 +145,7 @@ __global__ void k_diag(Geom G, Fields F, double* out) {
     if (i < G.Nx) {
         const long long c = idx3(G, i, j, k);
         m[0] = fabs(F.u[c]); m[1] = fabs(F.v[c]); m[2] = fmax(fabs(F.w[c]), k == G.Nz - 1 ? fabs(F.w[c + G.sz]) : 0.0);
-        m[3] = (k == 0) ? fabs(F.eta[idx2(G, i, j)]) : 0.0;
+        m[3] = (k == 0) ? fabs(F.eta[idx2b(G, i, j)]) : 0.0;
         m[4] = fabs(F.T[c]); m[5] = fabs(F.S[c]);
         // 1 / cell advection time scale: |u|/dx + |v|/dy + |w|/dz
         m[6] = m[0] / G.dxfc[j] + m[1] / G.dy + fabs(F.w[c]) / G.dzc[k];

@@ -18,6 +18,7 @@
 struct Geom {
     int Nx, Ny, Nz;
     int pitch, NyP;          // row pitch (elements), number of rows
+    int pitch2, X0b, Wb;     // barotropic 2-D arrays: own pitch / origin so that they can carry a halo of Wb columns
     long long sz;            // plane stride = pitch * NyP
     // per-latitude metrics, indexable for j = -OB_H-1 .. Ny+OB_H+1 (pointers pre-offset so [j] works)
     const double *dxfc, *dxcf, *azcc, *azcf, *fff, *taux, *sflux, *tref;
@@ -41,6 +42,8 @@ __device__ __forceinline__ long long idx3(const Geom& G, int i, int j, int k) {
     return (long long)k * G.sz + (long long)(j + OB_H) * G.pitch + (i + OB_X0);
 }
 __device__ __forceinline__ int idx2(const Geom& G, int i, int j) { return (j + OB_H) * G.pitch + (i + OB_X0); }
+// barotropic arrays (eta, U, V, averages, G^U, G^V, H): wide x-halo on multi-GPU runs
+__device__ __forceinline__ int idx2b(const Geom& G, int i, int j) { return (j + OB_H) * G.pitch2 + (i + G.X0b); }
 
 // ---- node predicates.  kb rows outside the y-domain hold Nz, so the j-range test is implicit.
 __device__ __forceinline__ bool active(const Geom& G, int i, int j, int k) {

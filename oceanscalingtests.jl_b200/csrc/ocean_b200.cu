@@ -22,6 +22,9 @@ struct ob200_handle {
     Geom G;
     Fields F;
     MomPlan mom_plan;
+    double *F_Hfc = nullptr, *F_Hcf = nullptr;
+    double *bsendW = nullptr, *bsendE = nullptr, *brecvW = nullptr, *brecvE = nullptr;
+    size_t bcount = 0;
     bool periodic_local = true;
     bool own_stream = true;
     cudaStream_t stream = nullptr, comm_stream = nullptr;
@@ -87,6 +90,10 @@ int setup_geometry(ob200_handle* h) {
     G.pitch = OB_X0 + ((c.Nx + OB_H + 15) / 16) * 16;
     G.NyP = c.Ny + 1 + 2 * OB_H;
     G.sz = (long long)G.pitch * G.NyP;
+    // barotropic arrays: halo of Wb columns (M + 1 on x-slabs: exchanged once, then no communication in the loop)
+    G.Wb = h->periodic_local ? OB_H : std::max(OB_H, c.n_substeps + 1);
+    G.X0b = ((G.Wb + 15) / 16) * 16;
+    G.pitch2 = G.X0b + ((c.Nx + G.Wb + 15) / 16) * 16;
     const double pi = M_PI;
     const double dlam = (c.lon_east - c.lon_west) / c.Nx_global;
     const double dphi = (c.lat_north - c.lat_south) / c.Ny;
@@ -136,14 +143,38 @@ int setup_geometry(ob200_handle* h) {
     // bathymetry -> first active level per column; rows outside the y-domain are fully inactive
     const size_t n2 = (size_t)G.pitch * G.NyP;
     std::vector<int> kb(n2, Nz), kfast(n2, Nz);
-    const int nxh = c.Nx + 2 * OB_H;
+    const int bh = c.bottom_halo_columns, nxh = c.Nx + 2 * bh;
+    std::vector<int> kbw((size_t)nxh * (c.Ny + 2), Nz);   // wide copy incl. one inactive row south and north
     for (int j = 0; j < c.Ny; j++)
         for (int ii = 0; ii < nxh; ii++) {
             const double hgt = c.bottom_height[(size_t)j * nxh + ii];
             int k0 = 0;
             while (k0 < Nz && zc[k0 + 1] <= hgt) k0++;
-            kb[(size_t)(j + OB_H) * G.pitch + (ii - OB_H + OB_X0)] = k0;
+            kbw[(size_t)(j + 1) * nxh + ii] = k0;
+            const int i = ii - bh;
+            if (i >= -OB_H && i < c.Nx + OB_H) kb[(size_t)(j + OB_H) * G.pitch + (i + OB_X0)] = k0;
         }
+    {   // wet column depths at u / v points: sum of dz over non-peripheral nodes, wide halo
+        const size_t n2b = (size_t)G.pitch2 * G.NyP;
+        std::vector<double> Hfc(n2b, 0.0), Hcf(n2b, 0.0);
+        const int lim = std::min(bh, G.Wb);
+        for (int j = 0; j <= c.Ny; j++)
+            for (int i = -lim + 1; i < c.Nx + lim; i++) {
+                const int ii = i + bh;
+                const int kc = kbw[(size_t)(j + 1) * nxh + ii];
+                const int ku = std::max(kc, kbw[(size_t)(j + 1) * nxh + ii - 1]);
+                const int kv = std::max(kc, kbw[(size_t)j * nxh + ii]);
+                double a = 0.0, b = 0.0;
+                for (int k = ku; k < Nz; k++) a += dzc[k + 1];
+                for (int k = kv; k < Nz; k++) b += dzc[k + 1];
+                Hfc[(size_t)(j + OB_H) * G.pitch2 + (i + G.X0b)] = a;
+                Hcf[(size_t)(j + OB_H) * G.pitch2 + (i + G.X0b)] = b;
+            }
+        if (int rc = dev_alloc(h, &h->F_Hfc, n2b, false)) return rc;
+        if (int rc = dev_alloc(h, &h->F_Hcf, n2b, false)) return rc;
+        cudaMemcpy(h->F_Hfc, Hfc.data(), n2b * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(h->F_Hcf, Hcf.data(), n2b * sizeof(double), cudaMemcpyHostToDevice);
+    }
     // first level from which the mask-free full-order stencils are valid: every cell within 5 columns / rows
     // wet and in the domain; the level just above a neighbour's sea floor still needs the conditional
     // vertical flux, hence K + 1 unless K == 0.  Only when the configured orders are the defaults (9, 5, 7).
@@ -212,46 +243,49 @@ int alloc_fields(ob200_handle* h) {
     if (G.qgleith)
         for (double** p : {&F.nuL, &F.qx, &F.qy})
             if (int rc = dev_alloc(h, p, n3)) return rc;
-    double** f2[] = {&F.eta, &F.U, &F.V, &F.etab, &F.Ub, &F.Vb, &F.GU, &F.GV, &F.Hfc, &F.Hcf, &F.Ld};
+    const size_t n2b = (size_t)G.pitch2 * G.NyP;
+    double** f2[] = {&F.eta, &F.U, &F.V, &F.etab, &F.Ub, &F.Vb, &F.GU, &F.GV};
     for (double** p : f2)
-        if (int rc = dev_alloc(h, p, n2)) return rc;
+        if (int rc = dev_alloc(h, p, n2b)) return rc;
+    F.Hfc = h->F_Hfc; F.Hcf = h->F_Hcf;
+    if (int rc = dev_alloc(h, &F.Ld, n2)) return rc;
     return OB200_OK;
 }
 
-struct FieldRef { double* p; int ny, nz; bool three_d; };
+struct FieldRef { double* p; int ny, nz; int layout; };   // layout: 0 = 3-D, 1 = 2-D plane layout, 2 = barotropic
 FieldRef field_ref(ob200_handle* h, int id) {
     const Geom& G = h->G;
     Fields& F = h->F;
     const int Ny = G.Ny, Nz = G.Nz;
     switch (id) {
-        case OB200_F_U: return {F.u, Ny, Nz, true};
-        case OB200_F_V: return {F.v, Ny + 1, Nz, true};
-        case OB200_F_W: return {F.w, Ny, Nz + 1, true};
-        case OB200_F_T: return {F.T, Ny, Nz, true};
-        case OB200_F_S: return {F.S, Ny, Nz, true};
-        case OB200_F_P: return {F.p, Ny, Nz, true};
-        case OB200_F_KAPPA_C: return {F.kc, Ny, Nz + 1, true};
-        case OB200_F_KAPPA_U: return {F.ku, Ny, Nz + 1, true};
-        case OB200_F_GU: return {F.Gu, Ny, Nz, true};
-        case OB200_F_GV: return {F.Gv, Ny + 1, Nz, true};
-        case OB200_F_GT: return {F.GT, Ny, Nz, true};
-        case OB200_F_GS: return {F.GS, Ny, Nz, true};
-        case OB200_F_GU_PREV: return {F.Gu0, Ny, Nz, true};
-        case OB200_F_GV_PREV: return {F.Gv0, Ny + 1, Nz, true};
-        case OB200_F_GT_PREV: return {F.GT0, Ny, Nz, true};
-        case OB200_F_GS_PREV: return {F.GS0, Ny, Nz, true};
-        case OB200_F_ETA: return {F.eta, Ny, 1, false};
-        case OB200_F_UBAR: return {F.Ub, Ny, 1, false};
-        case OB200_F_VBAR: return {F.Vb, Ny + 1, 1, false};
-        case OB200_F_UTRANS: return {F.U, Ny, 1, false};
-        case OB200_F_VTRANS: return {F.V, Ny + 1, 1, false};
-        case OB200_F_GUBT: return {F.GU, Ny, 1, false};
-        case OB200_F_GVBT: return {F.GV, Ny + 1, 1, false};
-        case OB200_F_NU_LEITH: return {F.nuL, Ny, Nz, true};
-        case OB200_F_QX: return {F.qx, Ny, Nz + 1, true};
-        case OB200_F_QY: return {F.qy, Ny, Nz + 1, true};
-        case OB200_F_LD: return {F.Ld, Ny, 1, false};
-        default: return {nullptr, 0, 0, false};
+        case OB200_F_U: return {F.u, Ny, Nz, 0};
+        case OB200_F_V: return {F.v, Ny + 1, Nz, 0};
+        case OB200_F_W: return {F.w, Ny, Nz + 1, 0};
+        case OB200_F_T: return {F.T, Ny, Nz, 0};
+        case OB200_F_S: return {F.S, Ny, Nz, 0};
+        case OB200_F_P: return {F.p, Ny, Nz, 0};
+        case OB200_F_KAPPA_C: return {F.kc, Ny, Nz + 1, 0};
+        case OB200_F_KAPPA_U: return {F.ku, Ny, Nz + 1, 0};
+        case OB200_F_GU: return {F.Gu, Ny, Nz, 0};
+        case OB200_F_GV: return {F.Gv, Ny + 1, Nz, 0};
+        case OB200_F_GT: return {F.GT, Ny, Nz, 0};
+        case OB200_F_GS: return {F.GS, Ny, Nz, 0};
+        case OB200_F_GU_PREV: return {F.Gu0, Ny, Nz, 0};
+        case OB200_F_GV_PREV: return {F.Gv0, Ny + 1, Nz, 0};
+        case OB200_F_GT_PREV: return {F.GT0, Ny, Nz, 0};
+        case OB200_F_GS_PREV: return {F.GS0, Ny, Nz, 0};
+        case OB200_F_ETA: return {F.eta, Ny, 1, 2};
+        case OB200_F_UBAR: return {F.Ub, Ny, 1, 2};
+        case OB200_F_VBAR: return {F.Vb, Ny + 1, 1, 2};
+        case OB200_F_UTRANS: return {F.U, Ny, 1, 2};
+        case OB200_F_VTRANS: return {F.V, Ny + 1, 1, 2};
+        case OB200_F_GUBT: return {F.GU, Ny, 1, 2};
+        case OB200_F_GVBT: return {F.GV, Ny + 1, 1, 2};
+        case OB200_F_NU_LEITH: return {F.nuL, Ny, Nz, 0};
+        case OB200_F_QX: return {F.qx, Ny, Nz + 1, 0};
+        case OB200_F_QY: return {F.qy, Ny, Nz + 1, 0};
+        case OB200_F_LD: return {F.Ld, Ny, 1, 1};
+        default: return {nullptr, 0, 0, 0};
     }
 }
 
@@ -262,9 +296,11 @@ int exchange_halos(ob200_handle* h) {
     const int r = h->cfg.rank, n = h->cfg.nranks;
     const int west = (r + n - 1) % n, east = (r + 1) % n;
     launch_pack_x(h->G, h->F, h->sendW, h->sendE, h->stream);
+    // order matters on a 2-rank ring (west == east == the same peer): NCCL pairs sends and receives between two
+    // ranks in issue order, and my west halo must receive the peer's EAST edge -> east-bound message first
     ncclGroupStart();
-    ncclSend(h->sendW, h->xcount, ncclDouble, west, h->comm, h->stream);
     ncclSend(h->sendE, h->xcount, ncclDouble, east, h->comm, h->stream);
+    ncclSend(h->sendW, h->xcount, ncclDouble, west, h->comm, h->stream);
     ncclRecv(h->recvW, h->xcount, ncclDouble, west, h->comm, h->stream);
     ncclRecv(h->recvE, h->xcount, ncclDouble, east, h->comm, h->stream);
     ncclResult_t rc = ncclGroupEnd();
@@ -301,17 +337,37 @@ void swap_tendencies(ob200_handle* h) {   // store_tendencies!: G^- <- G^n by po
     std::swap(F.Gu, F.Gu0); std::swap(F.Gv, F.Gv0); std::swap(F.GT, F.GT0); std::swap(F.GS, F.GS0);
 }
 
+int barotropic_wide_exchange(ob200_handle* h) {
+    // one exchange of Wb-column halos of Ubar, Vbar, eta, G^U, G^V before the substep loop
+    if (!h->comm) return h->fail(OB200_ESTATE, "barotropic_loop", "nranks > 1 but ob200_comm_init was not called");
+    const int r = h->cfg.rank, n = h->cfg.nranks, W = h->G.Wb;
+    const int west = (r + n - 1) % n, east = (r + 1) % n;
+    launch_pack_baro(h->G, h->F, h->bsendW, h->bsendE, W, false, h->stream);
+    ncclGroupStart();   // east-bound first: see exchange_halos
+    ncclSend(h->bsendE, h->bcount, ncclDouble, east, h->comm, h->stream);
+    ncclSend(h->bsendW, h->bcount, ncclDouble, west, h->comm, h->stream);
+    ncclRecv(h->brecvW, h->bcount, ncclDouble, west, h->comm, h->stream);
+    ncclRecv(h->brecvE, h->bcount, ncclDouble, east, h->comm, h->stream);
+    ncclResult_t rc = ncclGroupEnd();
+    if (rc != ncclSuccess) return h->fail(OB200_ENCCL, "barotropic halo exchange", ncclGetErrorString(rc));
+    launch_pack_baro(h->G, h->F, h->brecvW, h->brecvE, W, true, h->stream);
+    return OB200_OK;
+}
+
 int barotropic_loop(ob200_handle* h, double dt) {
     const double dtau = h->cfg.frac_dtau * dt;
-    launch_baro_init(h->G, h->F, h->periodic_local, h->stream);
-    if (!h->periodic_local) return h->fail(OB200_ESTATE, "barotropic_loop", "distributed barotropic solver not initialised");
+    const bool per = h->periodic_local;
+    const int ex = per ? 0 : h->G.Wb - 1;
+    if (!per)
+        if (int rc = barotropic_wide_exchange(h)) return rc;
+    launch_baro_init(h->G, h->F, per, ex, h->stream);
     if (h->persistent_baro) {
-        if (launch_baro_persistent(h->G, h->F, dtau, h->d_weights, h->cfg.n_substeps, true, h->stream) != 0)
+        if (launch_baro_persistent(h->G, h->F, dtau, h->d_weights, h->cfg.n_substeps, per, ex, h->stream) != 0)
             return h->fail(OB200_ECUDA, "cooperative launch", cudaGetErrorString(cudaGetLastError()));
     } else {
         for (int m = 0; m < h->cfg.n_substeps; m++) {
-            launch_baro_eta(h->G, h->F, dtau, true, h->stream);
-            launch_baro_vel(h->G, h->F, dtau, h->weights[m], true, h->stream);
+            launch_baro_eta(h->G, h->F, dtau, per, ex, h->stream);
+            launch_baro_vel(h->G, h->F, dtau, h->weights[m], per, ex, h->stream);
         }
     }
     launch_baro_finish(h->G, h->F, h->stream);
@@ -364,8 +420,10 @@ int ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out) {
     if (!cfg || !out) { g_last_error = "null argument"; return OB200_EINVAL; }
     if (cfg->struct_bytes != (int32_t)sizeof(ob200_config)) { g_last_error = "ob200_config size mismatch (ABI)"; return OB200_EINVAL; }
     if (cfg->Nx < 2 * OB_H || cfg->Ny < 2 || cfg->Nz < 2 || cfg->n_substeps < 1 || cfg->n_substeps > OB200_MAX_SUBSTEPS ||
-        !cfg->z_faces || !cfg->bottom_height || !cfg->averaging_weights || cfg->nranks < 1) {
-        g_last_error = "invalid ob200_config (sizes / null arrays; Nx must be >= 14)";
+        !cfg->z_faces || !cfg->bottom_height || !cfg->averaging_weights || cfg->nranks < 1 ||
+        cfg->bottom_halo_columns < OB_H || (cfg->nranks > 1 && cfg->bottom_halo_columns < cfg->n_substeps + 1) ||
+        (cfg->nranks > 1 && cfg->Nx < cfg->n_substeps + 1)) {
+        g_last_error = "invalid ob200_config (sizes / null arrays; Nx >= 14; x-slabs need Nx and bottom_halo_columns >= n_substeps + 1)";
         return OB200_EINVAL;
     }
     int ndev = 0;
@@ -390,7 +448,6 @@ int ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out) {
     h->cfg.z_faces = nullptr; h->cfg.bottom_height = nullptr; h->cfg.averaging_weights = nullptr;  // borrowed only during create
     cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     for (auto& ev : h->ev) cudaEventCreate(&ev);
-    launch_column_depths(h->G, h->F, h->stream);
     e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) { g_last_error = std::string("setup kernels: ") + cudaGetErrorString(e); ob200_destroy(h); return OB200_ECUDA; }
     *out = h;
@@ -416,14 +473,14 @@ static int copy_common(ob200_handle* h, int32_t field, double* buf, int on_devic
     if (!r.p) return h->fail(OB200_EINVAL, "field", "unknown or unallocated field id");
     if (hx < 0 || hy < 0 || hz < 0) return h->fail(OB200_EINVAL, "halo", "negative halo");
     const Geom& G = h->G;
-    const size_t n = (size_t)(G.Nx + 2 * hx) * (r.ny + 2 * hy) * (r.three_d ? (r.nz + 2 * hz) : 1);
+    const size_t n = (size_t)(G.Nx + 2 * hx) * (r.ny + 2 * hy) * (r.layout == 0 ? (r.nz + 2 * hz) : 1);
     double* d = buf;
     if (!on_device) {
         OB_CUDA_CHECK(h, cudaMalloc((void**)&d, n * sizeof(double)));
         if (to_field) OB_CUDA_CHECK(h, cudaMemcpyAsync(d, buf, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         else if (hx | hy | hz) OB_CUDA_CHECK(h, cudaMemsetAsync(d, 0, n * sizeof(double), h->stream));
     }
-    launch_copy_field(G, r.p, d, r.ny, r.nz, hx, hy, hz, r.three_d, to_field, h->stream);
+    launch_copy_field(G, r.p, d, r.ny, r.nz, hx, hy, hz, r.layout, to_field, h->stream);
     if (!on_device) {
         if (!to_field) OB_CUDA_CHECK(h, cudaMemcpyAsync(buf, d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
@@ -490,11 +547,11 @@ int ob200_run_stage(ob200_handle* h, int32_t stage, double dt, int32_t arg) {
     switch (stage) {
         case OB200_ST_BAROTROPIC_FORCING: launch_barotropic_forcing(h->G, h->F, chi, h->stream); break;
         case OB200_ST_AB2_IMPLICIT: launch_ab2_implicit(h->G, h->F, dt, chi, h->stream); break;
-        case OB200_ST_BAROTROPIC_INIT: launch_baro_init(h->G, h->F, h->periodic_local, h->stream); break;
-        case OB200_ST_BAROTROPIC_ETA: launch_baro_eta(h->G, h->F, dtau, h->periodic_local, h->stream); break;
+        case OB200_ST_BAROTROPIC_INIT: launch_baro_init(h->G, h->F, h->periodic_local, 0, h->stream); break;
+        case OB200_ST_BAROTROPIC_ETA: launch_baro_eta(h->G, h->F, dtau, h->periodic_local, 0, h->stream); break;
         case OB200_ST_BAROTROPIC_VEL:
             if (arg < 0 || arg >= h->cfg.n_substeps) return h->fail(OB200_EINVAL, "substep", "index out of range");
-            launch_baro_vel(h->G, h->F, dtau, h->weights[arg], h->periodic_local, h->stream);
+            launch_baro_vel(h->G, h->F, dtau, h->weights[arg], h->periodic_local, 0, h->stream);
             break;
         case OB200_ST_BAROTROPIC_FINISH: launch_baro_finish(h->G, h->F, h->stream); break;
         case OB200_ST_CORRECT_AND_STORE: launch_correct(h->G, h->F, h->stream); swap_tendencies(h); break;
@@ -595,6 +652,9 @@ int ob200_comm_init(ob200_handle* h, const void* id128) {
     h->xcount = pack_x_count(h->G);
     for (double** p : {&h->sendW, &h->sendE, &h->recvW, &h->recvE})
         if (int r2 = dev_alloc(h, p, h->xcount)) return r2;
+    h->bcount = pack_baro_count(h->G, h->G.Wb);
+    for (double** p : {&h->bsendW, &h->bsendE, &h->brecvW, &h->brecvE})
+        if (int r2 = dev_alloc(h, p, h->bcount)) return r2;
     return OB200_OK;
 }
 

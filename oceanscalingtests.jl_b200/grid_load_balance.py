@@ -114,10 +114,10 @@ class LatitudeLongitudeGrid:
         return float(self.radius * (self.dphi * np.pi / 180))
 
     # --- bathymetry ----------------------------------------------------------------
-    def bottom_height_local(self) -> np.ndarray:
+    def bottom_height_local(self, halo: Optional[int] = None) -> np.ndarray:
         """(Ny, Nx + 2*halo) bottom height including the periodic / neighbour x-halo columns
         (`partition_global_array`, bathymetry_and_forcings.jl:70-71, plus halo columns)."""
-        h = self.halo
+        h = self.halo if halo is None else halo
         cols = (np.arange(-h, self.Nx + h) + self.i_offset) % self.Nx_global
         if self.bottom_height_global is None:
             return np.full((self.Ny, self.Nx + 2 * h), -1.0e10)

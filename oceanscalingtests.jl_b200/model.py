@@ -167,7 +167,10 @@ def build_config(grid: LatitudeLongitudeGrid, free_surface: SplitExplicitFreeSur
     if leith is not None:
         cfg.leith_C, cfg.leith_min_N2, cfg.leith_Vscale = leith.C, leith.min_N2, leith.Vscale
     zf = np.ascontiguousarray(grid.z_faces, dtype=np.float64)
-    bh = np.ascontiguousarray(grid.bottom_height_local(), dtype=np.float64)
+    # x-slabs carry a barotropic halo of M + 1 columns, exchanged once per step
+    halo_b = grid.halo if grid.nranks == 1 else max(grid.halo, len(w) + 1)
+    cfg.bottom_halo_columns = halo_b
+    bh = np.ascontiguousarray(grid.bottom_height_local(halo_b), dtype=np.float64)
     cfg.z_faces = _abi.as_double_ptr(zf)
     cfg.bottom_height = _abi.as_double_ptr(bh)
     cfg.averaging_weights = _abi.as_double_ptr(w)
@@ -286,7 +289,7 @@ class HydrostaticFreeSurfaceModel:
     def __init__(self, *, grid: LatitudeLongitudeGrid, free_surface: SplitExplicitFreeSurface, eos: str = "linear",
                  closure=(VerticalScalarDiffusivity(), RiBasedVerticalDiffusivity()),
                  boundary_conditions: Optional[BoundaryConditions] = None, advection_orders=(9, 5, 7),
-                 device: int = 0, backend_factory=None):
+                 device: int = 0, backend_factory=None, comm=None):
         self.grid = grid
         self.free_surface = free_surface
         self.closure = tuple(closure)
@@ -297,6 +300,13 @@ class HydrostaticFreeSurfaceModel:
                                             advection_orders=advection_orders)
         factory = backend_factory or B200Backend
         self.backend = factory(self.cfg, device) if factory is B200Backend else factory(self.cfg)
+        if grid.nranks > 1 and hasattr(self.backend, "comm_init"):
+            # NCCL ring bootstrap (replaces MPI.Init + Distributed(...), experiments/run.jl:9-27): rank 0 creates the
+            # unique id, `comm.bcast_bytes` (torch.distributed here, MPI.Bcast in Julia) hands it to every rank
+            if comm is None:
+                raise ValueError("x-slab models need `comm` (an object with bcast_bytes) to bootstrap NCCL")
+            uid = self.backend.comm_unique_id() if grid.rank == 0 else None
+            self.backend.comm_init(comm.bcast_bytes(uid))
         for i, key in enumerate(("taux", "tauy", "Qs", "Fs", "Tr", "Sr")):
             if key in self.boundary_conditions.forcing_arrays:
                 self.backend.set_forcing(i, self.boundary_conditions.forcing_arrays[key])

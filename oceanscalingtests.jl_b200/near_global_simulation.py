@@ -34,7 +34,7 @@ def equation_of_state(experiment: str) -> str:
     return "linear" if experiment == "DoubleDrake" else "teos10"
 
 
-class _Comm:
+class Comm:
     """What the reference gets from MPI.COMM_WORLD, on top of torch.distributed (if initialised)."""
 
     def __init__(self):
@@ -113,7 +113,7 @@ def scaling_test_simulation(resolution, ranks, dt, stop_time, *, device: int = 0
                             boundary_layer_parameterization=None, extra_closures=(), backend_factory=None,
                             realistic_inputs=None, profile_steps=(10, 10, 30)):
     """near_global_simulation.jl:36-176.  `ranks` = (Rx, 1, 1); this process's slab is rank `comm.rank`."""
-    comm = _Comm()
+    comm = Comm()
     if Depth is None:
         Depth = experiment_depth(experiment)
     min_dt, max_dt = (dt, dt) if np.isscalar(dt) else dt
@@ -145,10 +145,7 @@ def scaling_test_simulation(resolution, ranks, dt, stop_time, *, device: int = 0
 
     model = HydrostaticFreeSurfaceModel(grid=grid, free_surface=free_surface, eos=equation_of_state(experiment),
                                         closure=closure, boundary_conditions=boundary_conditions, device=device,
-                                        backend_factory=backend_factory)
-    if grid.nranks > 1 and hasattr(model.backend, "comm_init"):
-        uid = model.backend.comm_unique_id() if comm.rank == 0 else None
-        model.backend.comm_init(comm.bcast_bytes(uid))
+                                        backend_factory=backend_factory, comm=comm)
 
     if profile:
         return profiled_time_steps(model, max_dt, resolution, comm=comm, warmup=profile_steps[0],
@@ -177,7 +174,7 @@ def profiled_time_steps(model, dt, resolution, *, comm=None, warmup=10, gc_steps
     """near_global_simulation.jl:178-216: warm-up steps, then gc_steps x profiled_steps timed steps, mean
     wall time per step averaged over ranks.  Unlike the reference, the device is synchronised around the
     timed region (the reference's @elapsed has no sync).  Returns seconds per step."""
-    comm = comm or _Comm()
+    comm = comm or Comm()
     for _ in range(warmup):
         time_step(model, dt)
     model.backend.sync()

@@ -237,9 +237,11 @@ struct Oracle {
         }
         // bathymetry -> first active level (GridFittedBottom, centre condition: zc <= h is solid)
         kb_.assign((size_t)NxP * NyP, Nz);
+        const int bh = c.bottom_halo_columns, nxh = Nx + 2 * bh;   // the host may carry a wider halo than H
+        if (bh < H) { err = "bottom_halo_columns < 7"; return OB200_EINVAL; }
         for (int j = 0; j < Ny; j++)
             for (int ii = 0; ii < NxP; ii++) {
-                double hgt = c.bottom_height[(size_t)j * NxP + ii];
+                double hgt = c.bottom_height[(size_t)j * nxh + (ii - H + bh)];
                 int k0 = 0;
                 while (k0 < Nz && zc(k0) <= hgt) k0++;
                 kb_[(size_t)(j + H) * NxP + ii] = k0;

@@ -47,7 +47,7 @@ class Case:
         return pkg.LatitudeLongitudeGrid(self.Nx, self.Ny, self.Nz, zf, rank=rank, partition=part,
                                          bottom_height_global=bottom)
 
-    def make_model(self, pkg, backend_factory, rank=0, ranks=None, device=0, initialize=True):
+    def make_model(self, pkg, backend_factory, rank=0, ranks=None, device=0, initialize=True, comm=None):
         grid = self.grid(pkg, rank, ranks)
         res = self.Nx / 360.0
         max_dt = 3240.0 / res
@@ -60,7 +60,7 @@ class Case:
         eos = "linear" if self.experiment == "DoubleDrake" else "teos10"
         model = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=fs, eos=eos, closure=closure,
                                                 boundary_conditions=bcs, device=device,
-                                                backend_factory=backend_factory)
+                                                backend_factory=backend_factory, comm=comm)
         if initialize:
             self.initialize(pkg, model)
         return model

@@ -1,0 +1,51 @@
+"""Multi-GPU parity worker, launched by torchrun (one rank per GPU): the x-slab run through libocean_b200.so
+(NCCL halo exchange + wide-halo barotropic solver) must reproduce the single-GPU run of the same case."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+import __graft_entry__ as ge  # noqa: E402
+import cases  # noqa: E402
+
+
+def main():
+    case_name, nsteps = sys.argv[1], int(sys.argv[2])
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = ge.package()
+    c = cases.build_case(case_name)
+    m = c.make_model(pkg, None, rank=rank, ranks=world, device=local, comm=pkg.Comm())
+    for _ in range(nsteps):
+        pkg.time_step(m, c.dt)
+    m.backend.sync()
+    names = ("U", "V", "W", "ETA", "T", "S", "KAPPA_U", "GU", "GT")
+    ok = True
+    for n in names:
+        parts = [None] * world
+        dist.all_gather_object(parts, m.get(n))
+        if rank == 0:
+            full = np.concatenate(parts, axis=-1)
+            if n == names[0]:
+                ref = c.make_model(pkg, None, device=local)
+                for _ in range(nsteps):
+                    pkg.time_step(ref, c.dt)
+            same = np.array_equal(full, ref.get(n))
+            err = float(np.max(np.abs(full - ref.get(n))))
+            print(f"mgpu {case_name} x{world} {n}: identical={same} max|diff|={err:.3e}", flush=True)
+            ok = ok and same
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

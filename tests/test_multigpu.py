@@ -1,0 +1,23 @@
+"""x-slab runs on 2+ GPUs must equal the single-GPU run bit for bit (skipped unless >= 2 GPUs are visible)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("case_name", ["dd_mid", "bumpy"])
+def test_slabs_match_single_gpu(case_name):
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(HERE, "mgpu_worker.py"), case_name, "6"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
