@@ -367,38 +367,20 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
     return Gt;
 }
 
-// ---- general (masked, order-reducing) path, one thread per cell straight from global memory ----------------
-// Runs on the tiles listed in `slow_tiles` (near ridges, walls, sea floor) for the levels the tiled kernel skips.
-template <int TX, int TY>
-__global__ void __launch_bounds__(TX * TY) k_momentum_general(Geom G, Fields F, int NV, int ND, double time,
-                                                               const int* __restrict__ slow_tiles, int ntx) {
-    const int t = slow_tiles[2 * blockIdx.x], kf = slow_tiles[2 * blockIdx.x + 1];
-    const int k = blockIdx.y;
-    if (k >= kf) return;   // the tiled fast kernel owns levels k >= kf of this tile
-    const int i = (t % ntx) * TX + threadIdx.x, j = (t / ntx) * TY + threadIdx.y;
-    if (i >= G.Nx || j >= G.Ny) return;
-    const long long c = idx3(G, i, j, k);
-    const MomG M{G, F.u, F.v};
-    const bool fast = k >= __ldg(&G.kfast[idx2(G, i, j)]);
-    double gu, gv;
-    if (fast) {
-        gu = tend_u<false>(G, F, M, i, j, k, NV, ND, time);
-        gv = tend_v<false>(G, F, M, i, j, k, NV, ND, time);
-    } else {
-        gu = peripheral_fcc(G, i, j, k) ? 0.0 : tend_u<true>(G, F, M, i, j, k, NV, ND, time);
-        gv = peripheral_cfc(G, i, j, k) ? 0.0 : tend_v<true>(G, F, M, i, j, k, NV, ND, time);
-    }
-    F.Gu[c] = gu;
-    F.Gv[c] = gv;
-}
-
-// ---- fast path: shared-memory tile, all stencils full order, no masks ----------------------------------------
-// Block = TX x TY cells of one level; zeta, I_y(u), I_x(v), dxU, dyV, K are computed once per tile point
-// (instead of once per stencil point per thread) and every thread then reads its 9/9/5-point stencils from smem.
-template <int TX, int TY>
-__global__ void __launch_bounds__(TX * TY) k_momentum_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
-                                                             int klevels) {
+// ---- shared-memory tile kernel -----------------------------------------------------------------------------
+// Block = TX x TY cells of one level; u, v are staged (register-prefetched one level ahead), then zeta, I_y(u),
+// I_x(v), dxU, dyV, K are computed ONCE per tile point (instead of once per stencil point per thread) and every
+// thread reads its 9/9/5-point stencils from shared memory.
+//   GEN = false: tiles whose every stencil is full order and mask free (tile_kfast <= k)
+//   GEN = true : the remaining (tile, level) pairs near ridges, walls and the sea floor: conditional zeta,
+//                per-reconstruction order reduction, masked outputs.
+template <int TX, int TY, bool GEN>
+__global__ void __launch_bounds__(TX * TY, 2) k_momentum_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
+                                                             const int* __restrict__ slow_tiles, int ntx, int klevels,
+                                                             int NV, int ND) {
     using D = TileDims<TX, TY>;
+    constexpr int NT = TX * TY;
+    constexpr int RU = (D::NU + NT - 1) / NT;
     extern __shared__ double sm[];
     double* su = sm;
     double* sv = su + D::NU;
@@ -408,34 +390,57 @@ __global__ void __launch_bounds__(TX * TY) k_momentum_tiled(Geom G, Fields F, do
     double* sdx = svs + D::NZ;
     double* sdy = sdx + D::ND;
     double* sK = sdy + D::ND;
-    const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
-    const int kf = tile_kfast[blockIdx.y * gridDim.x + blockIdx.x];
+    int tile, kf;
+    if (GEN) { tile = slow_tiles[2 * blockIdx.x]; kf = slow_tiles[2 * blockIdx.x + 1]; }
+    else { tile = blockIdx.y * gridDim.x + blockIdx.x; kf = tile_kfast[tile]; }
+    const int i0 = (tile % ntx) * TX, j0 = (tile / ntx) * TY;
     const int tid = threadIdx.y * TX + threadIdx.x;
-    const int k_begin = max((int)blockIdx.z * klevels, kf), k_end = min(((int)blockIdx.z + 1) * klevels, G.Nz);
+    const int zc = GEN ? blockIdx.y : blockIdx.z;
+    const int k_begin = GEN ? zc * klevels : max(zc * klevels, kf);
+    const int k_end = GEN ? min(min((zc + 1) * klevels, kf), G.Nz) : min((zc + 1) * klevels, G.Nz);
+    if (k_begin >= k_end) return;
     const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
+    const bool mine = i < G.Nx && j < G.Ny;
     const MomS<TX, TY> M{su, sv, sz, sus, svs, sdx, sdy, sK, i0, j0};
+    int offu[RU];
+#pragma unroll
+    for (int r = 0; r < RU; r++) {
+        const int e = min(tid + r * NT, D::NU - 1);
+        const int a = e % D::PU, b = e / D::PU;
+        offu[r] = (int)idx3(G, min(i0 - D::HU + a, G.Nx + OB_H - 1), min(j0 - D::HU + b, G.Ny + OB_H), 0);
+    }
+    double ru[RU], rv[RU];
+    auto prefetch = [&](int k) {
+        const long long lev = (long long)k * G.sz;
+#pragma unroll
+        for (int r = 0; r < RU; r++) { ru[r] = F.u[offu[r] + lev]; rv[r] = F.v[offu[r] + lev]; }
+    };
+    prefetch(k_begin);
     for (int k = k_begin; k < k_end; k++) {
-        // stage u, v (indices clamped to the allocated halo; clamped values only feed discarded threads)
-        for (int e = tid; e < D::NU; e += TX * TY) {
-            const int a = e % D::PU, b = e / D::PU;
-            const int ii = min(i0 - D::HU + a, G.Nx + OB_H - 1), jj = min(j0 - D::HU + b, G.Ny + OB_H);
-            const long long c = idx3(G, ii, jj, k);
-            su[e] = F.u[c];
-            sv[e] = F.v[c];
+#pragma unroll
+        for (int r = 0; r < RU; r++) {
+            const int e = tid + r * NT;
+            if (e < D::NU) { su[e] = ru[r]; sv[e] = rv[r]; }
         }
         __syncthreads();
+        if (k + 1 < k_end) prefetch(k + 1);
         const double dzk = G.dzc[k];
-        for (int e = tid; e < D::NZ; e += TX * TY) {
+        for (int e = tid; e < D::NZ; e += NT) {
             const int a = e % D::PZ, b = e / D::PZ;
-            const int jj = j0 - D::HZ + b;
+            const int ii = i0 - D::HZ + a, jj = j0 - D::HZ + b;
             const int q = (b + D::HU - D::HZ) * D::PU + (a + D::HU - D::HZ);   // same point in the u/v tiles
-            const double dxv = G.dy * sv[q] - G.dy * sv[q - 1];
-            const double dyu = G.dxfc[jj] * su[q] - G.dxfc[jj - 1] * su[q - D::PU];
+            double dxv = G.dy * sv[q] - G.dy * sv[q - 1];
+            double dyu = G.dxfc[jj] * su[q] - G.dxfc[jj - 1] * su[q - D::PU];
+            if (GEN) {
+                const int ic = min(ii, G.Nx + OB_H - 1), jc = min(jj, G.Ny + OB_H);
+                if (inactive_cfc(G, ic - 1, jc, k) || inactive_cfc(G, ic, jc, k)) dxv = 0.0;
+                if (inactive_fcc(G, ic, jc - 1, k) || inactive_fcc(G, ic, jc, k)) dyu = 0.0;
+            }
             sz[e] = (dxv - dyu) / G.azcf[jj];
             sus[e] = 0.5 * (su[q - D::PU] + su[q]);
             svs[e] = 0.5 * (sv[q - 1] + sv[q]);
         }
-        for (int e = tid; e < D::ND; e += TX * TY) {
+        for (int e = tid; e < D::ND; e += NT) {
             const int a = e % D::PD, b = e / D::PD;
             const int jj = j0 - D::HD + b;
             const int q = (b + D::HU - D::HD) * D::PU + (a + D::HU - D::HD);
@@ -443,17 +448,22 @@ __global__ void __launch_bounds__(TX * TY) k_momentum_tiled(Geom G, Fields F, do
             sdx[e] = ax * su[q + 1] - ax * su[q];
             sdy[e] = G.dxcf[jj + 1] * dzk * sv[q + D::PU] - G.dxcf[jj] * dzk * sv[q];
         }
-        for (int e = tid; e < D::NK; e += TX * TY) {
+        for (int e = tid; e < D::NK; e += NT) {
             const int a = e % D::PK, b = e / D::PK;
             const int q = (b + D::HU - 1) * D::PU + (a + D::HU - 1);
             const double ua = su[q], ub = su[q + 1], va = sv[q], vb = sv[q + D::PU];
             sK[e] = (0.5 * (ua * ua + ub * ub) + 0.5 * (va * va + vb * vb)) / 2.0;
         }
         __syncthreads();
-        if (i < G.Nx && j < G.Ny) {
+        if (mine) {
             const long long c = idx3(G, i, j, k);
-            F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time);
-            F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time);
+            if (!GEN) {
+                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time);
+                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time);
+            } else {
+                F.Gu[c] = peripheral_fcc(G, i, j, k) ? 0.0 : tend_u<true>(G, F, M, i, j, k, NV, ND, time);
+                F.Gv[c] = peripheral_cfc(G, i, j, k) ? 0.0 : tend_v<true>(G, F, M, i, j, k, NV, ND, time);
+            }
         }
         __syncthreads();
     }
@@ -518,34 +528,6 @@ __device__ __forceinline__ double tend_c(const Geom& G, const Fields& F, const d
     return Gt;
 }
 
-// ---- general path: one thread per cell from global memory, on the slow tiles only ---------------------------
-template <int TX, int TY>
-__global__ void __launch_bounds__(TX * TY) k_tracers_general(Geom G, Fields F, int NT, double time,
-                                                              const int* __restrict__ slow_tiles, int ntx) {
-    const int t = slow_tiles[2 * blockIdx.x], kf = slow_tiles[2 * blockIdx.x + 1];
-    const int k = blockIdx.y;
-    if (k >= kf) return;
-    const int i = (t % ntx) * TX + threadIdx.x, j = (t / ntx) * TY + threadIdx.y;
-    if (i >= G.Nx || j >= G.Ny) return;
-    const long long c = idx3(G, i, j, k);
-    const bool fast = k >= __ldg(&G.kfast[idx2(G, i, j)]);
-    double jT = 0.0, jS = 0.0;
-    if (k == G.Nz - 1) {
-        jT = top_flux_T(G, F, i, j, F.T[c], time);
-        jS = top_flux_S(G, F, i, j, F.S[c], time);
-    }
-    double gT = 0.0, gS = 0.0;
-    if (fast) {
-        gT = tend_c<false>(G, F, F.T, i, j, k, NT, jT);
-        gS = tend_c<false>(G, F, F.S, i, j, k, NT, jS);
-    } else if (active(G, i, j, k)) {
-        gT = tend_c<true>(G, F, F.T, i, j, k, NT, jT);
-        gS = tend_c<true>(G, F, F.S, i, j, k, NT, jS);
-    }
-    F.GT[c] = gT;
-    F.GS[c] = gS;
-}
-
 // ---- fast path: T and S tiles in shared memory, every face flux computed ONCE (the reference computes each
 // face twice, once per adjacent cell), upwind side only, then each thread differences the fluxes of its cell.
 template <int TX, int TY>
@@ -554,85 +536,145 @@ struct TracerTile {
     static constexpr int PC = TX + 2 * HC, RC = TY + 2 * HC;       // cells [i0-4, i0+TX+3] x [j0-4, j0+TY+3]
     static constexpr int NC = PC * RC;
     static constexpr int NFX = (TX + 1) * TY, NFY = TX * (TY + 1); // faces per tracer
-    static constexpr int TOTAL = 2 * NC + 2 * (NFX + NFY);
+    static constexpr int TOTAL = 2 * NC + 3 * (NFX + NFY);   // tiles + fluxes + face velocities
 };
 
-template <int TX, int TY>
-__global__ void __launch_bounds__(TX * TY) k_tracers_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
-                                                            int klevels) {
+template <int TX, int TY, bool GEN>
+__global__ void __launch_bounds__(TX * TY, 2) k_tracers_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
+                                                            const int* __restrict__ slow_tiles, int ntx, int klevels, int NTR) {
     using D = TracerTile<TX, TY>;
+    constexpr int NT = TX * TY;
+    constexpr int RC = (D::NC + NT - 1) / NT;                 // tile elements per thread (per tracer)
+    constexpr int NFV = D::NFX + D::NFY;                      // face velocities per level
+    constexpr int RV = (NFV + NT - 1) / NT;
     extern __shared__ double sm[];
     double* sc = sm;                       // [2][RC][PC]
-    double* sfx = sc + 2 * D::NC;          // [2][TY][TX+1]
-    double* sfy = sfx + 2 * D::NFX;        // [2][TY+1][TX]
-    const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
-    const int kf = tile_kfast[blockIdx.y * gridDim.x + blockIdx.x];
+    double* sfx = sc + 2 * D::NC;          // [2][(TX+1)*TY x-faces | TX*(TY+1) y-faces]
+    double* svel = sfx + 2 * NFV;          // [NFX + NFY] face velocities u (x-faces) then v (y-faces)
+    int tile, kf;
+    if (GEN) { tile = slow_tiles[2 * blockIdx.x]; kf = slow_tiles[2 * blockIdx.x + 1]; }
+    else { tile = blockIdx.y * gridDim.x + blockIdx.x; kf = tile_kfast[tile]; }
+    const int i0 = (tile % ntx) * TX, j0 = (tile / ntx) * TY;
     const int tid = threadIdx.y * TX + threadIdx.x;
-    const int k_begin = max((int)blockIdx.z * klevels, kf), k_end = min(((int)blockIdx.z + 1) * klevels, G.Nz);
+    const int zc = GEN ? blockIdx.y : blockIdx.z;
+    const int k_begin = GEN ? zc * klevels : max(zc * klevels, kf);
+    const int k_end = GEN ? min(min((zc + 1) * klevels, kf), G.Nz) : min((zc + 1) * klevels, G.Nz);
+    if (k_begin >= k_end) return;
     const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
     const bool mine = i < G.Nx && j < G.Ny;
+    // per-thread global offsets (within a level) of the tile elements / face velocities this thread stages
+    int offc[RC], offv[RV];   // element offsets within one level (a plane is < 2^31 elements)
+#pragma unroll
+    for (int r = 0; r < RC; r++) {
+        const int e = min(tid + r * NT, D::NC - 1);
+        const int a = e % D::PC, b = e / D::PC;
+        offc[r] = (int)idx3(G, min(i0 - D::HC + a, G.Nx + OB_H - 1), min(j0 - D::HC + b, G.Ny + OB_H), 0);
+    }
+#pragma unroll
+    for (int r = 0; r < RV; r++) {
+        const int e = min(tid + r * NT, NFV - 1);
+        if (e < D::NFX) {
+            const int a = e % (TX + 1), b = e / (TX + 1);
+            offv[r] = (int)idx3(G, min(i0 + a, G.Nx + OB_H - 1), min(j0 + b, G.Ny - 1), 0);
+        } else {
+            const int f = e - D::NFX, a = f % TX, b = f / TX;
+            offv[r] = (int)idx3(G, min(i0 + a, G.Nx + OB_H - 1), min(j0 + b, G.Ny), 0);
+        }
+    }
+    double rT[RC], rS[RC], rV[RV];
+    auto prefetch = [&](int k) {   // issue the loads of level k; consumed one iteration later
+        const long long lev = (long long)k * G.sz;
+#pragma unroll
+        for (int r = 0; r < RC; r++) { rT[r] = F.T[offc[r] + lev]; rS[r] = F.S[offc[r] + lev]; }
+#pragma unroll
+        for (int r = 0; r < RV; r++) {
+            const int e = min(tid + r * NT, NFV - 1);
+            rV[r] = (e < D::NFX ? F.u : F.v)[offv[r] + lev];
+        }
+    };
+    prefetch(k_begin);
+    const long long cbase = mine ? idx3(G, i, j, 0) : 0;
+    const double az = G.azcc[min(j, G.Ny - 1)];
     for (int k = k_begin; k < k_end; k++) {
-        for (int e = tid; e < D::NC; e += TX * TY) {
-            const int a = e % D::PC, b = e / D::PC;
-            const int ii = min(i0 - D::HC + a, G.Nx + OB_H - 1), jj = min(j0 - D::HC + b, G.Ny + OB_H);
-            const long long c = idx3(G, ii, jj, k);
-            sc[e] = F.T[c];
-            sc[D::NC + e] = F.S[c];
+#pragma unroll
+        for (int r = 0; r < RC; r++) {
+            const int e = tid + r * NT;
+            if (e < D::NC) { sc[e] = rT[r]; sc[D::NC + e] = rS[r]; }
+        }
+#pragma unroll
+        for (int r = 0; r < RV; r++) {
+            const int e = tid + r * NT;
+            if (e < NFV) svel[e] = rV[r];
         }
         __syncthreads();
+        if (k + 1 < k_end) prefetch(k + 1);
+        // own-column values for the vertical flux, requested now, consumed after the flux phase
+        const int km = max(k - 1, 0), kp = min(k + 1, G.Nz - 1);
+        double wlo = 0, whi = 0, Tm = 0, Tp = 0, Sm = 0, Sp = 0;
+        if (mine) {
+            const long long c = cbase + (long long)k * G.sz;
+            wlo = F.w[c]; whi = F.w[c + G.sz];
+            Tm = F.T[cbase + (long long)km * G.sz]; Tp = F.T[cbase + (long long)kp * G.sz];
+            Sm = F.S[cbase + (long long)km * G.sz]; Sp = F.S[cbase + (long long)kp * G.sz];
+        }
         const double dzk = G.dzc[k];
-        // flat work list over (tracer, direction, face)
-        for (int e = tid; e < 2 * (D::NFX + D::NFY); e += TX * TY) {
-            const int tr = e / (D::NFX + D::NFY);
-            int f = e - tr * (D::NFX + D::NFY);
+        // flat work list over (tracer, direction, face): every face flux once, upwind side only.  The direction
+        // only changes the stride / metric, so x- and y-faces share one code path (no divergence, fewer registers).
+#pragma unroll 1
+        for (int e = tid; e < 2 * NFV; e += NT) {
+            const int tr = e / NFV;
+            const int f = e - tr * NFV;
             const double* cc = sc + tr * D::NC;
+            const double vel = svel[f];
+            const bool isx = f < D::NFX;
+            const int g = isx ? f : f - D::NFX;
+            const int w = isx ? TX + 1 : TX;
+            const int a = g % w, b = g / w;                      // face between cells (a-1,b),(a,b) or (a,b-1),(a,b)
+            const int stride = isx ? 1 : D::PC;
             double flux = 0.0;
-            if (f < D::NFX) {   // x-face between cells a-1 and a of row b
-                const int a = f % (TX + 1), b = f / (TX + 1);
-                const int ii = min(i0 + a, G.Nx + OB_H - 1), jj = min(j0 + b, G.Ny - 1);
-                const double vel = F.u[idx3(G, ii, jj, k)];
-                if (vel != 0.0) {
-                    const bool left = vel > 0.0;
-                    const int q = (b + D::HC) * D::PC + (a + D::HC);   // cell a in the tile
-                    const double r = recon_cell<4>(cc, left ? q - 4 : q + 3, left ? 1 : -1);
-                    flux = G.dy * dzk * (vel * r);
+            if (vel != 0.0) {
+                const bool left = vel > 0.0;
+                const int q = (b + D::HC) * D::PC + (a + D::HC);   // the cell on the high side of the face
+                const int jj = min(j0 + b, isx ? G.Ny - 1 : G.Ny);
+                const double metric = isx ? G.dy : G.dxcf[jj];
+                if (!GEN) {
+                    const double r = recon_cell<4>(cc, left ? q - 4 * stride : q + 3 * stride, left ? stride : -stride);
+                    flux = metric * dzk * (vel * r);
+                } else {
+                    const int ii = min(i0 + a, G.Nx + OB_H - 1);
+                    const bool per = isx ? peripheral_fcc(G, ii, jj, k) : peripheral_cfc(G, ii, jj, k);
+                    if (!per) {
+                        const int N = order_cells(G, ii, jj, k, NTR, isx);
+                        const long long st = left ? stride : -stride;
+                        const long long bq = left ? q - N * stride : q + (N - 1) * stride;
+                        const double r = OB_DISPATCH(N, recon_cell<1>(cc, bq, st), recon_cell<2>(cc, bq, st),
+                                                     recon_cell<3>(cc, bq, st), recon_cell<4>(cc, bq, st), recon_cell<4>(cc, bq, st));
+                        flux = metric * dzk * (vel * r);
+                    }
                 }
-                sfx[tr * D::NFX + f] = flux;
-            } else {            // y-face between cells b-1 and b of column a
-                f -= D::NFX;
-                const int a = f % TX, b = f / TX;
-                const int ii = min(i0 + a, G.Nx + OB_H - 1), jj = min(j0 + b, G.Ny);
-                const double vel = F.v[idx3(G, ii, jj, k)];
-                if (vel != 0.0) {
-                    const bool left = vel > 0.0;
-                    const int q = (b + D::HC) * D::PC + (a + D::HC);
-                    const double r = recon_cell<4>(cc, left ? q - 4 * D::PC : q + 3 * D::PC, left ? D::PC : -D::PC);
-                    flux = G.dxcf[jj] * dzk * (vel * r);
-                }
-                sfy[tr * D::NFY + f] = flux;
             }
+            sfx[e] = flux;   // [tracer][x-faces | y-faces]
         }
         __syncthreads();
         if (mine) {
-            const long long c = idx3(G, i, j, k);
-            const int km = max(k - 1, 0), kp = min(k + 1, G.Nz - 1);
-            const long long cm = idx3(G, i, j, km), cp = idx3(G, i, j, kp);
-            const double wlo = F.w[c], whi = F.w[c + G.sz], az = G.azcc[j];
+            const long long c = cbase + (long long)k * G.sz;
             const int fxi = threadIdx.y * (TX + 1) + threadIdx.x, fyi = threadIdx.y * TX + threadIdx.x;
             const int q = (threadIdx.y + D::HC) * D::PC + (threadIdx.x + D::HC);
 #pragma unroll
             for (int tr = 0; tr < 2; tr++) {
-                const double* cf = tr == 0 ? F.T : F.S;
                 const double ck = sc[tr * D::NC + q];
-                const double fzl = az * wlo * 0.5 * (cf[cm] + ck);
-                const double fzh = az * whi * 0.5 * (ck + cf[cp]);
-                const double fxw = sfx[tr * D::NFX + fxi], fxe = sfx[tr * D::NFX + fxi + 1];
-                const double fys = sfy[tr * D::NFY + fyi], fyn = sfy[tr * D::NFY + fyi + TX];
+                const double cm = tr == 0 ? Tm : Sm, cp = tr == 0 ? Tp : Sp;
+                double fzl = az * wlo * 0.5 * (cm + ck);
+                const double fzh = az * whi * 0.5 * (ck + cp);
+                if (GEN && k > 0 && !active(G, i, j, k - 1)) fzl = 0.0;   // immersed-peripheral bottom face
+                const double fxw = sfx[tr * NFV + fxi], fxe = sfx[tr * NFV + fxi + 1];
+                const double fys = sfx[tr * NFV + D::NFX + fyi], fyn = sfx[tr * NFV + D::NFX + fyi + TX];
                 double Gt = -((fxe - fxw) + (fyn - fys) + (fzh - fzl)) / (az * dzk);
                 if (k == G.Nz - 1) {
                     const double J = tr == 0 ? top_flux_T(G, F, i, j, ck, time) : top_flux_S(G, F, i, j, ck, time);
                     Gt -= J / dzk;
                 }
+                if (GEN && !active(G, i, j, k)) Gt = 0.0;
                 (tr == 0 ? F.GT : F.GS)[c] = Gt;
             }
         }
@@ -642,23 +684,26 @@ __global__ void __launch_bounds__(TX * TY) k_tracers_tiled(Geom G, Fields F, dou
 
 #define MOM_TX 32
 #define MOM_TY 8
+#define TEND_KLEV 8
 void launch_momentum(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st) {
     using D = TileDims<MOM_TX, MOM_TY>;
     static bool attr_set = false;
     const size_t smem = D::TOTAL * sizeof(double);
     if (!attr_set) {
-        cudaFuncSetAttribute(k_momentum_tiled<MOM_TX, MOM_TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_momentum_tiled<MOM_TX, MOM_TY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_momentum_tiled<MOM_TX, MOM_TY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
+    const int NV = (ord_vort + 1) / 2, ND = (ord_div + 1) / 2, nz = (G.Nz + TEND_KLEV - 1) / TEND_KLEV;
+    dim3 b(MOM_TX, MOM_TY);
     if (P.any_fast) {
-        const int klev = 8;
-        dim3 b(MOM_TX, MOM_TY), g(P.ntx, P.nty, (G.Nz + klev - 1) / klev);
-        k_momentum_tiled<MOM_TX, MOM_TY><<<g, b, smem, st>>>(G, F, time, P.tile_kfast, klev);
+        k_momentum_tiled<MOM_TX, MOM_TY, false><<<dim3(P.ntx, P.nty, nz), b, smem, st>>>(G, F, time, P.tile_kfast, P.slow_tiles,
+                                                                                       P.ntx, TEND_KLEV, NV, ND);
         OB_COUNT_LAUNCH(1);
     }
     if (P.nslow > 0) {
-        dim3 b(MOM_TX, MOM_TY), g(P.nslow, G.Nz);
-        k_momentum_general<MOM_TX, MOM_TY><<<g, b, 0, st>>>(G, F, (ord_vort + 1) / 2, (ord_div + 1) / 2, time, P.slow_tiles, P.ntx);
+        k_momentum_tiled<MOM_TX, MOM_TY, true><<<dim3(P.nslow, nz), b, smem, st>>>(G, F, time, P.tile_kfast, P.slow_tiles, P.ntx,
+                                                                                 TEND_KLEV, NV, ND);
         OB_COUNT_LAUNCH(1);
     }
 }
@@ -666,15 +711,16 @@ void mom_plan_tile_shape(int* tx, int* ty) { *tx = MOM_TX; *ty = MOM_TY; }
 void launch_tracers(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st) {
     using D = TracerTile<MOM_TX, MOM_TY>;
     const size_t smem = D::TOTAL * sizeof(double);
+    const int NTR = (ord_tracer + 1) / 2, nz = (G.Nz + TEND_KLEV - 1) / TEND_KLEV;
+    dim3 b(MOM_TX, MOM_TY);
     if (P.any_fast) {
-        const int klev = 8;
-        dim3 b(MOM_TX, MOM_TY), g(P.ntx, P.nty, (G.Nz + klev - 1) / klev);
-        k_tracers_tiled<MOM_TX, MOM_TY><<<g, b, smem, st>>>(G, F, time, P.tile_kfast, klev);
+        k_tracers_tiled<MOM_TX, MOM_TY, false><<<dim3(P.ntx, P.nty, nz), b, smem, st>>>(G, F, time, P.tile_kfast, P.slow_tiles,
+                                                                                      P.ntx, TEND_KLEV, NTR);
         OB_COUNT_LAUNCH(1);
     }
     if (P.nslow > 0) {
-        dim3 b(MOM_TX, MOM_TY), g(P.nslow, G.Nz);
-        k_tracers_general<MOM_TX, MOM_TY><<<g, b, 0, st>>>(G, F, (ord_tracer + 1) / 2, time, P.slow_tiles, P.ntx);
+        k_tracers_tiled<MOM_TX, MOM_TY, true><<<dim3(P.nslow, nz), b, smem, st>>>(G, F, time, P.tile_kfast, P.slow_tiles, P.ntx,
+                                                                                TEND_KLEV, NTR);
         OB_COUNT_LAUNCH(1);
     }
 }
