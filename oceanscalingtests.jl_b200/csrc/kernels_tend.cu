@@ -160,6 +160,21 @@ __device__ __forceinline__ double recon_cell(const double* __restrict__ c, long 
     return Weno<N>::combine(q, b);
 }
 
+// WENO-7 upwind-side reconstruction at the low face of tile cell q along a compile-time stride S: one 8-value
+// window (immediate LDS offsets) serves both upwind directions; the right-biased stencil is the mirror image.
+template <int S>
+__device__ __forceinline__ double recon7_window(const double* __restrict__ c, int q, bool left) {
+    double w[8];
+#pragma unroll
+    for (int m = 0; m < 8; m++) w[m] = c[q + (m - 4) * S];
+    double qq[7];
+#pragma unroll
+    for (int m = 0; m < 7; m++) qq[m] = left ? w[m] : w[7 - m];
+    double b[4];
+    Weno<4>::beta(qq, b);
+    return Weno<4>::combine(qq, b);
+}
+
 // runtime-order dispatch used by the general path
 #define OB_DISPATCH(N, CALL1, CALL2, CALL3, CALL4, CALL5) \
     ((N) >= 5 ? (CALL5) : (N) == 4 ? (CALL4) : (N) == 3 ? (CALL3) : (N) == 2 ? (CALL2) : (CALL1))
@@ -375,7 +390,7 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
 //   GEN = true : the remaining (tile, level) pairs near ridges, walls and the sea floor: conditional zeta,
 //                per-reconstruction order reduction, masked outputs.
 template <int TX, int TY, bool GEN>
-__global__ void __launch_bounds__(TX * TY, 2) k_momentum_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
+__global__ void __launch_bounds__(TX * TY, GEN ? 2 : 3) k_momentum_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
                                                              const int* __restrict__ slow_tiles, int ntx, int klevels,
                                                              int NV, int ND) {
     using D = TileDims<TX, TY>;
@@ -618,42 +633,78 @@ __global__ void __launch_bounds__(TX * TY, 2) k_tracers_tiled(Geom G, Fields F, 
             Sm = F.S[cbase + (long long)km * G.sz]; Sp = F.S[cbase + (long long)kp * G.sz];
         }
         const double dzk = G.dzc[k];
+        if (!GEN) {
+            // own cell: west face (x) and south face (y) of both tracers, compile-time strides
+            {
+                const int q = (threadIdx.y + D::HC) * D::PC + (threadIdx.x + D::HC);
+                const int fx = threadIdx.y * (TX + 1) + threadIdx.x, fy = D::NFX + threadIdx.y * TX + threadIdx.x;
+                const double ux = svel[fx], vy = svel[fy];
+                const double mx = G.dy * dzk, my = G.dxcf[min(j, G.Ny)] * dzk;
+#pragma unroll
+                for (int tr = 0; tr < 2; tr++) {
+                    const double* cc = sc + tr * D::NC;
+                    double flx = 0.0, fly = 0.0;
+                    if (ux != 0.0) flx = G.dy * dzk * (ux * recon7_window<1>(cc, q, ux > 0.0));
+                    if (vy != 0.0) fly = G.dxcf[min(j, G.Ny)] * dzk * (vy * recon7_window<D::PC>(cc, q, vy > 0.0));
+                    sfx[tr * NFV + fx] = flx;
+                    sfx[tr * NFV + fy] = fly;
+                }
+                (void)mx; (void)my;
+            }
+            // the tile's east column of x-faces and north row of y-faces: (TY + TX) faces x 2 tracers
+            if (tid < 2 * (TX + TY)) {
+                const int tr = tid / (TX + TY), g = tid - tr * (TX + TY);
+                const double* cc = sc + tr * D::NC;
+                const bool isx = g < TY;
+                const int a = isx ? TX : g - TY, b = isx ? g : TY;
+                const int f = isx ? b * (TX + 1) + a : D::NFX + b * TX + a;
+                const int q = (b + D::HC) * D::PC + (a + D::HC);
+                const double vel = svel[f];
+                double flux = 0.0;
+                if (vel != 0.0) {
+                    const double r = isx ? recon7_window<1>(cc, q, vel > 0.0) : recon7_window<D::PC>(cc, q, vel > 0.0);
+                    flux = (isx ? G.dy : G.dxcf[min(j0 + b, G.Ny)]) * dzk * (vel * r);
+                }
+                sfx[tr * NFV + f] = flux;
+            }
+        } else {
         // flat work list over (tracer, direction, face): every face flux once, upwind side only.  The direction
-        // only changes the stride / metric, so x- and y-faces share one code path (no divergence, fewer registers).
+            // only changes the stride / metric, so x- and y-faces share one code path (no divergence, fewer registers).
 #pragma unroll 1
-        for (int e = tid; e < 2 * NFV; e += NT) {
-            const int tr = e / NFV;
-            const int f = e - tr * NFV;
-            const double* cc = sc + tr * D::NC;
-            const double vel = svel[f];
-            const bool isx = f < D::NFX;
-            const int g = isx ? f : f - D::NFX;
-            const int w = isx ? TX + 1 : TX;
-            const int a = g % w, b = g / w;                      // face between cells (a-1,b),(a,b) or (a,b-1),(a,b)
-            const int stride = isx ? 1 : D::PC;
-            double flux = 0.0;
-            if (vel != 0.0) {
-                const bool left = vel > 0.0;
-                const int q = (b + D::HC) * D::PC + (a + D::HC);   // the cell on the high side of the face
-                const int jj = min(j0 + b, isx ? G.Ny - 1 : G.Ny);
-                const double metric = isx ? G.dy : G.dxcf[jj];
-                if (!GEN) {
-                    const double r = recon_cell<4>(cc, left ? q - 4 * stride : q + 3 * stride, left ? stride : -stride);
-                    flux = metric * dzk * (vel * r);
-                } else {
-                    const int ii = min(i0 + a, G.Nx + OB_H - 1);
-                    const bool per = isx ? peripheral_fcc(G, ii, jj, k) : peripheral_cfc(G, ii, jj, k);
-                    if (!per) {
-                        const int N = order_cells(G, ii, jj, k, NTR, isx);
-                        const long long st = left ? stride : -stride;
-                        const long long bq = left ? q - N * stride : q + (N - 1) * stride;
-                        const double r = OB_DISPATCH(N, recon_cell<1>(cc, bq, st), recon_cell<2>(cc, bq, st),
-                                                     recon_cell<3>(cc, bq, st), recon_cell<4>(cc, bq, st), recon_cell<4>(cc, bq, st));
+            for (int e = tid; e < 2 * NFV; e += NT) {
+                const int tr = e / NFV;
+                const int f = e - tr * NFV;
+                const double* cc = sc + tr * D::NC;
+                const double vel = svel[f];
+                const bool isx = f < D::NFX;
+                const int g = isx ? f : f - D::NFX;
+                const int w = isx ? TX + 1 : TX;
+                const int a = g % w, b = g / w;                      // face between cells (a-1,b),(a,b) or (a,b-1),(a,b)
+                const int stride = isx ? 1 : D::PC;
+                double flux = 0.0;
+                if (vel != 0.0) {
+                    const bool left = vel > 0.0;
+                    const int q = (b + D::HC) * D::PC + (a + D::HC);   // the cell on the high side of the face
+                    const int jj = min(j0 + b, isx ? G.Ny - 1 : G.Ny);
+                    const double metric = isx ? G.dy : G.dxcf[jj];
+                    if (!GEN) {
+                        const double r = recon_cell<4>(cc, left ? q - 4 * stride : q + 3 * stride, left ? stride : -stride);
                         flux = metric * dzk * (vel * r);
+                    } else {
+                        const int ii = min(i0 + a, G.Nx + OB_H - 1);
+                        const bool per = isx ? peripheral_fcc(G, ii, jj, k) : peripheral_cfc(G, ii, jj, k);
+                        if (!per) {
+                            const int N = order_cells(G, ii, jj, k, NTR, isx);
+                            const long long st = left ? stride : -stride;
+                            const long long bq = left ? q - N * stride : q + (N - 1) * stride;
+                            const double r = OB_DISPATCH(N, recon_cell<1>(cc, bq, st), recon_cell<2>(cc, bq, st),
+                                                         recon_cell<3>(cc, bq, st), recon_cell<4>(cc, bq, st), recon_cell<4>(cc, bq, st));
+                            flux = metric * dzk * (vel * r);
+                        }
                     }
                 }
+                sfx[e] = flux;   // [tracer][x-faces | y-faces]
             }
-            sfx[e] = flux;   // [tracer][x-faces | y-faces]
         }
         __syncthreads();
         if (mine) {
