@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libocean_b200.so")
+LIB_PATH = os.environ.get("OB200_LIB", os.path.join(HERE, "csrc", "libocean_b200.so"))   # OB200_LIB: tuning variants
 
 OB200_HALO = 7
 OB200_EOS_LINEAR, OB200_EOS_TEOS10 = 0, 1

@@ -192,6 +192,12 @@ def emit_device_code(tables, path):
         out.append("  }")
         out.append("  __device__ __forceinline__ static double combine(const double* __restrict__ q, const double* __restrict__ b) {")
         out.append("    const double tau = %s;" % taus[N])
+        # division-free Z-weights: alpha_s * P^2 = C_s * (P^2 + (tau * P_s)^2), P_s = prod_{r != s} d_r, d = beta + eps
+        out.append("    double d[%d], L[%d], R[%d];" % (N, N, N))
+        out.append("    " + " ".join("d[%d] = b[%d] + 1e-8;" % (s, s) for s in range(N)))
+        out.append("    L[0] = 1.0; " + " ".join("L[%d] = L[%d] * d[%d];" % (s + 1, s, s) for s in range(N - 1)))
+        out.append("    R[%d] = 1.0; " % (N - 1) + " ".join("R[%d] = R[%d] * d[%d];" % (s - 1, s, s) for s in range(N - 1, 0, -1)))
+        out.append("    const double Pt = L[%d] * d[%d]; const double PP = Pt * Pt;" % (N - 1, N - 1))
         out.append("    double asum = 0.0, r = 0.0;")
         for s in range(N):
             off = N - 1 - s
@@ -200,7 +206,7 @@ def emit_device_code(tables, path):
                 cst = "WP%d[%d]" % (N, s * N + a)
                 poly = "%s * q[%d]" % (cst, off + a) if poly is None else \
                     "fma(%s, q[%d], %s)" % (cst, off + a, poly)
-            out.append("    { const double t = tau / (b[%d] + 1e-8); const double al = WO%d[%d] * fma(t, t, 1.0);" % (s, N, s))
+            out.append("    { const double t = tau * (L[%d] * R[%d]); const double al = WO%d[%d] * fma(t, t, PP);" % (s, s, N, s))
             out.append("      asum += al; r = fma(al, %s, r); }" % poly)
         out.append("    return r / asum;")
         out.append("  }")

@@ -36,7 +36,7 @@ __device__ __forceinline__ double zeta_c(const Geom& G, const Fields& F, int i, 
     double dyu = G.dxfc[j] * F.u[c] - G.dxfc[j - 1] * F.u[c - G.pitch];
     if (inactive_cfc(G, i - 1, j, k) || inactive_cfc(G, i, j, k)) dxv = 0.0;
     if (inactive_fcc(G, i, j - 1, k) || inactive_fcc(G, i, j, k)) dyu = 0.0;
-    return (dxv - dyu) / G.azcf[j];
+    return (dxv - dyu) * G.razcf[j];
 }
 
 __global__ void k_leith_ld(Geom G, Fields F) {

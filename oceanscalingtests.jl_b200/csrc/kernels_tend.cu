@@ -32,7 +32,7 @@ struct MomG {
             if (inactive_cfc(G, i - 1, j, k) || inactive_cfc(G, i, j, k)) dxv = 0.0;
             if (inactive_fcc(G, i, j - 1, k) || inactive_fcc(G, i, j, k)) dyu = 0.0;
         }
-        return (dxv - dyu) / G.azcf[j];
+        return (dxv - dyu) * G.razcf[j];
     }
     __device__ __forceinline__ double dxU(int i, int j, int k) const {
         const long long c = idx3(G, i, j, k);
@@ -207,7 +207,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
     const double q00 = G.dxcf[j] * M.V(i - 1, j, k), q01 = G.dxcf[j + 1] * M.V(i - 1, j + 1, k);
     const double q10 = G.dxcf[j] * M.V(i, j, k), q11 = G.dxcf[j + 1] * M.V(i, j + 1, k);
     const double vavg = 0.5 * (0.5 * (q00 + q01) + 0.5 * (q10 + q11));
-    const double vhat = vavg / G.dxfc[j];
+    const double vhat = vavg * G.rdxfc[j];
     double Gt = 0.0;
     if (vhat != 0.0) {
         const bool left = vhat > 0.0;
@@ -250,9 +250,9 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
             // (the node above an active node is active for a grid-fitted bottom; the top face is a domain boundary)
         }
     }
-    Gt -= (Phi + fl_hi - fl_lo) / (az * G.dzc[k]);
+    Gt -= (Phi + fl_hi - fl_lo) * (G.razcc[j] * G.rdzc[k]);
     // (3) Bernoulli head  (4) Coriolis  (5) pressure gradient
-    Gt -= (M.Kh(i, j, k) - M.Kh(i - 1, j, k)) / G.dxfc[j];
+    Gt -= (M.Kh(i, j, k) - M.Kh(i - 1, j, k)) * G.rdxfc[j];
     int nact = 4;
     if (GEN) {
         nact = 0;
@@ -260,9 +260,9 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
             for (int b = 0; b < 2; b++) nact += peripheral_cfc(G, i - 1 + a, j + b, k) ? 0 : 1;
     }
     const double fbar = 0.5 * (G.fff[j] + G.fff[j + 1]);
-    const double cor = nact == 0 ? 0.0 : vavg / (0.25 * nact);
-    Gt += fbar * cor / G.dxfc[j];
-    Gt -= (F.p[c] - F.p[c - 1]) / G.dxfc[j];
+    const double cor = nact == 0 ? 0.0 : nact == 4 ? vavg : vavg / (0.25 * nact);
+    Gt += fbar * cor * G.rdxfc[j];
+    Gt -= (F.p[c] - F.p[c - 1]) * G.rdxfc[j];
     // (6) QG-Leith stress divergence
     if (G.qgleith) {
         const MomG Mg{G, F.u, F.v};
@@ -284,7 +284,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
         double J = 0.0;
         if (G.bc_kind == OB200_BC_DOUBLEDRAKE) J = G.taux[j];
         else if (G.bc_kind == OB200_BC_REALISTIC) J = interp_flux(G, F.forcing[0], i, j, G.Ny, time, false);
-        Gt -= J / G.dzc[k];
+        Gt -= J * G.rdzc[k];
     }
     if (k == 0) {
         double J = 0.0;
@@ -293,7 +293,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
             const double v0 = M.V(i - 1, j, k), v1 = M.V(i - 1, j + 1, k), v2 = M.V(i, j, k), v3 = M.V(i, j + 1, k);
             J = -G.mu_drag * uh * sqrt(uh * uh + 0.25 * (v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3));
         }
-        Gt += J / G.dzc[k];
+        Gt += J * G.rdzc[k];
     }
     return Gt;
 }
@@ -306,7 +306,7 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
     const double q00 = dy * M.U(i, j - 1, k), q10 = dy * M.U(i + 1, j - 1, k);
     const double q01 = dy * M.U(i, j, k), q11 = dy * M.U(i + 1, j, k);
     const double uavg = 0.5 * (0.5 * (q00 + q10) + 0.5 * (q01 + q11));
-    const double uhat = uavg / dy;
+    const double uhat = uavg * G.rdy;
     double Gt = 0.0;
     if (uhat != 0.0) {
         const bool left = uhat > 0.0;
@@ -342,8 +342,8 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
     if (GEN) {
         if (k > 0 && peripheral_cfc(G, i, j, k - 1)) fl_lo = 0.0;
     }
-    Gt -= (Phi + fl_hi - fl_lo) / (G.azcf[j] * G.dzc[k]);
-    Gt -= (M.Kh(i, j, k) - M.Kh(i, j - 1, k)) / dy;
+    Gt -= (Phi + fl_hi - fl_lo) * (G.razcf[j] * G.rdzc[k]);
+    Gt -= (M.Kh(i, j, k) - M.Kh(i, j - 1, k)) * G.rdy;
     int nact = 4;
     if (GEN) {
         nact = 0;
@@ -351,9 +351,9 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
             for (int b = 0; b < 2; b++) nact += peripheral_fcc(G, i + a, j - 1 + b, k) ? 0 : 1;
     }
     const double fbar = 0.5 * (G.fff[j] + G.fff[j]);
-    const double cor = nact == 0 ? 0.0 : uavg / (0.25 * nact);
-    Gt -= fbar * cor / dy;
-    Gt -= (F.p[c] - F.p[c - G.pitch]) / dy;
+    const double cor = nact == 0 ? 0.0 : nact == 4 ? uavg : uavg / (0.25 * nact);
+    Gt -= fbar * cor * G.rdy;
+    Gt -= (F.p[c] - F.p[c - G.pitch]) * G.rdy;
     if (G.qgleith) {
         const MomG Mg{G, F.u, F.v};
         const double ax = dy * G.dzc[k];
@@ -369,7 +369,7 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
                          (G.dxfc[j] * G.dzc[k] * fccc(i, j) - G.dxfc[j - 1] * G.dzc[k] * fccc(i, j - 1));
         Gt -= t / (G.azcf[j] * G.dzc[k]);
     }
-    if (k == G.Nz - 1 && G.bc_kind == OB200_BC_REALISTIC) Gt -= interp_flux(G, F.forcing[1], i, j, G.Ny + 1, time, false) / G.dzc[k];
+    if (k == G.Nz - 1 && G.bc_kind == OB200_BC_REALISTIC) Gt -= interp_flux(G, F.forcing[1], i, j, G.Ny + 1, time, false) * G.rdzc[k];
     if (k == 0) {
         double J = 0.0;
         if (G.bc_kind == OB200_BC_DOUBLEDRAKE) J = -G.mu_drag * vh;
@@ -377,7 +377,7 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
             const double u0 = M.U(i, j - 1, k), u1 = M.U(i + 1, j - 1, k), u2 = M.U(i, j, k), u3 = M.U(i + 1, j, k);
             J = -G.mu_drag * vh * sqrt(vh * vh + 0.25 * (u0 * u0 + u2 * u2 + u1 * u1 + u3 * u3));
         }
-        Gt += J / G.dzc[k];
+        Gt += J * G.rdzc[k];
     }
     return Gt;
 }
@@ -389,8 +389,14 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
 //   GEN = false: tiles whose every stencil is full order and mask free (tile_kfast <= k)
 //   GEN = true : the remaining (tile, level) pairs near ridges, walls and the sea floor: conditional zeta,
 //                per-reconstruction order reduction, masked outputs.
+#ifndef MOM_MINB
+#define MOM_MINB 3
+#endif
+#ifndef TRC_MINB
+#define TRC_MINB 2
+#endif
 template <int TX, int TY, bool GEN>
-__global__ void __launch_bounds__(TX * TY, GEN ? 2 : 3) k_momentum_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
+__global__ void __launch_bounds__(TX * TY, GEN ? 2 : MOM_MINB) k_momentum_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
                                                              const int* __restrict__ slow_tiles, int ntx, int klevels,
                                                              int NV, int ND) {
     using D = TileDims<TX, TY>;
@@ -451,7 +457,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : 3) k_momentum_tiled(Geom G,
                 if (inactive_cfc(G, ic - 1, jc, k) || inactive_cfc(G, ic, jc, k)) dxv = 0.0;
                 if (inactive_fcc(G, ic, jc - 1, k) || inactive_fcc(G, ic, jc, k)) dyu = 0.0;
             }
-            sz[e] = (dxv - dyu) / G.azcf[jj];
+            sz[e] = (dxv - dyu) * G.razcf[jj];
             sus[e] = 0.5 * (su[q - D::PU] + su[q]);
             svs[e] = 0.5 * (sv[q - 1] + sv[q]);
         }
@@ -538,8 +544,8 @@ __device__ __forceinline__ double tend_c(const Geom& G, const Fields& F, const d
     if (GEN) {
         if (k > 0 && !active(G, i, j, k - 1)) fzl = 0.0;
     }
-    double Gt = -((fxe - fxw) + (fyn - fys) + (fzh - fzl)) / (G.azcc[j] * G.dzc[k]);
-    if (k == G.Nz - 1) Gt -= topflux / G.dzc[k];
+    double Gt = -((fxe - fxw) + (fyn - fys) + (fzh - fzl)) * (G.razcc[j] * G.rdzc[k]);
+    if (k == G.Nz - 1) Gt -= topflux * G.rdzc[k];
     return Gt;
 }
 
@@ -555,7 +561,7 @@ struct TracerTile {
 };
 
 template <int TX, int TY, bool GEN>
-__global__ void __launch_bounds__(TX * TY, 2) k_tracers_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
+__global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
                                                             const int* __restrict__ slow_tiles, int ntx, int klevels, int NTR) {
     using D = TracerTile<TX, TY>;
     constexpr int NT = TX * TY;
@@ -609,7 +615,7 @@ __global__ void __launch_bounds__(TX * TY, 2) k_tracers_tiled(Geom G, Fields F, 
     };
     prefetch(k_begin);
     const long long cbase = mine ? idx3(G, i, j, 0) : 0;
-    const double az = G.azcc[min(j, G.Ny - 1)];
+    const double az = G.azcc[min(j, G.Ny - 1)], raz = G.razcc[min(j, G.Ny - 1)];
     for (int k = k_begin; k < k_end; k++) {
 #pragma unroll
         for (int r = 0; r < RC; r++) {
@@ -632,7 +638,7 @@ __global__ void __launch_bounds__(TX * TY, 2) k_tracers_tiled(Geom G, Fields F, 
             Tm = F.T[cbase + (long long)km * G.sz]; Tp = F.T[cbase + (long long)kp * G.sz];
             Sm = F.S[cbase + (long long)km * G.sz]; Sp = F.S[cbase + (long long)kp * G.sz];
         }
-        const double dzk = G.dzc[k];
+        const double dzk = G.dzc[k], rdzk = G.rdzc[k];
         if (!GEN) {
             // own cell: west face (x) and south face (y) of both tracers, compile-time strides
             {
@@ -720,10 +726,10 @@ __global__ void __launch_bounds__(TX * TY, 2) k_tracers_tiled(Geom G, Fields F, 
                 if (GEN && k > 0 && !active(G, i, j, k - 1)) fzl = 0.0;   // immersed-peripheral bottom face
                 const double fxw = sfx[tr * NFV + fxi], fxe = sfx[tr * NFV + fxi + 1];
                 const double fys = sfx[tr * NFV + D::NFX + fyi], fyn = sfx[tr * NFV + D::NFX + fyi + TX];
-                double Gt = -((fxe - fxw) + (fyn - fys) + (fzh - fzl)) / (az * dzk);
+                double Gt = -((fxe - fxw) + (fyn - fys) + (fzh - fzl)) * (raz * rdzk);
                 if (k == G.Nz - 1) {
                     const double J = tr == 0 ? top_flux_T(G, F, i, j, ck, time) : top_flux_S(G, F, i, j, ck, time);
-                    Gt -= J / dzk;
+                    Gt -= J * rdzk;
                 }
                 if (GEN && !active(G, i, j, k)) Gt = 0.0;
                 (tr == 0 ? F.GT : F.GS)[c] = Gt;

@@ -22,11 +22,12 @@ struct Geom {
     long long sz;            // plane stride = pitch * NyP
     // per-latitude metrics, indexable for j = -OB_H-1 .. Ny+OB_H+1 (pointers pre-offset so [j] works)
     const double *dxfc, *dxcf, *azcc, *azcf, *fff, *taux, *sflux, *tref;
+    const double *rdxfc, *razcc, *razcf;   // reciprocals used by the tendency kernels (DESIGN.md spec decision 8)
     // vertical metrics: dzc[k], zc[k] for k = -1..Nz (pre-offset), dzf[k] for k = 0..Nz
-    const double *dzc, *dzf, *zc;
+    const double *dzc, *dzf, *zc, *rdzc;
     const int* kb;           // first active level per column (2-D, field layout); Nz = no active cell
     const int* kfast;        // level from which the full-order, mask-free stencils are valid (2-D)
-    double dy;
+    double dy, rdy;
     double g, alpha, beta_s, rho0;
     int eos;
     double nu_z, kappa_z;

@@ -101,7 +101,7 @@ int setup_geometry(ob200_handle* h) {
     G.dy = c.radius * (dphi * pi / 180.0);
     // per-latitude metrics for j = -(H+1) .. Ny+H+1
     const int jo = OB_H + 1, nj = c.Ny + 2 * jo + 1;
-    std::vector<double> m[8];
+    std::vector<double> m[11];
     for (auto& v : m) v.assign(nj, 0.0);
     auto pf = [&](int j) { return (double)((long double)c.lat_south + (long double)j * (long double)dphi); };
     auto pc = [&](int j) { return (double)((long double)c.lat_south + ((long double)j + 0.5L) * (long double)dphi); };
@@ -117,9 +117,11 @@ int setup_geometry(ob200_handle* h) {
         m[5][jj] = wind_stress(c, pc(j));
         m[6][jj] = salinity_flux(c, pc(j));
         m[7][jj] = std::fmax(0.0, 30.0 * std::cos(1.2 * pi * pc(j) / 180.0));                // T_reference (:154)
+        m[8][jj] = 1.0 / m[0][jj]; m[9][jj] = 1.0 / m[2][jj]; m[10][jj] = 1.0 / m[3][jj];
     }
-    const double** dst[8] = {&G.dxfc, &G.dxcf, &G.azcc, &G.azcf, &G.fff, &G.taux, &G.sflux, &G.tref};
-    for (int q = 0; q < 8; q++) {
+    G.rdy = 1.0 / G.dy;
+    const double** dst[11] = {&G.dxfc, &G.dxcf, &G.azcc, &G.azcf, &G.fff, &G.taux, &G.sflux, &G.tref, &G.rdxfc, &G.razcc, &G.razcf};
+    for (int q = 0; q < 11; q++) {
         double* d = nullptr;
         if (int rc = dev_alloc(h, &d, nj, false)) return rc;
         cudaMemcpy(d, m[q].data(), nj * sizeof(double), cudaMemcpyHostToDevice);
@@ -132,7 +134,12 @@ int setup_geometry(ob200_handle* h) {
     dzc[0] = dzc[1]; dzc[Nz + 1] = dzc[Nz];
     zc[0] = c.z_faces[0] - 0.5 * dzc[0]; zc[Nz + 1] = c.z_faces[Nz] + 0.5 * dzc[Nz + 1];
     for (int k = 0; k <= Nz; k++) dzf[k] = zc[k + 1] - zc[k];
-    double *dzc_d, *zc_d, *dzf_d;
+    double *dzc_d, *zc_d, *dzf_d, *rdzc_d;
+    std::vector<double> rdzc(Nz + 2);
+    for (int k = 0; k < Nz + 2; k++) rdzc[k] = 1.0 / dzc[k];
+    if (int rc = dev_alloc(h, &rdzc_d, Nz + 2, false)) return rc;
+    cudaMemcpy(rdzc_d, rdzc.data(), (Nz + 2) * sizeof(double), cudaMemcpyHostToDevice);
+    G.rdzc = rdzc_d + 1;
     if (int rc = dev_alloc(h, &dzc_d, Nz + 2, false)) return rc;
     if (int rc = dev_alloc(h, &zc_d, Nz + 2, false)) return rc;
     if (int rc = dev_alloc(h, &dzf_d, Nz + 1, false)) return rc;

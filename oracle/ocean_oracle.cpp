@@ -143,6 +143,10 @@ struct Oracle {
     std::vector<double> zc_, dzc_, dzf_;
     // j-indexed with halo offset H: j = -H .. Ny+H
     std::vector<double> phif_, phic_, dxfc_, dxcf_, azcc_, azcf_, fff_;
+    // reciprocals (1.0 / x, correctly rounded) used by the tendency operators: a multiplication by the
+    // precomputed reciprocal replaces each division by a grid metric (<= 1 ulp from the reference's division)
+    std::vector<double> rdxfc_, razcc_, razcf_, rdzc_;
+    double rdy = 0;
     double dy = 0, dlam_rad = 0;
     std::vector<int> kb_;  // (NyP x NxP) first active level per column, Nz = none
     int NxP, NyP;
@@ -164,6 +168,10 @@ struct Oracle {
     inline double azcc(int j) const { return azcc_[j + H]; }
     inline double azcf(int j) const { return azcf_[j + H]; }
     inline double fff(int j) const { return fff_[j + H]; }
+    inline double rdxfc(int j) const { return rdxfc_[j + H]; }
+    inline double razcc(int j) const { return razcc_[j + H]; }
+    inline double razcf(int j) const { return razcf_[j + H]; }
+    inline double rdzc(int k) const { return rdzc_[k + 1]; }
     inline int kb(int i, int j) const { return kb_[(size_t)(j + H) * NxP + (i + H)]; }
 
     // ---- node predicates ---------------------------------------
@@ -235,6 +243,10 @@ struct Oracle {
             azcf_[jj] = c.radius * c.radius * dlam_rad * (sind(pc(j)) - sind(pc(j - 1)));
             fff_[jj] = 2.0 * c.rotation_rate * sind(pf(j));
         }
+        rdxfc_.resize(nj); razcc_.resize(nj); razcf_.resize(nj); rdzc_.resize(Nz + 2);
+        for (int jj = 0; jj < nj; jj++) { rdxfc_[jj] = 1.0 / dxfc_[jj]; razcc_[jj] = 1.0 / azcc_[jj]; razcf_[jj] = 1.0 / azcf_[jj]; }
+        for (int k = 0; k < Nz + 2; k++) rdzc_[k] = 1.0 / dzc_[k];
+        rdy = 1.0 / dy;
         // bathymetry -> first active level (GridFittedBottom, centre condition: zc <= h is solid)
         kb_.assign((size_t)NxP * NyP, Nz);
         const int bh = c.bottom_halo_columns, nxh = Nx + 2 * bh;   // the host may carry a wider halo than H
@@ -493,9 +505,17 @@ struct Oracle {
             case 4: tau = std::fabs(beta[0] + 3 * beta[1] - 3 * beta[2] - beta[3]); break;
             default: tau = std::fabs(beta[0] + 2 * beta[1] - 6 * beta[2] + 2 * beta[3] + beta[4]); break;
         }
+        // Z-weights alpha_s = C_s (1 + (tau / d_s)^2), d_s = beta_s + eps, evaluated division-free after scaling
+        // by P^2, P = prod d_r:  alpha_s P^2 = C_s (P^2 + (tau P_s)^2) with P_s = prod_{r != s} d_r (prefix * suffix).
+        // Algebraically identical to the reference's formula; one division per reconstruction instead of N + 1.
+        double d[5], L[5], R[5];
+        for (int s = 0; s < N; s++) d[s] = beta[s] + WENO_EPS;
+        L[0] = 1.0; for (int s = 0; s < N - 1; s++) L[s + 1] = L[s] * d[s];
+        R[N - 1] = 1.0; for (int s = N - 1; s > 0; s--) R[s - 1] = R[s] * d[s];
+        const double Pt = L[N - 1] * d[N - 1], PP = Pt * Pt;
         for (int s = 0; s < N; s++) {
-            double t = tau / (beta[s] + WENO_EPS);
-            alpha[s] = WENO_OPT[N][s] * std::fma(t, t, 1.0);
+            double t = tau * (L[s] * R[s]);
+            alpha[s] = WENO_OPT[N][s] * std::fma(t, t, PP);
             asum += alpha[s];
             int off = N - 1 - s;
             double ps = 0.0;
@@ -547,7 +567,7 @@ struct Oracle {
         double dxv = (inactive_cfc(i - 1, j, k) || inactive_cfc(i, j, k)) ? 0.0 : dy * v(i, j, k) - dy * v(i - 1, j, k);
         double dyu = (inactive_fcc(i, j - 1, k) || inactive_fcc(i, j, k)) ? 0.0
                                                                           : dxfc(j) * u(i, j, k) - dxfc(j - 1) * u(i, j - 1, k);
-        return (dxv - dyu) / azcf(j);
+        return (dxv - dyu) * razcf(j);
     }
     inline double dxU(int i, int j, int k) const { return dy * dzc(k) * u(i + 1, j, k) - dy * dzc(k) * u(i, j, k); }
     inline double dyV(int i, int j, int k) const {
@@ -562,7 +582,7 @@ struct Oracle {
         // (1) vorticity flux: - upwind(vhat, zetaL, zetaR), WENO(order_vorticity) in y, VelocityStencil
         double qv[2][2];
         for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) qv[a][b] = dxcf(j + b) * v(i - 1 + a, j + b, k);
-        double vhat = 0.5 * (0.5 * (qv[0][0] + qv[0][1]) + 0.5 * (qv[1][0] + qv[1][1])) / dxfc(j);
+        double vhat = 0.5 * (0.5 * (qv[0][0] + qv[0][1]) + 0.5 * (qv[1][0] + qv[1][1])) * rdxfc(j);
         int N = order_faces_y(i, j, k, (c.order_vorticity + 1) / 2);
         double zq[9], us[9], vs[9], zL, zR;
         for (int side = 0; side < 2; side++) {
@@ -593,30 +613,30 @@ struct Oracle {
             double W = 0.5 * (azcc(j) * w(i - 1, j, kf) + azcc(j) * w(i, j, kf));
             return W * 0.5 * (u(i, j, kf - 1) + u(i, j, kf));
         };
-        G -= (Phi + wflux(k + 1) - wflux(k)) / (azcc(j) * dzc(k));
+        G -= (Phi + wflux(k + 1) - wflux(k)) * (razcc(j) * rdzc(k));
         // (3) Bernoulli head, centred
-        G -= (Kh(i, j, k) - Kh(i - 1, j, k)) / dxfc(j);
+        G -= (Kh(i, j, k) - Kh(i - 1, j, k)) * rdxfc(j);
         // (4) Coriolis, ActiveCellEnstrophyConserving: x_f_cross_U = -f * <dx v>_active / dx
         int nact = 0;
         for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) nact += peripheral_cfc(i - 1 + a, j + b, k) ? 0 : 1;
         double fbar = 0.5 * (fff(j) + fff(j + 1));
         double vavg = 0.5 * (0.5 * (qv[0][0] + qv[0][1]) + 0.5 * (qv[1][0] + qv[1][1]));
-        double cor = nact == 0 ? 0.0 : vavg / (0.25 * nact);
-        G += fbar * cor / dxfc(j);
+        double cor = nact == 0 ? 0.0 : nact == 4 ? vavg : vavg / (0.25 * nact);
+        G += fbar * cor * rdxfc(j);
         // (5) hydrostatic pressure gradient
-        G -= (p(i, j, k) - p(i - 1, j, k)) / dxfc(j);
+        G -= (p(i, j, k) - p(i - 1, j, k)) * rdxfc(j);
         // (6) optional QG-Leith horizontal viscosity, vector-invariant form
         if (c.qgleith_enabled) G -= leith_div_tau_u(i, j, k);
         // (7) flux boundary conditions (_apply_z_bcs!)
-        if (k == Nz - 1) G -= top_flux_u(i, j) / dzc(k);
-        if (k == 0) G += bottom_flux_u(i, j) / dzc(k);
+        if (k == Nz - 1) G -= top_flux_u(i, j) * rdzc(k);
+        if (k == 0) G += bottom_flux_u(i, j) * rdzc(k);
         return G;
     }
 
     double tendency_v(int i, int j, int k) const {
         double qu[2][2];
         for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) qu[a][b] = dy * u(i + a, j - 1 + b, k);
-        double uhat = 0.5 * (0.5 * (qu[0][0] + qu[1][0]) + 0.5 * (qu[0][1] + qu[1][1])) / dy;
+        double uhat = 0.5 * (0.5 * (qu[0][0] + qu[1][0]) + 0.5 * (qu[0][1] + qu[1][1])) * rdy;
         int N = order_faces_x(i, j, k, (c.order_vorticity + 1) / 2);
         double zq[9], us[9], vs[9], zL, zR;
         for (int side = 0; side < 2; side++) {
@@ -646,18 +666,18 @@ struct Oracle {
             double W = 0.5 * (azcc(j - 1) * w(i, j - 1, kf) + azcc(j) * w(i, j, kf));
             return W * 0.5 * (v(i, j, kf - 1) + v(i, j, kf));
         };
-        G -= (Phi + wflux(k + 1) - wflux(k)) / (azcf(j) * dzc(k));
-        G -= (Kh(i, j, k) - Kh(i, j - 1, k)) / dy;
+        G -= (Phi + wflux(k + 1) - wflux(k)) * (razcf(j) * rdzc(k));
+        G -= (Kh(i, j, k) - Kh(i, j - 1, k)) * rdy;
         int nact = 0;
         for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) nact += peripheral_fcc(i + a, j - 1 + b, k) ? 0 : 1;
         double fbar = 0.5 * (fff(j) + fff(j));
         double uavg = 0.5 * (0.5 * (qu[0][0] + qu[1][0]) + 0.5 * (qu[0][1] + qu[1][1]));
-        double cor = nact == 0 ? 0.0 : uavg / (0.25 * nact);
-        G -= fbar * cor / dy;
-        G -= (p(i, j, k) - p(i, j - 1, k)) / dy;
+        double cor = nact == 0 ? 0.0 : nact == 4 ? uavg : uavg / (0.25 * nact);
+        G -= fbar * cor * rdy;
+        G -= (p(i, j, k) - p(i, j - 1, k)) * rdy;
         if (c.qgleith_enabled) G -= leith_div_tau_v(i, j, k);
-        if (k == Nz - 1) G -= top_flux_v(i, j) / dzc(k);
-        if (k == 0) G += bottom_flux_v(i, j) / dzc(k);
+        if (k == Nz - 1) G -= top_flux_v(i, j) * rdzc(k);
+        if (k == 0) G += bottom_flux_v(i, j) * rdzc(k);
         return G;
     }
 
@@ -717,9 +737,9 @@ struct Oracle {
             if (imm_peripheral_ccf(i, j, kf)) return 0.0;
             return azcc(j) * w(i, j, kf) * 0.5 * (cfld(i, j, kf - 1) + cfld(i, j, kf));
         };
-        double G = -((flux_x(i + 1) - flux_x(i)) + (flux_y(j + 1) - flux_y(j)) + (flux_z(k + 1) - flux_z(k))) /
-                   (azcc(j) * dzc(k));
-        if (k == Nz - 1) G -= top_flux / dzc(k);
+        double G = -((flux_x(i + 1) - flux_x(i)) + (flux_y(j + 1) - flux_y(j)) + (flux_z(k + 1) - flux_z(k))) *
+                   (razcc(j) * rdzc(k));
+        if (k == Nz - 1) G -= top_flux * rdzc(k);
         return G;
     }
 
