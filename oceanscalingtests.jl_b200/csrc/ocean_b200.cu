@@ -391,8 +391,7 @@ int step_body(ob200_handle* h, double dt, bool euler) {
     int e = 0;
     auto mark = [&]() { if (h->timing) cudaEventRecord(h->ev[e++], h->stream); };
     mark();
-    launch_barotropic_forcing(G, h->F, chi, h->stream);
-    launch_ab2_implicit(G, h->F, dt, chi, h->stream);
+    launch_ab2_implicit(G, h->F, dt, chi, h->stream);   // also produces G^U, G^V (barotropic forcing)
     mark();
     if (int rc = barotropic_loop(h, dt)) return rc;
     mark();
