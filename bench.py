@@ -41,7 +41,7 @@ WORKLOADS = {
 }
 # algorithmic bytes per cell (SURVEY 8d / DESIGN.md): momentum kernel reads u,v,w,p and writes Gu,Gv
 MOMENTUM_BYTES_PER_CELL = 48.0
-GROUP_NAMES = ["ab2_implicit+baro_forcing", "barotropic_substeps", "corrector", "halos", "w_p", "ri_kappa",
+GROUP_NAMES = ["ab2_implicit+baro_forcing", "barotropic_substeps", "corrector", "halos", "w+Ri_sweep", "pHY+kappa_sweep",
                "momentum_tendencies", "tracer_tendencies"]
 
 
@@ -309,7 +309,7 @@ def main():
     local_cells = grid.Nx * Ny * Nz
     mom_ms = groups[6] / args.steps
     achieved = MOMENTUM_BYTES_PER_CELL * local_cells / (mom_ms * 1e-3) / 1e9 if mom_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "k_momentum (fused Gu,Gv tendencies)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_momentum_tiled (fused Gu,Gv tendencies; fast + masked tiles)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": MOMENTUM_BYTES_PER_CELL,
                 "ms_per_launch": mom_ms, "note": "FP64-ALU-bound WENO stencil (SURVEY F10); HBM fraction reported as the contract asks"}

@@ -5,7 +5,7 @@ host-side mirror of the reference's Julia interface (same names and argument mea
 The directory name contains a dot, so import it through `__graft_entry__.package()` (or
 tests/conftest.py), which registers it as the module `ocean_b200`.
 """
-from . import _abi
+from . import _abi, synthetic
 from .bathymetry_and_forcings import (T_reference, cubic_profile, double_drake_bathymetry, exponential_profile,
                                       exponential_z_faces, linear_z_faces, salinity_flux,
                                       salinity_flux_coefficients, wind_stress, wind_stress_coefficients)

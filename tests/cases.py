@@ -35,6 +35,8 @@ class Case:
         lam, phi = g0.lam_c()[None, :], g0.phi_c()[:, None]
         if self.experiment == "Quiescent" and self.bathymetry == "experiment":
             bottom = None
+        elif self.experiment == "RealisticOcean":
+            bottom = pkg.synthetic.realistic_bathymetry(self.Nx, self.Ny, self.depth)
         elif self.bathymetry == "bumpy":
             # smooth seamounts + a continent: exercises k-dependent immersed masks
             bottom = -self.depth * (1.0 - 0.85 * np.exp(-((lam - 40.0) / 25.0) ** 2 - ((phi - 10.0) / 18.0) ** 2)
@@ -53,7 +55,10 @@ class Case:
         max_dt = 3240.0 / res
         nsub = pkg.barotropic_substeps(max_dt, grid)
         fs = pkg.SplitExplicitFreeSurface(substeps=nsub)
-        bcs = pkg.set_boundary_conditions("DoubleDrake" if self.experiment == "DoubleDrake" else "Quiescent", grid)
+        if self.experiment == "RealisticOcean":
+            bcs = pkg.set_boundary_conditions("RealisticOcean", grid, forcing_arrays=pkg.synthetic.forcing_arrays(grid))
+        else:
+            bcs = pkg.set_boundary_conditions("DoubleDrake" if self.experiment == "DoubleDrake" else "Quiescent", grid)
         closure = (pkg.VerticalScalarDiffusivity(), pkg.RiBasedVerticalDiffusivity())
         if self.qgleith:
             closure = closure + (pkg.QGLeith(),)
@@ -66,6 +71,14 @@ class Case:
         return model
 
     def initialize(self, pkg, model):
+        if self.experiment == "RealisticOcean":
+            T0, S0 = pkg.synthetic.initial_T_S(model.grid)
+            r = math.pi / 180.0
+            pkg.set_model(model, T=T0, S=S0,
+                          u=lambda lam, phi, z: 0.05 * np.sin(2 * lam * r) * np.cos(phi * r) * np.exp(z / 2000.0),
+                          v=lambda lam, phi, z: 0.03 * np.cos(3 * lam * r) * np.sin(2 * phi * r) * np.exp(z / 1000.0))
+            model.backend.set_clock(1.7 * 86400.0, 0, float("inf"))   # mid-interval: exercises the time interpolation
+            return
         if self.experiment == "DoubleDrake":
             pkg.initialize_model(model, "DoubleDrake")
         if not self.perturb:
@@ -99,6 +112,9 @@ CASES = {
     "dd_mid": Case("dd_mid", 180, 75, 12, dt=1200.0),
     "dd_leith": Case("dd_leith", 90, 40, 8, dt=1200.0, qgleith=True),
     "bumpy": Case("bumpy", 96, 48, 12, dt=900.0, bathymetry="bumpy"),
+    # RealisticOcean-shaped (BASELINE configs[3]): TEOS-10, synthetic continents, time-interpolated fluxes +
+    # restoring, quadratic bottom drag
+    "realistic": Case("realistic", 96, 48, 12, experiment="RealisticOcean", dt=600.0, depth=5244.5),
     "quiescent": Case("quiescent", 90, 40, 8, experiment="Quiescent", dt=3240.0, perturb=False),
     # C1: BASELINE.json configs[0]
     "c1": Case("c1", 360, 150, 10, experiment="Quiescent", dt=3240.0, perturb=False),
