@@ -200,6 +200,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
+    # the driver parses ONE JSON line from stdout: keep library chatter (e.g. "NCCL version ...") off it
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -244,14 +247,16 @@ def main():
             torch.cuda.synchronize()
 
     upload()
+    # clocks / throttle reasons are sampled from the warm-up through the end of the timed region (the timed region
+    # alone can be shorter than one nvidia-smi period on 8 GPUs; the load is the same in both)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         pkg.time_step(model, dt)
     barrier()
 
     # ---- timed region: K steps, state resident in HBM -------------------------------------------------
     model.backend.set_option("timing", 1)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     groups = np.zeros(len(GROUP_NAMES))
     _, launches0 = model.backend.timing()
     barrier()
@@ -271,6 +276,11 @@ def main():
         t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
+    per_rank_groups = None
+    if world > 1:
+        gl = [None] * world
+        dist.all_gather_object(gl, [float(g / args.steps) for g in groups])
+        per_rank_groups = gl
     mx, _ = model.backend.diagnostics()
     if not all(np.isfinite(mx)) or mx[0] > 10.0:
         raise SystemExit(f"bench.py: the run blew up (max-abs {mx})")
@@ -304,6 +314,8 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
 
     peak, peak_src = measured_peak()
     local_cells = grid.Nx * Ny * Nz
@@ -323,6 +335,8 @@ def main():
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches1 - launches0),
            "stage_ms": {n: float(g / args.steps) for n, g in zip(GROUP_NAMES, groups)},
            "roofline": roofline}
+    if per_rank_groups is not None:
+        out["stage_ms_per_rank"] = [[round(x, 3) for x in r] for r in per_rank_groups]
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample(pkg, args)
     print(json.dumps(out), flush=True)

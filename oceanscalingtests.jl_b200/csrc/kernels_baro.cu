@@ -98,16 +98,24 @@ void launch_baro_finish(const Geom& G, const Fields& F, cudaStream_t st) {
 // ---- persistent variant: all substeps in one cooperative launch --------------------------------------
 __global__ void __launch_bounds__(256) k_baro_persistent(Geom G, Fields F, double dtau, const double* __restrict__ wts,
                                                           int M, bool periodic, int ex) {
+    // rows are dealt to warps, columns to lanes: no integer division in the substep loop, coalesced rows
     cg::grid_group grid = cg::this_grid();
-    const int nxe = G.Nx + 2 * ex;
-    const long long n = (long long)nxe * G.Ny;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nth = (long long)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int xchunks = (G.Nx + 2 * ex + 255) / 256;           // a warp sweeps 256 columns of one row at a time
+    const int nitems = G.Ny * xchunks;
     for (int m = 0; m < M; m++) {
-        for (long long t = tid; t < n; t += nth) eta_update(G, F, (int)(t % nxe) - ex, (int)(t / nxe), dtau, periodic);
+        for (int it = warp; it < nitems; it += nwarps) {
+            const int j = it / xchunks, i0 = (it - j * xchunks) * 256 - ex;
+            for (int i = i0 + lane; i < min(i0 + 256, G.Nx + ex); i += 32) eta_update(G, F, i, j, dtau, periodic);
+        }
         grid.sync();
         const double wgt = wts[m];
-        for (long long t = tid; t < n; t += nth) vel_update(G, F, (int)(t % nxe) - ex, (int)(t / nxe), dtau, wgt, periodic);
+        for (int it = warp; it < nitems; it += nwarps) {
+            const int j = it / xchunks, i0 = (it - j * xchunks) * 256 - ex;
+            for (int i = i0 + lane; i < min(i0 + 256, G.Nx + ex); i += 32) vel_update(G, F, i, j, dtau, wgt, periodic);
+        }
         grid.sync();
     }
 }
@@ -120,7 +128,7 @@ int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const do
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_baro_persistent, 256, 0);
-        nblk = sms * (per > 4 ? 4 : per);
+        nblk = sms * per;
     }
     Geom g = G; Fields f = F;
     void* args[] = {&g, &f, &dtau, &wts, &M, &periodic, &ex};

@@ -481,6 +481,10 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : MOM_MINB) k_momentum_tiled(
             if (!GEN) {
                 F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time);
                 F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time);
+            } else if (k >= __ldg(&G.kfast[idx2(G, i, j)])) {
+                // most cells of a masked tile are still far from any boundary: full-order, check-free path
+                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time);
+                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time);
             } else {
                 F.Gu[c] = peripheral_fcc(G, i, j, k) ? 0.0 : tend_u<true>(G, F, M, i, j, k, NV, ND, time);
                 F.Gv[c] = peripheral_cfc(G, i, j, k) ? 0.0 : tend_v<true>(G, F, M, i, j, k, NV, ND, time);
