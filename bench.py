@@ -41,8 +41,9 @@ WORKLOADS = {
 }
 # algorithmic bytes per cell (SURVEY 8d / DESIGN.md): momentum kernel reads u,v,w,p and writes Gu,Gv
 MOMENTUM_BYTES_PER_CELL = 48.0
+# stage groups of ob200_timing (include/ocean_b200.h); group 8 is the T,S part of group 0
 GROUP_NAMES = ["ab2_implicit+baro_forcing", "barotropic_substeps", "corrector", "halos", "w+Ri_sweep", "pHY+kappa_sweep",
-               "momentum_tendencies", "tracer_tendencies"]
+               "momentum_tendencies", "tracer_tendencies", "TS_solve(part_of_ab2_implicit)"]
 
 
 def measured_peak():
@@ -223,6 +224,8 @@ def main():
                                             device=local_rank, comm=pkg.Comm())
     if args.persistent_barotropic:
         model.backend.set_option("persistent_barotropic", 1)
+    if os.environ.get("OB200_OVERLAP", "0") == "1":
+        model.backend.set_option("overlap", 1)
     state = initial_state(pkg, case, grid)
     # pinned host copies of the initial state (what a host application owns)
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in state.items()}

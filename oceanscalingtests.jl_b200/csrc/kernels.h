@@ -7,7 +7,7 @@ extern long long ob_launch_count;   // kernels launched by this library (bench.p
 
 struct Fields {
     // 3-D (Nz+1 planes)
-    double *u, *v, *w, *T, *S, *p, *kc, *ku, *Ri, *scratch;
+    double *u, *v, *w, *T, *S, *p, *kc, *ku, *Ri, *scratch, *scratch2;
     double *Gu, *Gv, *GT, *GS, *Gu0, *Gv0, *GT0, *GS0;
     double *nuL, *qx, *qy;
     // 2-D
@@ -31,7 +31,9 @@ void launch_diagnostics(const Geom& G, const Fields& F, double* out8, cudaStream
 void launch_w_p(const Geom& G, const Fields& F, cudaStream_t st);
 void launch_ri_kappa(const Geom& G, const Fields& F, double time, cudaStream_t st);
 void launch_barotropic_forcing(const Geom& G, const Fields& F, double chi, cudaStream_t st);
-void launch_ab2_implicit(const Geom& G, const Fields& F, double dt, double chi, cudaStream_t st);
+// momentum (u, v: also G^U, G^V) and tracer (T, S) solves can run on different streams (separate scratch arrays)
+void launch_ab2_implicit_uv(const Geom& G, const Fields& F, double dt, double chi, cudaStream_t st);
+void launch_ab2_implicit_ts(const Geom& G, const Fields& F, double dt, double chi, cudaStream_t st);
 void launch_correct(const Geom& G, const Fields& F, cudaStream_t st);
 
 // kernels_baro.cu

@@ -30,7 +30,10 @@ struct ob200_handle {
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     cudaEvent_t ev[20];
     cudaEvent_t ev_comm[2];
-    bool timing = false, use_graph = false, persistent_baro = false;
+    bool timing = false, use_graph = false, persistent_baro = false, overlap = false;
+    cudaStream_t stream2 = nullptr;            // tracer work that can overlap the momentum / barotropic chain
+    cudaEvent_t ev_join[4];                    // step start, T/S solved, w ready, tracer tendencies done
+    cudaEvent_t ev2[4];                        // timing events on stream2
     float last_ms[16];
     int n_timed = 0;
     std::vector<void*> allocs;
@@ -243,7 +246,7 @@ int alloc_fields(ob200_handle* h) {
     Fields& F = h->F;
     std::memset(&F, 0, sizeof(F));
     const size_t n3 = (size_t)G.sz * (G.Nz + 1), n2 = (size_t)G.sz;
-    double** f3[] = {&F.u, &F.v, &F.w, &F.T, &F.S, &F.p, &F.kc, &F.ku, &F.Ri, &F.scratch,
+    double** f3[] = {&F.u, &F.v, &F.w, &F.T, &F.S, &F.p, &F.kc, &F.ku, &F.Ri, &F.scratch, &F.scratch2,
                      &F.Gu, &F.Gv, &F.GT, &F.GS, &F.Gu0, &F.Gv0, &F.GT0, &F.GS0};
     for (double** p : f3)
         if (int rc = dev_alloc(h, p, n3)) return rc;
@@ -381,35 +384,94 @@ int barotropic_loop(ob200_handle* h, double dt) {
     return OB200_OK;
 }
 
+// One time step.  Two streams: the tracer chain (AB2 + implicit solve of T, S; later the T, S
+// tendencies) is independent of the momentum / barotropic chain until the halo exchange, and the FP64-bound
+// tracer tendencies overlap the HBM-bound pHY' + kappa sweep.  Joined by events; ob200_sync waits for both.
+int step_body_serial(ob200_handle* h, double dt, bool euler);
+
 int step_body(ob200_handle* h, double dt, bool euler) {
+    if (!h->overlap) return step_body_serial(h, dt, euler);
     const double chi = euler ? -0.5 : h->cfg.ab2_chi;
     const Geom& G = h->G;
+    cudaStream_t s1 = h->stream, s2 = h->stream2;
     if (euler) {
         const size_t n3 = (size_t)G.sz * (G.Nz + 1) * sizeof(double);
-        for (double* g : {h->F.Gu0, h->F.Gv0, h->F.GT0, h->F.GS0}) cudaMemsetAsync(g, 0, n3, h->stream);
+        for (double* g : {h->F.Gu0, h->F.Gv0, h->F.GT0, h->F.GS0}) cudaMemsetAsync(g, 0, n3, s1);
     }
     int e = 0;
-    auto mark = [&]() { if (h->timing) cudaEventRecord(h->ev[e++], h->stream); };
+    auto mark = [&]() { if (h->timing) cudaEventRecord(h->ev[e++], s1); };
+    auto mark2 = [&](int q) { if (h->timing) cudaEventRecord(h->ev2[q], s2); };
+    if (h->overlap) { cudaEventRecord(h->ev_join[0], s1); cudaStreamWaitEvent(s2, h->ev_join[0], 0); }
+    mark2(0);
+    launch_ab2_implicit_ts(G, h->F, dt, chi, s2);
+    mark2(1);
+    if (h->overlap) cudaEventRecord(h->ev_join[1], s2);
     mark();
-    launch_ab2_implicit(G, h->F, dt, chi, h->stream);   // also produces G^U, G^V (barotropic forcing)
+    launch_ab2_implicit_uv(G, h->F, dt, chi, s1);   // also produces G^U, G^V (barotropic forcing)
     mark();
     if (int rc = barotropic_loop(h, dt)) return rc;
     mark();
-    launch_correct(G, h->F, h->stream);
+    launch_correct(G, h->F, s1);
+    swap_tendencies(h);
+    mark();
+    h->time += dt; h->iteration += 1; h->last_dt = dt;
+    if (h->overlap) cudaStreamWaitEvent(s1, h->ev_join[1], 0);   // halos need the new T, S
+    if (int rc = mask_and_halos(h)) return rc;
+    mark();
+    launch_w_p(G, h->F, s1);
+    if (h->overlap) { cudaEventRecord(h->ev_join[2], s1); cudaStreamWaitEvent(s2, h->ev_join[2], 0); }
+    mark2(2);
+    launch_tracers(G, h->F, h->mom_plan, h->cfg.order_tracer, h->time, s2);
+    mark2(3);
+    if (h->overlap) cudaEventRecord(h->ev_join[3], s2);
+    mark();
+    launch_ri_kappa(G, h->F, h->time, s1);
+    if (G.qgleith) launch_leith(G, h->F, s1);
+    mark();
+    launch_momentum(G, h->F, h->mom_plan, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, s1);
+    mark();
+    if (h->overlap) cudaStreamWaitEvent(s1, h->ev_join[3], 0);   // the step ends when both chains have finished
+    h->n_timed = e - 1;
+    return OB200_OK;
+}
+
+// Default: everything on one stream, in the reference's order.  (Measured on B200 at C3: the two-stream variant
+// above gives no gain -- 64.2 vs 64.2 ms/step -- because the FP64-bound tendency kernels occupy every SM's
+// register file, so the HBM-bound sweeps cannot co-reside; it is kept behind option "overlap".)
+int step_body_serial(ob200_handle* h, double dt, bool euler) {
+    const double chi = euler ? -0.5 : h->cfg.ab2_chi;
+    const Geom& G = h->G;
+    cudaStream_t s1 = h->stream;
+    if (euler) {
+        const size_t n3 = (size_t)G.sz * (G.Nz + 1) * sizeof(double);
+        for (double* g : {h->F.Gu0, h->F.Gv0, h->F.GT0, h->F.GS0}) cudaMemsetAsync(g, 0, n3, s1);
+    }
+    int e = 0;
+    auto mark = [&]() { if (h->timing) cudaEventRecord(h->ev[e++], s1); };
+    if (h->timing) cudaEventRecord(h->ev2[0], s1);
+    launch_ab2_implicit_ts(G, h->F, dt, chi, s1);
+    if (h->timing) cudaEventRecord(h->ev2[1], s1);
+    mark();
+    launch_ab2_implicit_uv(G, h->F, dt, chi, s1);   // also produces G^U, G^V (barotropic forcing)
+    mark();
+    if (int rc = barotropic_loop(h, dt)) return rc;
+    mark();
+    launch_correct(G, h->F, s1);
     swap_tendencies(h);
     mark();
     h->time += dt; h->iteration += 1; h->last_dt = dt;
     if (int rc = mask_and_halos(h)) return rc;
     mark();
-    launch_w_p(G, h->F, h->stream);
+    launch_w_p(G, h->F, s1);
     mark();
-    launch_ri_kappa(G, h->F, h->time, h->stream);
-    if (G.qgleith) launch_leith(G, h->F, h->stream);
+    launch_ri_kappa(G, h->F, h->time, s1);
+    if (G.qgleith) launch_leith(G, h->F, s1);
     mark();
-    launch_momentum(G, h->F, h->mom_plan, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, h->stream);
+    launch_momentum(G, h->F, h->mom_plan, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, s1);
     mark();
-    launch_tracers(G, h->F, h->mom_plan, h->cfg.order_tracer, h->time, h->stream);
-    mark();
+    if (h->timing) cudaEventRecord(h->ev2[2], s1);
+    launch_tracers(G, h->F, h->mom_plan, h->cfg.order_tracer, h->time, s1);
+    if (h->timing) cudaEventRecord(h->ev2[3], s1);
     h->n_timed = e - 1;
     return OB200_OK;
 }
@@ -453,7 +515,10 @@ int ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out) {
     cudaMemcpy(h->d_weights, h->weights.data(), cfg->n_substeps * sizeof(double), cudaMemcpyHostToDevice);
     h->cfg.z_faces = nullptr; h->cfg.bottom_height = nullptr; h->cfg.averaging_weights = nullptr;  // borrowed only during create
     cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     for (auto& ev : h->ev) cudaEventCreate(&ev);
+    for (auto& ev : h->ev2) cudaEventCreate(&ev);
+    for (auto& ev : h->ev_join) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) { g_last_error = std::string("setup kernels: ") + cudaGetErrorString(e); ob200_destroy(h); return OB200_ECUDA; }
     *out = h;
@@ -468,6 +533,9 @@ void ob200_destroy(ob200_handle* h) {
     if (h->comm) ncclCommDestroy(h->comm);
     for (void* p : h->allocs) cudaFree(p);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->ev2) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->ev_join) if (ev) cudaEventDestroy(ev);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -552,7 +620,10 @@ int ob200_run_stage(ob200_handle* h, int32_t stage, double dt, int32_t arg) {
     int rc = OB200_OK;
     switch (stage) {
         case OB200_ST_BAROTROPIC_FORCING: launch_barotropic_forcing(h->G, h->F, chi, h->stream); break;
-        case OB200_ST_AB2_IMPLICIT: launch_ab2_implicit(h->G, h->F, dt, chi, h->stream); break;
+        case OB200_ST_AB2_IMPLICIT:
+            launch_ab2_implicit_uv(h->G, h->F, dt, chi, h->stream);
+            launch_ab2_implicit_ts(h->G, h->F, dt, chi, h->stream);
+            break;
         case OB200_ST_BAROTROPIC_INIT: launch_baro_init(h->G, h->F, h->periodic_local, 0, h->stream); break;
         case OB200_ST_BAROTROPIC_ETA: launch_baro_eta(h->G, h->F, dtau, h->periodic_local, 0, h->stream); break;
         case OB200_ST_BAROTROPIC_VEL:
@@ -615,8 +686,15 @@ int ob200_get_timing(ob200_handle* h, ob200_timing* t) {
     t->launches = ob_launch_count;
     if (!h->timing || h->n_timed <= 0) return OB200_OK;
     OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
-    for (int q = 0; q < h->n_timed && q < 16; q++) cudaEventElapsedTime(&t->ms[q], h->ev[q], h->ev[q + 1]);
-    t->n = h->n_timed;
+    // stream-1 marks: ab2(u,v) | barotropic | corrector | halos | w+Ri | pHY'+kappa | momentum ; stream 2: T,S solve, tracers
+    float g[8] = {0};
+    for (int q = 0; q < 7 && q < h->n_timed; q++) cudaEventElapsedTime(&g[q], h->ev[q], h->ev[q + 1]);
+    float ts = 0, tr = 0;
+    cudaEventElapsedTime(&ts, h->ev2[0], h->ev2[1]);
+    cudaEventElapsedTime(&tr, h->ev2[2], h->ev2[3]);
+    t->ms[0] = g[0] + ts; t->ms[1] = g[1]; t->ms[2] = g[2]; t->ms[3] = g[3]; t->ms[4] = g[4]; t->ms[5] = g[5];
+    t->ms[6] = g[6]; t->ms[7] = tr; t->ms[8] = ts;
+    t->n = 9;
     return OB200_OK;
 }
 
@@ -634,6 +712,7 @@ int ob200_set_option(ob200_handle* h, const char* name, int32_t value) {
     if (!h || !name) return OB200_EINVAL;
     if (!std::strcmp(name, "timing")) h->timing = value != 0;
     else if (!std::strcmp(name, "persistent_barotropic")) h->persistent_baro = value != 0;
+    else if (!std::strcmp(name, "overlap")) h->overlap = value != 0;
     else return h->fail(OB200_EINVAL, "option", name);
     return OB200_OK;
 }
