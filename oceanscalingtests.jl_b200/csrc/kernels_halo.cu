@@ -138,27 +138,38 @@ void launch_unpack_x(const Geom& G, const Fields& F, const double* recvW, const 
 __device__ __forceinline__ void atomic_max_pos(double* addr, double v) {   // v >= 0
     atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
 }
-__global__ void k_diag(Geom G, Fields F, double* out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y, k = blockIdx.z;
+__global__ void __launch_bounds__(256) k_diag(Geom G, Fields F, double* out) {
+    // one block per (row j, level-chunk): threads stride over i and 8 levels, then one atomic per block and quantity
+    __shared__ double red[7][8];
+    const int j = blockIdx.y, k0 = blockIdx.z * 8;
     double m[7] = {0, 0, 0, 0, 0, 0, 0};
-    if (i < G.Nx) {
-        const long long c = idx3(G, i, j, k);
-        m[0] = fabs(F.u[c]); m[1] = fabs(F.v[c]); m[2] = fmax(fabs(F.w[c]), k == G.Nz - 1 ? fabs(F.w[c + G.sz]) : 0.0);
-        m[3] = (k == 0) ? fabs(F.eta[idx2b(G, i, j)]) : 0.0;
-        m[4] = fabs(F.T[c]); m[5] = fabs(F.S[c]);
-        // 1 / cell advection time scale: |u|/dx + |v|/dy + |w|/dz
-        m[6] = m[0] / G.dxfc[j] + m[1] / G.dy + fabs(F.w[c]) / G.dzc[k];
-    }
+    for (int k = k0; k < min(k0 + 8, G.Nz); k++)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < G.Nx; i += gridDim.x * blockDim.x) {
+            const long long c = idx3(G, i, j, k);
+            const double au = fabs(F.u[c]), av = fabs(F.v[c]), aw = fabs(F.w[c]);
+            m[0] = fmax(m[0], au); m[1] = fmax(m[1], av);
+            m[2] = fmax(m[2], fmax(aw, k == G.Nz - 1 ? fabs(F.w[c + G.sz]) : 0.0));
+            if (k == 0) m[3] = fmax(m[3], fabs(F.eta[idx2b(G, i, j)]));
+            m[4] = fmax(m[4], fabs(F.T[c])); m[5] = fmax(m[5], fabs(F.S[c]));
+            // 1 / cell advection time scale: |u|/dx + |v|/dy + |w|/dz
+            m[6] = fmax(m[6], au / G.dxfc[j] + av / G.dy + aw / G.dzc[k]);
+        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int q = 0; q < 7; q++) {
         double v = m[q];
         for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if ((threadIdx.x & 31) == 0 && v > 0.0) atomic_max_pos(out + q, v);
+        if (lane == 0) red[q][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double v = 0.0;
+        for (int w = 0; w < 8; w++) v = fmax(v, red[threadIdx.x][w]);
+        if (v > 0.0) atomic_max_pos(out + threadIdx.x, v);
     }
 }
 void launch_diagnostics(const Geom& G, const Fields& F, double* out8, cudaStream_t st) {
     cudaMemsetAsync(out8, 0, 8 * sizeof(double), st);
-    dim3 b(128), g((G.Nx + 127) / 128, G.Ny, G.Nz);
+    dim3 b(256), g(2, G.Ny, (G.Nz + 7) / 8);
     k_diag<<<g, b, 0, st>>>(G, F, out8);
     OB_COUNT_LAUNCH(1);
 }

@@ -390,10 +390,10 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
 //   GEN = true : the remaining (tile, level) pairs near ridges, walls and the sea floor: conditional zeta,
 //                per-reconstruction order reduction, masked outputs.
 #ifndef MOM_MINB
-#define MOM_MINB 3
+#define MOM_MINB 4
 #endif
 #ifndef TRC_MINB
-#define TRC_MINB 2
+#define TRC_MINB 3
 #endif
 template <int TX, int TY, bool GEN>
 __global__ void __launch_bounds__(TX * TY, GEN ? 2 : MOM_MINB) k_momentum_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,

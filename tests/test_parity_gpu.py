@@ -116,3 +116,24 @@ def test_persistent_barotropic_matches_launch_loop(pkg, gpu_lib):
         pkg.time_step(m2, c.dt)
     for n in PROG:
         assert np.array_equal(m1.get(n), m2.get(n)), n
+
+
+def test_diagnostics_and_wizard_run(pkg, gpu_lib):
+    """ob200_diagnostics (progress max-abs + CFL time scale) against numpy, and the TimeStepWizard loop of `run`."""
+    c = cases.build_case("dd_small")
+    m = c.make_model(pkg, None)
+    for _ in range(3):
+        pkg.time_step(m, c.dt)
+    mx, cfl_dt = m.backend.diagnostics()
+    for q, n in enumerate(("U", "V", "W", "ETA", "T", "S")):
+        assert mx[q] == float(np.max(np.abs(m.get(n)))), n
+    g = m.grid
+    u, v, w = m.get("U"), m.get("V")[:, :-1, :], m.get("W")[:-1]
+    dx = (g.radius * np.cos(np.pi * g.phi_c() / 180) * (g.dlam * np.pi / 180))[None, :, None]
+    dz = np.diff(g.z_faces)[:, None, None]
+    rate = np.abs(u) / dx + np.abs(v) / g.minimum_yspacing() + np.abs(w) / dz
+    assert abs(cfl_dt - 1.0 / rate.max()) <= 1e-12 * cfl_dt
+    sim = pkg.Simulation(m, dt=5.0, stop_time=1e9, max_dt=2000.0, min_dt=5.0, stop_iteration=m.clock["iteration"] + 25)
+    pkg.run(sim)
+    assert m.clock["iteration"] == 28 and 5.0 < sim.dt <= 2000.0      # the wizard grew the step (max_change 1.1)
+    assert np.all(np.isfinite(m.get("U")))
