@@ -224,6 +224,8 @@ def main():
                                             device=local_rank, comm=pkg.Comm())
     if args.persistent_barotropic:
         model.backend.set_option("persistent_barotropic", 1)
+    if os.environ.get("OB200_BARO_GRAPH", "1") == "0":
+        model.backend.set_option("barotropic_graph", 0)
     if os.environ.get("OB200_OVERLAP", "0") == "1":
         model.backend.set_option("overlap", 1)
     state = initial_state(pkg, case, grid)

@@ -30,7 +30,7 @@ struct ob200_handle {
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     cudaEvent_t ev[20];
     cudaEvent_t ev_comm[2];
-    bool timing = false, use_graph = false, persistent_baro = false, overlap = false;
+    bool timing = false, use_graph = true, persistent_baro = false, overlap = false;
     cudaStream_t stream2 = nullptr;            // tracer work that can overlap the momentum / barotropic chain
     cudaEvent_t ev_join[4];                    // step start, T/S solved, w ready, tracer tendencies done
     cudaEvent_t ev2[4];                        // timing events on stream2
@@ -374,6 +374,28 @@ int barotropic_loop(ob200_handle* h, double dt) {
     if (h->persistent_baro) {
         if (launch_baro_persistent(h->G, h->F, dtau, h->d_weights, h->cfg.n_substeps, per, ex, h->stream) != 0)
             return h->fail(OB200_ECUDA, "cooperative launch", cudaGetErrorString(cudaGetLastError()));
+    } else if (h->use_graph) {
+        // the 2 M tiny launches are launch-rate-bound on narrow slabs: replay them as one CUDA graph (re-captured
+        // when dt changes; all kernel arguments are baked in)
+        if (!h->graph_exec || h->graph_dt != dt) {
+            if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            const long long before = ob_launch_count;
+            OB_CUDA_CHECK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            for (int m = 0; m < h->cfg.n_substeps; m++) {
+                launch_baro_eta(h->G, h->F, dtau, per, ex, h->stream);
+                launch_baro_vel(h->G, h->F, dtau, h->weights[m], per, ex, h->stream);
+            }
+            launch_baro_finish(h->G, h->F, h->stream);
+            OB_CUDA_CHECK(h, cudaStreamEndCapture(h->stream, &graph));
+            ob_launch_count = before;   // capture enqueues nothing
+            OB_CUDA_CHECK(h, cudaGraphInstantiate(&h->graph_exec, graph, 0));
+            cudaGraphDestroy(graph);
+            h->graph_dt = dt;
+        }
+        OB_CUDA_CHECK(h, cudaGraphLaunch(h->graph_exec, h->stream));
+        OB_COUNT_LAUNCH(2 * h->cfg.n_substeps + 1);
+        return OB200_OK;
     } else {
         for (int m = 0; m < h->cfg.n_substeps; m++) {
             launch_baro_eta(h->G, h->F, dtau, per, ex, h->stream);
@@ -713,6 +735,7 @@ int ob200_set_option(ob200_handle* h, const char* name, int32_t value) {
     if (!std::strcmp(name, "timing")) h->timing = value != 0;
     else if (!std::strcmp(name, "persistent_barotropic")) h->persistent_baro = value != 0;
     else if (!std::strcmp(name, "overlap")) h->overlap = value != 0;
+    else if (!std::strcmp(name, "barotropic_graph")) h->use_graph = value != 0;
     else return h->fail(OB200_EINVAL, "option", name);
     return OB200_OK;
 }
