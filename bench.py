@@ -148,7 +148,8 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": "grid-cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps * (Nx / sector),
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"DoubleDrake {Nx}x{Ny}x{Nz} dt={dt:g}s (CPU: bounded sample, ms_per_step extrapolated to the full grid)"},
+           "config": {"workload": f"DoubleDrake {Nx}x{Ny}x{Nz} dt={dt:g}s",
+                      "note": "CPU oracle on a bounded sample of the workload; ms_per_step extrapolated to the full grid"},
            "sypd": dt / (el / args.steps * (Nx / sector)) / 365.0,
            "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -333,7 +334,8 @@ def main():
     out = {"metric": "grid-cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"DoubleDrake {Nx}x{Ny}x{Nz} dt={dt:g}s, {fs.substeps}->{len(fs.averaging_weights)} barotropic substeps",
+           "config": {"workload": f"DoubleDrake {Nx}x{Ny}x{Nz} dt={dt:g}s",
+                      "barotropic_substeps": f"{fs.substeps}->{len(fs.averaging_weights)}",
                       "partition": f"x-slabs {list(grid.partition.sizes)}",
                       "l2": "inputs (44 GB of fields per step at 1 GPU) exceed the 126 MB L2; no flush needed"},
            "sypd": dt / (elapsed / args.steps) / 365.0,
