@@ -16,7 +16,7 @@ __device__ __forceinline__ double b_at(const Geom& G, const Fields& F, int i, in
 }
 __device__ __forceinline__ double dzb(const Geom& G, const Fields& F, int i, int j, int k) {
     if (!active(G, i, j, k - 1) || !active(G, i, j, k)) return 0.0;
-    return (b_at(G, F, i, j, k) - b_at(G, F, i, j, k - 1)) / G.dzf[k];
+    return (b_at(G, F, i, j, k) - b_at(G, F, i, j, k - 1)) * G.rdzf[k];
 }
 __device__ __forceinline__ double dxb(const Geom& G, const Fields& F, int i, int j, int k) {
     if (!active(G, i - 1, j, k) || !active(G, i, j, k)) return 0.0;
@@ -28,7 +28,7 @@ __device__ __forceinline__ double dyb(const Geom& G, const Fields& F, int i, int
 }
 __device__ __forceinline__ double divxy(const Geom& G, const Fields& F, int i, int j, int k) {
     const long long c = idx3(G, i, j, k);
-    return (G.dy * F.u[c + 1] - G.dy * F.u[c] + G.dxcf[j + 1] * F.v[c + G.pitch] - G.dxcf[j] * F.v[c]) / G.azcc[j];
+    return (G.dy * F.u[c + 1] - G.dy * F.u[c] + G.dxcf[j + 1] * F.v[c + G.pitch] - G.dxcf[j] * F.v[c]) * G.razcc[j];
 }
 __device__ __forceinline__ double zeta_c(const Geom& G, const Fields& F, int i, int j, int k) {
     const long long c = idx3(G, i, j, k);

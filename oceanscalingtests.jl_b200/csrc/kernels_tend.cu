@@ -48,6 +48,10 @@ struct MomG {
         const double a = u[c], b = u[c + 1], cc = v[c], d = v[c + G.pitch];
         return (0.5 * (a * a + b * b) + 0.5 * (cc * cc + d * d)) / 2.0;
     }
+    __device__ __forceinline__ double divxy(int i, int j, int k) const {   // horizontal divergence at ccc
+        const long long c = idx3(G, i, j, k);
+        return (G.dy * u[c + 1] - G.dy * u[c] + G.dxcf[j + 1] * v[c + G.pitch] - G.dxcf[j] * v[c]) * G.razcc[j];
+    }
 };
 
 // shared-memory tile geometry for the fast path (TX x TY cells per block)
@@ -267,7 +271,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
     if (G.qgleith) {
         const MomG Mg{G, F.u, F.v};
         const double ax = G.dy * G.dzc[k];
-        auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * ((Mg.dxU(a, b, k) / G.dzc[k] + Mg.dyV(a, b, k) / G.dzc[k]) / G.azcc[b]) : 0.0; };
+        auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * Mg.divxy(a, b, k) : 0.0; };
         auto fffc = [&](int a, int b) {
             const bool per = !active(G, a - 1, b - 1, k) || !active(G, a, b - 1, k) || !active(G, a - 1, b, k) || !active(G, a, b, k);
             if (per && in_domain(G, b - 1, k) && in_domain(G, b, k)) return 0.0;
@@ -357,7 +361,7 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
     if (G.qgleith) {
         const MomG Mg{G, F.u, F.v};
         const double ax = dy * G.dzc[k];
-        auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * ((Mg.dxU(a, b, k) / G.dzc[k] + Mg.dyV(a, b, k) / G.dzc[k]) / G.azcc[b]) : 0.0; };
+        auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * Mg.divxy(a, b, k) : 0.0; };
         auto fffc = [&](int a, int b) {
             const bool per = !active(G, a - 1, b - 1, k) || !active(G, a, b - 1, k) || !active(G, a - 1, b, k) || !active(G, a, b, k);
             if (per && in_domain(G, b - 1, k) && in_domain(G, b, k)) return 0.0;

@@ -24,7 +24,7 @@ struct Geom {
     const double *dxfc, *dxcf, *azcc, *azcf, *fff, *taux, *sflux, *tref;
     const double *rdxfc, *razcc, *razcf;   // reciprocals used by the tendency kernels (DESIGN.md spec decision 8)
     // vertical metrics: dzc[k], zc[k] for k = -1..Nz (pre-offset), dzf[k] for k = 0..Nz
-    const double *dzc, *dzf, *zc, *rdzc;
+    const double *dzc, *dzf, *zc, *rdzc, *rdzf, *rupz, *rloz;   // rupz[k] = 1/(dzc[k] dzf[k+1]), rloz[k] = 1/(dzc[k] dzf[k])
     const int* kb;           // first active level per column (2-D, field layout); Nz = no active cell
     const int* kfast;        // level from which the full-order, mask-free stencils are valid (2-D)
     double dy, rdy;
@@ -32,7 +32,7 @@ struct Geom {
     int eos;
     double nu_z, kappa_z;
     int ri_enabled;
-    double ri_nu0, ri_kappa0, ri_kappa_ca, ri_Cen, ri_Cav, ri_Ri0, ri_Ridelta;
+    double ri_nu0, ri_kappa0, ri_kappa_ca, ri_Cen, ri_Cav, ri_Ri0, ri_Ridelta, r1cav, rRidelta;
     int bc_kind;
     double lambda_T, mu_drag;
     int qgleith;

@@ -143,6 +143,18 @@ int setup_geometry(ob200_handle* h) {
     if (int rc = dev_alloc(h, &rdzc_d, Nz + 2, false)) return rc;
     cudaMemcpy(rdzc_d, rdzc.data(), (Nz + 2) * sizeof(double), cudaMemcpyHostToDevice);
     G.rdzc = rdzc_d + 1;
+    {
+        std::vector<double> rdzf(Nz + 1), rupz(Nz + 1, 0.0), rloz(Nz + 1, 0.0);
+        for (int k = 0; k <= Nz; k++) rdzf[k] = 1.0 / dzf[k];
+        for (int k = 0; k < Nz; k++) { rupz[k] = 1.0 / (dzc[k + 1] * dzf[k + 1]); rloz[k] = 1.0 / (dzc[k + 1] * dzf[k]); }
+        double* d[3];
+        const std::vector<double>* src[3] = {&rdzf, &rupz, &rloz};
+        for (int q = 0; q < 3; q++) {
+            if (int rc = dev_alloc(h, &d[q], Nz + 1, false)) return rc;
+            cudaMemcpy(d[q], src[q]->data(), (Nz + 1) * sizeof(double), cudaMemcpyHostToDevice);
+        }
+        G.rdzf = d[0]; G.rupz = d[1]; G.rloz = d[2];
+    }
     if (int rc = dev_alloc(h, &dzc_d, Nz + 2, false)) return rc;
     if (int rc = dev_alloc(h, &zc_d, Nz + 2, false)) return rc;
     if (int rc = dev_alloc(h, &dzf_d, Nz + 1, false)) return rc;
@@ -236,6 +248,7 @@ int setup_geometry(ob200_handle* h) {
     G.nu_z = c.nu_z; G.kappa_z = c.kappa_z; G.ri_enabled = c.ri_enabled;
     G.ri_nu0 = c.ri_nu0; G.ri_kappa0 = c.ri_kappa0; G.ri_kappa_ca = c.ri_kappa_ca; G.ri_Cen = c.ri_Cen;
     G.ri_Cav = c.ri_Cav; G.ri_Ri0 = c.ri_Ri0; G.ri_Ridelta = c.ri_Ridelta;
+    G.r1cav = 1.0 / (1.0 + c.ri_Cav); G.rRidelta = 1.0 / c.ri_Ridelta;
     G.bc_kind = c.bc_kind; G.lambda_T = c.T_restoring_lambda; G.mu_drag = c.drag_mu;
     G.qgleith = c.qgleith_enabled; G.leith_C = c.leith_C; G.leith_minN2 = c.leith_min_N2; G.leith_Vscale = c.leith_Vscale;
     return OB200_OK;

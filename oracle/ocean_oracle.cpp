@@ -145,8 +145,8 @@ struct Oracle {
     std::vector<double> phif_, phic_, dxfc_, dxcf_, azcc_, azcf_, fff_;
     // reciprocals (1.0 / x, correctly rounded) used by the tendency operators: a multiplication by the
     // precomputed reciprocal replaces each division by a grid metric (<= 1 ulp from the reference's division)
-    std::vector<double> rdxfc_, razcc_, razcf_, rdzc_;
-    double rdy = 0;
+    std::vector<double> rdxfc_, razcc_, razcf_, rdzc_, rdzf_, rupz_, rloz_;
+    double rdy = 0, r1cav = 0, rRidelta = 0;
     double dy = 0, dlam_rad = 0;
     std::vector<int> kb_;  // (NyP x NxP) first active level per column, Nz = none
     int NxP, NyP;
@@ -172,6 +172,7 @@ struct Oracle {
     inline double razcc(int j) const { return razcc_[j + H]; }
     inline double razcf(int j) const { return razcf_[j + H]; }
     inline double rdzc(int k) const { return rdzc_[k + 1]; }
+    inline double rdzf(int k) const { return rdzf_[k]; }
     inline int kb(int i, int j) const { return kb_[(size_t)(j + H) * NxP + (i + H)]; }
 
     // ---- node predicates ---------------------------------------
@@ -247,6 +248,10 @@ struct Oracle {
         for (int jj = 0; jj < nj; jj++) { rdxfc_[jj] = 1.0 / dxfc_[jj]; razcc_[jj] = 1.0 / azcc_[jj]; razcf_[jj] = 1.0 / azcf_[jj]; }
         for (int k = 0; k < Nz + 2; k++) rdzc_[k] = 1.0 / dzc_[k];
         rdy = 1.0 / dy;
+        rdzf_.resize(Nz + 1); rupz_.assign(Nz + 1, 0.0); rloz_.assign(Nz + 1, 0.0);
+        for (int k = 0; k <= Nz; k++) rdzf_[k] = 1.0 / dzf_[k];
+        for (int k = 0; k < Nz; k++) { rupz_[k] = 1.0 / (dzc(k) * dzf(k + 1)); rloz_[k] = 1.0 / (dzc(k) * dzf(k)); }
+        r1cav = 1.0 / (1.0 + c.ri_Cav); rRidelta = 1.0 / c.ri_Ridelta;
         // bathymetry -> first active level (GridFittedBottom, centre condition: zc <= h is solid)
         kb_.assign((size_t)NxP * NyP, Nz);
         const int bh = c.bottom_halo_columns, nxh = Nx + 2 * bh;   // the host may carry a wider halo than H
@@ -282,7 +287,7 @@ struct Oracle {
     // d b / dz at (c,c,f) face k with the immersed conditional difference
     inline double dz_b(int i, int j, int k) const {
         if (!active(i, j, k - 1) || !active(i, j, k)) return 0.0;
-        return (buoyancy(i, j, k) - buoyancy(i, j, k - 1)) / dzf(k);
+        return (buoyancy(i, j, k) - buoyancy(i, j, k - 1)) * rdzf(k);
     }
 
     // ---- boundary-condition functions (bathymetry_and_forcings.jl:110-159) ----
@@ -403,7 +408,7 @@ struct Oracle {
 
     // ---- _compute_w_from_continuity! --------------------------------
     inline double div_xy(int i, int j, int k) const {
-        return (dy * u(i + 1, j, k) - dy * u(i, j, k) + dxcf(j + 1) * v(i, j + 1, k) - dxcf(j) * v(i, j, k)) / azcc(j);
+        return (dy * u(i + 1, j, k) - dy * u(i, j, k) + dxcf(j + 1) * v(i, j + 1, k) - dxcf(j) * v(i, j, k)) * razcc(j);
     }
     void compute_w() {
 #pragma omp parallel for
@@ -426,11 +431,11 @@ struct Oracle {
     // ---- RiBasedVerticalDiffusivity -----------------------------------
     inline double dz_u(int i, int j, int k) const {  // d/dz at (f,c,f), conditional on both u-nodes being active
         if (inactive_fcc(i, j, k) || inactive_fcc(i, j, k - 1)) return 0.0;
-        return (u(i, j, k) - u(i, j, k - 1)) / dzf(k);
+        return (u(i, j, k) - u(i, j, k - 1)) * rdzf(k);
     }
     inline double dz_v(int i, int j, int k) const {
         if (inactive_cfc(i, j, k) || inactive_cfc(i, j, k - 1)) return 0.0;
-        return (v(i, j, k) - v(i, j, k - 1)) / dzf(k);
+        return (v(i, j, k) - v(i, j, k - 1)) * rdzf(k);
     }
     void compute_ri_number() {
 #pragma omp parallel for
@@ -464,12 +469,12 @@ struct Oracle {
                             return 0.25 * (Ri(a - 1, b - 1, k) + Ri(a, b - 1, k) + Ri(a - 1, b, k) + Ri(a, b, k));
                         };
                         double Rif = 0.25 * (ff(i, j) + ff(i + 1, j) + ff(i, j + 1) + ff(i + 1, j + 1));
-                        double tau = 0.5 * (1.0 - det_tanh((Rif - c.ri_Ri0) / c.ri_Ridelta));
+                        double tau = 0.5 * (1.0 - det_tanh((Rif - c.ri_Ri0) * rRidelta));
                         kcp = c.ri_kappa0 * tau + kca + ken;
                         kup = c.ri_nu0 * tau;
                     }
-                    kc(i, j, k) = (c.ri_Cav * kc(i, j, k) + kcp) / (1.0 + c.ri_Cav);
-                    ku(i, j, k) = (c.ri_Cav * ku(i, j, k) + kup) / (1.0 + c.ri_Cav);
+                    kc(i, j, k) = (c.ri_Cav * kc(i, j, k) + kcp) * r1cav;
+                    ku(i, j, k) = (c.ri_Cav * ku(i, j, k) + kup) * r1cav;
                 }
             }
     }
@@ -875,8 +880,8 @@ struct Oracle {
     void implicit_column(F3& f, int i, int j, double dt, KF Kface) {
         std::vector<double> t(Nz + 1), lo(Nz + 1), up(Nz + 1);
         for (int k = 0; k < Nz; k++) {
-            up[k] = (k < Nz - 1) ? -dt * Kface(k + 1) / (dzc(k) * dzf(k + 1)) : 0.0;
-            lo[k] = (k > 0) ? -dt * Kface(k) / (dzc(k) * dzf(k)) : 0.0;  // coupling of row k to k-1
+            up[k] = (k < Nz - 1) ? -dt * Kface(k + 1) * rupz_[k] : 0.0;
+            lo[k] = (k > 0) ? -dt * Kface(k) * rloz_[k] : 0.0;  // coupling of row k to k-1
         }
         double beta = 1.0 - up[0] - lo[0];
         f(i, j, 0) = f(i, j, 0) / beta;
