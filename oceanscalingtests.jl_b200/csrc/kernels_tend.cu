@@ -747,9 +747,15 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(G
     }
 }
 
+#ifndef MOM_TX
 #define MOM_TX 32
+#endif
+#ifndef MOM_TY
 #define MOM_TY 8
+#endif
+#ifndef TEND_KLEV
 #define TEND_KLEV 8
+#endif
 void launch_momentum(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st) {
     using D = TileDims<MOM_TX, MOM_TY>;
     static bool attr_set = false;
