@@ -92,9 +92,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def make_case(workload: str, ranks: int) -> cases.Case:
+def make_case(workload: str, ranks: int, balance: str = "equal") -> cases.Case:
     Nx, Ny, Nz, dt = WORKLOADS[workload]
-    return cases.Case(workload, Nx, Ny, Nz, experiment="DoubleDrake", dt=dt, perturb=True, ranks=ranks)
+    return cases.Case(workload, Nx, Ny, Nz, experiment="DoubleDrake", dt=dt, perturb=True, ranks=ranks, balance=balance)
 
 
 def initial_state(pkg, case, grid):
@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("OB200_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-columns", type=int, default=72)
+    ap.add_argument("--balance", default=os.environ.get("OB200_BALANCE", "cost"), choices=["equal", "cost"],
+                    help="x-slab widths: equal (reference default for DoubleDrake) or balanced by kernel cost")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--persistent-barotropic", type=int, default=int(os.environ.get("OB200_PERSISTENT_BARO", "0")))
@@ -215,7 +217,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     pkg = ge.package()
-    case = make_case(args.workload, world)
+    case = make_case(args.workload, world, args.balance)
     Nx, Ny, Nz, dt = WORKLOADS[args.workload]
     grid = case.grid(pkg, rank, world)
     g0 = case.grid(pkg, 0, 1)
@@ -336,7 +338,7 @@ def main():
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"DoubleDrake {Nx}x{Ny}x{Nz} dt={dt:g}s",
                       "barotropic_substeps": f"{fs.substeps}->{len(fs.averaging_weights)}",
-                      "partition": f"x-slabs {list(grid.partition.sizes)}",
+                      "partition": f"x-slabs {list(grid.partition.sizes)} ({args.balance if world > 1 else 'single'})",
                       "l2": "inputs (44 GB of fields per step at 1 GPU) exceed the 126 MB L2; no flush needed"},
            "sypd": dt / (elapsed / args.steps) / 365.0,
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches1 - launches0),

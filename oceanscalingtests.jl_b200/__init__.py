@@ -11,7 +11,7 @@ from .bathymetry_and_forcings import (T_reference, cubic_profile, double_drake_b
                                       salinity_flux_coefficients, wind_stress, wind_stress_coefficients)
 from .boundary_and_initial_conditions import initialize_model, set_boundary_conditions
 from .grid_load_balance import (LatitudeLongitudeGrid, Partition, assess_x_load, assess_y_load, calculate_local_N,
-                                load_balanced_grid, redistribute_size_to_fulfill_memory_limitation)
+                                kernel_cost_per_column, load_balanced_grid, redistribute_size_to_fulfill_memory_limitation)
 from .model import (B200Backend, BoundaryConditions, HydrostaticFreeSurfaceModel, QGLeith,
                     RiBasedVerticalDiffusivity, SplitExplicitFreeSurface, VerticalScalarDiffusivity,
                     barotropic_substeps, build_config, set_model, substeps, time_step, weights_from_substeps)

@@ -27,6 +27,7 @@ class Case:
     qgleith: bool = False
     bathymetry: str = "experiment"    # "experiment" | "bumpy" (k-dependent masks)
     ranks: int = 1
+    balance: str = "equal"            # "equal" (reference: Partition(ranks...)) | "cost" (kernel-cost-balanced slabs)
 
     def grid(self, pkg, rank=0, ranks=None):
         ranks = ranks or self.ranks
@@ -45,7 +46,10 @@ class Case:
             bottom = bottom + 0 * lam
         else:
             bottom = pkg.double_drake_bathymetry(lam, phi)
-        part = pkg.Partition.equal(self.Nx, ranks)
+        if self.balance == "cost" and ranks > 1:
+            part = pkg.Partition.balanced(pkg.kernel_cost_per_column(bottom, self.Nx, self.Ny), ranks, min_columns=40)
+        else:
+            part = pkg.Partition.equal(self.Nx, ranks)
         return pkg.LatitudeLongitudeGrid(self.Nx, self.Ny, self.Nz, zf, rank=rank, partition=part,
                                          bottom_height_global=bottom)
 

@@ -134,3 +134,19 @@ def test_product_fails_loudly_without_gpu(pkg):
     import cases
     with pytest.raises(RuntimeError, match="no CUDA device|ob200_create failed"):
         cases.build_case("dd_small").make_model(pkg, None)
+
+
+def test_cost_balanced_partition(pkg):
+    import cases
+    c = cases.Case("c3", 2160, 900, 4, ranks=8, balance="cost")
+    g = c.grid(pkg, 0, 8)
+    sizes = g.partition.sizes
+    assert sum(sizes) == 2160 and min(sizes) >= 40
+    cost = pkg.kernel_cost_per_column(g.bottom_height_global, 2160, 900)
+    loads = [cost[g.partition.offset(r):g.partition.offset(r) + sizes[r]].sum() for r in range(8)]
+    assert max(loads) / (sum(loads) / 8) < 1.02          # balanced to 2 %
+    eq = pkg.Partition.equal(2160, 8)
+    eq_loads = [cost[eq.offset(r):eq.offset(r) + 270].sum() for r in range(8)]
+    assert max(loads) < max(eq_loads)                    # better than the equal split
+    assert pkg.Partition.balanced(np.ones(100), 1).sizes == (100,)
+    assert pkg.Partition.balanced(np.ones(100), 4).sizes == (25, 25, 25, 25)
