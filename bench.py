@@ -190,7 +190,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("OB200_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-columns", type=int, default=72)
-    ap.add_argument("--balance", default=os.environ.get("OB200_BALANCE", "cost"), choices=["equal", "cost"],
+    ap.add_argument("--balance", default=os.environ.get("OB200_BALANCE", "equal"), choices=["equal", "cost"],
                     help="x-slab widths: equal (reference default for DoubleDrake) or balanced by kernel cost")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
