@@ -137,3 +137,41 @@ def test_diagnostics_and_wizard_run(pkg, gpu_lib):
     pkg.run(sim)
     assert m.clock["iteration"] == 28 and 5.0 < sim.dt <= 2000.0      # the wizard grew the step (max_change 1.1)
     assert np.all(np.isfinite(m.get("U")))
+
+
+def test_parent_array_layout_round_trip(pkg, gpu_lib):
+    """ob200_set_field / ob200_get_field with Oceananigans parent-array halos (7,7,7) on DEVICE buffers -- what the
+    Julia glue passes (julia/OceanB200.jl set_field!/get_field!)."""
+    import torch
+    c = cases.build_case("dd_small")
+    m = c.make_model(pkg, None)
+    Nx, Ny, Nz = m.grid.size()
+    H = 7
+    for name, ny, nz, hz in (("T", Ny, Nz, H), ("V", Ny + 1, Nz, H), ("W", Ny, Nz + 1, H), ("ETA", Ny, 1, 0)):
+        fid = pkg._abi.FIELD_ID[name]
+        ref = m.get(name)
+        shape = (nz + 2 * hz, ny + 2 * H, Nx + 2 * H) if name != "ETA" else (ny + 2 * H, Nx + 2 * H)
+        buf = torch.full(shape, -7.0, dtype=torch.float64, device="cuda")
+        m.backend.get_field_device(fid, buf.data_ptr(), (H, H, hz))
+        m.backend.sync()
+        inner = buf[hz:hz + nz, H:H + ny, H:H + Nx] if name != "ETA" else buf[H:H + ny, H:H + Nx]
+        assert np.array_equal(inner.cpu().numpy().reshape(ref.shape), ref), name
+        assert float(buf[0, 0, 0] if name != "ETA" else buf[0, 0]) == -7.0      # halos of the caller's array untouched
+        # write it back shifted and read through the host path
+        m.backend.set_field_device(fid, (buf + 1.0).data_ptr(), (H, H, hz))
+        m.backend.sync()
+        assert np.array_equal(m.get(name), ref + 1.0), name
+
+
+def test_abi_error_paths(pkg, gpu_lib):
+    import ctypes as C
+    lib = gpu_lib
+    c = cases.build_case("dd_small")
+    m = c.make_model(pkg, None)
+    assert lib.ob200_set_field(m.backend.h, 999, m.get("T").ctypes.data, 0, 0, 0, 0) == -1      # OB200_EINVAL
+    assert b"field" in lib.ob200_last_error(m.backend.h)
+    assert lib.ob200_run_stage(m.backend.h, 99, 0.0, 0) == -1
+    cfg = pkg._abi.ob200_config()                     # zeroed config: rejected, no handle, message available
+    h = C.c_void_p()
+    assert lib.ob200_create(C.byref(cfg), 0, C.byref(h)) == -1 and not h.value
+    assert lib.ob200_last_error(None)
