@@ -1,5 +1,7 @@
 // Host-callable launchers of the CUDA kernels (one translation unit per kernel family).
 #pragma once
+#include <cuda.h>   // CUtensorMap (driver types only; the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include "ob_common.cuh"
 
 extern long long ob_launch_count;   // kernels launched by this library (bench.py reports it as gpu_launches)
@@ -56,7 +58,12 @@ struct MomPlan {
     bool any_fast = false;
     int* tile_kfast = nullptr;   // device, ntx * nty
     int* slow_tiles = nullptr;   // device, 2 * nslow
+    // TMA descriptors (cp.async.bulk.tensor) of the 3-D fields u, v (momentum tile box) and T, S (tracer tile box)
+    bool use_tma = false;
+    CUtensorMap tm_u, tm_v, tm_T, tm_S;
 };
+// tile boxes (elements) the tendency kernels fetch with one TMA copy per field and level
+void tend_tile_boxes(int* mom_x, int* mom_y, int* trc_x, int* trc_y);
 void mom_plan_tile_shape(int* tx, int* ty);
 void launch_momentum(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st);
 void launch_tracers(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st);

@@ -12,6 +12,33 @@
 #include "ob_bc.cuh"
 #include "weno_gen.cuh"
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers: one elected thread fetches a whole (box_x, box_y, 1) tile of a
+// 3-D field into shared memory; completion is signalled on an mbarrier by transaction bytes.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "OB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra OB_DONE;\n"
+        "bra OB_WAIT;\n"
+        "OB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* tm, unsigned long long* bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
 // ---- accessors: the same operators read either straight from HBM/L1 (MomG) or from a shared-memory tile
 // in which zeta, the tangential-velocity stencils, the divergence pieces and K were computed once (MomS).
 struct MomG {
@@ -58,14 +85,19 @@ struct MomG {
 template <int TX, int TY>
 struct TileDims {
     static constexpr int HU = 5;                         // halo of the u, v tiles
-    static constexpr int PU = TX + 2 * HU + 1, RU = TY + 2 * HU + 1;   // i in [i0-5, i0+TX+5], j in [j0-5, j0+TY+5]
+    // i in [i0-6, i0+TX+5], j in [j0-5, j0+TY+5]: one extra column on the left because a TMA box must start on a
+    // 16-byte boundary in global memory (an odd start column of doubles raises "illegal instruction") and its rows
+    // must be a multiple of 16 bytes
+    static constexpr int HUX = HU + 1;
+    static constexpr int PU = TX + HUX + HU + 1, RU = TY + 2 * HU + 1;
     static constexpr int HZ = 4;                         // zeta / us / vs: i in [i0-4, i0+TX+4], j likewise
     static constexpr int PZ = TX + 2 * HZ + 1, RZ = TY + 2 * HZ + 1;
     static constexpr int HD = 3;                         // dxU, dyV: [i0-3, i0+TX+2]
     static constexpr int PD = TX + 2 * HD, RD = TY + 2 * HD;
     static constexpr int PK = TX + 1, RK = TY + 1;       // K: [i0-1, i0+TX-1]
     static constexpr int NU = PU * RU, NZ = PZ * RZ, ND = PD * RD, NK = PK * RK;
-    static constexpr int TOTAL = 2 * NU + 3 * NZ + 2 * ND + NK;   // doubles
+    static constexpr int NUP = (NU + 15) / 16 * 16;      // tile slot padded to 128 bytes (TMA destination alignment)
+    static constexpr int TOTAL = 4 * NUP + 3 * NZ + 2 * ND + NK;   // doubles: u, v double-buffered + derived fields
 };
 
 template <int TX, int TY>
@@ -73,8 +105,8 @@ struct MomS {
     using D = TileDims<TX, TY>;
     const double *su, *sv, *sz, *sus, *svs, *sdx, *sdy, *sK;
     int i0, j0;
-    __device__ __forceinline__ double U(int i, int j, int) const { return su[(j - j0 + D::HU) * D::PU + (i - i0 + D::HU)]; }
-    __device__ __forceinline__ double V(int i, int j, int) const { return sv[(j - j0 + D::HU) * D::PU + (i - i0 + D::HU)]; }
+    __device__ __forceinline__ double U(int i, int j, int) const { return su[(j - j0 + D::HU) * D::PU + (i - i0 + D::HUX)]; }
+    __device__ __forceinline__ double V(int i, int j, int) const { return sv[(j - j0 + D::HU) * D::PU + (i - i0 + D::HUX)]; }
     __device__ __forceinline__ double usm(int i, int j, int) const { return sus[(j - j0 + D::HZ) * D::PZ + (i - i0 + D::HZ)]; }
     __device__ __forceinline__ double vsm(int i, int j, int) const { return svs[(j - j0 + D::HZ) * D::PZ + (i - i0 + D::HZ)]; }
     template <bool GEN>
@@ -399,17 +431,19 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
 #ifndef TRC_MINB
 #define TRC_MINB 3
 #endif
-template <int TX, int TY, bool GEN>
+//   TMA = true : the u, v tiles of level k+1 are fetched by one thread with cp.async.bulk.tensor into the second
+//                shared-memory buffer while level k is being computed (mbarrier completion); false: register staging
+template <int TX, int TY, bool GEN, bool TMA>
 __global__ void __launch_bounds__(TX * TY, GEN ? 2 : MOM_MINB) k_momentum_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
                                                              const int* __restrict__ slow_tiles, int ntx, int klevels,
-                                                             int NV, int ND) {
+                                                             int NV, int ND, const __grid_constant__ CUtensorMap tmu,
+                                                             const __grid_constant__ CUtensorMap tmv) {
     using D = TileDims<TX, TY>;
     constexpr int NT = TX * TY;
     constexpr int RU = (D::NU + NT - 1) / NT;
-    extern __shared__ double sm[];
-    double* su = sm;
-    double* sv = su + D::NU;
-    double* sz = sv + D::NU;
+    extern __shared__ __align__(128) double sm[];
+    __shared__ unsigned long long bar[2];
+    double* sz = sm + 4 * D::NUP;   // [u0 | v0 | u1 | v1] tile buffers first (128-byte aligned slots)
     double* sus = sz + D::NZ;
     double* svs = sus + D::NZ;
     double* sdx = svs + D::NZ;
@@ -426,34 +460,62 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : MOM_MINB) k_momentum_tiled(
     if (k_begin >= k_end) return;
     const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
     const bool mine = i < G.Nx && j < G.Ny;
-    const MomS<TX, TY> M{su, sv, sz, sus, svs, sdx, sdy, sK, i0, j0};
-    int offu[RU];
-#pragma unroll
-    for (int r = 0; r < RU; r++) {
-        const int e = min(tid + r * NT, D::NU - 1);
-        const int a = e % D::PU, b = e / D::PU;
-        offu[r] = (int)idx3(G, min(i0 - D::HU + a, G.Nx + OB_H - 1), min(j0 - D::HU + b, G.Ny + OB_H), 0);
-    }
-    double ru[RU], rv[RU];
+    const int tx0 = i0 - D::HUX + OB_X0, ty0 = j0 - D::HU + OB_H;   // tile origin in array coordinates (even column)
+    constexpr unsigned TILE_BYTES = D::NU * sizeof(double);
+    int offu[TMA ? 1 : RU];
+    double ru[TMA ? 1 : RU], rv[TMA ? 1 : RU];
     auto prefetch = [&](int k) {
         const long long lev = (long long)k * G.sz;
 #pragma unroll
-        for (int r = 0; r < RU; r++) { ru[r] = F.u[offu[r] + lev]; rv[r] = F.v[offu[r] + lev]; }
+        for (int r = 0; r < (TMA ? 0 : RU); r++) { ru[r] = F.u[offu[r] + lev]; rv[r] = F.v[offu[r] + lev]; }
     };
-    prefetch(k_begin);
-    for (int k = k_begin; k < k_end; k++) {
-#pragma unroll
-        for (int r = 0; r < RU; r++) {
-            const int e = tid + r * NT;
-            if (e < D::NU) { su[e] = ru[r]; sv[e] = rv[r]; }
-        }
+    if (TMA) {
+        if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
         __syncthreads();
-        if (k + 1 < k_end) prefetch(k + 1);
+        if (tid == 0) {
+            mbar_expect_tx(&bar[0], 2 * TILE_BYTES);
+            tma_load_tile(sm, &tmu, &bar[0], tx0, ty0, k_begin);
+            tma_load_tile(sm + D::NUP, &tmv, &bar[0], tx0, ty0, k_begin);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < (TMA ? 0 : RU); r++) {
+            const int e = min(tid + r * NT, D::NU - 1);
+            const int a = e % D::PU, b = e / D::PU;
+            offu[r] = (int)idx3(G, min(i0 - D::HUX + a, G.Nx + OB_H - 1), min(j0 - D::HU + b, G.Ny + OB_H), 0);
+        }
+        prefetch(k_begin);
+    }
+    int it = 0;
+    for (int k = k_begin; k < k_end; k++, it++) {
+        const int buf = TMA ? (it & 1) : 0;
+        double* su = sm + buf * 2 * D::NUP;
+        double* sv = su + D::NUP;
+        const MomS<TX, TY> M{su, sv, sz, sus, svs, sdx, sdy, sK, i0, j0};
+        if (TMA) {
+            // the other buffer was last read in the previous iteration, which ended with a block barrier
+            if (tid == 0 && k + 1 < k_end) {
+                fence_proxy_async();
+                double* nu = sm + (buf ^ 1) * 2 * D::NUP;
+                mbar_expect_tx(&bar[buf ^ 1], 2 * TILE_BYTES);
+                tma_load_tile(nu, &tmu, &bar[buf ^ 1], tx0, ty0, k + 1);
+                tma_load_tile(nu + D::NUP, &tmv, &bar[buf ^ 1], tx0, ty0, k + 1);
+            }
+            mbar_wait(&bar[buf], (it >> 1) & 1);
+        } else {
+#pragma unroll
+            for (int r = 0; r < (TMA ? 0 : RU); r++) {
+                const int e = tid + r * NT;
+                if (e < D::NU) { su[e] = ru[r]; sv[e] = rv[r]; }
+            }
+            __syncthreads();
+            if (k + 1 < k_end) prefetch(k + 1);
+        }
         const double dzk = G.dzc[k];
         for (int e = tid; e < D::NZ; e += NT) {
             const int a = e % D::PZ, b = e / D::PZ;
             const int ii = i0 - D::HZ + a, jj = j0 - D::HZ + b;
-            const int q = (b + D::HU - D::HZ) * D::PU + (a + D::HU - D::HZ);   // same point in the u/v tiles
+            const int q = (b + D::HU - D::HZ) * D::PU + (a + D::HUX - D::HZ);   // same point in the u/v tiles
             double dxv = G.dy * sv[q] - G.dy * sv[q - 1];
             double dyu = G.dxfc[jj] * su[q] - G.dxfc[jj - 1] * su[q - D::PU];
             if (GEN) {
@@ -468,14 +530,14 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : MOM_MINB) k_momentum_tiled(
         for (int e = tid; e < D::ND; e += NT) {
             const int a = e % D::PD, b = e / D::PD;
             const int jj = j0 - D::HD + b;
-            const int q = (b + D::HU - D::HD) * D::PU + (a + D::HU - D::HD);
+            const int q = (b + D::HU - D::HD) * D::PU + (a + D::HUX - D::HD);
             const double ax = G.dy * dzk;
             sdx[e] = ax * su[q + 1] - ax * su[q];
             sdy[e] = G.dxcf[jj + 1] * dzk * sv[q + D::PU] - G.dxcf[jj] * dzk * sv[q];
         }
         for (int e = tid; e < D::NK; e += NT) {
             const int a = e % D::PK, b = e / D::PK;
-            const int q = (b + D::HU - 1) * D::PU + (a + D::HU - 1);
+            const int q = (b + D::HU - 1) * D::PU + (a + D::HUX - 1);
             const double ua = su[q], ub = su[q + 1], va = sv[q], vb = sv[q + D::PU];
             sK[e] = (0.5 * (ua * ua + ub * ub) + 0.5 * (va * va + vb * vb)) / 2.0;
         }
@@ -564,21 +626,24 @@ struct TracerTile {
     static constexpr int HC = 4;                                   // WENO-7 halo
     static constexpr int PC = TX + 2 * HC, RC = TY + 2 * HC;       // cells [i0-4, i0+TX+3] x [j0-4, j0+TY+3]
     static constexpr int NC = PC * RC;
+    static constexpr int NCP = (NC + 15) / 16 * 16;                // tile slot padded to 128 bytes
     static constexpr int NFX = (TX + 1) * TY, NFY = TX * (TY + 1); // faces per tracer
-    static constexpr int TOTAL = 2 * NC + 3 * (NFX + NFY);   // tiles + fluxes + face velocities
+    static constexpr int TOTAL = 4 * NCP + 3 * (NFX + NFY);  // T, S tiles double-buffered + fluxes + face velocities
 };
 
-template <int TX, int TY, bool GEN>
+template <int TX, int TY, bool GEN, bool TMA>
 __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
-                                                            const int* __restrict__ slow_tiles, int ntx, int klevels, int NTR) {
+                                                            const int* __restrict__ slow_tiles, int ntx, int klevels, int NTR,
+                                                            const __grid_constant__ CUtensorMap tmT,
+                                                            const __grid_constant__ CUtensorMap tmS) {
     using D = TracerTile<TX, TY>;
     constexpr int NT = TX * TY;
     constexpr int RC = (D::NC + NT - 1) / NT;                 // tile elements per thread (per tracer)
     constexpr int NFV = D::NFX + D::NFY;                      // face velocities per level
     constexpr int RV = (NFV + NT - 1) / NT;
-    extern __shared__ double sm[];
-    double* sc = sm;                       // [2][RC][PC]
-    double* sfx = sc + 2 * D::NC;          // [2][(TX+1)*TY x-faces | TX*(TY+1) y-faces]
+    extern __shared__ __align__(128) double sm[];
+    __shared__ unsigned long long bar[2];
+    double* sfx = sm + 4 * D::NCP;         // after the [T0 | S0 | T1 | S1] tile buffers: [2][(TX+1)*TY x-faces | TX*(TY+1) y-faces]
     double* svel = sfx + 2 * NFV;          // [NFX + NFY] face velocities u (x-faces) then v (y-faces)
     int tile, kf;
     if (GEN) { tile = slow_tiles[2 * blockIdx.x]; kf = slow_tiles[2 * blockIdx.x + 1]; }
@@ -592,9 +657,9 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(G
     const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
     const bool mine = i < G.Nx && j < G.Ny;
     // per-thread global offsets (within a level) of the tile elements / face velocities this thread stages
-    int offc[RC], offv[RV];   // element offsets within one level (a plane is < 2^31 elements)
+    int offc[TMA ? 1 : RC], offv[RV];   // element offsets within one level (a plane is < 2^31 elements)
 #pragma unroll
-    for (int r = 0; r < RC; r++) {
+    for (int r = 0; r < (TMA ? 0 : RC); r++) {
         const int e = min(tid + r * NT, D::NC - 1);
         const int a = e % D::PC, b = e / D::PC;
         offc[r] = (int)idx3(G, min(i0 - D::HC + a, G.Nx + OB_H - 1), min(j0 - D::HC + b, G.Ny + OB_H), 0);
@@ -610,25 +675,47 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(G
             offv[r] = (int)idx3(G, min(i0 + a, G.Nx + OB_H - 1), min(j0 + b, G.Ny), 0);
         }
     }
-    double rT[RC], rS[RC], rV[RV];
+    double rT[TMA ? 1 : RC], rS[TMA ? 1 : RC], rV[RV];
+    const int tx0 = i0 - D::HC + OB_X0, ty0 = j0 - D::HC + OB_H;   // tile origin in array coordinates
+    constexpr unsigned TILE_BYTES = D::NC * sizeof(double);
     auto prefetch = [&](int k) {   // issue the loads of level k; consumed one iteration later
         const long long lev = (long long)k * G.sz;
 #pragma unroll
-        for (int r = 0; r < RC; r++) { rT[r] = F.T[offc[r] + lev]; rS[r] = F.S[offc[r] + lev]; }
+        for (int r = 0; r < (TMA ? 0 : RC); r++) { rT[r] = F.T[offc[r] + lev]; rS[r] = F.S[offc[r] + lev]; }
 #pragma unroll
         for (int r = 0; r < RV; r++) {
             const int e = min(tid + r * NT, NFV - 1);
             rV[r] = (e < D::NFX ? F.u : F.v)[offv[r] + lev];
         }
     };
+    if (TMA) {
+        if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar[0], 2 * TILE_BYTES);
+            tma_load_tile(sm, &tmT, &bar[0], tx0, ty0, k_begin);
+            tma_load_tile(sm + D::NCP, &tmS, &bar[0], tx0, ty0, k_begin);
+        }
+    }
     prefetch(k_begin);
     const long long cbase = mine ? idx3(G, i, j, 0) : 0;
     const double az = G.azcc[min(j, G.Ny - 1)], raz = G.razcc[min(j, G.Ny - 1)];
-    for (int k = k_begin; k < k_end; k++) {
+    int it = 0;
+    for (int k = k_begin; k < k_end; k++, it++) {
+        const int buf = TMA ? (it & 1) : 0;
+        double* sc = sm + buf * 2 * D::NCP;   // T tile, then S tile at + NCP
+        if (TMA && tid == 0 && k + 1 < k_end) {
+            // the other buffer was last read in the previous iteration, which ended with a block barrier
+            fence_proxy_async();
+            double* nx = sm + (buf ^ 1) * 2 * D::NCP;
+            mbar_expect_tx(&bar[buf ^ 1], 2 * TILE_BYTES);
+            tma_load_tile(nx, &tmT, &bar[buf ^ 1], tx0, ty0, k + 1);
+            tma_load_tile(nx + D::NCP, &tmS, &bar[buf ^ 1], tx0, ty0, k + 1);
+        }
 #pragma unroll
-        for (int r = 0; r < RC; r++) {
+        for (int r = 0; r < (TMA ? 0 : RC); r++) {
             const int e = tid + r * NT;
-            if (e < D::NC) { sc[e] = rT[r]; sc[D::NC + e] = rS[r]; }
+            if (e < D::NC) { sc[e] = rT[r]; sc[D::NCP + e] = rS[r]; }
         }
 #pragma unroll
         for (int r = 0; r < RV; r++) {
@@ -636,6 +723,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(G
             if (e < NFV) svel[e] = rV[r];
         }
         __syncthreads();
+        if (TMA) mbar_wait(&bar[buf], (it >> 1) & 1);
         if (k + 1 < k_end) prefetch(k + 1);
         // own-column values for the vertical flux, requested now, consumed after the flux phase
         const int km = max(k - 1, 0), kp = min(k + 1, G.Nz - 1);
@@ -656,7 +744,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(G
                 const double mx = G.dy * dzk, my = G.dxcf[min(j, G.Ny)] * dzk;
 #pragma unroll
                 for (int tr = 0; tr < 2; tr++) {
-                    const double* cc = sc + tr * D::NC;
+                    const double* cc = sc + tr * D::NCP;
                     double flx = 0.0, fly = 0.0;
                     if (ux != 0.0) flx = G.dy * dzk * (ux * recon7_window<1>(cc, q, ux > 0.0));
                     if (vy != 0.0) fly = G.dxcf[min(j, G.Ny)] * dzk * (vy * recon7_window<D::PC>(cc, q, vy > 0.0));
@@ -668,7 +756,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(G
             // the tile's east column of x-faces and north row of y-faces: (TY + TX) faces x 2 tracers
             if (tid < 2 * (TX + TY)) {
                 const int tr = tid / (TX + TY), g = tid - tr * (TX + TY);
-                const double* cc = sc + tr * D::NC;
+                const double* cc = sc + tr * D::NCP;
                 const bool isx = g < TY;
                 const int a = isx ? TX : g - TY, b = isx ? g : TY;
                 const int f = isx ? b * (TX + 1) + a : D::NFX + b * TX + a;
@@ -688,7 +776,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(G
             for (int e = tid; e < 2 * NFV; e += NT) {
                 const int tr = e / NFV;
                 const int f = e - tr * NFV;
-                const double* cc = sc + tr * D::NC;
+                const double* cc = sc + tr * D::NCP;
                 const double vel = svel[f];
                 const bool isx = f < D::NFX;
                 const int g = isx ? f : f - D::NFX;
@@ -727,7 +815,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(G
             const int q = (threadIdx.y + D::HC) * D::PC + (threadIdx.x + D::HC);
 #pragma unroll
             for (int tr = 0; tr < 2; tr++) {
-                const double ck = sc[tr * D::NC + q];
+                const double ck = sc[tr * D::NCP + q];
                 const double cm = tr == 0 ? Tm : Sm, cp = tr == 0 ? Tp : Sp;
                 double fzl = az * wlo * 0.5 * (cm + ck);
                 const double fzh = az * whi * 0.5 * (ck + cp);
@@ -757,42 +845,62 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(G
 #ifndef TEND_KLEV
 #define TEND_KLEV 8
 #endif
-void launch_momentum(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st) {
+template <bool TMA>
+static void launch_momentum_t(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st) {
     using D = TileDims<MOM_TX, MOM_TY>;
     static bool attr_set = false;
     const size_t smem = D::TOTAL * sizeof(double);
     if (!attr_set) {
-        cudaFuncSetAttribute(k_momentum_tiled<MOM_TX, MOM_TY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_momentum_tiled<MOM_TX, MOM_TY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_momentum_tiled<MOM_TX, MOM_TY, false, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_momentum_tiled<MOM_TX, MOM_TY, true, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
     const int NV = (ord_vort + 1) / 2, ND = (ord_div + 1) / 2, nz = (G.Nz + TEND_KLEV - 1) / TEND_KLEV;
     dim3 b(MOM_TX, MOM_TY);
     if (P.any_fast) {
-        k_momentum_tiled<MOM_TX, MOM_TY, false><<<dim3(P.ntx, P.nty, nz), b, smem, st>>>(G, F, time, P.tile_kfast, P.slow_tiles,
-                                                                                       P.ntx, TEND_KLEV, NV, ND);
+        k_momentum_tiled<MOM_TX, MOM_TY, false, TMA><<<dim3(P.ntx, P.nty, nz), b, smem, st>>>(
+            G, F, time, P.tile_kfast, P.slow_tiles, P.ntx, TEND_KLEV, NV, ND, P.tm_u, P.tm_v);
         OB_COUNT_LAUNCH(1);
     }
     if (P.nslow > 0) {
-        k_momentum_tiled<MOM_TX, MOM_TY, true><<<dim3(P.nslow, nz), b, smem, st>>>(G, F, time, P.tile_kfast, P.slow_tiles, P.ntx,
-                                                                                 TEND_KLEV, NV, ND);
+        k_momentum_tiled<MOM_TX, MOM_TY, true, TMA><<<dim3(P.nslow, nz), b, smem, st>>>(
+            G, F, time, P.tile_kfast, P.slow_tiles, P.ntx, TEND_KLEV, NV, ND, P.tm_u, P.tm_v);
         OB_COUNT_LAUNCH(1);
     }
 }
+void launch_momentum(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st) {
+    if (P.use_tma) launch_momentum_t<true>(G, F, P, ord_vort, ord_div, time, st);
+    else launch_momentum_t<false>(G, F, P, ord_vort, ord_div, time, st);
+}
 void mom_plan_tile_shape(int* tx, int* ty) { *tx = MOM_TX; *ty = MOM_TY; }
-void launch_tracers(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st) {
+void tend_tile_boxes(int* mom_x, int* mom_y, int* trc_x, int* trc_y) {
+    *mom_x = TileDims<MOM_TX, MOM_TY>::PU; *mom_y = TileDims<MOM_TX, MOM_TY>::RU;
+    *trc_x = TracerTile<MOM_TX, MOM_TY>::PC; *trc_y = TracerTile<MOM_TX, MOM_TY>::RC;
+}
+template <bool TMA>
+static void launch_tracers_t(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st) {
     using D = TracerTile<MOM_TX, MOM_TY>;
+    static bool attr_set = false;
     const size_t smem = D::TOTAL * sizeof(double);
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_tracers_tiled<MOM_TX, MOM_TY, false, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_tracers_tiled<MOM_TX, MOM_TY, true, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
     const int NTR = (ord_tracer + 1) / 2, nz = (G.Nz + TEND_KLEV - 1) / TEND_KLEV;
     dim3 b(MOM_TX, MOM_TY);
     if (P.any_fast) {
-        k_tracers_tiled<MOM_TX, MOM_TY, false><<<dim3(P.ntx, P.nty, nz), b, smem, st>>>(G, F, time, P.tile_kfast, P.slow_tiles,
-                                                                                      P.ntx, TEND_KLEV, NTR);
+        k_tracers_tiled<MOM_TX, MOM_TY, false, TMA><<<dim3(P.ntx, P.nty, nz), b, smem, st>>>(
+            G, F, time, P.tile_kfast, P.slow_tiles, P.ntx, TEND_KLEV, NTR, P.tm_T, P.tm_S);
         OB_COUNT_LAUNCH(1);
     }
     if (P.nslow > 0) {
-        k_tracers_tiled<MOM_TX, MOM_TY, true><<<dim3(P.nslow, nz), b, smem, st>>>(G, F, time, P.tile_kfast, P.slow_tiles, P.ntx,
-                                                                                TEND_KLEV, NTR);
+        k_tracers_tiled<MOM_TX, MOM_TY, true, TMA><<<dim3(P.nslow, nz), b, smem, st>>>(
+            G, F, time, P.tile_kfast, P.slow_tiles, P.ntx, TEND_KLEV, NTR, P.tm_T, P.tm_S);
         OB_COUNT_LAUNCH(1);
     }
+}
+void launch_tracers(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st) {
+    if (P.use_tma) launch_tracers_t<true>(G, F, P, ord_tracer, time, st);
+    else launch_tracers_t<false>(G, F, P, ord_tracer, time, st);
 }

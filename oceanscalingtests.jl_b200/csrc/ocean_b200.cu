@@ -4,10 +4,12 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
+#include <cudaTypedefs.h>
 #include <nccl.h>
 #include <nvtx3/nvToolsExt.h>
 
@@ -254,6 +256,27 @@ int setup_geometry(ob200_handle* h) {
     return OB200_OK;
 }
 
+// TMA descriptor of one 3-D field: dims (pitch, NyP, Nz+1) doubles, box (bx, by, 1); out-of-range elements read 0
+int encode_tile_map(ob200_handle* h, CUtensorMap* tm, double* base, int bx, int by) {
+    static PFN_cuTensorMapEncodeTiled encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+            return h->fail(OB200_ECUDA, "cuTensorMapEncodeTiled", "driver entry point not found");
+        encode = (PFN_cuTensorMapEncodeTiled)fn;
+    }
+    const Geom& G = h->G;
+    cuuint64_t dims[3] = {(cuuint64_t)G.pitch, (cuuint64_t)G.NyP, (cuuint64_t)(G.Nz + 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)G.pitch * 8, (cuuint64_t)G.sz * 8};
+    cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return h->fail(OB200_ECUDA, "cuTensorMapEncodeTiled", "encode failed");
+    return OB200_OK;
+}
+
 int alloc_fields(ob200_handle* h) {
     const Geom& G = h->G;
     Fields& F = h->F;
@@ -272,6 +295,19 @@ int alloc_fields(ob200_handle* h) {
         if (int rc = dev_alloc(h, p, n2b)) return rc;
     F.Hfc = h->F_Hfc; F.Hcf = h->F_Hcf;
     if (int rc = dev_alloc(h, &F.Ld, n2)) return rc;
+    {   // TMA descriptors for the tile staging of the tendency kernels (OB200_NO_TMA=1 falls back to register staging)
+        MomPlan& P = h->mom_plan;
+        int mx, my, tx, ty;
+        tend_tile_boxes(&mx, &my, &tx, &ty);
+        const char* e = getenv("OB200_NO_TMA");
+        P.use_tma = !(e && e[0] == '1');
+        if (P.use_tma) {
+            if (int rc = encode_tile_map(h, &P.tm_u, F.u, mx, my)) return rc;
+            if (int rc = encode_tile_map(h, &P.tm_v, F.v, mx, my)) return rc;
+            if (int rc = encode_tile_map(h, &P.tm_T, F.T, tx, ty)) return rc;
+            if (int rc = encode_tile_map(h, &P.tm_S, F.S, tx, ty)) return rc;
+        }
+    }
     return OB200_OK;
 }
 
