@@ -429,7 +429,7 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
 #define MOM_MINB 4
 #endif
 #ifndef TRC_MINB
-#define TRC_MINB 3
+#define TRC_MINB 4
 #endif
 //   TMA = true : the u, v tiles of level k+1 are fetched by one thread with cp.async.bulk.tensor into the second
 //                shared-memory buffer while level k is being computed (mbarrier completion); false: register staging
