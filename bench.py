@@ -332,8 +332,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_momentum_tiled (fused Gu,Gv tendencies; fast + masked tiles)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the two momentum launches of one step, from the
-                # `ncu --set full` capture summarised in profiles/r01_final_ncu_full.txt (C3, 1 GPU): 13.29 GB
-                "traffic": 13.29e9 if (args.workload == "c3" and world == 1) else None,
+                # `ncu --set full` capture summarised in profiles/r01_final_ncu_full.txt (C3, 1 GPU): 12.87 GB
+                "traffic": 12.87e9 if (args.workload == "c3" and world == 1) else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": MOMENTUM_BYTES_PER_CELL,
                 "ms_per_launch": mom_ms, "note": "FP64-ALU-bound WENO stencil (SURVEY F10); HBM fraction reported as the contract asks"}
     out = {"metric": "grid-cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
