@@ -331,6 +331,11 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
         }
         Gt += J * G.rdzc[k];
     }
+    // immersed quadratic bottom drag (RealisticOcean): first non-peripheral node above the sea floor
+    if (GEN && G.bc_kind == OB200_BC_REALISTIC && k > 0 && peripheral_fcc(G, i, j, k - 1)) {
+        const double v0 = M.V(i - 1, j, k), v1 = M.V(i - 1, j + 1, k), v2 = M.V(i, j, k), v3 = M.V(i, j + 1, k);
+        Gt += -G.mu_drag * uh * sqrt(uh * uh + 0.25 * (v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3)) * G.rdzc[k];
+    }
     return Gt;
 }
 
@@ -414,6 +419,10 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
             J = -G.mu_drag * vh * sqrt(vh * vh + 0.25 * (u0 * u0 + u2 * u2 + u1 * u1 + u3 * u3));
         }
         Gt += J * G.rdzc[k];
+    }
+    if (GEN && G.bc_kind == OB200_BC_REALISTIC && k > 0 && peripheral_cfc(G, i, j, k - 1)) {
+        const double u0 = M.U(i, j - 1, k), u1 = M.U(i + 1, j - 1, k), u2 = M.U(i, j, k), u3 = M.U(i + 1, j, k);
+        Gt += -G.mu_drag * vh * sqrt(vh * vh + 0.25 * (u0 * u0 + u2 * u2 + u1 * u1 + u3 * u3)) * G.rdzc[k];
     }
     return Gt;
 }

@@ -635,6 +635,11 @@ struct Oracle {
         // (7) flux boundary conditions (_apply_z_bcs!)
         if (k == Nz - 1) G -= top_flux_u(i, j) * rdzc(k);
         if (k == 0) G += bottom_flux_u(i, j) * rdzc(k);
+        // ImmersedBoundaryCondition(bottom = u_immersed_quadratic_bottom_drag) (boundary_and_initial_conditions.jl:124-134,
+        // bathymetry_and_forcings.jl:138): the same drag law where the sea floor lies above level 0, i.e. on the first
+        // non-peripheral node above a peripheral one [OCN-recall for where the immersed flux is applied]
+        if (c.bc_kind == OB200_BC_REALISTIC && k > 0 && peripheral_fcc(i, j, k - 1))
+            G += -c.drag_mu * u(i, j, k) * speed_fcc(i, j, k) * rdzc(k);
         return G;
     }
 
@@ -683,6 +688,8 @@ struct Oracle {
         if (c.qgleith_enabled) G -= leith_div_tau_v(i, j, k);
         if (k == Nz - 1) G -= top_flux_v(i, j) * rdzc(k);
         if (k == 0) G += bottom_flux_v(i, j) * rdzc(k);
+        if (c.bc_kind == OB200_BC_REALISTIC && k > 0 && peripheral_cfc(i, j, k - 1))
+            G += -c.drag_mu * v(i, j, k) * speed_cfc(i, j, k) * rdzc(k);
         return G;
     }
 

@@ -175,3 +175,53 @@ def test_abi_error_paths(pkg, gpu_lib):
     h = C.c_void_p()
     assert lib.ob200_create(C.byref(cfg), 0, C.byref(h)) == -1 and not h.value
     assert lib.ob200_last_error(None)
+
+
+def test_non_default_advection_orders(pkg, orc, gpu_lib):
+    """Orders other than (9, 5, 7) run the general order-reducing path everywhere (kfast = Nz)."""
+    c = cases.build_case("dd_small")
+    models = []
+    for factory in (None, orc.OracleBackend):
+        grid = c.grid(pkg)
+        fs = pkg.SplitExplicitFreeSurface(substeps=30)
+        m = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=fs, eos="linear", advection_orders=(5, 3, 5),
+                                            boundary_conditions=pkg.set_boundary_conditions("DoubleDrake", grid),
+                                            backend_factory=factory)
+        c.initialize(pkg, m)
+        models.append(m)
+    for _ in range(5):
+        for m in models:
+            pkg.time_step(m, c.dt)
+    compare(models[0], models[1], PROG + ("GU", "GV", "GT", "GS"), 1e-12, "orders (5,3,5)")
+
+
+def test_stage_by_stage_equals_time_step(pkg, gpu_lib):
+    """ob200_run_stage in the order of SURVEY 3.2 reproduces ob200_time_step (what a host that interleaves its own
+    halo exchange, e.g. Julia's CUDA-aware MPI, would call)."""
+    ST = pkg._abi.STAGE_ID
+    c = cases.build_case("bumpy")
+    a, b = c.make_model(pkg, None), c.make_model(pkg, None)
+    nsub = len(a.free_surface.averaging_weights)
+    for step in range(3):
+        pkg.time_step(a, c.dt)
+        be = b.backend
+        t, it, last_dt = be.clock()
+        if it == 0:
+            be.update_state()
+        if c.dt != last_dt:       # Euler step: G^- is zeroed
+            for name in ("GU_PREV", "GV_PREV", "GT_PREV", "GS_PREV"):
+                b.set(name, 0.0)
+        be.run_stage(ST["BAROTROPIC_FORCING"], c.dt)
+        be.run_stage(ST["AB2_IMPLICIT"], c.dt)
+        be.run_stage(ST["BAROTROPIC_INIT"], c.dt)
+        for m in range(nsub):
+            be.run_stage(ST["BAROTROPIC_ETA"], c.dt, m)
+            be.run_stage(ST["BAROTROPIC_VEL"], c.dt, m)
+        be.run_stage(ST["BAROTROPIC_FINISH"], c.dt)
+        be.run_stage(ST["CORRECT_AND_STORE"], c.dt)
+        be.set_clock(t + c.dt, it + 1, c.dt)
+        be.run_stage(ST["MASK_AND_LOCAL_HALOS"])
+        be.run_stage(ST["AUXILIARIES"])
+        be.run_stage(ST["TENDENCIES"])
+    for n in PROG + ("GU", "GT", "KAPPA_U"):
+        assert np.array_equal(a.get(n), b.get(n)), n
