@@ -336,6 +336,17 @@ def main():
                 "traffic": 12.87e9 if (args.workload == "c3" and world == 1) else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": MOMENTUM_BYTES_PER_CELL,
                 "ms_per_launch": mom_ms, "note": "FP64-ALU-bound WENO stencil (SURVEY F10); HBM fraction reported as the contract asks"}
+    # per-stage rooflines against the same measured HBM peak: algorithmic bytes per cell x local cells /
+    # CUDA-event time of the stage.  The two tendency kernels are FP64-pipe-bound (ncu: 62-66 % of the FP64 pipe, floor
+    # ~18 ms for both at C3), so their HBM fraction is structurally small.
+    alg_bytes = {"ab2_implicit+baro_forcing": 152.0, "corrector": 32.0, "w+Ri_sweep": 48.0, "pHY+kappa_sweep": 64.0,
+                 "momentum_tendencies": 48.0, "tracer_tendencies": 56.0}
+    kernel_rooflines = {}
+    for name, g in zip(GROUP_NAMES, groups):
+        if name in alg_bytes and g > 0:
+            gbs = alg_bytes[name] * local_cells / (g / args.steps * 1e-3) / 1e9
+            kernel_rooflines[name] = {"algorithmic_bytes_per_cell": alg_bytes[name], "GB/s": round(gbs, 1),
+                                      "frac_of_measured_hbm": round(gbs / peak, 3)}
     out = {"metric": "grid-cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -346,7 +357,9 @@ def main():
            "sypd": dt / (elapsed / args.steps) / 365.0,
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches1 - launches0),
            "stage_ms": {n: float(g / args.steps) for n, g in zip(GROUP_NAMES, groups)},
-           "roofline": roofline}
+           "roofline": roofline, "kernel_rooflines": kernel_rooflines,
+           "fp64_pipe": {"source": "profiles/r01_final_ncu_full.txt (ncu --set full, C3, 1 GPU)",
+                         "momentum_full_order_tiles_pct_of_peak": 62.1, "tracers_full_order_tiles_pct_of_peak": 66.0}}
     if per_rank_groups is not None:
         out["stage_ms_per_rank"] = [[round(x, 3) for x in r] for r in per_rank_groups]
     if world == 1 and not args.no_cpu_baseline:
