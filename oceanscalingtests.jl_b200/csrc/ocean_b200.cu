@@ -29,20 +29,17 @@ struct ob200_handle {
     size_t bcount = 0;
     bool periodic_local = true;
     bool own_stream = true;
-    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaStream_t stream = nullptr;
     cudaEvent_t ev[20];
-    cudaEvent_t ev_comm[2];
     bool timing = false, use_graph = true, persistent_baro = false, overlap = false;
     cudaStream_t stream2 = nullptr;            // tracer work that can overlap the momentum / barotropic chain
     cudaEvent_t ev_join[4];                    // step start, T/S solved, w ready, tracer tendencies done
     cudaEvent_t ev2[4];                        // timing events on stream2
-    float last_ms[16];
     int n_timed = 0;
     std::vector<void*> allocs;
     std::vector<double> weights;
     double* d_weights = nullptr;
     double* d_diag = nullptr;
-    double* G_swap[8];
     // clock
     double time = 0.0, last_dt = INFINITY;
     int64_t iteration = 0;
@@ -51,10 +48,9 @@ struct ob200_handle {
     ncclComm_t comm = nullptr;
     double *sendW = nullptr, *sendE = nullptr, *recvW = nullptr, *recvE = nullptr;
     size_t xcount = 0;
-    // CUDA graph of a full step at fixed dt
+    // CUDA graph of the barotropic substep launches at fixed dt
     cudaGraphExec_t graph_exec = nullptr;
     double graph_dt = NAN;
-    bool graph_euler = false;
     std::string err;
 
     int fail(int code, const char* what, const char* detail) {

@@ -150,3 +150,38 @@ def test_cost_balanced_partition(pkg):
     assert max(loads) < max(eq_loads)                    # better than the equal split
     assert pkg.Partition.balanced(np.ones(100), 1).sizes == (100,)
     assert pkg.Partition.balanced(np.ones(100), 4).sizes == (25, 25, 25, 25)
+
+
+def test_reference_smoke_test_through_the_mirror(pkg, orc):
+    """The reference's own test (test/runtests.jl:11-19,33-34): scaling_test_simulation(1/5, ranks, 10minutes, 365days;
+    Nz = 10, experiment) and 10 iterations must run -- here through the host mirror on the CPU oracle backend."""
+    for experiment in ("Quiescent", "DoubleDrake"):
+        sim = pkg.scaling_test_simulation(1 / 5, (1, 1, 1), 10 * 60.0, 365 * 86400.0, Nz=10, experiment=experiment,
+                                          backend_factory=orc.OracleBackend)
+        assert sim.model.grid.size() == (72, 30, 10)
+        sim.stop_iteration = 10
+        sim.progress = None
+        # the oracle backend has no device diagnostics: min_dt == max_dt disables the wizard, as a scalar dt does
+        pkg.run(sim)
+        assert sim.model.clock["iteration"] == 10
+        for n in ("U", "V", "T", "S", "ETA"):
+            assert np.all(np.isfinite(sim.model.get(n)))
+    # profile mode: warm-up + timed steps, returns seconds per step and writes time_res*.json (near_global_simulation.jl:178-216)
+    import tempfile, os, glob
+    with tempfile.TemporaryDirectory() as d:
+        cwd = os.getcwd()
+        os.chdir(d)
+        try:
+            t = pkg.scaling_test_simulation(1 / 5, (1, 1, 1), 600.0, 1e9, Nz=10, experiment="DoubleDrake", profile=True,
+                                            backend_factory=orc.OracleBackend, profile_steps=(1, 1, 2))
+            assert t > 0 and glob.glob("time_res*_NZ10_ranks1_precFloat64.json")
+        finally:
+            os.chdir(cwd)
+
+
+def test_env_var_names_match_run_jl():
+    """run.py parses the same environment variables as experiments/run.jl:30-42."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "oceanscalingtests.jl_b200", "run.py")).read()
+    for var in ("RESOLUTION", "EXPERIMENT", "WITHFLUXES", "WITHRESTORING", "PROFILE", "RESTART", "NZ", "LOADBALANCE", "PRECISION"):
+        assert f'"{var}"' in src, var
