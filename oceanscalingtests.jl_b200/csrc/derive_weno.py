@@ -190,6 +190,25 @@ def emit_device_code(tables, path):
                 acc = "q[%d] * (%s)" % (off + a, inner) if acc is None else "fma(q[%d], %s, %s)" % (off + a, inner, acc)
             out.append("    b[%d] = %s;" % (s, acc))
         out.append("  }")
+        # two fields at once (VelocityStencil: u and v): statement pairs share each coefficient load
+        out.append("  __device__ __forceinline__ static void beta2(const double* __restrict__ q, const double* __restrict__ p,")
+        out.append("                                                double* __restrict__ b, double* __restrict__ c) {")
+        for s in range(N):
+            off = N - 1 - s
+            for (src, dst) in (("q", "b"), ("p", "c")):
+                m = 0
+                acc = None
+                for a in range(N):
+                    inner = None
+                    for bb in range(a, N):
+                        cst = "WB%d[%d]" % (N, s * nb + m)
+                        term = "%s * %s[%d]" % (cst, src, off + bb) if inner is None else \
+                            "fma(%s, %s[%d], %s)" % (cst, src, off + bb, inner)
+                        inner = term
+                        m += 1
+                    acc = "%s[%d] * (%s)" % (src, off + a, inner) if acc is None else "fma(%s[%d], %s, %s)" % (src, off + a, inner, acc)
+                out.append("    %s[%d] = %s;" % (dst, s, acc))
+        out.append("  }")
         out.append("  __device__ __forceinline__ static double combine(const double* __restrict__ q, const double* __restrict__ b) {")
         out.append("    const double tau = %s;" % taus[N])
         # division-free Z-weights: alpha_s * P^2 = C_s * (P^2 + (tau * P_s)^2), P_s = prod_{r != s} d_r, d = beta + eps
@@ -215,6 +234,7 @@ def emit_device_code(tables, path):
     out.append("template <> struct Weno<1> {")
     out.append("  static constexpr int NQ = 1;")
     out.append("  __device__ __forceinline__ static void beta(const double*, double*) {}")
+    out.append("  __device__ __forceinline__ static void beta2(const double*, const double*, double*, double*) {}")
     out.append("  __device__ __forceinline__ static double combine(const double* q, const double*) { return q[0]; }")
     out.append("};")
     out.append("")

@@ -130,8 +130,7 @@ __device__ __forceinline__ double recon_vort_y(const A& M, int i, int j, int k, 
     }
     if (N == 1) return zq[0];
     double bu[N], bv[N];
-    Weno<N>::beta(us, bu);
-    Weno<N>::beta(vs, bv);
+    Weno<N>::beta2(us, vs, bu, bv);
 #pragma unroll
     for (int s = 0; s < N; s++) bu[s] = 0.5 * (bu[s] + bv[s]);
     return Weno<N>::combine(zq, bu);
@@ -149,8 +148,7 @@ __device__ __forceinline__ double recon_vort_x(const A& M, int i, int j, int k, 
     }
     if (N == 1) return zq[0];
     double bu[N], bv[N];
-    Weno<N>::beta(us, bu);
-    Weno<N>::beta(vs, bv);
+    Weno<N>::beta2(us, vs, bu, bv);
 #pragma unroll
     for (int s = 0; s < N; s++) bu[s] = 0.5 * (bu[s] + bv[s]);
     return Weno<N>::combine(zq, bu);
