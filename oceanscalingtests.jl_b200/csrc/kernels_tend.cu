@@ -230,12 +230,62 @@ __device__ __forceinline__ int order_faces(const Geom& G, int i, int j, int k, i
     return 0;
 }
 
+// ---- masked tiles: every node predicate is a threshold in k (active(i,j,k) <=> k >= kb(i,j) for a grid-fitted
+// bottom), so the order / peripheral / Coriolis tests of a column are folded ONCE per block into level thresholds
+// instead of ~500 kb look-ups per thread per level.
+#define OB_NEVER 0x7fffffff
+__device__ __forceinline__ int kb_at(const Geom& G, int i, int j) { return __ldg(&G.kb[idx2(G, i, j)]); }
+struct GenThr {
+    int per_u, per_v;      // (f,c,c) / (c,f,c) node peripheral below this level
+    int kfast;             // full-order, mask-free stencils from this level
+    int vy[6], vx[6];      // vorticity reconstruction of half-order N valid from vy[N] (G^u, along y) / vx[N] (G^v, along x)
+    int dx[4], dy[4];      // divergence reconstruction of half-order N valid from dx[N] / dy[N]
+    int cu[4], cv[4];      // Coriolis: the four tangential-velocity nodes are non-peripheral from these levels
+};
+__device__ __forceinline__ void gen_thresholds(const Geom& G, int i, int j, int NV, int ND, GenThr& T) {
+    T.per_u = max(kb_at(G, i - 1, j), kb_at(G, i, j));
+    T.per_v = max(kb_at(G, i, j - 1), kb_at(G, i, j));
+    T.kfast = __ldg(&G.kfast[idx2(G, i, j)]);
+    int ty = 0, tx = 0;
+    T.vy[0] = T.vx[0] = 0;
+#pragma unroll
+    for (int N = 1; N <= 5; N++) {   // order N adds the face nodes j-N+1 and j+N (resp. i-N+1, i+N)
+        ty = max(ty, max(min(kb_at(G, i, j - N), kb_at(G, i, j - N + 1)), min(kb_at(G, i, j + N - 1), kb_at(G, i, j + N))));
+        tx = max(tx, max(min(kb_at(G, i - N, j), kb_at(G, i - N + 1, j)), min(kb_at(G, i + N - 1, j), kb_at(G, i + N, j))));
+        T.vy[N] = N <= NV ? ty : OB_NEVER;
+        T.vx[N] = N <= NV ? tx : OB_NEVER;
+    }
+    ty = tx = 0;
+    T.dx[0] = T.dy[0] = 0;
+#pragma unroll
+    for (int N = 1; N <= 3; N++) {   // order N adds the cells i-N and i+N-1 (resp. j-N, j+N-1)
+        tx = max(tx, max(kb_at(G, i - N, j), kb_at(G, i + N - 1, j)));
+        ty = max(ty, max(kb_at(G, i, j - N), kb_at(G, i, j + N - 1)));
+        T.dx[N] = N <= ND ? tx : OB_NEVER;
+        T.dy[N] = N <= ND ? ty : OB_NEVER;
+    }
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            T.cu[2 * a + b] = max(kb_at(G, i - 1 + a, j + b - 1), kb_at(G, i - 1 + a, j + b));      // (c,f,c) node (i-1+a, j+b)
+            T.cv[2 * a + b] = max(kb_at(G, i + a - 1, j - 1 + b), kb_at(G, i + a, j - 1 + b));      // (f,c,c) node (i+a, j-1+b)
+        }
+}
+__device__ __forceinline__ int order_from(const int* thr, int Nmax, int k) {
+    int N = 0;
+#pragma unroll
+    for (int n = 1; n <= 5; n++)
+        if (n <= Nmax && k >= thr[n]) N = n;   // thresholds are non-decreasing in n
+    return N;
+}
+
 // ================================================================================================
 // momentum tendencies
 // ================================================================================================
 template <bool GEN, class A>
 __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A& M, int i, int j, int k, int NV, int ND,
-                                         double time) {
+                                         double time, const GenThr& T) {
     const long long c = idx3(G, i, j, k);
     // (1) vorticity flux
     const double q00 = G.dxcf[j] * M.V(i - 1, j, k), q01 = G.dxcf[j + 1] * M.V(i - 1, j + 1, k);
@@ -248,7 +298,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
         double z;
         if (!GEN) z = recon_vort_y<5, false>(M, i, j, k, left);
         else {
-            const int N = order_faces(G, i, j, k, NV, false);
+            const int N = order_from(T.vy, 5, k);
             z = OB_DISPATCH(N, (recon_vort_y<1, true>(M, i, j, k, left)), (recon_vort_y<2, true>(M, i, j, k, left)),
                             (recon_vort_y<3, true>(M, i, j, k, left)), (recon_vort_y<4, true>(M, i, j, k, left)),
                             (recon_vort_y<5, true>(M, i, j, k, left)));
@@ -263,7 +313,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
         double d;
         if (!GEN) d = recon_div_x<3>(M, i, j, k, left);
         else {
-            const int N = order_cells(G, i, j, k, ND, true);
+            const int N = order_from(T.dx, 3, k);
             d = OB_DISPATCH(N, (recon_div_x<1>(M, i, j, k, left)), (recon_div_x<2>(M, i, j, k, left)),
                             (recon_div_x<3>(M, i, j, k, left)), (recon_div_x<3>(M, i, j, k, left)),
                             (recon_div_x<3>(M, i, j, k, left)));
@@ -280,7 +330,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
         fl_hi = Whi * 0.5 * (uh + F.u[idx3(G, i, j, kp)]);
         if (GEN) {
             // immersed-peripheral (f,c,f) faces carry no flux: the node below is peripheral but inside the domain
-            if (k > 0 && peripheral_fcc(G, i, j, k - 1)) fl_lo = 0.0;
+            if (k > 0 && k <= T.per_u) fl_lo = 0.0;
             // (the node above an active node is active for a grid-fitted bottom; the top face is a domain boundary)
         }
     }
@@ -290,8 +340,8 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
     int nact = 4;
     if (GEN) {
         nact = 0;
-        for (int a = 0; a < 2; a++)
-            for (int b = 0; b < 2; b++) nact += peripheral_cfc(G, i - 1 + a, j + b, k) ? 0 : 1;
+#pragma unroll
+        for (int n = 0; n < 4; n++) nact += k >= T.cu[n] ? 1 : 0;
     }
     const double fbar = 0.5 * (G.fff[j] + G.fff[j + 1]);
     const double cor = nact == 0 ? 0.0 : nact == 4 ? vavg : vavg / (0.25 * nact);
@@ -330,7 +380,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
         Gt += J * G.rdzc[k];
     }
     // immersed quadratic bottom drag (RealisticOcean): first non-peripheral node above the sea floor
-    if (GEN && G.bc_kind == OB200_BC_REALISTIC && k > 0 && peripheral_fcc(G, i, j, k - 1)) {
+    if (GEN && G.bc_kind == OB200_BC_REALISTIC && k > 0 && k <= T.per_u) {
         const double v0 = M.V(i - 1, j, k), v1 = M.V(i - 1, j + 1, k), v2 = M.V(i, j, k), v3 = M.V(i, j + 1, k);
         Gt += -G.mu_drag * uh * sqrt(uh * uh + 0.25 * (v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3)) * G.rdzc[k];
     }
@@ -339,7 +389,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
 
 template <bool GEN, class A>
 __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A& M, int i, int j, int k, int NV, int ND,
-                                         double time) {
+                                         double time, const GenThr& T) {
     const long long c = idx3(G, i, j, k);
     const double dy = G.dy;
     const double q00 = dy * M.U(i, j - 1, k), q10 = dy * M.U(i + 1, j - 1, k);
@@ -352,7 +402,7 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
         double z;
         if (!GEN) z = recon_vort_x<5, false>(M, i, j, k, left);
         else {
-            const int N = order_faces(G, i, j, k, NV, true);
+            const int N = order_from(T.vx, 5, k);
             z = OB_DISPATCH(N, (recon_vort_x<1, true>(M, i, j, k, left)), (recon_vort_x<2, true>(M, i, j, k, left)),
                             (recon_vort_x<3, true>(M, i, j, k, left)), (recon_vort_x<4, true>(M, i, j, k, left)),
                             (recon_vort_x<5, true>(M, i, j, k, left)));
@@ -366,7 +416,7 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
         double d;
         if (!GEN) d = recon_div_y<3>(M, i, j, k, left);
         else {
-            const int N = order_cells(G, i, j, k, ND, false);
+            const int N = order_from(T.dy, 3, k);
             d = OB_DISPATCH(N, (recon_div_y<1>(M, i, j, k, left)), (recon_div_y<2>(M, i, j, k, left)),
                             (recon_div_y<3>(M, i, j, k, left)), (recon_div_y<3>(M, i, j, k, left)),
                             (recon_div_y<3>(M, i, j, k, left)));
@@ -379,15 +429,15 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
     double fl_lo = Wlo * 0.5 * (F.v[idx3(G, i, j, km)] + vh);
     const double fl_hi = Whi * 0.5 * (vh + F.v[idx3(G, i, j, kp)]);
     if (GEN) {
-        if (k > 0 && peripheral_cfc(G, i, j, k - 1)) fl_lo = 0.0;
+        if (k > 0 && k <= T.per_v) fl_lo = 0.0;
     }
     Gt -= (Phi + fl_hi - fl_lo) * (G.razcf[j] * G.rdzc[k]);
     Gt -= (M.Kh(i, j, k) - M.Kh(i, j - 1, k)) * G.rdy;
     int nact = 4;
     if (GEN) {
         nact = 0;
-        for (int a = 0; a < 2; a++)
-            for (int b = 0; b < 2; b++) nact += peripheral_fcc(G, i + a, j - 1 + b, k) ? 0 : 1;
+#pragma unroll
+        for (int n = 0; n < 4; n++) nact += k >= T.cv[n] ? 1 : 0;
     }
     const double fbar = 0.5 * (G.fff[j] + G.fff[j]);
     const double cor = nact == 0 ? 0.0 : nact == 4 ? uavg : uavg / (0.25 * nact);
@@ -418,7 +468,7 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
         }
         Gt += J * G.rdzc[k];
     }
-    if (GEN && G.bc_kind == OB200_BC_REALISTIC && k > 0 && peripheral_cfc(G, i, j, k - 1)) {
+    if (GEN && G.bc_kind == OB200_BC_REALISTIC && k > 0 && k <= T.per_v) {
         const double u0 = M.U(i, j - 1, k), u1 = M.U(i + 1, j - 1, k), u2 = M.U(i, j, k), u3 = M.U(i + 1, j, k);
         Gt += -G.mu_drag * vh * sqrt(vh * vh + 0.25 * (u0 * u0 + u2 * u2 + u1 * u1 + u3 * u3)) * G.rdzc[k];
     }
@@ -493,6 +543,23 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : MOM_MINB) k_momentum_tiled(
         }
         prefetch(k_begin);
     }
+    // masked tiles: level thresholds of this thread's column and of the zeta points it stages (k independent)
+    constexpr int RZE = (D::NZ + NT - 1) / NT;
+    GenThr T;
+    int zthr[GEN ? RZE : 1];
+    if (GEN) {
+        if (mine) gen_thresholds(G, i, j, NV, ND, T);
+#pragma unroll
+        for (int r = 0; r < RZE; r++) {
+            const int e = min(tid + r * NT, D::NZ - 1);
+            const int a = e % D::PZ, b = e / D::PZ;
+            const int ic = min(i0 - D::HZ + a, G.Nx + OB_H - 1), jc = min(j0 - D::HZ + b, G.Ny + OB_H);
+            const int k00 = kb_at(G, ic - 1, jc - 1), k10 = kb_at(G, ic, jc - 1), k01 = kb_at(G, ic - 1, jc), k11 = kb_at(G, ic, jc);
+            const int kzx = max(min(k00, k01), min(k10, k11));   // delta_x v touches an inactive (c,f,c) node below this level
+            const int kzy = max(min(k00, k10), min(k01, k11));   // delta_y u touches an inactive (f,c,c) node below this level
+            zthr[r] = (kzx << 16) | kzy;
+        }
+    }
     int it = 0;
     for (int k = k_begin; k < k_end; k++, it++) {
         const int buf = TMA ? (it & 1) : 0;
@@ -519,20 +586,28 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : MOM_MINB) k_momentum_tiled(
             if (k + 1 < k_end) prefetch(k + 1);
         }
         const double dzk = G.dzc[k];
-        for (int e = tid; e < D::NZ; e += NT) {
+        auto stage_zeta = [&](int e, int kzx, int kzy) {
             const int a = e % D::PZ, b = e / D::PZ;
-            const int ii = i0 - D::HZ + a, jj = j0 - D::HZ + b;
+            const int jj = j0 - D::HZ + b;
             const int q = (b + D::HU - D::HZ) * D::PU + (a + D::HUX - D::HZ);   // same point in the u/v tiles
             double dxv = G.dy * sv[q] - G.dy * sv[q - 1];
             double dyu = G.dxfc[jj] * su[q] - G.dxfc[jj - 1] * su[q - D::PU];
-            if (GEN) {
-                const int ic = min(ii, G.Nx + OB_H - 1), jc = min(jj, G.Ny + OB_H);
-                if (inactive_cfc(G, ic - 1, jc, k) || inactive_cfc(G, ic, jc, k)) dxv = 0.0;
-                if (inactive_fcc(G, ic, jc - 1, k) || inactive_fcc(G, ic, jc, k)) dyu = 0.0;
+            if (GEN) {   // conditional differences: a difference that touches an inactive node is zero
+                if (k < kzx) dxv = 0.0;
+                if (k < kzy) dyu = 0.0;
             }
             sz[e] = (dxv - dyu) * G.razcf[jj];
             sus[e] = 0.5 * (su[q - D::PU] + su[q]);
             svs[e] = 0.5 * (sv[q - 1] + sv[q]);
+        };
+        if (GEN) {
+#pragma unroll
+            for (int r = 0; r < RZE; r++) {
+                const int e = tid + r * NT;
+                if (e < D::NZ) stage_zeta(e, zthr[r] >> 16, zthr[r] & 0xffff);
+            }
+        } else {
+            for (int e = tid; e < D::NZ; e += NT) stage_zeta(e, 0, 0);
         }
         for (int e = tid; e < D::ND; e += NT) {
             const int a = e % D::PD, b = e / D::PD;
@@ -552,15 +627,15 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : MOM_MINB) k_momentum_tiled(
         if (mine) {
             const long long c = idx3(G, i, j, k);
             if (!GEN) {
-                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time);
-                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time);
-            } else if (k >= __ldg(&G.kfast[idx2(G, i, j)])) {
+                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time, T);
+                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time, T);
+            } else if (k >= T.kfast) {
                 // most cells of a masked tile are still far from any boundary: full-order, check-free path
-                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time);
-                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time);
+                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time, T);
+                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time, T);
             } else {
-                F.Gu[c] = peripheral_fcc(G, i, j, k) ? 0.0 : tend_u<true>(G, F, M, i, j, k, NV, ND, time);
-                F.Gv[c] = peripheral_cfc(G, i, j, k) ? 0.0 : tend_v<true>(G, F, M, i, j, k, NV, ND, time);
+                F.Gu[c] = k < T.per_u ? 0.0 : tend_u<true>(G, F, M, i, j, k, NV, ND, time, T);
+                F.Gv[c] = k < T.per_v ? 0.0 : tend_v<true>(G, F, M, i, j, k, NV, ND, time, T);
             }
         }
         __syncthreads();
@@ -707,6 +782,31 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(G
     prefetch(k_begin);
     const long long cbase = mine ? idx3(G, i, j, 0) : 0;
     const double az = G.azcc[min(j, G.Ny - 1)], raz = G.razcc[min(j, G.Ny - 1)];
+    // masked tiles: per-face level thresholds of the reconstruction order (packed 16 bit), k independent
+    constexpr int RFE = (NFV + NT - 1) / NT;
+    int fthr[GEN ? 2 * RFE : 1];
+    int kb_own = 0;
+    if (GEN) {
+        kb_own = mine ? kb_at(G, i, j) : 0;
+#pragma unroll
+        for (int r = 0; r < RFE; r++) {
+            const int f = min(tid + r * NT, NFV - 1);
+            const bool isx = f < D::NFX;
+            const int g = isx ? f : f - D::NFX;
+            const int w = isx ? TX + 1 : TX;
+            const int a = g % w, b = g / w;
+            const int ii = min(i0 + a, G.Nx + OB_H - 1), jj = min(j0 + b, isx ? G.Ny - 1 : G.Ny);
+            int t = 0, thr[5];
+#pragma unroll
+            for (int N = 1; N <= 4; N++) {   // order N adds the cells -N and N-1 along the face normal
+                t = isx ? max(t, max(kb_at(G, ii - N, jj), kb_at(G, ii + N - 1, jj)))
+                        : max(t, max(kb_at(G, ii, jj - N), kb_at(G, ii, jj + N - 1)));
+                thr[N] = N <= NTR ? t : 0x7fff;
+            }
+            fthr[2 * r] = (thr[2] << 16) | thr[1];
+            fthr[2 * r + 1] = (thr[4] << 16) | thr[3];
+        }
+    }
     int it = 0;
     for (int k = k_begin; k < k_end; k++, it++) {
         const int buf = TMA ? (it & 1) : 0;
@@ -777,42 +877,44 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(G
                 sfx[tr * NFV + f] = flux;
             }
         } else {
-        // flat work list over (tracer, direction, face): every face flux once, upwind side only.  The direction
-            // only changes the stride / metric, so x- and y-faces share one code path (no divergence, fewer registers).
-#pragma unroll 1
-            for (int e = tid; e < 2 * NFV; e += NT) {
-                const int tr = e / NFV;
-                const int f = e - tr * NFV;
-                const double* cc = sc + tr * D::NCP;
-                const double vel = svel[f];
-                const bool isx = f < D::NFX;
-                const int g = isx ? f : f - D::NFX;
-                const int w = isx ? TX + 1 : TX;
-                const int a = g % w, b = g / w;                      // face between cells (a-1,b),(a,b) or (a,b-1),(a,b)
-                const int stride = isx ? 1 : D::PC;
-                double flux = 0.0;
-                if (vel != 0.0) {
-                    const bool left = vel > 0.0;
-                    const int q = (b + D::HC) * D::PC + (a + D::HC);   // the cell on the high side of the face
-                    const int jj = min(j0 + b, isx ? G.Ny - 1 : G.Ny);
-                    const double metric = isx ? G.dy : G.dxcf[jj];
-                    if (!GEN) {
-                        const double r = recon_cell<4>(cc, left ? q - 4 * stride : q + 3 * stride, left ? stride : -stride);
-                        flux = metric * dzk * (vel * r);
-                    } else {
-                        const int ii = min(i0 + a, G.Nx + OB_H - 1);
-                        const bool per = isx ? peripheral_fcc(G, ii, jj, k) : peripheral_cfc(G, ii, jj, k);
-                        if (!per) {
-                            const int N = order_cells(G, ii, jj, k, NTR, isx);
-                            const long long st = left ? stride : -stride;
-                            const long long bq = left ? q - N * stride : q + (N - 1) * stride;
-                            const double r = OB_DISPATCH(N, recon_cell<1>(cc, bq, st), recon_cell<2>(cc, bq, st),
-                                                         recon_cell<3>(cc, bq, st), recon_cell<4>(cc, bq, st), recon_cell<4>(cc, bq, st));
-                            flux = metric * dzk * (vel * r);
+            // flat work list over (direction, face): every face flux once, upwind side only.  The direction only
+            // changes the stride / metric, so x- and y-faces share one code path; the reconstruction order of a face
+            // comes from its precomputed level thresholds (order 0 = peripheral face, no flux).
+#pragma unroll
+            for (int r = 0; r < RFE; r++) {
+                const int f = tid + r * NT;
+                if (f < NFV) {
+                    const double vel = svel[f];
+                    const bool isx = f < D::NFX;
+                    const int g = isx ? f : f - D::NFX;
+                    const int w = isx ? TX + 1 : TX;
+                    const int a = g % w, b = g / w;                      // face between cells (a-1,b),(a,b) or (a,b-1),(a,b)
+                    const int stride = isx ? 1 : D::PC;
+                    const int t12 = fthr[2 * r], t34 = fthr[2 * r + 1];
+                    int N = 0;
+                    if (k >= (t12 & 0xffff)) N = 1;
+                    if (k >= (t12 >> 16)) N = 2;
+                    if (k >= (t34 & 0xffff)) N = 3;
+                    if (k >= (t34 >> 16)) N = 4;
+                    double flux[2] = {0.0, 0.0};
+                    if (vel != 0.0 && N > 0) {
+                        const bool left = vel > 0.0;
+                        const int q = (b + D::HC) * D::PC + (a + D::HC);   // the cell on the high side of the face
+                        const int jj = min(j0 + b, isx ? G.Ny - 1 : G.Ny);
+                        const double metric = isx ? G.dy : G.dxcf[jj];
+                        const long long st = left ? stride : -stride;
+                        const long long bq = left ? q - N * stride : q + (N - 1) * stride;
+#pragma unroll
+                        for (int tr = 0; tr < 2; tr++) {
+                            const double* cc = sc + tr * D::NCP;
+                            const double rr = OB_DISPATCH(N, recon_cell<1>(cc, bq, st), recon_cell<2>(cc, bq, st),
+                                                          recon_cell<3>(cc, bq, st), recon_cell<4>(cc, bq, st), recon_cell<4>(cc, bq, st));
+                            flux[tr] = metric * dzk * (vel * rr);
                         }
                     }
+                    sfx[f] = flux[0];   // [tracer][x-faces | y-faces]
+                    sfx[NFV + f] = flux[1];
                 }
-                sfx[e] = flux;   // [tracer][x-faces | y-faces]
             }
         }
         __syncthreads();
@@ -826,7 +928,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(G
                 const double cm = tr == 0 ? Tm : Sm, cp = tr == 0 ? Tp : Sp;
                 double fzl = az * wlo * 0.5 * (cm + ck);
                 const double fzh = az * whi * 0.5 * (ck + cp);
-                if (GEN && k > 0 && !active(G, i, j, k - 1)) fzl = 0.0;   // immersed-peripheral bottom face
+                if (GEN && k > 0 && k <= kb_own) fzl = 0.0;   // immersed-peripheral bottom face
                 const double fxw = sfx[tr * NFV + fxi], fxe = sfx[tr * NFV + fxi + 1];
                 const double fys = sfx[tr * NFV + D::NFX + fyi], fyn = sfx[tr * NFV + D::NFX + fyi + TX];
                 double Gt = -((fxe - fxw) + (fyn - fys) + (fzh - fzl)) * (raz * rdzk);
@@ -834,7 +936,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(G
                     const double J = tr == 0 ? top_flux_T(G, F, i, j, ck, time) : top_flux_S(G, F, i, j, ck, time);
                     Gt -= J * rdzk;
                 }
-                if (GEN && !active(G, i, j, k)) Gt = 0.0;
+                if (GEN && k < kb_own) Gt = 0.0;
                 (tr == 0 ? F.GT : F.GS)[c] = Gt;
             }
         }

@@ -554,11 +554,11 @@ const char* ob200_last_error(const ob200_handle* h) { return h ? h->err.c_str() 
 int ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out) {
     if (!cfg || !out) { g_last_error = "null argument"; return OB200_EINVAL; }
     if (cfg->struct_bytes != (int32_t)sizeof(ob200_config)) { g_last_error = "ob200_config size mismatch (ABI)"; return OB200_EINVAL; }
-    if (cfg->Nx < 2 * OB_H || cfg->Ny < 2 || cfg->Nz < 2 || cfg->n_substeps < 1 || cfg->n_substeps > OB200_MAX_SUBSTEPS ||
+    if (cfg->Nx < 2 * OB_H || cfg->Ny < 2 || cfg->Nz < 2 || cfg->Nz > 32767 || cfg->n_substeps < 1 || cfg->n_substeps > OB200_MAX_SUBSTEPS ||
         !cfg->z_faces || !cfg->bottom_height || !cfg->averaging_weights || cfg->nranks < 1 ||
         cfg->bottom_halo_columns < OB_H || (cfg->nranks > 1 && cfg->bottom_halo_columns < cfg->n_substeps + 1) ||
         (cfg->nranks > 1 && cfg->Nx < cfg->n_substeps + 1)) {
-        g_last_error = "invalid ob200_config (sizes / null arrays; Nx >= 14; x-slabs need Nx and bottom_halo_columns >= n_substeps + 1)";
+        g_last_error = "invalid ob200_config (sizes / null arrays; Nx >= 14; Nz <= 32767; x-slabs need Nx and bottom_halo_columns >= n_substeps + 1)";
         return OB200_EINVAL;
     }
     int ndev = 0;
