@@ -158,6 +158,10 @@ int ob200_set_field(ob200_handle* h, int32_t field, const double* buf, int32_t b
                     int32_t hx, int32_t hy, int32_t hz);
 int ob200_get_field(ob200_handle* h, int32_t field, double* buf, int32_t buf_on_device,
                     int32_t hx, int32_t hy, int32_t hz);
+/* One horizontal level k (0-based) of a 3-D field as a (ny + 2 hy) x (Nx + 2 hx) window: what the surface writer's
+ * `Field(model.velocities.u; indices = (:, :, Nz))` views read (src/simulation_outputs.jl:17-25).                  */
+int ob200_get_level(ob200_handle* h, int32_t field, int32_t k, double* buf, int32_t buf_on_device,
+                    int32_t hx, int32_t hy);
 /* RealisticOcean forcing arrays (src/boundary_and_initial_conditions.jl:90-105):
  * which = 0 taux, 1 tauy, 2 Qs, 3 Fs, 4 Tr, 5 Sr; Nx x Ny(+1 for tauy) x 6.   */
 int ob200_set_forcing(ob200_handle* h, int32_t which, const double* buf, int32_t buf_on_device);
@@ -180,6 +184,10 @@ int ob200_set_clock(ob200_handle* h, double time, int64_t iteration, double last
 int ob200_diagnostics(ob200_handle* h, double maxabs[6], double* cfl_dt);
 int ob200_get_timing(ob200_handle* h, ob200_timing* t);
 int ob200_set_stream(ob200_handle* h, void* cuda_stream);
+/* Options: "timing" (stage timing, above), "barotropic_graph" (default 1), "persistent_barotropic", "overlap"
+ * (tuning variants, default 0), "transfer_x_halo" = n: ob200_set_field / ob200_get_field also copy n (<= 7, <= hx)
+ * x-halo columns each side -- the checkpointer uses it for state whose halo columns are not recomputed by
+ * update_state! (time-filtered diffusivities, barotropic averages; src/simulation_outputs.jl:36-40,45-70).      */
 int ob200_set_option(ob200_handle* h, const char* name, int32_t value);
 
 /* --- multi-GPU: x-slab ring over NCCL (replaces Oceananigans' MPI halo

@@ -83,7 +83,7 @@ def as_double_ptr(a: np.ndarray):
 # every symbol include/ocean_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = [
     "ob200_create", "ob200_destroy", "ob200_last_error", "ob200_version",
-    "ob200_set_field", "ob200_get_field", "ob200_set_forcing",
+    "ob200_set_field", "ob200_get_field", "ob200_get_level", "ob200_set_forcing",
     "ob200_update_state", "ob200_time_step", "ob200_time_steps", "ob200_run_stage", "ob200_sync",
     "ob200_get_clock", "ob200_set_clock", "ob200_diagnostics", "ob200_get_timing", "ob200_set_stream",
     "ob200_set_option", "ob200_comm_unique_id", "ob200_comm_init",
@@ -120,6 +120,8 @@ def load_library(path: str | None = None):
     for f in (lib.ob200_set_field, lib.ob200_get_field):
         f.argtypes = [H, C.c_int32, dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         f.restype = C.c_int
+    lib.ob200_get_level.argtypes = [H, C.c_int32, C.c_int32, dp, C.c_int32, C.c_int32, C.c_int32]
+    lib.ob200_get_level.restype = C.c_int
     lib.ob200_set_forcing.argtypes = [H, C.c_int32, dp, C.c_int32]
     lib.ob200_set_forcing.restype = C.c_int
     lib.ob200_update_state.argtypes = [H]

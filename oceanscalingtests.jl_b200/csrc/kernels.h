@@ -23,7 +23,7 @@ void launch_fill_halos(const Geom& G, const Fields& F, bool periodic_x, cudaStre
 void launch_mask_fields(const Geom& G, const Fields& F, cudaStream_t st);
 // layout: 0 = 3-D field, 1 = 2-D in the 3-D plane layout (Ld), 2 = 2-D barotropic layout
 void launch_copy_field(const Geom& G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, int layout,
-                       bool to_field, cudaStream_t st);
+                       bool to_field, int ex, cudaStream_t st);
 void launch_pack_x(const Geom& G, const Fields& F, double* sendW, double* sendE, cudaStream_t st);
 void launch_unpack_x(const Geom& G, const Fields& F, const double* recvW, const double* recvE, cudaStream_t st);
 size_t pack_x_count(const Geom& G);

@@ -80,19 +80,19 @@ void launch_mask_fields(const Geom& G, const Fields& F, cudaStream_t st) {
 
 // interior <-> user buffer laid out like an Oceananigans parent array with halos (hx, hy, hz)
 __global__ void k_copy_field(Geom G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, int layout,
-                             bool to_field) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                             bool to_field, int ex) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - ex;   // ex x-halo columns travel too (option transfer_x_halo)
     const int j = blockIdx.y, k = blockIdx.z;
-    if (i >= G.Nx) return;
+    if (i >= G.Nx + ex) return;
     const size_t sx = G.Nx + 2 * hx, sy = ny + 2 * hy;
     const size_t b = ((size_t)(k + (layout == 0 ? hz : 0)) * sy + (j + hy)) * sx + (i + hx);
     const long long c = layout == 0 ? idx3(G, i, j, k) : layout == 1 ? (long long)idx2(G, i, j) : (long long)idx2b(G, i, j);
     if (to_field) field[c] = buf[b]; else buf[b] = field[c];
 }
 void launch_copy_field(const Geom& G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, int layout,
-                       bool to_field, cudaStream_t st) {
-    dim3 b(128), g((G.Nx + 127) / 128, ny, nz);
-    k_copy_field<<<g, b, 0, st>>>(G, field, buf, ny, nz, hx, hy, hz, layout, to_field);
+                       bool to_field, int ex, cudaStream_t st) {
+    dim3 b(128), g((G.Nx + 2 * ex + 127) / 128, ny, nz);
+    k_copy_field<<<g, b, 0, st>>>(G, field, buf, ny, nz, hx, hy, hz, layout, to_field, ex);
     OB_COUNT_LAUNCH(1);
 }
 

@@ -488,10 +488,13 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
 #ifndef TRC_MINB
 #define TRC_MINB 4
 #endif
+#ifndef GEN_MINB
+#define GEN_MINB 2   // masked-tile instances: resident blocks per SM
+#endif
 //   TMA = true : the u, v tiles of level k+1 are fetched by one thread with cp.async.bulk.tensor into the second
 //                shared-memory buffer while level k is being computed (mbarrier completion); false: register staging
 template <int TX, int TY, bool GEN, bool TMA>
-__global__ void __launch_bounds__(TX * TY, GEN ? 2 : MOM_MINB) k_momentum_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
+__global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
                                                              const int* __restrict__ slow_tiles, int ntx, int klevels,
                                                              int NV, int ND, const __grid_constant__ CUtensorMap tmu,
                                                              const __grid_constant__ CUtensorMap tmv) {
@@ -714,7 +717,7 @@ struct TracerTile {
 };
 
 template <int TX, int TY, bool GEN, bool TMA>
-__global__ void __launch_bounds__(TX * TY, GEN ? 2 : TRC_MINB) k_tracers_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
+__global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_tiled(Geom G, Fields F, double time, const int* __restrict__ tile_kfast,
                                                             const int* __restrict__ slow_tiles, int ntx, int klevels, int NTR,
                                                             const __grid_constant__ CUtensorMap tmT,
                                                             const __grid_constant__ CUtensorMap tmS) {

@@ -32,6 +32,7 @@ struct ob200_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[20];
     bool timing = false, use_graph = true, persistent_baro = false, overlap = false;
+    int transfer_x_halo = 0;   // x-halo columns copied by set/get_field besides the interior (checkpoint of halo-carrying state)
     cudaStream_t stream2 = nullptr;            // tracer work that can overlap the momentum / barotropic chain
     cudaEvent_t ev_join[4];                    // step start, T/S solved, w ready, tracer tendencies done
     cudaEvent_t ev2[4];                        // timing events on stream2
@@ -607,13 +608,18 @@ void ob200_destroy(ob200_handle* h) {
     delete h;
 }
 
-static int copy_common(ob200_handle* h, int32_t field, double* buf, int on_device, int hx, int hy, int hz, bool to_field) {
+static int copy_common(ob200_handle* h, int32_t field, double* buf, int on_device, int hx, int hy, int hz, bool to_field,
+                       int level = -1) {
     if (!h || !buf) return OB200_EINVAL;
     cudaSetDevice(h->device);
     FieldRef r = field_ref(h, field);
     if (!r.p) return h->fail(OB200_EINVAL, "field", "unknown or unallocated field id");
     if (hx < 0 || hy < 0 || hz < 0) return h->fail(OB200_EINVAL, "halo", "negative halo");
     const Geom& G = h->G;
+    if (level >= 0) {   // one horizontal level of a 3-D field, as a (1, ny + 2 hy, Nx + 2 hx) window
+        if (r.layout != 0 || level >= r.nz) return h->fail(OB200_EINVAL, "level", "not a level of a 3-D field");
+        r.p += (size_t)level * G.sz; r.nz = 1; hz = 0;
+    }
     const size_t n = (size_t)(G.Nx + 2 * hx) * (r.ny + 2 * hy) * (r.layout == 0 ? (r.nz + 2 * hz) : 1);
     double* d = buf;
     if (!on_device) {
@@ -621,7 +627,8 @@ static int copy_common(ob200_handle* h, int32_t field, double* buf, int on_devic
         if (to_field) OB_CUDA_CHECK(h, cudaMemcpyAsync(d, buf, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         else if (hx | hy | hz) OB_CUDA_CHECK(h, cudaMemsetAsync(d, 0, n * sizeof(double), h->stream));
     }
-    launch_copy_field(G, r.p, d, r.ny, r.nz, hx, hy, hz, r.layout, to_field, h->stream);
+    const int ex = std::min(std::min(h->transfer_x_halo, hx), OB_H);
+    launch_copy_field(G, r.p, d, r.ny, r.nz, hx, hy, hz, r.layout, to_field, ex, h->stream);
     if (!on_device) {
         if (!to_field) OB_CUDA_CHECK(h, cudaMemcpyAsync(buf, d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
@@ -636,6 +643,10 @@ int ob200_set_field(ob200_handle* h, int32_t field, const double* buf, int32_t o
 }
 int ob200_get_field(ob200_handle* h, int32_t field, double* buf, int32_t on_device, int32_t hx, int32_t hy, int32_t hz) {
     return copy_common(h, field, buf, on_device, hx, hy, hz, false);
+}
+
+int ob200_get_level(ob200_handle* h, int32_t field, int32_t k, double* buf, int32_t on_device, int32_t hx, int32_t hy) {
+    return copy_common(h, field, buf, on_device, hx, hy, 0, false, k);
 }
 
 int ob200_set_forcing(ob200_handle* h, int32_t which, const double* buf, int32_t on_device) {
@@ -781,6 +792,7 @@ int ob200_set_option(ob200_handle* h, const char* name, int32_t value) {
     else if (!std::strcmp(name, "persistent_barotropic")) h->persistent_baro = value != 0;
     else if (!std::strcmp(name, "overlap")) h->overlap = value != 0;
     else if (!std::strcmp(name, "barotropic_graph")) h->use_graph = value != 0;
+    else if (!std::strcmp(name, "transfer_x_halo")) h->transfer_x_halo = value < 0 ? 0 : value;
     else return h->fail(OB200_EINVAL, "option", name);
     return OB200_OK;
 }

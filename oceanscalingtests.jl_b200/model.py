@@ -115,6 +115,7 @@ class BoundaryConditions:
     T_restoring_lambda: float = 0.0
     drag_mu: float = 0.0
     forcing_arrays: dict = field(default_factory=dict)  # RealisticOcean: taux,tauy,Qs,Fs,Tr,Sr
+    providers: dict = field(default_factory=dict)       # "fluxes" / "restoring": (grid, filenum) -> arrays (data/*.jld2)
 
 
 def build_config(grid: LatitudeLongitudeGrid, free_surface: SplitExplicitFreeSurface, *, eos: str,
@@ -197,13 +198,20 @@ class B200Backend:
             msg = self.lib.ob200_last_error(self.h)
             raise RuntimeError(f"libocean_b200 error {rc}: {msg.decode() if msg else ''}")
 
-    def set_field(self, fid, arr: np.ndarray):
+    def set_field(self, fid, arr: np.ndarray, halo=(0, 0, 0)):
+        """`arr`: interior-shaped, or parent-shaped with `halo` = (hx, hy, hz) cells around the interior."""
         arr = np.ascontiguousarray(arr, dtype=np.float64)
-        self._check(self.lib.ob200_set_field(self.h, fid, arr.ctypes.data, 0, 0, 0, 0))
+        self._check(self.lib.ob200_set_field(self.h, fid, arr.ctypes.data, 0, *halo))
 
-    def get_field(self, fid, shape) -> np.ndarray:
+    def get_field(self, fid, shape, halo=(0, 0, 0)) -> np.ndarray:
         out = np.empty(shape, dtype=np.float64)
-        self._check(self.lib.ob200_get_field(self.h, fid, out.ctypes.data, 0, 0, 0, 0))
+        self._check(self.lib.ob200_get_field(self.h, fid, out.ctypes.data, 0, *halo))
+        return out
+
+    def get_level(self, fid, k: int, shape2d, halo=(0, 0)) -> np.ndarray:
+        """One horizontal level of a 3-D field, (ny + 2 hy, Nx + 2 hx)."""
+        out = np.empty(shape2d, dtype=np.float64)
+        self._check(self.lib.ob200_get_level(self.h, fid, int(k), out.ctypes.data, 0, *halo))
         return out
 
     def set_field_device(self, fid, ptr: int, halo=(0, 0, 0)):
@@ -321,6 +329,55 @@ class HydrostaticFreeSurfaceModel:
         shape = _abi.field_shape(name, *self.grid.size())
         a = np.broadcast_to(np.asarray(arr, dtype=np.float64), shape)
         self.backend.set_field(_abi.FIELD_ID[name], np.ascontiguousarray(a))
+
+    def parent_shape(self, name: str, halo: int = 7):
+        shape = _abi.field_shape(name, *self.grid.size())
+        if len(shape) == 2:
+            return (1, shape[0] + 2 * halo, shape[1] + 2 * halo)
+        return tuple(n + 2 * halo for n in shape)
+
+    def get_parent(self, name: str, halo: int = 7, x_halo_data: bool = False) -> np.ndarray:
+        """Oceananigans parent array (k, j, i) with `halo` cells around the interior.  Halo cells are zero unless
+        `x_halo_data`, which also copies the x-halo columns the device holds (option transfer_x_halo)."""
+        two_d = len(_abi.field_shape(name, *self.grid.size())) == 2
+        if x_halo_data:
+            self.backend.set_option("transfer_x_halo", halo)
+        try:
+            return self.backend.get_field(_abi.FIELD_ID[name], self.parent_shape(name, halo), (halo, halo, 0 if two_d else halo))
+        finally:
+            if x_halo_data:
+                self.backend.set_option("transfer_x_halo", 0)
+
+    def get_level(self, name: str, k: int, halo: int = 0, x_halo_data: bool = False) -> np.ndarray:
+        """Level k (0-based) of a 3-D field as a (ny + 2 halo, Nx + 2 halo) window -- the surface writer's
+        `Field(...; indices = (:, :, Nz))` (simulation_outputs.jl:17-25) without moving the whole field."""
+        nz, ny, nx = _abi.field_shape(name, *self.grid.size())
+        if x_halo_data:
+            self.backend.set_option("transfer_x_halo", halo)
+        try:
+            return self.backend.get_level(_abi.FIELD_ID[name], k, (ny + 2 * halo, nx + 2 * halo), (halo, halo))
+        finally:
+            if x_halo_data:
+                self.backend.set_option("transfer_x_halo", 0)
+
+    def set_parent(self, name: str, parent, x_halo_data: bool = False) -> None:
+        """Inverse of get_parent; the halo width is inferred from the array ("allow different halo size")."""
+        shape = _abi.field_shape(name, *self.grid.size())
+        p = np.asarray(parent, dtype=np.float64)
+        if len(shape) == 2 and p.ndim == 2:
+            p = p[None]
+        core = (1,) + tuple(shape) if len(shape) == 2 else tuple(shape)
+        off = [a - b for a, b in zip(p.shape, core)]
+        if any(o < 0 or o % 2 for o in off) or off[1] != off[2]:
+            raise ValueError(f"{name}: parent array {p.shape} does not wrap an interior of {core}")
+        halo = (off[2] // 2, off[1] // 2, off[0] // 2)
+        if x_halo_data:
+            self.backend.set_option("transfer_x_halo", halo[0])
+        try:
+            self.backend.set_field(_abi.FIELD_ID[name], p, halo)
+        finally:
+            if x_halo_data:
+                self.backend.set_option("transfer_x_halo", 0)
 
     @property
     def clock(self):

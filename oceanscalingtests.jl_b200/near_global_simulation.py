@@ -15,10 +15,12 @@ from typing import Callable, Optional
 import numpy as np
 
 from .bathymetry_and_forcings import exponential_z_faces
-from .boundary_and_initial_conditions import initialize_model, set_boundary_conditions
+from .boundary_and_initial_conditions import (initialize_model, set_boundary_conditions, update_fluxes,
+                                              update_restoring)
 from .grid_load_balance import load_balanced_grid
 from .model import (HydrostaticFreeSurfaceModel, QGLeith, RiBasedVerticalDiffusivity, SplitExplicitFreeSurface,
                     VerticalScalarDiffusivity, barotropic_substeps, substeps, time_step)
+from .simulation_outputs import IterationInterval, TimeInterval, set_from_checkpoint
 
 minutes = 60.0
 days = 86400.0
@@ -71,8 +73,19 @@ class Comm:
 
 
 @dataclass
+class Callback:
+    """Oceananigans `Callback(func, schedule)`."""
+    func: Callable
+    schedule: object
+
+    def __call__(self, sim):
+        return self.func(sim)
+
+
+@dataclass
 class Simulation:
-    """Simulation(model; Δt, stop_time) with the reference's callbacks (near_global_simulation.jl:134-162)."""
+    """Simulation(model; Δt, stop_time) with the reference's callbacks (near_global_simulation.jl:134-173) and output
+    writers (simulation_outputs.jl:29-40)."""
     model: HydrostaticFreeSurfaceModel
     dt: float
     stop_time: float
@@ -83,25 +96,83 @@ class Simulation:
     wizard_max_change: float = 1.1
     progress: Optional[Callable] = None
     run_wall_time: float = 0.0
+    callbacks: dict = field(default_factory=dict)
+    output_writers: dict = field(default_factory=dict)
+    align_time_step: bool = True
+    initialized: bool = False
 
 
-def run(sim: Simulation) -> None:
-    """Oceananigans `run!` loop: TimeStepWizard every 10 iterations, progress every 100."""
+def time_step_wizard(sim: Simulation) -> None:
+    """TimeStepWizard(cfl=0.35; max_change=1.1, max_Δt, min_Δt) -- near_global_simulation.jl:160."""
+    if not sim.max_dt > sim.min_dt:
+        return
+    _, cfl_dt = sim.model.backend.diagnostics()
+    new_dt = sim.wizard_cfl * cfl_dt
+    new_dt = min(sim.wizard_max_change * sim.dt, new_dt)
+    new_dt = max(0.5 * sim.dt, new_dt)           # min_change default 0.5
+    sim.dt = float(min(max(new_dt, sim.min_dt), sim.max_dt))
+
+
+def _all_callbacks(sim: Simulation) -> list:
+    """The reference's callbacks in insertion order: progress (every 100 iterations), wizard (every 10), then the
+    experiment's (update_fluxes / update_restoring) and the user's."""
+    cbs = []
+    if sim.progress is not None:
+        cbs.append(Callback(sim.progress, IterationInterval(100)))
+    cbs.append(Callback(time_step_wizard, IterationInterval(10)))
+    cbs.extend(sim.callbacks.values())
+    return cbs
+
+
+def aligned_time_step(sim: Simulation, dt: float) -> float:
+    """Oceananigans `aligned_time_step`: shorten Δt so that the model lands exactly on the next actuation time of every
+    TimeInterval schedule (callbacks and output writers) and on the stop time."""
+    t = sim.model.clock["time"]
+    aligned = dt
+    for obj in list(sim.callbacks.values()) + list(sim.output_writers.values()):
+        sched = obj.schedule
+        if isinstance(sched, TimeInterval):
+            gap = sched.next_actuation_time() - t
+            if gap > 0:
+                aligned = min(aligned, gap)
+    aligned = min(aligned, sim.stop_time - t)
+    return max(aligned, 0.0)
+
+
+def initialize_simulation(sim: Simulation) -> None:
+    """Oceananigans `initialize!(sim)`: every callback runs once and every writer writes the initial state."""
     m = sim.model
+    for obj in list(sim.callbacks.values()) + list(sim.output_writers.values()):
+        obj.schedule.initialize(m)
+    for cb in _all_callbacks(sim):
+        cb(sim)
+    for w in sim.output_writers.values():
+        w.write(m)
+    sim.initialized = True
+
+
+def run(sim: Simulation, pickup=False) -> None:
+    """Oceananigans `run!(simulation; pickup)`: restore from a checkpoint file when `pickup` names one
+    (experiments/run.jl:59-60), then step until stop_time / stop_iteration with callbacks and writers after each step."""
+    m = sim.model
+    if pickup:
+        set_from_checkpoint(m, pickup)
     t0 = _time.time()
+    if not sim.initialized:
+        initialize_simulation(sim)
+    cbs = _all_callbacks(sim)
     while True:
         clk = m.clock
         if clk["time"] >= sim.stop_time or (sim.stop_iteration is not None and clk["iteration"] >= sim.stop_iteration):
             break
-        if clk["iteration"] % 10 == 0 and sim.max_dt > sim.min_dt:
-            _, cfl_dt = m.backend.diagnostics()
-            new_dt = sim.wizard_cfl * cfl_dt
-            new_dt = min(sim.wizard_max_change * sim.dt, new_dt)
-            new_dt = max(0.5 * sim.dt, new_dt)           # min_change default 0.5
-            sim.dt = float(min(max(new_dt, sim.min_dt), sim.max_dt))
-        if clk["iteration"] % 100 == 0 and sim.progress is not None:
-            sim.progress(sim)
-        time_step(m, sim.dt)
+        dt = aligned_time_step(sim, sim.dt) if sim.align_time_step else sim.dt
+        time_step(m, dt)
+        for cb in cbs:
+            if cb.schedule(m):
+                cb(sim)
+        for w in sim.output_writers.values():
+            if w.schedule(m):
+                w.write(m)
     m.backend.sync()
     sim.run_wall_time = _time.time() - t0
 
@@ -140,8 +211,10 @@ def scaling_test_simulation(resolution, ranks, dt, stop_time, *, device: int = 0
     forcing = None
     if experiment == "RealisticOcean" and realistic_inputs and with_fluxes:
         forcing = realistic_inputs["forcing"](grid)
+    providers = {k: realistic_inputs[k] for k in ("fluxes", "restoring") if realistic_inputs and k in realistic_inputs}
     boundary_conditions = set_boundary_conditions(experiment, grid, with_fluxes=with_fluxes,
-                                                  with_restoring=with_restoring, forcing_arrays=forcing)
+                                                  with_restoring=with_restoring, forcing_arrays=forcing,
+                                                  providers=providers)
 
     model = HydrostaticFreeSurfaceModel(grid=grid, free_surface=free_surface, eos=equation_of_state(experiment),
                                         closure=closure, boundary_conditions=boundary_conditions, device=device,
@@ -166,6 +239,12 @@ def scaling_test_simulation(resolution, ranks, dt, stop_time, *, device: int = 0
               (comm.rank, c["time"], c["iteration"], s.dt, *mx), flush=True)
 
     sim.progress = progress
+    if experiment == "RealisticOcean":      # near_global_simulation.jl:163-172
+        if with_fluxes:
+            sim.callbacks["update_fluxes"] = Callback(update_fluxes, TimeInterval(5 * days))
+        if with_restoring:
+            repeat_year = os.environ.get("REPEATYEAR", "true").lower() in ("true", "1")
+            sim.callbacks["update_restoring"] = Callback(update_restoring, TimeInterval((1 if repeat_year else 15) * days))
     return sim
 
 

@@ -55,7 +55,8 @@ def main():
     if experiment == "RealisticOcean":
         depth = pkg.experiment_depth(experiment)
         realistic = {"bathymetry": lambda Nx, Ny: pkg.synthetic.realistic_bathymetry(Nx, Ny, depth),
-                     "forcing": pkg.synthetic.forcing_arrays, "initial": pkg.synthetic.initial_T_S}
+                     "forcing": pkg.synthetic.forcing_arrays, "initial": pkg.synthetic.initial_T_S,
+                     "fluxes": pkg.synthetic.flux_file, "restoring": pkg.synthetic.restoring_file}
     sim = pkg.scaling_test_simulation(resolution, ranks, (min_dt, max_dt), stop_time, device=local, Nz=Nz,
                                       experiment=experiment, restart=restart, profile=profile, with_fluxes=with_fluxes,
                                       with_restoring=with_restoring, loadbalance=loadbalance, realistic_inputs=realistic)
@@ -66,7 +67,10 @@ def main():
         stop_it = os.environ.get("STOP_ITERATION")
         if stop_it:
             sim.stop_iteration = int(stop_it)
-        pkg.run(sim)
+        output_dir = os.environ.get("OUTPUTDIR", "./")       # run.jl:39,57-60
+        pkg.set_outputs(sim, experiment, output_dir=output_dir, overwrite_existing=False, checkpoint_time=10 * 86400.0)
+        pickup = os.path.join(output_dir, f"RealisticOcean_checkpoint_{rank}_iteration{restart}.npz") if restart else False
+        pkg.run(sim, pickup=pickup)
         if rank == 0:
             print(f"[ Info: simulation took {sim.run_wall_time:.2f} s", flush=True)
     if world > 1:

@@ -34,16 +34,31 @@ def initial_T_S(grid):
     return np.clip(T, -2.0, 30.0), np.clip(S, 33.0, 37.0)
 
 
-def forcing_arrays(grid) -> dict:
-    """taux (6,Ny,Nx), tauy (6,Ny+1,Nx), Qs, Fs, Tr, Sr (6,Ny,Nx): six time slices (days 0..5 / 0..15)."""
+def forcing_arrays(grid, flux_filenum: int = 1, restoring_filenum: int = 1) -> dict:
+    """taux (6,Ny,Nx), tauy (6,Ny+1,Nx), Qs, Fs, Tr, Sr (6,Ny,Nx): six time slices -- days 0..5 of flux file
+    `flux_filenum` (data/fluxes_<n>.jld2) and days 0, 3, .., 15 of restoring file `restoring_filenum`
+    (data/restoring_<n>.jld2).  Consecutive files are continuous: slice 6 of file n equals slice 1 of file n + 1."""
     r = np.pi / 180.0
     lam = grid.lam_c()[None, None, :]
     phi, phif = grid.phi_c()[None, :, None], grid.phi_f()[None, :, None]
-    t = np.arange(6, dtype=np.float64)[:, None, None]
+    t = (np.arange(6, dtype=np.float64) + 5.0 * (flux_filenum - 1))[:, None, None]
+    tr = (3.0 * np.arange(6, dtype=np.float64) + 15.0 * (restoring_filenum - 1))[:, None, None] / 3.0
     taux = -1e-4 * np.cos(3 * phi * r) * (1.0 + 0.1 * np.sin(lam * r + 0.4 * t))
     tauy = 2e-5 * np.sin(2 * phif * r) * np.cos(2 * lam * r + 0.3 * t)
     Qs = 2e-5 * np.cos(2 * phi * r) * (1.0 + 0.2 * np.sin(lam * r - 0.2 * t))
     Fs = 1e-6 * np.sin(3 * phi * r) * np.cos(lam * r + 0.1 * t)
-    Tr = -2.0 + 31.0 * np.cos(phi * r) ** 2 + 0.2 * np.sin(lam * r + 0.5 * t)
-    Sr = 35.0 + 1.2 * np.cos(2 * phi * r) + 0.05 * np.cos(2 * lam * r - 0.3 * t)
+    Tr = -2.0 + 31.0 * np.cos(phi * r) ** 2 + 0.2 * np.sin(lam * r + 0.5 * tr)
+    Sr = 35.0 + 1.2 * np.cos(2 * phi * r) + 0.05 * np.cos(2 * lam * r - 0.3 * tr)
     return {k: np.ascontiguousarray(v) for k, v in dict(taux=taux, tauy=tauy, Qs=Qs, Fs=Fs, Tr=Tr, Sr=Sr).items()}
+
+
+def flux_file(grid, filenum: int) -> dict:
+    """Stand-in for `jldopen("data/fluxes_$(filenum).jld2")` already partitioned to the rank's slab."""
+    a = forcing_arrays(grid, flux_filenum=filenum)
+    return {k: a[k] for k in ("taux", "tauy", "Qs", "Fs")}
+
+
+def restoring_file(grid, filenum: int) -> dict:
+    """Stand-in for `jldopen("data/restoring_$(filenum).jld2")` already partitioned to the rank's slab."""
+    a = forcing_arrays(grid, restoring_filenum=filenum)
+    return {k: a[k] for k in ("Tr", "Sr")}

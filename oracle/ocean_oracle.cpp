@@ -1065,13 +1065,15 @@ struct Oracle {
             default: return {0, 0, 0, 0};
         }
     }
+    int xfer_halo = 0;
     int copy_field(int id, double* buf, int hx, int hy, int hz, bool set) {
         Ref r = ref(id);
         if (!r.f3 && !r.f2) { err = "bad field id"; return OB200_EINVAL; }
         size_t sx = Nx + 2 * hx, sy = r.ny + 2 * hy;
+        const int e = std::min(std::min(xfer_halo, hx), H);   // option transfer_x_halo: x-halo columns travel too
         for (int k = 0; k < r.nz; k++)
             for (int j = 0; j < r.ny; j++)
-                for (int i = 0; i < Nx; i++) {
+                for (int i = -e; i < Nx + e; i++) {
                     double& b = buf[((size_t)(k + (r.f3 ? hz : 0)) * sy + (j + hy)) * sx + (i + hx)];
                     double& x = r.f3 ? (*r.f3)(i, j, k) : (*r.f2)(i, j);
                     if (set) x = b; else b = x;
@@ -1110,6 +1112,10 @@ int oracle_set_field(void* h, int id, const double* buf, int hx, int hy, int hz)
 }
 int oracle_get_field(void* h, int id, double* buf, int hx, int hy, int hz) {
     return ((Oracle*)h)->copy_field(id, buf, hx, hy, hz, false);
+}
+int oracle_set_option(void* h, const char* name, int value) {
+    if (!std::strcmp(name, "transfer_x_halo")) { ((Oracle*)h)->xfer_halo = value; return OB200_OK; }
+    return OB200_EINVAL;
 }
 int oracle_get_strip(void* h, int id, double* buf, int side, int width, int interior_edge) {
     return ((Oracle*)h)->copy_strip(id, buf, side, width, interior_edge != 0, false);

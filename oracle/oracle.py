@@ -48,6 +48,8 @@ def load():
         f.restype = C.c_int
     lib.oracle_set_forcing.argtypes = [H, C.c_int, dp]
     lib.oracle_set_forcing.restype = C.c_int
+    lib.oracle_set_option.argtypes = [H, C.c_char_p, C.c_int]
+    lib.oracle_set_option.restype = C.c_int
     lib.oracle_update_state.argtypes = [H]
     lib.oracle_time_step.argtypes = [H, C.c_double]
     lib.oracle_run_stage.argtypes = [H, C.c_int, C.c_double, C.c_int]
@@ -79,14 +81,25 @@ class OracleBackend:
         if rc != 0:
             raise RuntimeError(f"oracle error {rc}")
 
-    def set_field(self, fid, arr):
+    def set_field(self, fid, arr, halo=(0, 0, 0)):
         arr = np.ascontiguousarray(arr, dtype=np.float64)
-        self._check(self.lib.oracle_set_field(self.h, fid, arr.ctypes.data, 0, 0, 0))
+        self._check(self.lib.oracle_set_field(self.h, fid, arr.ctypes.data, *halo))
 
-    def get_field(self, fid, shape):
-        out = np.empty(shape, dtype=np.float64)
-        self._check(self.lib.oracle_get_field(self.h, fid, out.ctypes.data, 0, 0, 0))
+    def get_field(self, fid, shape, halo=(0, 0, 0)):
+        out = np.zeros(shape, dtype=np.float64) if any(halo) else np.empty(shape, dtype=np.float64)
+        self._check(self.lib.oracle_get_field(self.h, fid, out.ctypes.data, *halo))
         return out
+
+    def get_level(self, fid, k, shape2d, halo=(0, 0)):
+        hx, hy = halo
+        full = self.get_field(fid, (self._nz(fid), shape2d[0], shape2d[1]), (hx, hy, 0))
+        return np.ascontiguousarray(full[k])
+
+    def _nz(self, fid):
+        return self.Nz + 1 if fid in (2, 6, 7, 24, 25) else self.Nz      # W, KAPPA_C, KAPPA_U, QX, QY
+
+    def set_option(self, name, value):
+        self._check(self.lib.oracle_set_option(self.h, name.encode(), int(value)))
 
     def get_strip(self, fid, n, side, width, interior_edge):
         out = np.empty(n, dtype=np.float64)
