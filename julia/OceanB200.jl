@@ -120,4 +120,29 @@ function comm_init!(h::Handle, comm, MPI)
     check(h.ptr, ccall((:ob200_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), h.ptr, id))
 end
 
+# ---- checkpoint containers ------------------------------------------------------------------------------------
+# The Python host mirror (simulation_outputs.py) stores the reference's JLD2 groups under the same names in an
+# uncompressed zip of .npy members.  With NPZ.jl (not in the reference's Manifest; `] add NPZ`) the two directions are:
+#
+#   checkpoint_to_npz("RealisticOcean_checkpoint_0_iteration1000.jld2", "RealisticOcean_checkpoint_0_iteration1000.npz")
+#   npz_to_checkpoint(...)   # the inverse, for `run!(simulation, pickup = file)` (experiments/run.jl:59-60)
+#
+# Julia arrays are (i, j, k) column-major; numpy reads the same bytes as (k, j, i) C-ordered, so `permutedims` with
+# (3, 2, 1) converts between what NPZ.jl writes and what the Python side expects.
+const CHECKPOINT_GROUPS = vcat(["$n/data" for n in ("u", "v", "T", "S", "η")],
+                               ["timestepper/$G/$n/data" for G in ("Gⁿ", "G⁻") for n in ("u", "v", "T", "S")])
+
+function checkpoint_to_npz(jld2path, npzpath; JLD2, NPZ)
+    JLD2.jldopen(jld2path, "r") do file
+        out = Dict{String, Any}()
+        for g in CHECKPOINT_GROUPS
+            haskey(file, g) && (out[g] = permutedims(Array(file[g]), (3, 2, 1)))
+        end
+        clock = file["clock"]
+        out["clock/time"] = Float64(clock.time)
+        out["clock/iteration"] = Int64(clock.iteration)
+        NPZ.npzwrite(npzpath, out)
+    end
+end
+
 end # module
