@@ -122,11 +122,11 @@ end
 
 # ---- checkpoint containers ------------------------------------------------------------------------------------
 # The Python host mirror (simulation_outputs.py) stores the reference's JLD2 groups under the same names in an
-# uncompressed zip of .npy members.  With NPZ.jl (not in the reference's Manifest; `] add NPZ`) the two directions are:
+# uncompressed zip of .npy members.  With NPZ.jl (not in the reference's Manifest; `] add NPZ`):
 #
 #   checkpoint_to_npz("RealisticOcean_checkpoint_0_iteration1000.jld2", "RealisticOcean_checkpoint_0_iteration1000.npz")
-#   npz_to_checkpoint(...)   # the inverse, for `run!(simulation, pickup = file)` (experiments/run.jl:59-60)
 #
+# (the inverse reads the same group names back with `NPZ.npzread` and writes them with `JLD2.jldopen(path, "w")`).
 # Julia arrays are (i, j, k) column-major; numpy reads the same bytes as (k, j, i) C-ordered, so `permutedims` with
 # (3, 2, 1) converts between what NPZ.jl writes and what the Python side expects.
 const CHECKPOINT_GROUPS = vcat(["$n/data" for n in ("u", "v", "T", "S", "η")],

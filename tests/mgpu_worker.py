@@ -22,8 +22,24 @@ def main():
     pkg = ge.package()
     c = cases.build_case(case_name)
     m = c.make_model(pkg, None, rank=rank, ranks=world, device=local, comm=pkg.Comm())
-    for _ in range(nsteps):
-        pkg.time_step(m, c.dt)
+    restart = len(sys.argv) > 3 and sys.argv[3] == "restart"
+    if restart:
+        # per-rank checkpoint half way (simulation_outputs.jl:36-40 names the files by rank), then a fresh handle
+        # restored from it finishes the run: the slab halos of the state Oceananigans omits travel in the file
+        import tempfile
+        half = nsteps // 2
+        for _ in range(half):
+            pkg.time_step(m, c.dt)
+        d = tempfile.mkdtemp(prefix=f"ob200_ck_{rank}_")
+        path = pkg.Checkpointer(d, f"DoubleDrake_checkpoint_{rank}", pkg.TimeInterval(86400.0)).write(m)
+        m.backend.close()
+        m = c.make_model(pkg, None, rank=rank, ranks=world, device=local, comm=pkg.Comm(), initialize=False)
+        pkg.set_from_checkpoint(m, path)
+        for _ in range(nsteps - half):
+            pkg.time_step(m, c.dt)
+    else:
+        for _ in range(nsteps):
+            pkg.time_step(m, c.dt)
     m.backend.sync()
     names = ("U", "V", "W", "ETA", "T", "S", "KAPPA_U", "GU", "GT")
     ok = True

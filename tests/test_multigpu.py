@@ -21,3 +21,15 @@ def test_slabs_match_single_gpu(case_name):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_slab_checkpoint_restart_matches_single_gpu():
+    """2 slabs: 3 steps, per-rank checkpoint, fresh handles restored from the files, 3 more steps == 6 steps on 1 GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29733", os.path.join(HERE, "mgpu_worker.py"), "dd_mid", "6", "restart"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
