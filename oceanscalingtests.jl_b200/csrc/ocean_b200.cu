@@ -620,19 +620,25 @@ static int copy_common(ob200_handle* h, int32_t field, double* buf, int on_devic
         if (r.layout != 0 || level >= r.nz) return h->fail(OB200_EINVAL, "level", "not a level of a 3-D field");
         r.p += (size_t)level * G.sz; r.nz = 1; hz = 0;
     }
-    const size_t n = (size_t)(G.Nx + 2 * hx) * (r.ny + 2 * hy) * (r.layout == 0 ? (r.nz + 2 * hz) : 1);
-    double* d = buf;
-    if (!on_device) {
-        OB_CUDA_CHECK(h, cudaMalloc((void**)&d, n * sizeof(double)));
-        if (to_field) OB_CUDA_CHECK(h, cudaMemcpyAsync(d, buf, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        else if (hx | hy | hz) OB_CUDA_CHECK(h, cudaMemsetAsync(d, 0, n * sizeof(double), h->stream));
-    }
     const int ex = std::min(std::min(h->transfer_x_halo, hx), OB_H);
-    launch_copy_field(G, r.p, d, r.ny, r.nz, hx, hy, hz, r.layout, to_field, ex, h->stream);
-    if (!on_device) {
-        if (!to_field) OB_CUDA_CHECK(h, cudaMemcpyAsync(buf, d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (on_device) {
+        launch_copy_field(G, r.p, buf, r.ny, r.nz, hx, hy, hz, r.layout, to_field, ex, h->stream);
+    } else {
+        // host buffer: ONE strided DMA between the dense parent-array window and the pitched device layout (no staging
+        // copy, no staging allocation); pinned host memory moves at the PCIe rate
+        const int pitch = r.layout == 2 ? G.pitch2 : G.pitch, x0 = r.layout == 2 ? G.X0b : OB_X0;
+        const size_t sx = (size_t)G.Nx + 2 * hx, sy = (size_t)r.ny + 2 * hy;
+        cudaMemcpy3DParms p = {};
+        const cudaPitchedPtr host = make_cudaPitchedPtr(buf, sx * sizeof(double), sx, sy);
+        const cudaPitchedPtr dev = make_cudaPitchedPtr(r.p, (size_t)pitch * sizeof(double), pitch, G.NyP);
+        const cudaPos hpos = make_cudaPos((size_t)(hx - ex) * sizeof(double), hy, r.layout == 0 ? hz : 0);
+        const cudaPos dpos = make_cudaPos((size_t)(x0 - ex) * sizeof(double), OB_H, 0);
+        p.srcPtr = to_field ? host : dev; p.srcPos = to_field ? hpos : dpos;
+        p.dstPtr = to_field ? dev : host; p.dstPos = to_field ? dpos : hpos;
+        p.extent = make_cudaExtent((size_t)(G.Nx + 2 * ex) * sizeof(double), r.ny, r.nz);
+        p.kind = to_field ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        OB_CUDA_CHECK(h, cudaMemcpy3DAsync(&p, h->stream));
         OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
-        cudaFree(d);
     }
     OB_CUDA_CHECK(h, cudaGetLastError());
     if (to_field) h->fields_dirty = true;

@@ -204,13 +204,13 @@ class B200Backend:
         self._check(self.lib.ob200_set_field(self.h, fid, arr.ctypes.data, 0, *halo))
 
     def get_field(self, fid, shape, halo=(0, 0, 0)) -> np.ndarray:
-        out = np.empty(shape, dtype=np.float64)
+        out = np.zeros(shape, dtype=np.float64) if any(halo) else np.empty(shape, dtype=np.float64)   # halo cells are not written
         self._check(self.lib.ob200_get_field(self.h, fid, out.ctypes.data, 0, *halo))
         return out
 
     def get_level(self, fid, k: int, shape2d, halo=(0, 0)) -> np.ndarray:
         """One horizontal level of a 3-D field, (ny + 2 hy, Nx + 2 hx)."""
-        out = np.empty(shape2d, dtype=np.float64)
+        out = np.zeros(shape2d, dtype=np.float64) if any(halo) else np.empty(shape2d, dtype=np.float64)
         self._check(self.lib.ob200_get_level(self.h, fid, int(k), out.ctypes.data, 0, *halo))
         return out
 

@@ -161,6 +161,20 @@ def test_parent_array_layout_round_trip(pkg, gpu_lib):
         m.backend.set_field_device(fid, (buf + 1.0).data_ptr(), (H, H, hz))
         m.backend.sync()
         assert np.array_equal(m.get(name), ref + 1.0), name
+        # the same window through HOST buffers (one strided DMA each way): interior only, caller's halos untouched
+        hbuf = np.full(shape, -7.0)
+        lib = m.backend.lib
+        assert lib.ob200_get_field(m.backend.h, fid, hbuf.ctypes.data, 0, H, H, hz) == 0
+        hin = hbuf[hz:hz + nz, H:H + ny, H:H + Nx] if name != "ETA" else hbuf[H:H + ny, H:H + Nx]
+        assert np.array_equal(hin.reshape(ref.shape), ref + 1.0), name
+        assert hbuf.flat[0] == -7.0 and hbuf.flat[-1] == -7.0
+        assert int(np.sum(hbuf == -7.0)) >= hbuf.size - ref.size - 1
+        hbuf += 2.0
+        assert lib.ob200_set_field(m.backend.h, fid, hbuf.ctypes.data, 0, H, H, hz) == 0
+        assert np.array_equal(m.get(name), (ref + 1.0) + 2.0), name
+        if name == "W":      # one level: the surface writer's window
+            lev = m.get_level("W", Nz - 1, H)
+            assert lev.shape == (Ny + 2 * H, Nx + 2 * H) and np.array_equal(lev[H:-H, H:-H], ((ref + 1.0) + 2.0)[Nz - 1])
 
 
 def test_abi_error_paths(pkg, gpu_lib):
