@@ -469,36 +469,34 @@ int step_body(ob200_handle* h, double dt, bool euler) {
     int e = 0;
     auto mark = [&]() { if (h->timing) cudaEventRecord(h->ev[e++], s1); };
     auto mark2 = [&](int q) { if (h->timing) cudaEventRecord(h->ev2[q], s2); };
-    if (h->overlap) { cudaEventRecord(h->ev_join[0], s1); cudaStreamWaitEvent(s2, h->ev_join[0], 0); }
-    mark2(0);
-    launch_ab2_implicit_ts(G, h->F, dt, chi, s2);
-    mark2(1);
-    if (h->overlap) cudaEventRecord(h->ev_join[1], s2);
     mark();
     launch_ab2_implicit_uv(G, h->F, dt, chi, s1);   // also produces G^U, G^V (barotropic forcing)
     mark();
+    // the T, S solve (HBM-bound) runs beside the barotropic substeps (launch-latency-bound, SMs mostly idle)
+    cudaEventRecord(h->ev_join[0], s1); cudaStreamWaitEvent(s2, h->ev_join[0], 0);
+    mark2(0);
+    launch_ab2_implicit_ts(G, h->F, dt, chi, s2);
+    mark2(1);
+    cudaEventRecord(h->ev_join[1], s2);
     if (int rc = barotropic_loop(h, dt)) return rc;
     mark();
     launch_correct(G, h->F, s1);
     swap_tendencies(h);
     mark();
     h->time += dt; h->iteration += 1; h->last_dt = dt;
-    if (h->overlap) cudaStreamWaitEvent(s1, h->ev_join[1], 0);   // halos need the new T, S
+    cudaStreamWaitEvent(s1, h->ev_join[1], 0);   // halos need the new T, S
     if (int rc = mask_and_halos(h)) return rc;
     mark();
     launch_w_p(G, h->F, s1);
-    if (h->overlap) { cudaEventRecord(h->ev_join[2], s1); cudaStreamWaitEvent(s2, h->ev_join[2], 0); }
-    mark2(2);
-    launch_tracers(G, h->F, h->mom_plan, h->cfg.order_tracer, h->time, s2);
-    mark2(3);
-    if (h->overlap) cudaEventRecord(h->ev_join[3], s2);
     mark();
     launch_ri_kappa(G, h->F, h->time, s1);
     if (G.qgleith) launch_leith(G, h->F, s1);
     mark();
     launch_momentum(G, h->F, h->mom_plan, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, s1);
     mark();
-    if (h->overlap) cudaStreamWaitEvent(s1, h->ev_join[3], 0);   // the step ends when both chains have finished
+    if (h->timing) cudaEventRecord(h->ev2[2], s1);
+    launch_tracers(G, h->F, h->mom_plan, h->cfg.order_tracer, h->time, s1);
+    if (h->timing) cudaEventRecord(h->ev2[3], s1);
     h->n_timed = e - 1;
     return OB200_OK;
 }

@@ -118,6 +118,18 @@ def test_persistent_barotropic_matches_launch_loop(pkg, gpu_lib):
         assert np.array_equal(m1.get(n), m2.get(n)), n
 
 
+def test_two_stream_overlap_matches_serial_order(pkg, gpu_lib):
+    """Option "overlap": the T, S solve runs on a second stream beside the barotropic substeps; same bits."""
+    c = cases.build_case("bumpy")
+    m1, m2 = c.make_model(pkg, None), c.make_model(pkg, None)
+    m2.backend.set_option("overlap", 1)
+    for _ in range(6):
+        pkg.time_step(m1, c.dt)
+        pkg.time_step(m2, c.dt)
+    for n in PROG + ("GU", "GT", "KAPPA_C"):
+        assert np.array_equal(m1.get(n), m2.get(n)), n
+
+
 def test_diagnostics_and_wizard_run(pkg, gpu_lib):
     """ob200_diagnostics (progress max-abs + CFL time scale) against numpy, and the TimeStepWizard loop of `run`."""
     c = cases.build_case("dd_small")
