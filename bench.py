@@ -65,7 +65,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -74,22 +74,37 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout: float = 20.0):
+        """nvidia-smi needs a second or more to start (longer with 8 ranks starting one each): the load only begins
+        once it is sampling, otherwise a short run ends before the first sample."""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin: float = 0.0, t_end: float = float("inf")):
+        """Summary of the samples that arrived in [t_begin, t_end] (perf_counter times): warm-up + timed region."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.03)              # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if t_begin <= t <= t_end + 0.03]
+        window = "warm-up + timed region"
+        if not rows and self.rows:    # region shorter than one sampling period: the sample closest to it
+            mid = 0.5 * (t_begin + min(t_end, self.rows[-1][0]))
+            rows = [min(self.rows, key=lambda tr: abs(tr[0] - mid))[1]]
+            window = "nearest sample (region shorter than the sampling period)"
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[q] for r in self.rows if len(r) >= 7 for q in range(4) if r[3 + q].lower() == "active"})
+        reasons = sorted({names[q] for r in rows if len(r) >= 7 for q in range(4) if r[3 + q].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def make_case(workload: str, ranks: int, balance: str = "equal") -> cases.Case:
@@ -259,6 +274,9 @@ def main():
     # alone can be shorter than one nvidia-smi period on 8 GPUs; the load is the same in both)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.wait_first()
+    barrier()
+    t_load = time.perf_counter()
     for _ in range(args.warmup):
         pkg.time_step(model, dt)
     barrier()
@@ -277,7 +295,7 @@ def main():
         groups[:len(ms)] += ms
     barrier()
     elapsed = time.perf_counter() - t0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_load, time.perf_counter())
     _, launches1 = model.backend.timing()
     model.backend.set_option("timing", 0)
     if world > 1:
@@ -333,7 +351,7 @@ def main():
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the two momentum launches of one step, from the
                 # `ncu --set full` capture summarised in profiles/r01_final_ncu_full.txt (C3, 1 GPU): 12.87 GB
-                "traffic": 12.87e9 if (args.workload == "c3" and world == 1) else None,
+                "traffic": 12.71e9 if (args.workload == "c3" and world == 1) else None,   # ncu dram read+write, both instances
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": MOMENTUM_BYTES_PER_CELL,
                 "ms_per_launch": mom_ms, "note": "FP64-ALU-bound WENO stencil (SURVEY F10); HBM fraction reported as the contract asks"}
     # per-stage rooflines against the same measured HBM peak: algorithmic bytes per cell x local cells /
@@ -359,7 +377,7 @@ def main():
            "stage_ms": {n: float(g / args.steps) for n, g in zip(GROUP_NAMES, groups)},
            "roofline": roofline, "kernel_rooflines": kernel_rooflines,
            "fp64_pipe": {"source": "profiles/r01_final_ncu_full.txt (ncu --set full, C3, 1 GPU)",
-                         "momentum_full_order_tiles_pct_of_peak": 62.1, "tracers_full_order_tiles_pct_of_peak": 66.0}}
+                         "momentum_full_order_tiles_pct_of_peak": 64.7, "tracers_full_order_tiles_pct_of_peak": 66.2}}
     if per_rank_groups is not None:
         out["stage_ms_per_rank"] = [[round(x, 3) for x in r] for r in per_rank_groups]
     if world == 1 and not args.no_cpu_baseline:

@@ -452,9 +452,10 @@ int barotropic_loop(ob200_handle* h, double dt) {
     return OB200_OK;
 }
 
-// One time step.  Two streams: the tracer chain (AB2 + implicit solve of T, S; later the T, S
-// tendencies) is independent of the momentum / barotropic chain until the halo exchange, and the FP64-bound
-// tracer tendencies overlap the HBM-bound pHY' + kappa sweep.  Joined by events; ob200_sync waits for both.
+// One time step.  Option "overlap": the T, S solve (HBM-bound, independent of the momentum / barotropic
+// chain until the halo exchange) runs on a second stream beside the launch-latency-bound barotropic substeps; joined
+// by events before the exchange.  Bit-identical to the serial order; measured without gain on one B200 at C3 (the
+// long-lived solver blocks fill every SM, the substep kernels queue behind them), so the default is the serial order.
 int step_body_serial(ob200_handle* h, double dt, bool euler);
 
 int step_body(ob200_handle* h, double dt, bool euler) {
@@ -501,9 +502,7 @@ int step_body(ob200_handle* h, double dt, bool euler) {
     return OB200_OK;
 }
 
-// Default: everything on one stream, in the reference's order.  (Measured on B200 at C3: the two-stream variant
-// above gives no gain -- 64.2 vs 64.2 ms/step -- because the FP64-bound tendency kernels occupy every SM's
-// register file, so the HBM-bound sweeps cannot co-reside; it is kept behind option "overlap".)
+// Default: everything on one stream, in the reference's order (53.1 vs 53.0 ms/step with "overlap" at C3).
 int step_body_serial(ob200_handle* h, double dt, bool euler) {
     const double chi = euler ? -0.5 : h->cfg.ab2_chi;
     const Geom& G = h->G;
