@@ -184,8 +184,8 @@ int ob200_set_clock(ob200_handle* h, double time, int64_t iteration, double last
 int ob200_diagnostics(ob200_handle* h, double maxabs[6], double* cfl_dt);
 int ob200_get_timing(ob200_handle* h, ob200_timing* t);
 int ob200_set_stream(ob200_handle* h, void* cuda_stream);
-/* Options: "timing" (stage timing, above), "barotropic_graph" (default 1), "persistent_barotropic", "overlap"
- * (tuning variants, default 0), "transfer_x_halo" = n: ob200_set_field / ob200_get_field also copy n (<= 7, <= hx)
+/* Options: "timing" (stage timing, above), "barotropic_graph" (default 1), "persistent_barotropic", "overlap",
+ * "overlap_exchange" (tuning variants, default 0; bit-identical, measured not faster -- DESIGN.md), "transfer_x_halo" = n: ob200_set_field / ob200_get_field also copy n (<= 7, <= hx)
  * x-halo columns each side -- the checkpointer uses it for state whose halo columns are not recomputed by
  * update_state! (time-filtered diffusivities, barotropic averages; src/simulation_outputs.jl:36-40,45-70).      */
 int ob200_set_option(ob200_handle* h, const char* name, int32_t value);

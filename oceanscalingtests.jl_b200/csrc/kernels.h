@@ -30,8 +30,11 @@ size_t pack_x_count(const Geom& G);
 void launch_diagnostics(const Geom& G, const Fields& F, double* out8, cudaStream_t st);
 
 // kernels_column.cu
-void launch_w_p(const Geom& G, const Fields& F, cudaStream_t st);
+void launch_w_p(const Geom& G, const Fields& F, cudaStream_t st);                       // all columns [-2, Nx + 2)
 void launch_ri_kappa(const Geom& G, const Fields& F, double time, cudaStream_t st);
+// the same sweeps on the columns [a0, a0 + n0) U [a1, a1 + n1)
+void launch_w_p(const Geom& G, const Fields& F, int a0, int n0, int a1, int n1, cudaStream_t st);
+void launch_ri_kappa(const Geom& G, const Fields& F, double time, int a0, int n0, int a1, int n1, cudaStream_t st);
 void launch_barotropic_forcing(const Geom& G, const Fields& F, double chi, cudaStream_t st);
 // momentum (u, v: also G^U, G^V) and tracer (T, S) solves can run on different streams (separate scratch arrays)
 void launch_ab2_implicit_uv(const Geom& G, const Fields& F, double dt, double chi, cudaStream_t st);

@@ -32,6 +32,7 @@ struct ob200_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[20];
     bool timing = false, use_graph = true, persistent_baro = false, overlap = false;
+    bool overlap_exchange = false;  // x-slabs: halo exchange on stream2 beside the interior columns of the auxiliary sweeps (option)
     int transfer_x_halo = 0;   // x-halo columns copied by set/get_field besides the interior (checkpoint of halo-carrying state)
     cudaStream_t stream2 = nullptr;            // tracer work that can overlap the momentum / barotropic chain
     cudaEvent_t ev_join[4];                    // step start, T/S solved, w ready, tracer tendencies done
@@ -346,22 +347,23 @@ FieldRef field_ref(ob200_handle* h, int id) {
 }
 
 // ---- stages ------------------------------------------------------------------------------------------
-int exchange_halos(ob200_handle* h) {
+int exchange_halos(ob200_handle* h, cudaStream_t st = nullptr) {
     if (h->periodic_local) return OB200_OK;
+    if (!st) st = h->stream;
     if (!h->comm) return h->fail(OB200_ESTATE, "exchange_halos", "nranks > 1 but ob200_comm_init was not called");
     const int r = h->cfg.rank, n = h->cfg.nranks;
     const int west = (r + n - 1) % n, east = (r + 1) % n;
-    launch_pack_x(h->G, h->F, h->sendW, h->sendE, h->stream);
+    launch_pack_x(h->G, h->F, h->sendW, h->sendE, st);
     // order matters on a 2-rank ring (west == east == the same peer): NCCL pairs sends and receives between two
     // ranks in issue order, and my west halo must receive the peer's EAST edge -> east-bound message first
     ncclGroupStart();
-    ncclSend(h->sendE, h->xcount, ncclDouble, east, h->comm, h->stream);
-    ncclSend(h->sendW, h->xcount, ncclDouble, west, h->comm, h->stream);
-    ncclRecv(h->recvW, h->xcount, ncclDouble, west, h->comm, h->stream);
-    ncclRecv(h->recvE, h->xcount, ncclDouble, east, h->comm, h->stream);
+    ncclSend(h->sendE, h->xcount, ncclDouble, east, h->comm, st);
+    ncclSend(h->sendW, h->xcount, ncclDouble, west, h->comm, st);
+    ncclRecv(h->recvW, h->xcount, ncclDouble, west, h->comm, st);
+    ncclRecv(h->recvE, h->xcount, ncclDouble, east, h->comm, st);
     ncclResult_t rc = ncclGroupEnd();
     if (rc != ncclSuccess) return h->fail(OB200_ENCCL, "halo exchange", ncclGetErrorString(rc));
-    launch_unpack_x(h->G, h->F, h->recvW, h->recvE, h->stream);
+    launch_unpack_x(h->G, h->F, h->recvW, h->recvE, st);
     return OB200_OK;
 }
 
@@ -382,9 +384,46 @@ void tendencies(ob200_handle* h) {
     launch_momentum(h->G, h->F, h->mom_plan, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, h->stream);
     launch_tracers(h->G, h->F, h->mom_plan, h->cfg.order_tracer, h->time, h->stream);
 }
+// mask + halos + the two auxiliary sweeps.  On x-slabs the NCCL exchange of the 7-column halos runs on the second
+// stream BESIDE the sweeps of the interior columns (w + Ri needs u(i + 1): columns [0, Nx - 1); pHY' + kappa reads Ri at
+// i - 1 .. i + 1: columns [1, Nx - 2)); the few columns whose stencils reach into the halo follow once it has arrived.
+// `ev` (3 events or null): after the halos were issued / w + Ri / pHY' + kappa, for the stage timing.
+// Option "overlap_exchange", off by default: bit-identical, but measured SLOWER on 2 B200 at C3 (halo + sweeps 3.89 vs
+// 3.58 ms): a column sweep is latency-bound (one thread marches 120 levels), so the extra launches for the few
+// halo-dependent columns cost a full sweep latency each (~0.35 ms), more than the 0.17 ms of exchange they hide.
+int halos_and_auxiliaries(ob200_handle* h, cudaEvent_t* ev) {
+    const Geom& G = h->G;
+    cudaStream_t s1 = h->stream, s2 = h->stream2;
+    const int Nx = G.Nx;
+    if (h->periodic_local || !h->overlap_exchange) {
+        if (int rc = mask_and_halos(h)) return rc;
+        if (ev) cudaEventRecord(ev[0], s1);
+        launch_w_p(G, h->F, s1);
+        if (ev) cudaEventRecord(ev[1], s1);
+        launch_ri_kappa(G, h->F, h->time, s1);
+        if (G.qgleith) launch_leith(G, h->F, s1);
+        if (ev) cudaEventRecord(ev[2], s1);
+        return OB200_OK;
+    }
+    if (h->fields_dirty) { launch_mask_fields(G, h->F, s1); h->fields_dirty = false; }
+    cudaEventRecord(h->ev_join[2], s1);
+    cudaStreamWaitEvent(s2, h->ev_join[2], 0);
+    if (int rc = exchange_halos(h, s2)) return rc;
+    cudaEventRecord(h->ev_join[3], s2);
+    if (ev) cudaEventRecord(ev[0], s1);
+    launch_w_p(G, h->F, 0, Nx - 1, 0, 0, s1);
+    launch_ri_kappa(G, h->F, h->time, 1, Nx - 3, 0, 0, s1);
+    cudaStreamWaitEvent(s1, h->ev_join[3], 0);
+    launch_fill_halos(G, h->F, false, s1);
+    launch_w_p(G, h->F, -2, 2, Nx - 1, 3, s1);
+    if (ev) cudaEventRecord(ev[1], s1);
+    launch_ri_kappa(G, h->F, h->time, -2, 3, Nx - 2, 4, s1);
+    if (G.qgleith) launch_leith(G, h->F, s1);
+    if (ev) cudaEventRecord(ev[2], s1);
+    return OB200_OK;
+}
 int update_state(ob200_handle* h) {
-    if (int rc = mask_and_halos(h)) return rc;
-    auxiliaries(h);
+    if (int rc = halos_and_auxiliaries(h, nullptr)) return rc;
     tendencies(h);
     return OB200_OK;
 }
@@ -525,13 +564,8 @@ int step_body_serial(ob200_handle* h, double dt, bool euler) {
     swap_tendencies(h);
     mark();
     h->time += dt; h->iteration += 1; h->last_dt = dt;
-    if (int rc = mask_and_halos(h)) return rc;
-    mark();
-    launch_w_p(G, h->F, s1);
-    mark();
-    launch_ri_kappa(G, h->F, h->time, s1);
-    if (G.qgleith) launch_leith(G, h->F, s1);
-    mark();
+    if (int rc = halos_and_auxiliaries(h, h->timing ? &h->ev[e] : nullptr)) return rc;
+    if (h->timing) e += 3;
     launch_momentum(G, h->F, h->mom_plan, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, s1);
     mark();
     if (h->timing) cudaEventRecord(h->ev2[2], s1);
@@ -795,6 +829,7 @@ int ob200_set_option(ob200_handle* h, const char* name, int32_t value) {
     else if (!std::strcmp(name, "persistent_barotropic")) h->persistent_baro = value != 0;
     else if (!std::strcmp(name, "overlap")) h->overlap = value != 0;
     else if (!std::strcmp(name, "barotropic_graph")) h->use_graph = value != 0;
+    else if (!std::strcmp(name, "overlap_exchange")) h->overlap_exchange = value != 0;
     else if (!std::strcmp(name, "transfer_x_halo")) h->transfer_x_halo = value < 0 ? 0 : value;
     else return h->fail(OB200_EINVAL, "option", name);
     return OB200_OK;

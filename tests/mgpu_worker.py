@@ -22,6 +22,9 @@ def main():
     pkg = ge.package()
     c = cases.build_case(case_name)
     m = c.make_model(pkg, None, rank=rank, ranks=world, device=local, comm=pkg.Comm())
+    if os.environ.get("OB200_OVERLAP_EXCHANGE") == "1":
+        # halo exchange on a second stream beside the interior columns of the auxiliary sweeps (option, same bits)
+        m.backend.set_option("overlap_exchange", 1)
     restart = len(sys.argv) > 3 and sys.argv[3] == "restart"
     if restart:
         # per-rank checkpoint half way (simulation_outputs.jl:36-40 names the files by rank), then a fresh handle

@@ -33,3 +33,15 @@ def test_slab_checkpoint_restart_matches_single_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_overlapped_exchange_option_matches_single_gpu():
+    """Option "overlap_exchange": NCCL halo exchange on a second stream beside the interior column sweeps; same bits."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29735", os.path.join(HERE, "mgpu_worker.py"), "bumpy", "6"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, OB200_OVERLAP_EXCHANGE="1"))
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
