@@ -38,6 +38,7 @@ WORKLOADS = {
     "c3": (2160, 900, 120, 540.0),    # DoubleDrake 1/6 deg NZ=120: the configuration the metric is quoted on
     "c2": (1080, 450, 120, 1080.0),   # DoubleDrake 1/3 deg NZ=120
     "small": (360, 150, 24, 3240.0),
+    "c3slab8": (270, 900, 120, 540.0),  # kernel shapes of one C3 x-slab at 8 GPUs, as a periodic domain (tuning only)
 }
 # algorithmic bytes per cell (SURVEY 8d / DESIGN.md): momentum kernel reads u,v,w,p and writes Gu,Gv
 MOMENTUM_BYTES_PER_CELL = 48.0
