@@ -187,3 +187,105 @@ def test_oracle_reproduces_golden_vectors(pkg, orc, name):
         pkg.time_step(m, c.dt)
     bad = cases.check_signature({n: m.get(n) for n in ("U", "V", "W", "ETA", "T", "S")}, gold, 1e-11)
     assert not bad, bad
+
+
+def test_implicit_vertical_diffusion_solves_the_backward_euler_system(pkg, orc):
+    """AB2 + implicit step of T against an independent restatement: T* = T + dt G^n (first step: forward Euler), then
+    (I - dt d/dz kappa d/dz) T+ = T* per column as a banded system solved by LAPACK (scipy), with kappa = kappa_z +
+    kappa_c on interior faces and zero on faces that touch the sea floor or a solid cell."""
+    from scipy.linalg import solve_banded
+    c = cases.build_case("bumpy")
+    m = c.make_model(pkg, orc.OracleBackend)
+    g = m.grid
+    T0, GT, kc = m.get("T"), m.get("GT"), m.get("KAPPA_C")
+    dt = c.dt
+    m.backend.run_stage(pkg._abi.STAGE_ID["AB2_IMPLICIT"], dt, 0)
+    T1 = m.get("T")
+    zf, zc = g.z_faces, g.z_c()
+    dzc = zf[1:] - zf[:-1]
+    dzf = np.empty(g.Nz + 1)
+    dzf[1:-1] = zc[1:] - zc[:-1]
+    dzf[0] = dzf[-1] = np.nan                       # boundary faces carry no flux
+    solid = g.immersed_cell_mask()                   # (Nz, Ny, Nx)
+    kappa_z = 3e-5                                   # near_global_simulation.jl:71
+    worst = 0.0
+    rng = [(j, i) for j in range(0, g.Ny, 5) for i in range(0, g.Nx, 7)]
+    for j, i in rng:
+        wet = ~solid[:, j, i]
+        if not wet.any():
+            continue
+        rhs = T0[:, j, i] + dt * GT[:, j, i]
+        K = np.zeros(g.Nz + 1)
+        for kf in range(1, g.Nz):
+            if wet[kf - 1] and wet[kf]:
+                K[kf] = kappa_z + kc[kf, j, i]
+        ab = np.zeros((3, g.Nz))
+        for k in range(g.Nz):
+            up = -dt * K[k + 1] / (dzc[k] * dzf[k + 1]) if k < g.Nz - 1 else 0.0
+            lo = -dt * K[k] / (dzc[k] * dzf[k]) if k > 0 else 0.0
+            ab[1, k] = 1.0 - up - lo
+            if k < g.Nz - 1:
+                ab[0, k + 1] = up
+            if k > 0:
+                ab[2, k - 1] = lo
+        sol = solve_banded((1, 1), ab, rhs)
+        scale = max(np.max(np.abs(sol)), 1e-30)
+        worst = max(worst, float(np.max(np.abs(sol - T1[:, j, i])) / scale))
+    assert worst < 1e-12, worst
+
+
+def test_w_satisfies_discrete_continuity(pkg, orc):
+    """_compute_w_from_continuity!: w(k+1) = w(k) - dz_k * div_xy(u, v)_k with w = 0 at the bottom,
+    restated with numpy on the interior (periodic in x, v = 0 on the walls)."""
+    c = cases.build_case("dd_small")
+    m = c.make_model(pkg, orc.OracleBackend)
+    g = m.grid
+    u, v, w = m.get("U"), m.get("V"), m.get("W")
+    rad = np.pi / 180.0
+    dy = g.radius * g.dphi * rad
+    dxcf = g.radius * np.cos(g.phi_f() * rad) * g.dlam * rad                       # dx at (c, f)
+    az = g.radius ** 2 * g.dlam * rad * (np.sin(g.phi_f()[1:] * rad) - np.sin(g.phi_f()[:-1] * rad))   # Az at (c, c)
+    dz = g.z_faces[1:] - g.z_faces[:-1]
+    div = (dy * (np.roll(u, -1, axis=2) - u) + dxcf[None, 1:, None] * v[:, 1:, :] - dxcf[None, :-1, None] * v[:, :-1, :]) / az[None, :, None]
+    wref = np.zeros_like(w)
+    for k in range(g.Nz):
+        wref[k + 1] = wref[k] - dz[k] * div[k]
+    scale = np.max(np.abs(wref))
+    assert scale > 0 and np.max(np.abs(w - wref)) / scale < 1e-12
+
+
+def test_hydrostatic_pressure_is_the_vertical_integral_of_buoyancy(pkg, orc):
+    """_update_hydrostatic_pressure! with the linear equation of state b = g (alpha T - beta S): top-down
+    trapezoidal integral, restated with numpy.  The top half-cell uses b(Nz+1) = b(Nz) (halo = top value)."""
+    c = cases.build_case("dd_small")
+    m = c.make_model(pkg, orc.OracleBackend)
+    g = m.grid
+    T, S, p = m.get("T"), m.get("S"), m.get("P")
+    b = m.cfg.gravity * (m.cfg.eos_alpha * T - m.cfg.eos_beta * S)
+    zc = g.z_c()
+    dzf = np.empty(g.Nz + 1)
+    dzf[1:-1] = zc[1:] - zc[:-1]
+    dzf[-1] = 2.0 * (g.z_faces[-1] - zc[-1])      # centre-to-centre spacing across the surface (reflected top cell)
+    pref = np.zeros_like(p)
+    pref[-1] = -0.5 * (b[-1] + b[-1]) * dzf[-1]
+    for k in range(g.Nz - 2, -1, -1):
+        pref[k] = pref[k + 1] - 0.5 * (b[k + 1] + b[k]) * dzf[k + 1]
+    wet = ~g.immersed_cell_mask()
+    scale = np.max(np.abs(pref[wet]))
+    assert scale > 0 and np.max(np.abs((p - pref)[wet])) / scale < 1e-12
+
+
+def test_free_surface_volume_is_conserved(pkg, orc):
+    """The split-explicit substeps are in flux form on a closed (walls N/S, periodic E/W) domain: sum(eta * Az) over
+    wet columns does not change, whatever the flow."""
+    c = cases.build_case("bumpy")
+    m = c.make_model(pkg, orc.OracleBackend)
+    g = m.grid
+    rad = np.pi / 180.0
+    az = g.radius ** 2 * g.dlam * rad * (np.sin(g.phi_f()[1:] * rad) - np.sin(g.phi_f()[:-1] * rad))
+    vol0 = float(np.sum(m.get("ETA") * az[:, None]))
+    ref = float(np.sum(np.abs(m.get("ETA")) * az[:, None]))
+    for _ in range(5):
+        pkg.time_step(m, c.dt)
+    vol1 = float(np.sum(m.get("ETA") * az[:, None]))
+    assert abs(vol1 - vol0) / ref < 1e-12
