@@ -39,7 +39,11 @@ WORKLOADS = {
     "c2": (1080, 450, 120, 1080.0),   # DoubleDrake 1/3 deg NZ=120
     "small": (360, 150, 24, 3240.0),
     "c3slab8": (270, 900, 120, 540.0),  # kernel shapes of one C3 x-slab at 8 GPUs, as a periodic domain (tuning only)
+    # BASELINE configs[3] starting point: RealisticOcean-shaped 1/4 deg NZ=100 per GPU (TEOS-10, synthetic continents,
+    # time-interpolated fluxes + restoring, quadratic + immersed bottom drag); not the metric's configuration
+    "c4quarter": (1440, 600, 100, 810.0),
 }
+REALISTIC = {"c4quarter"}
 # algorithmic bytes per cell (SURVEY 8d / DESIGN.md): momentum kernel reads u,v,w,p and writes Gu,Gv
 MOMENTUM_BYTES_PER_CELL = 48.0
 # stage groups of ob200_timing (include/ocean_b200.h); group 8 is the T,S part of group 0
@@ -110,12 +114,21 @@ class ClockSampler:
 
 def make_case(workload: str, ranks: int, balance: str = "equal") -> cases.Case:
     Nx, Ny, Nz, dt = WORKLOADS[workload]
+    if workload in REALISTIC:
+        return cases.Case(workload, Nx, Ny, Nz, experiment="RealisticOcean", dt=dt, depth=5244.5, ranks=ranks, balance=balance)
     return cases.Case(workload, Nx, Ny, Nz, experiment="DoubleDrake", dt=dt, perturb=True, ranks=ranks, balance=balance)
 
 
 def initial_state(pkg, case, grid):
     """Closed-form initial state as host arrays (the same formulas as tests/cases.py)."""
     D, r = case.depth, np.pi / 180.0
+    if case.experiment == "RealisticOcean":
+        T, S = pkg.synthetic.initial_T_S(grid)
+        lam, lamf = grid.lam_c()[None, None, :], (grid.lam_c() - 0.5 * grid.dlam)[None, None, :]
+        phi, phif, z = grid.phi_c()[None, :, None], grid.phi_f()[None, :, None], grid.z_c()[:, None, None]
+        u = 0.05 * np.sin(2 * lamf * r) * np.cos(phi * r) * np.exp(z / 2000.0)
+        v = 0.03 * np.cos(3 * lam * r) * np.sin(2 * phif * r) * np.exp(z / 1000.0)
+        return {"T": T, "S": S, "U": u, "V": v, "ETA": np.zeros((grid.Ny, grid.Nx))}
     lam, lamf = grid.lam_c()[None, None, :], (grid.lam_c() - 0.5 * grid.dlam)[None, None, :]
     phi, phif = grid.phi_c()[None, :, None], grid.phi_f()[None, :, None]
     z = grid.z_c()[:, None, None]
@@ -238,9 +251,13 @@ def main():
     grid = case.grid(pkg, rank, world)
     g0 = case.grid(pkg, 0, 1)
     fs = pkg.SplitExplicitFreeSurface(substeps=pkg.barotropic_substeps(dt, g0))
-    model = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=fs, eos="linear",
-                                            boundary_conditions=pkg.set_boundary_conditions("DoubleDrake", grid),
-                                            device=local_rank, comm=pkg.Comm())
+    if case.experiment == "RealisticOcean":
+        bcs = pkg.set_boundary_conditions("RealisticOcean", grid, forcing_arrays=pkg.synthetic.forcing_arrays(grid))
+        args.no_cpu_baseline = True      # the CPU baseline legs are set up for the metric's DoubleDrake configuration
+    else:
+        bcs = pkg.set_boundary_conditions("DoubleDrake", grid)
+    model = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=fs, eos=pkg.equation_of_state(case.experiment),
+                                            boundary_conditions=bcs, device=local_rank, comm=pkg.Comm())
     if args.persistent_barotropic:
         model.backend.set_option("persistent_barotropic", 1)
     if os.environ.get("OB200_BARO_GRAPH", "1") == "0":
@@ -369,7 +386,7 @@ def main():
     out = {"metric": "grid-cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"DoubleDrake {Nx}x{Ny}x{Nz} dt={dt:g}s",
+           "config": {"workload": f"{case.experiment} {Nx}x{Ny}x{Nz} dt={dt:g}s",
                       "barotropic_substeps": f"{fs.substeps}->{len(fs.averaging_weights)}",
                       "partition": f"x-slabs {list(grid.partition.sizes)} ({args.balance if world > 1 else 'single'})",
                       "l2": "inputs (44 GB of fields per step at 1 GPU) exceed the 126 MB L2; no flush needed"},
