@@ -60,7 +60,7 @@ struct MomPlan {
     int ntx = 0, nty = 0, nslow = 0;
     bool any_fast = false;
     int* tile_kfast = nullptr;   // device, ntx * nty
-    int* slow_tiles = nullptr;   // device, 2 * nslow
+    int* slow_tiles = nullptr;   // device, 3 * nslow: (tile, kfast, first level with an active cell in the tile)
     // TMA descriptors (cp.async.bulk.tensor) of the 3-D fields u, v (momentum tile box) and T, S (tracer tile box)
     bool use_tma = false;
     CUtensorMap tm_u, tm_v, tm_T, tm_S;

@@ -510,12 +510,13 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
     double* sdy = sdx + D::ND;
     double* sK = sdy + D::ND;
     int tile, kf;
-    if (GEN) { tile = slow_tiles[2 * blockIdx.x]; kf = slow_tiles[2 * blockIdx.x + 1]; }
+    int kskip = 0;   // masked tiles: levels below the shallowest sea floor of the tile are all solid -> G stays 0 (never written)
+    if (GEN) { tile = slow_tiles[3 * blockIdx.x]; kf = slow_tiles[3 * blockIdx.x + 1]; kskip = slow_tiles[3 * blockIdx.x + 2]; }
     else { tile = blockIdx.y * gridDim.x + blockIdx.x; kf = tile_kfast[tile]; }
     const int i0 = (tile % ntx) * TX, j0 = (tile / ntx) * TY;
     const int tid = threadIdx.y * TX + threadIdx.x;
     const int zc = GEN ? blockIdx.y : blockIdx.z;
-    const int k_begin = GEN ? zc * klevels : max(zc * klevels, kf);
+    const int k_begin = GEN ? max(zc * klevels, kskip) : max(zc * klevels, kf);
     const int k_end = GEN ? min(min((zc + 1) * klevels, kf), G.Nz) : min((zc + 1) * klevels, G.Nz);
     if (k_begin >= k_end) return;
     const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
@@ -731,12 +732,13 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
     double* sfx = sm + 4 * D::NCP;         // after the [T0 | S0 | T1 | S1] tile buffers: [2][(TX+1)*TY x-faces | TX*(TY+1) y-faces]
     double* svel = sfx + 2 * NFV;          // [NFX + NFY] face velocities u (x-faces) then v (y-faces)
     int tile, kf;
-    if (GEN) { tile = slow_tiles[2 * blockIdx.x]; kf = slow_tiles[2 * blockIdx.x + 1]; }
+    int kskip = 0;   // masked tiles: levels below the shallowest sea floor of the tile are all solid -> G stays 0 (never written)
+    if (GEN) { tile = slow_tiles[3 * blockIdx.x]; kf = slow_tiles[3 * blockIdx.x + 1]; kskip = slow_tiles[3 * blockIdx.x + 2]; }
     else { tile = blockIdx.y * gridDim.x + blockIdx.x; kf = tile_kfast[tile]; }
     const int i0 = (tile % ntx) * TX, j0 = (tile / ntx) * TY;
     const int tid = threadIdx.y * TX + threadIdx.x;
     const int zc = GEN ? blockIdx.y : blockIdx.z;
-    const int k_begin = GEN ? zc * klevels : max(zc * klevels, kf);
+    const int k_begin = GEN ? max(zc * klevels, kskip) : max(zc * klevels, kf);
     const int k_end = GEN ? min(min((zc + 1) * klevels, kf), G.Nz) : min((zc + 1) * klevels, G.Nz);
     if (k_begin >= k_end) return;
     const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;

@@ -227,15 +227,20 @@ int setup_geometry(ob200_handle* h) {
         std::vector<int> tk((size_t)P.ntx * P.nty, 0), slow;
         for (int b = 0; b < P.nty; b++)
             for (int a = 0; a < P.ntx; a++) {
-                int K = 0;
+                int K = 0, kmin = Nz;
                 for (int j = b * ty; j < std::min((b + 1) * ty, c.Ny); j++)
-                    for (int i = a * tx; i < std::min((a + 1) * tx, c.Nx); i++)
+                    for (int i = a * tx; i < std::min((a + 1) * tx, c.Nx); i++) {
                         K = std::max(K, kfast[(size_t)(j + OB_H) * G.pitch + (i + OB_X0)]);
+                        kmin = std::min(kmin, kb[(size_t)(j + OB_H) * G.pitch + (i + OB_X0)]);
+                    }
                 tk[(size_t)b * P.ntx + a] = K;
                 if (K < Nz) P.any_fast = true;
-                if (K > 0) { slow.push_back(b * P.ntx + a); slow.push_back(K); }
+                // levels below kmin hold no active cell of the tile: every G there is a masked zero (the arrays are
+                // zero-initialised and those entries are never written) -- the tile-level analogue of the
+                // reference's active_cells_map (grid_load_balance.jl:21-32); all-solid tiles are skipped entirely
+                if (K > 0 && kmin < K) { slow.push_back(b * P.ntx + a); slow.push_back(K); slow.push_back(kmin); }
             }
-        P.nslow = (int)slow.size() / 2;
+        P.nslow = (int)slow.size() / 3;
         if (int rc = dev_alloc(h, &P.tile_kfast, tk.size(), false)) return rc;
         cudaMemcpy(P.tile_kfast, tk.data(), tk.size() * sizeof(int), cudaMemcpyHostToDevice);
         if (P.nslow) {
