@@ -76,6 +76,7 @@ class OracleBackend:
         if not self.h:
             raise RuntimeError("oracle_create failed")
         self.Nx, self.Ny, self.Nz = cfg.Nx, cfg.Ny, cfg.Nz
+        self.grid_for_diagnostics = None      # set by tests that drive the TimeStepWizard on the oracle
 
     def _check(self, rc):
         if rc != 0:
@@ -97,6 +98,22 @@ class OracleBackend:
 
     def _nz(self, fid):
         return self.Nz + 1 if fid in (2, 6, 7, 24, 25) else self.Nz      # W, KAPPA_C, KAPPA_U, QX, QY
+
+    def diagnostics(self, grid=None):
+        """max |u|, |v|, |w|, |eta|, |T|, |S| and the advective CFL time scale 1 / max(|u|/dx + |v|/dy + |w|/dz)
+        (the progress callback and TimeStepWizard of near_global_simulation.jl:138-162), with numpy."""
+        g = self.grid_for_diagnostics if grid is None else grid
+        Nx, Ny, Nz = self.Nx, self.Ny, self.Nz
+        u = self.get_field(0, (Nz, Ny, Nx)); v = self.get_field(1, (Nz, Ny + 1, Nx)); w = self.get_field(2, (Nz + 1, Ny, Nx))
+        T = self.get_field(3, (Nz, Ny, Nx)); S = self.get_field(4, (Nz, Ny, Nx)); eta = self.get_field(16, (Ny, Nx))
+        mx = [float(np.max(np.abs(a))) for a in (u, v, w, eta, T, S)]
+        rad = np.pi / 180.0
+        dx = g.radius * np.cos(g.phi_c() * rad) * g.dlam * rad
+        dy = g.radius * g.dphi * rad
+        dz = g.z_faces[1:] - g.z_faces[:-1]
+        rate = np.abs(u) / dx[None, :, None] + np.abs(v[:, :-1, :]) / dy + np.abs(w[:-1]) / dz[:, None, None]
+        m = float(np.max(rate))
+        return mx, (1.0 / m if m > 0 else float("inf"))
 
     def set_option(self, name, value):
         self._check(self.lib.oracle_set_option(self.h, name.encode(), int(value)))

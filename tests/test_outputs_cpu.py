@@ -170,3 +170,22 @@ def test_partition_global_array(pkg):
     assert pkg.partition_global_array(g, loc) is not None
     with pytest.raises(ValueError):
         pkg.partition_global_array(g, a[..., :7])
+
+
+def test_time_step_wizard_follows_the_cfl(pkg, orc):
+    """TimeStepWizard(cfl=0.35; max_change=1.1, max_Δt, min_Δt) every 10 iterations (near_global_simulation.jl:160-162)
+    driven through `run` on the oracle: Δt grows by at most 10 % per update, never leaves [min_Δt, max_Δt], and a
+    changed Δt is followed by a forward-Euler step (last_dt bookkeeping)."""
+    case = build_case("dd_small")
+    m = case.make_model(pkg, orc.OracleBackend)
+    m.backend.grid_for_diagnostics = m.grid
+    sim = pkg.Simulation(m, dt=5.0, stop_time=1e9, max_dt=300.0, min_dt=5.0, stop_iteration=35)
+    seen = []
+    sim.callbacks["probe"] = pkg.Callback(lambda s: seen.append(s.dt), pkg.IterationInterval(1))
+    pkg.run(sim)
+    assert m.clock["iteration"] == 35
+    changes = [b / a for a, b in zip(seen[:-1], seen[1:]) if b != a]
+    assert len(changes) == 3 and all(abs(c - 1.1) < 1e-12 for c in changes)     # iterations 10, 20, 30 (and 0: 5 -> 5.5)
+    assert all(5.0 <= d <= 300.0 for d in seen)
+    _, cfl_dt = m.backend.diagnostics()
+    assert 0.35 * cfl_dt > seen[-1]            # still CFL-limited by max_change, not by the flow
