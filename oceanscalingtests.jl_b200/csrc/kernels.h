@@ -54,8 +54,9 @@ void launch_pack_baro(const Geom& G, const Fields& F, double* bufW, double* bufE
 
 // kernels_tend.cu
 // Per-tile plan of the momentum kernels: tile_kfast[t] = first level the shared-memory fast kernel may take for
-// tile t (max of kfast over the tile's columns; Nz = never); slow_tiles = (tile, kfast) pairs with kfast > 0,
-// handled below that level by the general masked kernel.
+// tile t (max of kfast over the tile's columns; Nz = never); slow_tiles = (tile, kfast, kmin) triples with kfast > 0,
+// handled on the levels [kmin, kfast) by the general masked kernel (kmin = first level with an active cell in the tile;
+// below it everything is a masked zero that is never written).
 struct MomPlan {
     int ntx = 0, nty = 0, nslow = 0;
     bool any_fast = false;

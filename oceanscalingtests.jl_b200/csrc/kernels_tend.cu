@@ -213,23 +213,6 @@ __device__ __forceinline__ double recon7_window(const double* __restrict__ c, in
 #define OB_DISPATCH(N, CALL1, CALL2, CALL3, CALL4, CALL5) \
     ((N) >= 5 ? (CALL5) : (N) == 4 ? (CALL4) : (N) == 3 ? (CALL3) : (N) == 2 ? (CALL2) : (CALL1))
 
-__device__ __forceinline__ int order_cells(const Geom& G, int i, int j, int k, int Nmax, bool along_x) {
-    for (int N = Nmax; N >= 1; N--) {
-        bool ok = true;
-        for (int m = -N; m <= N - 1 && ok; m++) ok = along_x ? active(G, i + m, j, k) : active(G, i, j + m, k);
-        if (ok) return N;
-    }
-    return 0;
-}
-__device__ __forceinline__ int order_faces(const Geom& G, int i, int j, int k, int Nmax, bool along_x) {
-    for (int N = Nmax; N >= 1; N--) {
-        bool ok = true;
-        for (int m = -N + 1; m <= N && ok; m++) ok = along_x ? !inactive_fcc(G, i + m, j, k) : !inactive_cfc(G, i, j + m, k);
-        if (ok) return N;
-    }
-    return 0;
-}
-
 // ---- masked tiles: every node predicate is a threshold in k (active(i,j,k) <=> k >= kb(i,j) for a grid-fitted
 // bottom), so the order / peripheral / Coriolis tests of a column are folded ONCE per block into level thresholds
 // instead of ~500 kb look-ups per thread per level.
@@ -649,62 +632,6 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
 // ================================================================================================
 // tracer tendencies (T and S share the velocity loads)
 // ================================================================================================
-template <bool GEN>
-__device__ __forceinline__ double flux_x(const Geom& G, const double* __restrict__ cf, const double* __restrict__ u,
-                                         int i, int j, int k, int NT) {
-    const long long c = idx3(G, i, j, k);
-    const double vel = u[c];
-    if (vel == 0.0) return 0.0;
-    const bool left = vel > 0.0;
-    double r;
-    if (!GEN) r = recon_cell<4>(cf, left ? c - 4 : c + 3, left ? 1 : -1);
-    else {
-        if (peripheral_fcc(G, i, j, k)) return 0.0;
-        const int N = order_cells(G, i, j, k, NT, true);
-        const long long b = left ? c - N : c + N - 1, s = left ? 1 : -1;
-        r = OB_DISPATCH(N, recon_cell<1>(cf, b, s), recon_cell<2>(cf, b, s), recon_cell<3>(cf, b, s), recon_cell<4>(cf, b, s),
-                        recon_cell<4>(cf, b, s));
-    }
-    return G.dy * G.dzc[k] * (vel * r);
-}
-template <bool GEN>
-__device__ __forceinline__ double flux_y(const Geom& G, const double* __restrict__ cf, const double* __restrict__ v,
-                                         int i, int j, int k, int NT) {
-    const long long c = idx3(G, i, j, k);
-    const double vel = v[c];
-    if (vel == 0.0) return 0.0;
-    const bool left = vel > 0.0;
-    double r;
-    if (!GEN) r = recon_cell<4>(cf, left ? c - 4 * (long long)G.pitch : c + 3 * (long long)G.pitch, left ? G.pitch : -G.pitch);
-    else {
-        if (peripheral_cfc(G, i, j, k)) return 0.0;
-        const int N = order_cells(G, i, j, k, NT, false);
-        const long long s = left ? G.pitch : -G.pitch;
-        const long long b = left ? c - (long long)N * G.pitch : c + (long long)(N - 1) * G.pitch;
-        r = OB_DISPATCH(N, recon_cell<1>(cf, b, s), recon_cell<2>(cf, b, s), recon_cell<3>(cf, b, s), recon_cell<4>(cf, b, s),
-                        recon_cell<4>(cf, b, s));
-    }
-    return G.dxcf[j] * G.dzc[k] * (vel * r);
-}
-
-template <bool GEN>
-__device__ __forceinline__ double tend_c(const Geom& G, const Fields& F, const double* __restrict__ cf, int i, int j, int k,
-                                         int NT, double topflux) {
-    const long long c = idx3(G, i, j, k);
-    const double fxw = flux_x<GEN>(G, cf, F.u, i, j, k, NT), fxe = flux_x<GEN>(G, cf, F.u, i + 1, j, k, NT);
-    const double fys = flux_y<GEN>(G, cf, F.v, i, j, k, NT), fyn = flux_y<GEN>(G, cf, F.v, i, j + 1, k, NT);
-    const int km = max(k - 1, 0), kp = min(k + 1, G.Nz - 1);
-    const double ck = cf[c];
-    double fzl = G.azcc[j] * F.w[c] * 0.5 * (cf[idx3(G, i, j, km)] + ck);
-    const double fzh = G.azcc[j] * F.w[c + G.sz] * 0.5 * (ck + cf[idx3(G, i, j, kp)]);
-    if (GEN) {
-        if (k > 0 && !active(G, i, j, k - 1)) fzl = 0.0;
-    }
-    double Gt = -((fxe - fxw) + (fyn - fys) + (fzh - fzl)) * (G.razcc[j] * G.rdzc[k]);
-    if (k == G.Nz - 1) Gt -= topflux * G.rdzc[k];
-    return Gt;
-}
-
 // ---- fast path: T and S tiles in shared memory, every face flux computed ONCE (the reference computes each
 // face twice, once per adjacent cell), upwind side only, then each thread differences the fluxes of its cell.
 template <int TX, int TY>
