@@ -395,7 +395,10 @@ def main():
            "stage_ms": {n: float(g / args.steps) for n, g in zip(GROUP_NAMES, groups)},
            "roofline": roofline, "kernel_rooflines": kernel_rooflines,
            "fp64_pipe": {"source": "profiles/r01_final_ncu_full.txt (ncu --set full, C3, 1 GPU)",
-                         "momentum_full_order_tiles_pct_of_peak": 64.7, "tracers_full_order_tiles_pct_of_peak": 66.2}}
+                         "momentum_full_order_tiles_pct_of_peak": 64.7, "tracers_full_order_tiles_pct_of_peak": 66.2,
+                         "peak_tflops": 37.2, "peak_source": "ncu dfma peak_sustained 64 /clk/SM x 148 SM x 2 flop x 1.965 GHz",
+                         "momentum_full_order_tiles_tflops": 17.5, "tracers_full_order_tiles_tflops": 17.2,
+                         "note": "FLOP/s counts DFMA as 2, DMUL/DADD as 1 (ncu sass op counters); the pipe figure counts issue slots"}}
     if per_rank_groups is not None:
         out["stage_ms_per_rank"] = [[round(x, 3) for x in r] for r in per_rank_groups]
     if world == 1 and not args.no_cpu_baseline:
