@@ -73,3 +73,60 @@ def test_partition_offsets_and_ring(pkg):
     assert g.bottom_height_local(37).shape == (40, 45 + 74)
     lam = g.lam_c()
     assert abs(lam[0] - (-180 + 45.5 * 4.0)) < 1e-12
+
+
+def _restart_worker(rank, world, port, case_name, n1, n2, tmpdir, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import importlib.util
+    import __graft_entry__ as ge
+    import cases
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg, orc = ge.package(), ge.oracle_module()
+    spec = importlib.util.spec_from_file_location("oracle_distributed", os.path.join(ROOT, "oracle", "distributed.py"))
+    od = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(od)
+    c = cases.build_case(case_name)
+
+    def slab_model(initialize):
+        m = c.make_model(pkg, orc.OracleBackend, rank=rank, ranks=world, initialize=False)
+        st = od.SlabStepper(m)
+        m.backend.update_state = st.update_state        # update_state! on a slab needs the neighbour exchange
+        if initialize:
+            c.initialize(pkg, m)
+        return m, st
+
+    m1, s1 = slab_model(True)
+    for _ in range(n1):
+        s1.time_step(c.dt)
+    path = pkg.Checkpointer(tmpdir, f"DoubleDrake_checkpoint_{rank}", pkg.TimeInterval(86400.0)).write(m1)
+    for _ in range(n2):
+        s1.time_step(c.dt)
+    m2, s2 = slab_model(False)
+    pkg.set_from_checkpoint(m2, path)                   # per-rank file, as simulation_outputs.jl:36-40 names them
+    for _ in range(n2):
+        s2.time_step(c.dt)
+    same = all(np.array_equal(m1.get(n), m2.get(n)) for n in ("U", "V", "W", "ETA", "T", "S", "KAPPA_C", "KAPPA_U", "GU", "GT"))
+    q.put((rank, bool(same), os.path.basename(path)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_checkpoint_restart_is_bit_reproducible(pkg, orc, tmp_path):
+    """2 x-slabs of the oracle over gloo: checkpoint per rank, restore into fresh slab models, continue -- the halo
+    columns of the state that update_state! does not recompute travel in each rank's file."""
+    world, n1, n2 = 2, 3, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 7
+    procs = [ctx.Process(target=_restart_worker, args=(r, world, port, "dd_small", n1, n2, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got == [(0, True, "DoubleDrake_checkpoint_0_iteration3.npz"), (1, True, "DoubleDrake_checkpoint_1_iteration3.npz")]
