@@ -132,8 +132,8 @@ typedef struct ob200_handle ob200_handle;
 /* Stage groups timed with CUDA events on the handle's stream when option "timing" = 1:
  * 0 barotropic forcing + AB2/implicit x4, 1 barotropic substeps, 2 corrector, 3 halos/exchange,
  * 4 w + Ri sweep, 5 pHY' + kappa sweep (+ QG-Leith), 6 momentum tendencies, 7 tracer tendencies,
- * 8 the T,S part of group 0.  With option "overlap" = 1 (default 0) groups 7 and 8 run on a second stream
- * and the groups no longer add up to the step time.                                                       */
+ * 8 the T,S part of group 0.  With option "overlap" = 1 (default 0) group 8 runs on a second stream beside
+ * group 1 and the groups no longer add up to the step time.                                               */
 #define OB200_TIMED_GROUPS 9
 typedef struct ob200_timing {
     int32_t n;                 /* number of timed stage groups (OB200_TIMED_GROUPS) */
