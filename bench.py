@@ -368,10 +368,17 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_momentum_tiled (fused Gu,Gv tendencies; fast + masked tiles)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the two momentum launches of one step, from the
-                # `ncu --set full` capture summarised in profiles/r01_final_ncu_full.txt (C3, 1 GPU): 12.87 GB
+                # `ncu --set full` capture summarised in profiles/r01_final_ncu_full.txt (C3, 1 GPU): 12.71 GB
                 "traffic": 12.71e9 if (args.workload == "c3" and world == 1) else None,   # ncu dram read+write, both instances
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": MOMENTUM_BYTES_PER_CELL,
                 "ms_per_launch": mom_ms, "note": "FP64-ALU-bound WENO stencil (SURVEY F10); HBM fraction reported as the contract asks"}
+    if args.workload == "c3" and world == 1 and mom_ms > 0:
+        # the roof that actually bounds this kernel: FP64 flops of one step's two momentum launches counted by ncu
+        # (SASS op counters, DFMA = 2, DMUL / DADD = 1: 2.86e11 full-order + 1.6e10 masked tiles) over the LIVE duration
+        flops = 3.02e11
+        roofline["fp64"] = {"achieved": flops / (mom_ms * 1e-3) / 1e12, "peak": 37.2, "unit": "TFLOP/s",
+                            "frac": flops / (mom_ms * 1e-3) / 1e12 / 37.2, "pipe_frac_ncu": 0.647,
+                            "peak_source": "ncu: 64 DFMA/clk/SM x 148 SM x 2 x 1.965 GHz"}
     # per-stage rooflines against the same measured HBM peak: algorithmic bytes per cell x local cells /
     # CUDA-event time of the stage.  The two tendency kernels are FP64-pipe-bound (ncu: 62-66 % of the FP64 pipe, floor
     # ~18 ms for both at C3), so their HBM fraction is structurally small.
