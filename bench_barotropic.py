@@ -11,7 +11,6 @@ import json
 import os
 import sys
 
-import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)

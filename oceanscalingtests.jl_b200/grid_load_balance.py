@@ -8,7 +8,7 @@ experiments/run.jl:22-27); x is periodic so the ranks form a ring.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Callable, Optional, Sequence
 
 import numpy as np

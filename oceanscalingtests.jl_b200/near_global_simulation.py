@@ -18,7 +18,7 @@ from .bathymetry_and_forcings import exponential_z_faces
 from .boundary_and_initial_conditions import (initialize_model, set_boundary_conditions, update_fluxes,
                                               update_restoring)
 from .grid_load_balance import load_balanced_grid
-from .model import (HydrostaticFreeSurfaceModel, QGLeith, RiBasedVerticalDiffusivity, SplitExplicitFreeSurface,
+from .model import (HydrostaticFreeSurfaceModel, RiBasedVerticalDiffusivity, SplitExplicitFreeSurface,
                     VerticalScalarDiffusivity, barotropic_substeps, substeps, time_step)
 from .simulation_outputs import IterationInterval, TimeInterval, set_from_checkpoint
 

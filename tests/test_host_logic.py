@@ -1,6 +1,5 @@
 """CPU tests of the host-side mirror of the reference's Julia configuration code."""
 import ctypes as C
-import math
 import os
 import subprocess
 
