@@ -378,7 +378,7 @@ def main():
         flops = 3.02e11
         roofline["fp64"] = {"achieved": flops / (mom_ms * 1e-3) / 1e12, "peak": 37.2, "unit": "TFLOP/s",
                             "frac": flops / (mom_ms * 1e-3) / 1e12 / 37.2, "pipe_frac_ncu": 0.647,
-                            "peak_source": "ncu: 64 DFMA/clk/SM x 148 SM x 2 x 1.965 GHz"}
+                            "peak_source": "measured 37.17 TFLOP/s with tools/fp64_peak.cu (= ncu: 64 DFMA/clk/SM x 148 SM x 2 x 1.965 GHz)"}
     # per-stage rooflines against the same measured HBM peak: algorithmic bytes per cell x local cells /
     # CUDA-event time of the stage.  The two tendency kernels are FP64-pipe-bound (ncu: 62-66 % of the FP64 pipe, floor
     # ~18 ms for both at C3), so their HBM fraction is structurally small.
@@ -403,7 +403,7 @@ def main():
            "roofline": roofline, "kernel_rooflines": kernel_rooflines,
            "fp64_pipe": {"source": "profiles/r01_final_ncu_full.txt (ncu --set full, C3, 1 GPU)",
                          "momentum_full_order_tiles_pct_of_peak": 64.7, "tracers_full_order_tiles_pct_of_peak": 66.2,
-                         "peak_tflops": 37.2, "peak_source": "ncu dfma peak_sustained 64 /clk/SM x 148 SM x 2 flop x 1.965 GHz",
+                         "peak_tflops": 37.2, "peak_source": "measured 37.17 with tools/fp64_peak.cu; ncu dfma peak_sustained 64 /clk/SM x 148 SM x 2 flop x 1.965 GHz",
                          "momentum_full_order_tiles_tflops": 17.5, "tracers_full_order_tiles_tflops": 17.2,
                          "note": "FLOP/s counts DFMA as 2, DMUL/DADD as 1 (ncu sass op counters); the pipe figure counts issue slots"}}
     if per_rank_groups is not None:
