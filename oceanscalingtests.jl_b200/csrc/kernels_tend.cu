@@ -889,12 +889,14 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
 template <bool TMA>
 static void launch_momentum_t(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st) {
     using D = TileDims<MOM_TX, MOM_TY>;
-    static bool attr_set = false;
+    static bool attr_set[64] = {};   // the opt-in to > 48 KB of dynamic shared memory is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
     const size_t smem = D::TOTAL * sizeof(double);
-    if (!attr_set) {
+    if (!attr_set[dev & 63]) {
         cudaFuncSetAttribute(k_momentum_tiled<MOM_TX, MOM_TY, false, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_momentum_tiled<MOM_TX, MOM_TY, true, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+        attr_set[dev & 63] = true;
     }
     const int NV = (ord_vort + 1) / 2, ND = (ord_div + 1) / 2, nz = (G.Nz + TEND_KLEV - 1) / TEND_KLEV;
     dim3 b(MOM_TX, MOM_TY);
@@ -921,12 +923,14 @@ void tend_tile_boxes(int* mom_x, int* mom_y, int* trc_x, int* trc_y) {
 template <bool TMA>
 static void launch_tracers_t(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st) {
     using D = TracerTile<MOM_TX, MOM_TY>;
-    static bool attr_set = false;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
     const size_t smem = D::TOTAL * sizeof(double);
-    if (!attr_set) {
+    if (!attr_set[dev & 63]) {
         cudaFuncSetAttribute(k_tracers_tiled<MOM_TX, MOM_TY, false, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_tracers_tiled<MOM_TX, MOM_TY, true, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+        attr_set[dev & 63] = true;
     }
     const int NTR = (ord_tracer + 1) / 2, nz = (G.Nz + TEND_KLEV - 1) / TEND_KLEV;
     dim3 b(MOM_TX, MOM_TY);
