@@ -184,3 +184,24 @@ def test_env_var_names_match_run_jl():
     src = open(os.path.join(root, "oceanscalingtests.jl_b200", "run.py")).read()
     for var in ("RESOLUTION", "EXPERIMENT", "WITHFLUXES", "WITHRESTORING", "PROFILE", "RESTART", "NZ", "LOADBALANCE", "PRECISION"):
         assert f'"{var}"' in src, var
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU oracle on a bounded sample) runs without a GPU, prints exactly one JSON line
+    with the contract's keys on rank 0, and nothing on the other ranks of a torchrun launch."""
+    import json
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "small", "--steps", "2",
+           "--warmup", "1", "--cpu-columns", "16"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "grid-cell-steps/s" and d["unit"] == "cell-steps/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 2
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
