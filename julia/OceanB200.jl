@@ -92,6 +92,13 @@ function push_state!(h::Handle, model)
     check(h.ptr, ccall((:ob200_update_state, LIB), Cint, (Ptr{Cvoid},), h.ptr))
 end
 
+"One horizontal level of a 3-D field into a Julia-owned 2-D device array (the surface writer's `indices = (:, :, Nz)` views,
+src/simulation_outputs.jl:17-25) without moving the whole field; `k` is 1-based like the reference's index."
+function get_level!(dst::CuArray{Float64, 2}, h::Handle, id, k; halo = (0, 0))
+    check(h.ptr, ccall((:ob200_get_level, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, CuPtr{Float64}, Int32, Int32, Int32),
+                       h.ptr, id, k - 1, pointer(dst), 1, halo[1], halo[2]))
+end
+
 "Refresh the Julia-owned arrays the output writers / checkpointer read (src/simulation_outputs.jl:14-37,47-64)."
 function pull_state!(model, h::Handle)
     u, v, w = model.velocities
