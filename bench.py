@@ -51,6 +51,35 @@ GROUP_NAMES = ["ab2_implicit+baro_forcing", "barotropic_substeps", "corrector", 
                "momentum_tendencies", "tracer_tendencies", "TS_solve(part_of_ab2_implicit)"]
 
 
+def workload_config(pkg, args, world):
+    """The `config` object of the JSON line -- built the same way by both arms so that they describe the same workload."""
+    case = make_case(args.workload, world, args.balance)
+    Nx, Ny, Nz, dt = WORKLOADS[args.workload]
+    g0 = case.grid(pkg, 0, 1)
+    fs = pkg.SplitExplicitFreeSurface(substeps=pkg.barotropic_substeps(dt, g0))
+    sizes = list(case.grid(pkg, 0, world).partition.sizes)
+    return {"workload": f"{case.experiment} {Nx}x{Ny}x{Nz} dt={dt:g}s",
+            "barotropic_substeps": f"{fs.substeps}->{len(fs.averaging_weights)}",
+            "partition": f"x-slabs {sizes} ({args.balance if world > 1 else 'single'})",
+            "l2": f"inputs ({21 * 8 * Nx * Ny * Nz / 1e9:.1f} GB of fields per step over all GPUs) exceed the 126 MB L2; no flush needed"}
+
+
+def ncu_metrics(workload: str, world: int):
+    """Per-launch ncu figures of the dominant kernel (dram bytes, FP64 op counts, pipe utilisation) from the committed
+    capture summary profiles/ncu_metrics.json (written by profiles/summarize.py from the `ncu --set full` report, with
+    the git hash of the tree that was profiled).  None when the capture was taken on another workload / GPU count."""
+    p = os.path.join(ROOT, "profiles", "ncu_metrics.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        m = json.load(open(p))
+    except Exception:
+        return None
+    if m.get("workload") != workload or int(m.get("n_gpus", 0)) != world:
+        return None
+    return m
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -143,12 +172,16 @@ def initial_state(pkg, case, grid):
 
 def run_reference(args, rank, world):
     """The reference arm: the CPU oracle (port of the reference's algorithm; Julia/Oceananigans cannot run here)
-    on a bounded sample of the workload -- a 12-degree periodic sector of the same grid (same spacing, levels,
-    bathymetry rule, forcing), all host threads."""
+    on a bounded sample of the workload -- a periodic sector of the same grid (same spacing, levels, bathymetry rule,
+    forcing, one ridge inside), all host threads.  `ms_per_step` is the measured time of one step ON THE SAMPLE (nothing
+    is extrapolated); `value` = sample cells x steps / elapsed."""
     if rank != 0:
         return
     pkg, orc = ge.package(), ge.oracle_module()
     orc.build()
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: size the OpenMP team explicitly
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = orc.set_num_threads(ncpu)
     Nx, Ny, Nz, dt = WORKLOADS[args.workload]
     # bounded sample: shrink the sector when many steps are requested so the run ends within a few minutes
     sector = max(16, min(args.cpu_columns, Nx, int(args.cpu_columns * 13 / max(13, args.steps + args.warmup))))
@@ -172,15 +205,15 @@ def run_reference(args, rank, world):
     el = time.perf_counter() - t0
     cells = sector * Ny * Nz
     value = cells * args.steps / el
-    cores = os.cpu_count()
-    sample = f"{sector}x{Ny}x{Nz} periodic sector ({cells / 1e6:.2f} M cells, {100.0 * sector / Nx:.1f}% of the workload), {args.steps} steps"
+    sample = (f"{sector}x{Ny}x{Nz} periodic sector of the workload grid ({cells / 1e6:.2f} M cells, {100.0 * sector / Nx:.1f}% of "
+              f"the columns), {args.steps} timed steps, OpenMP {threads} threads")
     out = {"impl": "reference", "metric": "grid-cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps * (Nx / sector),
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"DoubleDrake {Nx}x{Ny}x{Nz} dt={dt:g}s",
-                      "note": "CPU oracle on a bounded sample of the workload; ms_per_step extrapolated to the full grid"},
-           "sypd": dt / (el / args.steps * (Nx / sector)) / 365.0,
-           "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": cores, "kind": "port", "sample": sample},
+           "config": workload_config(pkg, args, world),
+           "timed_region": "one step of the bounded sample (cpu_baseline.sample); value = sample cells x steps / elapsed",
+           "sypd_full_grid_equivalent": dt / (el / args.steps * (Nx / sector)) / 365.0,
+           "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -189,6 +222,8 @@ def cpu_baseline_sample(pkg, args, budget_s=20.0):
     """Bounded CPU-oracle sample for the main arm's `cpu_baseline` object (rank 0, N = 1 only)."""
     orc = ge.oracle_module()
     orc.build()
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = orc.set_num_threads(ncpu)
     Nx, Ny, Nz, dt = WORKLOADS[args.workload]
     sector = 32
     zf = pkg.exponential_z_faces(Nz, 3000.0)
@@ -207,8 +242,8 @@ def cpu_baseline_sample(pkg, args, budget_s=20.0):
         n += 1
     el = time.perf_counter() - t0
     cells = sector * Ny * Nz
-    return {"value": cells * n / el, "unit": "cell-steps/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{sector}x{Ny}x{Nz} periodic sector ({cells / 1e6:.2f} M cells), {n} steps, OpenMP all cores"}
+    return {"value": cells * n / el, "unit": "cell-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{sector}x{Ny}x{Nz} periodic sector ({cells / 1e6:.2f} M cells), {n} steps, OpenMP {threads} threads"}
 
 
 def main():
@@ -264,6 +299,9 @@ def main():
         model.backend.set_option("barotropic_graph", 0)
     if os.environ.get("OB200_OVERLAP", "0") == "1":
         model.backend.set_option("overlap", 1)
+    for env, opt in (("OB200_CONCURRENT_MASKED", "concurrent_masked_tiles"), ("OB200_OVERLAP_EXCHANGE", "overlap_exchange")):
+        if env in os.environ:
+            model.backend.set_option(opt, int(os.environ[env]))
     state = initial_state(pkg, case, grid)
     # pinned host copies of the initial state (what a host application owns)
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in state.items()}
@@ -326,8 +364,13 @@ def main():
         dist.all_gather_object(gl, [float(g / args.steps) for g in groups])
         per_rank_groups = gl
     mx, _ = model.backend.diagnostics()
+    if world > 1:      # maximum(abs, field) over the whole domain: x-slab runs are bit-identical to the 1-GPU run, so these
+        t = torch.tensor(mx, dtype=torch.float64, device="cuda")     # six numbers must not depend on the GPU count
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mx = [float(x) for x in t.tolist()]
     if not all(np.isfinite(mx)) or mx[0] > 10.0:
         raise SystemExit(f"bench.py: the run blew up (max-abs {mx})")
+    it_done = model.clock["iteration"]
 
     cells = Nx * Ny * Nz
     value = cells * args.steps / elapsed
@@ -352,7 +395,8 @@ def main():
         d2h = sum(t.numel() * 8 for t in out_pinned.values())
         e2e = {"value": cells * args.steps / e2e_el, "unit": "cell-steps/s",
                "h2d_bytes_per_step": int(h2d * world / args.steps), "d2h_bytes_per_step": int(d2h * world / args.steps),
-               "what": "pinned host initial state -> set! -> K x time_step! -> prognostic fields to pinned host"}
+               "what": "pinned host initial state -> set! -> K x time_step! -> prognostic fields to pinned host; the copies happen "
+                       "once per K steps (a time stepper keeps its state on the device), so the per-step byte counts are the totals / K"}
 
     if rank != 0:
         if world > 1:
@@ -365,20 +409,22 @@ def main():
     local_cells = grid.Nx * Ny * Nz
     mom_ms = groups[6] / args.steps
     achieved = MOMENTUM_BYTES_PER_CELL * local_cells / (mom_ms * 1e-3) / 1e9 if mom_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "k_momentum_tiled (fused Gu,Gv tendencies; fast + masked tiles)", "achieved": achieved, "peak": peak,
+    prof = ncu_metrics(args.workload, world)     # committed ncu capture of THIS workload / GPU count, else None
+    roofline = {"bound": "hbm", "kernel": "k_momentum_tiled (fused Gu,Gv tendencies; full-order tiles)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the two momentum launches of one step, from the
-                # `ncu --set full` capture summarised in profiles/r01_final_ncu_full.txt (C3, 1 GPU): 12.71 GB
-                "traffic": 12.71e9 if (args.workload == "c3" and world == 1) else None,   # ncu dram read+write, both instances
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the committed capture summary
+                "traffic": prof["momentum"]["dram_bytes"] if prof else None,
+                "traffic_source": (f"profiles/ncu_metrics.json (tree {prof.get('git', '?')}, {prof.get('source', '?')})" if prof else None),
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": MOMENTUM_BYTES_PER_CELL,
                 "ms_per_launch": mom_ms, "note": "FP64-ALU-bound WENO stencil (SURVEY F10); HBM fraction reported as the contract asks"}
-    if args.workload == "c3" and world == 1 and mom_ms > 0:
-        # the roof that actually bounds this kernel: FP64 flops of one step's two momentum launches counted by ncu
-        # (SASS op counters, DFMA = 2, DMUL / DADD = 1: 2.86e11 full-order + 1.6e10 masked tiles) over the LIVE duration
-        flops = 3.02e11
-        roofline["fp64"] = {"achieved": flops / (mom_ms * 1e-3) / 1e12, "peak": 37.2, "unit": "TFLOP/s",
-                            "frac": flops / (mom_ms * 1e-3) / 1e12 / 37.2, "pipe_frac_ncu": 0.647,
-                            "peak_source": "measured 37.17 TFLOP/s with tools/fp64_peak.cu (= ncu: 64 DFMA/clk/SM x 148 SM x 2 x 1.965 GHz)"}
+    if prof and mom_ms > 0 and "fp64_flops" in prof["momentum"]:
+        # the roof that actually bounds this kernel: FP64 flops per launch counted by ncu (SASS op counters, DFMA = 2,
+        # DMUL / DADD = 1) over the LIVE duration; peak measured with tools/fp64_peak.cu
+        flops = prof["momentum"]["fp64_flops"]
+        pk = prof.get("fp64_peak_tflops", 37.2)
+        roofline["fp64"] = {"achieved": flops / (mom_ms * 1e-3) / 1e12, "peak": pk, "unit": "TFLOP/s",
+                            "frac": flops / (mom_ms * 1e-3) / 1e12 / pk, "pipe_frac_ncu": prof["momentum"].get("fp64_pipe_frac"),
+                            "peak_source": prof.get("fp64_peak_source", "tools/fp64_peak.cu")}
     # per-stage rooflines against the same measured HBM peak: algorithmic bytes per cell x local cells /
     # CUDA-event time of the stage.  The two tendency kernels are FP64-pipe-bound (ncu: 62-66 % of the FP64 pipe, floor
     # ~18 ms for both at C3), so their HBM fraction is structurally small.
@@ -393,19 +439,16 @@ def main():
     out = {"metric": "grid-cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"{case.experiment} {Nx}x{Ny}x{Nz} dt={dt:g}s",
-                      "barotropic_substeps": f"{fs.substeps}->{len(fs.averaging_weights)}",
-                      "partition": f"x-slabs {list(grid.partition.sizes)} ({args.balance if world > 1 else 'single'})",
-                      "l2": "inputs (44 GB of fields per step at 1 GPU) exceed the 126 MB L2; no flush needed"},
+           "config": workload_config(pkg, args, world),
            "sypd": dt / (elapsed / args.steps) / 365.0,
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches1 - launches0),
            "stage_ms": {n: float(g / args.steps) for n, g in zip(GROUP_NAMES, groups)},
            "roofline": roofline, "kernel_rooflines": kernel_rooflines,
-           "fp64_pipe": {"source": "profiles/r01_final_ncu_full.txt (ncu --set full, C3, 1 GPU)",
-                         "momentum_full_order_tiles_pct_of_peak": 64.7, "tracers_full_order_tiles_pct_of_peak": 66.2,
-                         "peak_tflops": 37.2, "peak_source": "measured 37.17 with tools/fp64_peak.cu; ncu dfma peak_sustained 64 /clk/SM x 148 SM x 2 flop x 1.965 GHz",
-                         "momentum_full_order_tiles_tflops": 17.5, "tracers_full_order_tiles_tflops": 17.2,
-                         "note": "FLOP/s counts DFMA as 2, DMUL/DADD as 1 (ncu sass op counters); the pipe figure counts issue slots"}}
+           # maximum(abs, .) of the prognostic fields over the whole domain after `iteration` steps (the reference's progress
+           # line, near_global_simulation.jl:138-160): identical at every GPU count when the slab exchange is right
+           "diagnostics": {"iteration": int(it_done), "max_abs": dict(zip(("u", "v", "w", "eta", "T", "S"), [float(x) for x in mx]))}}
+    if prof:
+        out["ncu"] = {k: prof[k] for k in prof if k not in ("workload", "n_gpus")}
     if per_rank_groups is not None:
         out["stage_ms_per_rank"] = [[round(x, 3) for x in r] for r in per_rank_groups]
     if world == 1 and not args.no_cpu_baseline:

@@ -69,7 +69,8 @@ struct MomPlan {
 // tile boxes (elements) the tendency kernels fetch with one TMA copy per field and level
 void tend_tile_boxes(int* mom_x, int* mom_y, int* trc_x, int* trc_y);
 void mom_plan_tile_shape(int* tx, int* ty);
-void launch_momentum(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st);
-void launch_tracers(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st);
+// `which`: 1 = full-order tiles, 2 = masked tiles, 3 = both (they write disjoint (tile, level) sets)
+void launch_momentum(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st, int which = 3);
+void launch_tracers(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st, int which = 3);
 // kernels_leith.cu
 void launch_leith(const Geom& G, const Fields& F, cudaStream_t st);

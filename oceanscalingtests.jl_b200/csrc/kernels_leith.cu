@@ -14,9 +14,10 @@ __device__ __forceinline__ double b_at(const Geom& G, const Fields& F, int i, in
     const long long c = idx3(G, i, j, k);
     return buoyancy_of(G, F.T[c], F.S[c], k);
 }
-__device__ __forceinline__ double dzb(const Geom& G, const Fields& F, int i, int j, int k) {
+__device__ __forceinline__ double dzb(const Geom& G, const Fields& F, int i, int j, int k) {   // N^2, see n2_face
     if (!active(G, i, j, k - 1) || !active(G, i, j, k)) return 0.0;
-    return (b_at(G, F, i, j, k) - b_at(G, F, i, j, k - 1)) * G.rdzf[k];
+    const long long c = idx3(G, i, j, k);
+    return n2_face(G, F.T[c - G.sz], F.S[c - G.sz], F.T[c], F.S[c], k);
 }
 __device__ __forceinline__ double dxb(const Geom& G, const Fields& F, int i, int j, int k) {
     if (!active(G, i - 1, j, k) || !active(G, i, j, k)) return 0.0;

@@ -886,8 +886,10 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
 #ifndef TEND_KLEV
 #define TEND_KLEV 8
 #endif
+// `which`: bit 0 = the full-order tiles, bit 1 = the masked tiles (disjoint (tile, level) sets of G: the two instances may
+// run concurrently on different streams)
 template <bool TMA>
-static void launch_momentum_t(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st) {
+static void launch_momentum_t(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st, int which) {
     using D = TileDims<MOM_TX, MOM_TY>;
     static bool attr_set[64] = {};   // the opt-in to > 48 KB of dynamic shared memory is per device
     int dev = 0;
@@ -900,20 +902,20 @@ static void launch_momentum_t(const Geom& G, const Fields& F, const MomPlan& P, 
     }
     const int NV = (ord_vort + 1) / 2, ND = (ord_div + 1) / 2, nz = (G.Nz + TEND_KLEV - 1) / TEND_KLEV;
     dim3 b(MOM_TX, MOM_TY);
-    if (P.any_fast) {
+    if (P.any_fast && (which & 1)) {
         k_momentum_tiled<MOM_TX, MOM_TY, false, TMA><<<dim3(P.ntx, P.nty, nz), b, smem, st>>>(
             G, F, time, P.tile_kfast, P.slow_tiles, P.ntx, TEND_KLEV, NV, ND, P.tm_u, P.tm_v);
         OB_COUNT_LAUNCH(1);
     }
-    if (P.nslow > 0) {
+    if (P.nslow > 0 && (which & 2)) {
         k_momentum_tiled<MOM_TX, MOM_TY, true, TMA><<<dim3(P.nslow, nz), b, smem, st>>>(
             G, F, time, P.tile_kfast, P.slow_tiles, P.ntx, TEND_KLEV, NV, ND, P.tm_u, P.tm_v);
         OB_COUNT_LAUNCH(1);
     }
 }
-void launch_momentum(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st) {
-    if (P.use_tma) launch_momentum_t<true>(G, F, P, ord_vort, ord_div, time, st);
-    else launch_momentum_t<false>(G, F, P, ord_vort, ord_div, time, st);
+void launch_momentum(const Geom& G, const Fields& F, const MomPlan& P, int ord_vort, int ord_div, double time, cudaStream_t st, int which) {
+    if (P.use_tma) launch_momentum_t<true>(G, F, P, ord_vort, ord_div, time, st, which);
+    else launch_momentum_t<false>(G, F, P, ord_vort, ord_div, time, st, which);
 }
 void mom_plan_tile_shape(int* tx, int* ty) { *tx = MOM_TX; *ty = MOM_TY; }
 void tend_tile_boxes(int* mom_x, int* mom_y, int* trc_x, int* trc_y) {
@@ -921,7 +923,7 @@ void tend_tile_boxes(int* mom_x, int* mom_y, int* trc_x, int* trc_y) {
     *trc_x = TracerTile<MOM_TX, MOM_TY>::PC; *trc_y = TracerTile<MOM_TX, MOM_TY>::RC;
 }
 template <bool TMA>
-static void launch_tracers_t(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st) {
+static void launch_tracers_t(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st, int which) {
     using D = TracerTile<MOM_TX, MOM_TY>;
     static bool attr_set[64] = {};
     int dev = 0;
@@ -934,18 +936,18 @@ static void launch_tracers_t(const Geom& G, const Fields& F, const MomPlan& P, i
     }
     const int NTR = (ord_tracer + 1) / 2, nz = (G.Nz + TEND_KLEV - 1) / TEND_KLEV;
     dim3 b(MOM_TX, MOM_TY);
-    if (P.any_fast) {
+    if (P.any_fast && (which & 1)) {
         k_tracers_tiled<MOM_TX, MOM_TY, false, TMA><<<dim3(P.ntx, P.nty, nz), b, smem, st>>>(
             G, F, time, P.tile_kfast, P.slow_tiles, P.ntx, TEND_KLEV, NTR, P.tm_T, P.tm_S);
         OB_COUNT_LAUNCH(1);
     }
-    if (P.nslow > 0) {
+    if (P.nslow > 0 && (which & 2)) {
         k_tracers_tiled<MOM_TX, MOM_TY, true, TMA><<<dim3(P.nslow, nz), b, smem, st>>>(
             G, F, time, P.tile_kfast, P.slow_tiles, P.ntx, TEND_KLEV, NTR, P.tm_T, P.tm_S);
         OB_COUNT_LAUNCH(1);
     }
 }
-void launch_tracers(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st) {
-    if (P.use_tma) launch_tracers_t<true>(G, F, P, ord_tracer, time, st);
-    else launch_tracers_t<false>(G, F, P, ord_tracer, time, st);
+void launch_tracers(const Geom& G, const Fields& F, const MomPlan& P, int ord_tracer, double time, cudaStream_t st, int which) {
+    if (P.use_tma) launch_tracers_t<true>(G, F, P, ord_tracer, time, st, which);
+    else launch_tracers_t<false>(G, F, P, ord_tracer, time, st, which);
 }

@@ -25,6 +25,7 @@ struct Geom {
     const double *rdxfc, *razcc, *razcf;   // reciprocals used by the tendency kernels (DESIGN.md spec decision 8)
     // vertical metrics: dzc[k], zc[k] for k = -1..Nz (pre-offset), dzf[k] for k = 0..Nz
     const double *dzc, *dzf, *zc, *rdzc, *rdzf, *rupz, *rloz;   // rupz[k] = 1/(dzc[k] dzf[k+1]), rloz[k] = 1/(dzc[k] dzf[k])
+    const double* zfa;       // z of the (c,c,f) faces, k = 0..Nz (the caller's z_faces)
     const int* kb;           // first active level per column (2-D, field layout); Nz = no active cell
     const int* kfast;        // level from which the full-order, mask-free stencils are valid (2-D)
     double dy, rdy;
@@ -122,6 +123,21 @@ __device__ __forceinline__ double teos_rprime(double Th, double SA, double Z, do
 __device__ __forceinline__ double buoyancy_of(const Geom& G, double T, double S, int k) {
     if (G.eos == OB200_EOS_LINEAR) return G.g * (G.alpha * T - G.beta_s * S);
     return -G.g * teos_rprime<false>(T, S, G.zc[k], nullptr, nullptr) / G.rho0;
+}
+
+// N^2 on the (c,c,f) face kf between the cells kf - 1 (Tm, Sm) and kf (Tk, Sk): Oceananigans' `∂z_b` for SeawaterBuoyancy,
+//     g (alpha ∂z T - beta ∂z S),   alpha, beta evaluated AT THE FACE from the z-averaged T, S and the face depth
+// -- not a difference of in-situ buoyancies, which for TEOS-10 would add the compressibility term ∂rho'/∂z at fixed T, S.
+// The caller applies the immersed conditional (zero when either cell is inactive).
+__device__ __forceinline__ double n2_face(const Geom& G, double Tm, double Sm, double Tk, double Sk, int kf) {
+    double al = G.alpha, be = G.beta_s;
+    if (G.eos != OB200_EOS_LINEAR) {
+        double dTh, dSA;
+        teos_rprime<true>(0.5 * (Tm + Tk), 0.5 * (Sm + Sk), G.zfa[kf], &dTh, &dSA);
+        al = -dTh / G.rho0; be = dSA / G.rho0;
+    }
+    const double rdzf = G.rdzf[kf];
+    return G.g * (al * ((Tk - Tm) * rdzf) - be * ((Sk - Sm) * rdzf));
 }
 
 // Deterministic tanh from +,-,*,/ only (the library is compiled with -fmad=false): the same operation

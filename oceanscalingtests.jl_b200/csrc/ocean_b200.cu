@@ -35,6 +35,9 @@ struct ob200_handle {
     bool overlap_exchange = false;  // x-slabs: halo exchange on stream2 beside the interior columns of the auxiliary sweeps (option)
     int transfer_x_halo = 0;   // x-halo columns copied by set/get_field besides the interior (checkpoint of halo-carrying state)
     cudaStream_t stream2 = nullptr;            // tracer work that can overlap the momentum / barotropic chain
+    cudaStream_t stream3 = nullptr;            // masked tendency tiles beside the full-order tiles
+    cudaEvent_t ev_tend[2] = {nullptr, nullptr};   // auxiliaries done (fork), masked tiles done (join)
+    bool concurrent_masked = true;             // option "concurrent_masked_tiles"
     cudaEvent_t ev_join[4];                    // step start, T/S solved, w ready, tracer tendencies done
     cudaEvent_t ev2[4];                        // timing events on stream2
     int n_timed = 0;
@@ -162,6 +165,12 @@ int setup_geometry(ob200_handle* h) {
     cudaMemcpy(zc_d, zc.data(), (Nz + 2) * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemcpy(dzf_d, dzf.data(), (Nz + 1) * sizeof(double), cudaMemcpyHostToDevice);
     G.dzc = dzc_d + 1; G.zc = zc_d + 1; G.dzf = dzf_d;
+    {
+        double* zfa_d;
+        if (int rc = dev_alloc(h, &zfa_d, Nz + 1, false)) return rc;
+        cudaMemcpy(zfa_d, c.z_faces, (Nz + 1) * sizeof(double), cudaMemcpyHostToDevice);
+        G.zfa = zfa_d;
+    }
     // bathymetry -> first active level per column; rows outside the y-domain are fully inactive
     const size_t n2 = (size_t)G.pitch * G.NyP;
     std::vector<int> kb(n2, Nz), kfast(n2, Nz);
@@ -385,9 +394,27 @@ void auxiliaries(ob200_handle* h) {
     launch_ri_kappa(h->G, h->F, h->time, h->stream);
     if (h->G.qgleith) launch_leith(h->G, h->F, h->stream);
 }
-void tendencies(ob200_handle* h) {
-    launch_momentum(h->G, h->F, h->mom_plan, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, h->stream);
-    launch_tracers(h->G, h->F, h->mom_plan, h->cfg.order_tracer, h->time, h->stream);
+// Tendencies.  The masked tiles (walls, ridges, sea floor: latency-bound, 2 resident blocks per SM) write (tile, level)
+// sets disjoint from those of the full-order tiles (FP64-pipe-bound), so their two launches run on a third stream BESIDE
+// the full-order launches and fill the issue slots those leave idle; joined before anything reads G.
+// `mid` / `end` (events or null): recorded on the main stream between momentum and tracers / after the join (stage timing).
+void tendencies(ob200_handle* h, cudaEvent_t mid = nullptr, cudaEvent_t end = nullptr) {
+    const Geom& G = h->G;
+    cudaStream_t s1 = h->stream, s3 = h->stream3;
+    const MomPlan& P = h->mom_plan;
+    const bool fork = h->concurrent_masked && P.nslow > 0 && P.any_fast;
+    if (fork) {
+        cudaEventRecord(h->ev_tend[0], s1);
+        cudaStreamWaitEvent(s3, h->ev_tend[0], 0);
+        launch_momentum(G, h->F, P, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, s3, 2);
+        launch_tracers(G, h->F, P, h->cfg.order_tracer, h->time, s3, 2);
+        cudaEventRecord(h->ev_tend[1], s3);
+    }
+    launch_momentum(G, h->F, P, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, s1, fork ? 1 : 3);
+    if (mid) cudaEventRecord(mid, s1);
+    launch_tracers(G, h->F, P, h->cfg.order_tracer, h->time, s1, fork ? 1 : 3);
+    if (fork) cudaStreamWaitEvent(s1, h->ev_tend[1], 0);
+    if (end) cudaEventRecord(end, s1);
 }
 // mask + halos + the two auxiliary sweeps.  On x-slabs the NCCL exchange of the 7-column halos runs on the second
 // stream BESIDE the sweeps of the interior columns (w + Ri needs u(i + 1): columns [0, Nx - 1); pHY' + kappa reads Ri at
@@ -537,11 +564,8 @@ int step_body(ob200_handle* h, double dt, bool euler) {
     launch_ri_kappa(G, h->F, h->time, s1);
     if (G.qgleith) launch_leith(G, h->F, s1);
     mark();
-    launch_momentum(G, h->F, h->mom_plan, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, s1);
-    mark();
-    if (h->timing) cudaEventRecord(h->ev2[2], s1);
-    launch_tracers(G, h->F, h->mom_plan, h->cfg.order_tracer, h->time, s1);
-    if (h->timing) cudaEventRecord(h->ev2[3], s1);
+    if (h->timing) { tendencies(h, h->ev[e], h->ev2[3]); e++; }   // ev[e]: momentum done; ev2[3]: tracers + masked tiles done
+    else tendencies(h);
     h->n_timed = e - 1;
     return OB200_OK;
 }
@@ -571,11 +595,8 @@ int step_body_serial(ob200_handle* h, double dt, bool euler) {
     h->time += dt; h->iteration += 1; h->last_dt = dt;
     if (int rc = halos_and_auxiliaries(h, h->timing ? &h->ev[e] : nullptr)) return rc;
     if (h->timing) e += 3;
-    launch_momentum(G, h->F, h->mom_plan, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, s1);
-    mark();
-    if (h->timing) cudaEventRecord(h->ev2[2], s1);
-    launch_tracers(G, h->F, h->mom_plan, h->cfg.order_tracer, h->time, s1);
-    if (h->timing) cudaEventRecord(h->ev2[3], s1);
+    if (h->timing) { tendencies(h, h->ev[e], h->ev2[3]); e++; }   // ev[e]: momentum done; ev2[3]: tracers + masked tiles done
+    else tendencies(h);
     h->n_timed = e - 1;
     return OB200_OK;
 }
@@ -620,6 +641,8 @@ int ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out) {
     h->cfg.z_faces = nullptr; h->cfg.bottom_height = nullptr; h->cfg.averaging_weights = nullptr;  // borrowed only during create
     cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking);
+    for (auto& ev : h->ev_tend) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : h->ev) cudaEventCreate(&ev);
     for (auto& ev : h->ev2) cudaEventCreate(&ev);
     for (auto& ev : h->ev_join) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -639,7 +662,9 @@ void ob200_destroy(ob200_handle* h) {
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->ev2) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->ev_join) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->ev_tend) if (ev) cudaEventDestroy(ev);
     if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -811,7 +836,7 @@ int ob200_get_timing(ob200_handle* h, ob200_timing* t) {
     for (int q = 0; q < 7 && q < h->n_timed; q++) cudaEventElapsedTime(&g[q], h->ev[q], h->ev[q + 1]);
     float ts = 0, tr = 0;
     cudaEventElapsedTime(&ts, h->ev2[0], h->ev2[1]);
-    cudaEventElapsedTime(&tr, h->ev2[2], h->ev2[3]);
+    cudaEventElapsedTime(&tr, h->ev[7], h->ev2[3]);
     t->ms[0] = g[0] + ts; t->ms[1] = g[1]; t->ms[2] = g[2]; t->ms[3] = g[3]; t->ms[4] = g[4]; t->ms[5] = g[5];
     t->ms[6] = g[6]; t->ms[7] = tr; t->ms[8] = ts;
     t->n = 9;
@@ -835,6 +860,7 @@ int ob200_set_option(ob200_handle* h, const char* name, int32_t value) {
     else if (!std::strcmp(name, "overlap")) h->overlap = value != 0;
     else if (!std::strcmp(name, "barotropic_graph")) h->use_graph = value != 0;
     else if (!std::strcmp(name, "overlap_exchange")) h->overlap_exchange = value != 0;
+    else if (!std::strcmp(name, "concurrent_masked_tiles")) h->concurrent_masked = value != 0;
     else if (!std::strcmp(name, "transfer_x_halo")) h->transfer_x_halo = value < 0 ? 0 : value;
     else return h->fail(OB200_EINVAL, "option", name);
     return OB200_OK;

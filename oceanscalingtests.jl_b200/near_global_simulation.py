@@ -100,6 +100,7 @@ class Simulation:
     output_writers: dict = field(default_factory=dict)
     align_time_step: bool = True
     initialized: bool = False
+    comm: Optional[Comm] = None        # x-slab runs: the wizard's time scale is reduced over the ranks
 
 
 def time_step_wizard(sim: Simulation) -> None:
@@ -107,6 +108,11 @@ def time_step_wizard(sim: Simulation) -> None:
     if not sim.max_dt > sim.min_dt:
         return
     _, cfl_dt = sim.model.backend.diagnostics()
+    # the advective time scale is a minimum over the WHOLE domain (Oceananigans reduces it over the ranks): without this
+    # every x-slab would pick its own dt, the clocks diverge and the next NCCL exchange pairs mismatched steps
+    comm = sim.comm if sim.comm is not None else (Comm() if sim.model.grid.nranks > 1 else None)
+    if comm is not None and comm.size > 1:
+        cfl_dt = comm.allreduce(cfl_dt, "min")
     new_dt = sim.wizard_cfl * cfl_dt
     new_dt = min(sim.wizard_max_change * sim.dt, new_dt)
     new_dt = max(0.5 * sim.dt, new_dt)           # min_change default 0.5
@@ -230,7 +236,7 @@ def scaling_test_simulation(resolution, ranks, dt, stop_time, *, device: int = 0
         kw = dict(initial_T=T0, initial_S=S0)
     initialize_model(model, experiment, restart=restart, **kw)
 
-    sim = Simulation(model, dt=min_dt, stop_time=stop_time, max_dt=max_dt, min_dt=min_dt)
+    sim = Simulation(model, dt=min_dt, stop_time=stop_time, max_dt=max_dt, min_dt=min_dt, comm=comm)
 
     def progress(s):
         mx, _ = s.model.backend.diagnostics()

@@ -16,11 +16,24 @@
 // in-repo configuration files cited per function.  Deviations chosen for
 // definiteness are listed in DESIGN.md ("Spec decisions").
 //
+// TWO ARITHMETIC MODES (option "reference_arithmetic"):
+//   0 (default) PRODUCT arithmetic: the few places where the CUDA product deliberately departs from the reference's
+//     operation sequence by <= 1 ulp per operation -- reciprocal metrics, division-free Z-weights, explicit fma in the
+//     WENO forms, a +,-,*,/ tanh, the corrector's column sum accumulated top-down -- are evaluated the same way here,
+//     so that GPU-vs-oracle regression tests can demand BIT equality.
+//   1 REFERENCE arithmetic (FROZEN -- do not edit to follow the product): what Oceananigans v0.90.1 evaluates as far
+//     as SURVEY Appendix A records it: a true division for every metric, alpha_s = C_s (1 + (tau / (beta_s + eps))^2)
+//     with its N + N divisions, plain multiply-add chains (no fma), libm tanh, kappa / dz / dz in the solver,
+//     bottom-up column sums.  tests/test_parity_gpu.py reports the GPU's relative L-infinity distance to THIS mode
+//     after 100 steps against the north-star bar of 1e-10.
+//
 // Structure mirrors the reference's launch sequence: one function
 // per Oceananigans kernel, full halo'd arrays, both upwind sides evaluated,
 // runtime-order WENO, explicit masking -- deliberately NOT the fused/tiled
 // structure of the CUDA product, so that the two are independent restatements.
 // =============================================================================
+#include <omp.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -157,6 +170,13 @@ struct Oracle {
     double time = 0, last_dt = INFINITY;
     int64_t iteration = 0;
     std::string err;
+    bool refar = false;   // reference arithmetic (see the header)
+    int refbits = 7;   // bisect mask: 1 metrics, 2 WENO, 4 tanh
+    // x / metric: a true division (reference) or a multiplication by the correctly rounded reciprocal (product)
+    inline double mdiv(double x, double m, double rm) const { return (refar && (refbits & 1)) ? x / m : x * rm; }
+    // 1 / V = 1 / (Az dz): Oceananigans evaluates `1 / V * (...)`
+    inline double rvol(double az, double raz, int k) const { return (refar && (refbits & 1)) ? 1.0 / (az * dzc(k)) : raz * rdzc(k); }
+    inline double tanh_(double x) const { return (refar && (refbits & 4)) ? std::tanh(x) : det_tanh(x); }
 
     inline double zc(int k) const { return zc_[k + 1]; }
     inline double dzc(int k) const { return dzc_[k + 1]; }
@@ -284,10 +304,22 @@ struct Oracle {
         if (c.eos_kind == OB200_EOS_LINEAR) return c.gravity * (c.eos_alpha * T(i, j, k) - c.eos_beta * S(i, j, k));
         return -c.gravity * teos.rprime(T(i, j, k), S(i, j, k), zc(k)) / c.eos_rho0;
     }
-    // d b / dz at (c,c,f) face k with the immersed conditional difference
+    // N^2 = d b / dz at the (c,c,f) face k.  Oceananigans' `∂z_b` for SeawaterBuoyancy is
+    //     g (thermal_expansionᶜᶜᶠ ∂zᶜᶜᶠ(T) − haline_contractionᶜᶜᶠ ∂zᶜᶜᶠ(S)),
+    // the coefficients evaluated AT THE FACE from the z-averaged T, S and the face depth [OCN-recall] -- not a difference
+    // of in-situ buoyancies, which for TEOS-10 would add the compressibility term ∂ρ'/∂z at fixed T, S (1e-6 .. 4e-6 s^-2).
+    // ∂z is the immersed conditional difference: zero when either cell is inactive.
     inline double dz_b(int i, int j, int k) const {
         if (!active(i, j, k - 1) || !active(i, j, k)) return 0.0;
-        return (buoyancy(i, j, k) - buoyancy(i, j, k - 1)) * rdzf(k);
+        double al = c.eos_alpha, be = c.eos_beta;
+        if (c.eos_kind == OB200_EOS_TEOS10) {
+            double dTh, dSA;
+            teos.rprime(0.5 * (T(i, j, k - 1) + T(i, j, k)), 0.5 * (S(i, j, k - 1) + S(i, j, k)), zf[k], &dTh, &dSA);
+            al = -dTh / c.eos_rho0; be = dSA / c.eos_rho0;
+        }
+        const double dTz = mdiv(T(i, j, k) - T(i, j, k - 1), dzf(k), rdzf(k));
+        const double dSz = mdiv(S(i, j, k) - S(i, j, k - 1), dzf(k), rdzf(k));
+        return c.gravity * (al * dTz - be * dSz);
     }
 
     // ---- boundary-condition functions (bathymetry_and_forcings.jl:110-159) ----
@@ -408,7 +440,7 @@ struct Oracle {
 
     // ---- _compute_w_from_continuity! --------------------------------
     inline double div_xy(int i, int j, int k) const {
-        return (dy * u(i + 1, j, k) - dy * u(i, j, k) + dxcf(j + 1) * v(i, j + 1, k) - dxcf(j) * v(i, j, k)) * razcc(j);
+        return mdiv(dy * u(i + 1, j, k) - dy * u(i, j, k) + dxcf(j + 1) * v(i, j + 1, k) - dxcf(j) * v(i, j, k), azcc(j), razcc(j));
     }
     void compute_w() {
 #pragma omp parallel for
@@ -431,11 +463,11 @@ struct Oracle {
     // ---- RiBasedVerticalDiffusivity -----------------------------------
     inline double dz_u(int i, int j, int k) const {  // d/dz at (f,c,f), conditional on both u-nodes being active
         if (inactive_fcc(i, j, k) || inactive_fcc(i, j, k - 1)) return 0.0;
-        return (u(i, j, k) - u(i, j, k - 1)) * rdzf(k);
+        return mdiv(u(i, j, k) - u(i, j, k - 1), dzf(k), rdzf(k));
     }
     inline double dz_v(int i, int j, int k) const {
         if (inactive_cfc(i, j, k) || inactive_cfc(i, j, k - 1)) return 0.0;
-        return (v(i, j, k) - v(i, j, k - 1)) * rdzf(k);
+        return mdiv(v(i, j, k) - v(i, j, k - 1), dzf(k), rdzf(k));
     }
     void compute_ri_number() {
 #pragma omp parallel for
@@ -469,12 +501,12 @@ struct Oracle {
                             return 0.25 * (Ri(a - 1, b - 1, k) + Ri(a, b - 1, k) + Ri(a - 1, b, k) + Ri(a, b, k));
                         };
                         double Rif = 0.25 * (ff(i, j) + ff(i + 1, j) + ff(i, j + 1) + ff(i + 1, j + 1));
-                        double tau = 0.5 * (1.0 - det_tanh((Rif - c.ri_Ri0) * rRidelta));
+                        double tau = 0.5 * (1.0 - tanh_(mdiv(Rif - c.ri_Ri0, c.ri_Ridelta, rRidelta)));
                         kcp = c.ri_kappa0 * tau + kca + ken;
                         kup = c.ri_nu0 * tau;
                     }
-                    kc(i, j, k) = (c.ri_Cav * kc(i, j, k) + kcp) * r1cav;
-                    ku(i, j, k) = (c.ri_Cav * ku(i, j, k) + kup) * r1cav;
+                    kc(i, j, k) = mdiv(c.ri_Cav * kc(i, j, k) + kcp, 1.0 + c.ri_Cav, r1cav);
+                    ku(i, j, k) = mdiv(c.ri_Cav * ku(i, j, k) + kup, 1.0 + c.ri_Cav, r1cav);
                 }
             }
     }
@@ -483,6 +515,49 @@ struct Oracle {
     // q[0..2N-2]: stencil values ordered upwind-ward mirrored so that the same routine
     // serves left- and right-biased reconstructions.  sa/sb: fields the smoothness is
     // measured on (VelocityStencil: two fields averaged; otherwise sb == nullptr).
+    // reference arithmetic: the Horner-like sum psi_a * (C_aa psi_a + C_ab psi_b + ...) of Oceananigans' `smoothness_sum`
+    // with plain multiplications and additions, left to right [OCN-recall]
+    static double beta_of_ref(int N, int s, const double* ps) {
+        const double* C = WENO_SMOOTH[N][s];
+        double b = 0.0; int m = 0;
+        for (int a = 0; a < N; a++) {
+            double inner = C[m++] * ps[a];
+            for (int bb = a + 1; bb < N; bb++) inner = inner + C[m++] * ps[bb];
+            b = (a == 0) ? ps[a] * inner : b + ps[a] * inner;
+        }
+        return b;
+    }
+    static double weno_ref(int N, const double* q, const double* sa, const double* sb) {
+        if (N == 1) return q[0];
+        double beta[5], alpha[5], asum = 0.0;
+        for (int s = 0; s < N; s++) {
+            int off = N - 1 - s;
+            beta[s] = beta_of_ref(N, s, sa + off);
+            if (sb) beta[s] = (beta[s] + beta_of_ref(N, s, sb + off)) / 2;
+        }
+        double tau;
+        switch (N) {
+            case 2: tau = std::fabs(beta[0] - beta[1]); break;
+            case 3: tau = std::fabs(beta[0] - beta[2]); break;
+            case 4: tau = std::fabs(beta[0] + 3 * beta[1] - 3 * beta[2] - beta[3]); break;
+            default: tau = std::fabs(beta[0] + 2 * beta[1] - 6 * beta[2] + 2 * beta[3] + beta[4]); break;
+        }
+        // alpha_s = C_s (1 + (tau / (beta_s + eps))^2);  w = alpha / sum(alpha);  result = sum(w_s p_s)
+        for (int s = 0; s < N; s++) {
+            const double r = tau / (beta[s] + WENO_EPS);
+            alpha[s] = WENO_OPT[N][s] * (1.0 + r * r);
+            asum = (s == 0) ? alpha[s] : asum + alpha[s];
+        }
+        double res = 0.0;
+        for (int s = 0; s < N; s++) {
+            int off = N - 1 - s;
+            double ps = WENO_COEFF[N][s][0] * q[off];
+            for (int a = 1; a < N; a++) ps = ps + WENO_COEFF[N][s][a] * q[off + a];
+            const double w = alpha[s] / asum;
+            res = (s == 0) ? w * ps : res + w * ps;
+        }
+        return res;
+    }
     static double beta_of(int N, int s, const double* ps) {
         const double* C = WENO_SMOOTH[N][s];
         // explicit fma in a fixed order (see DESIGN.md "Arithmetic contract"): the quadratic form cancels
@@ -495,8 +570,9 @@ struct Oracle {
         }
         return b;
     }
-    static double weno(int N, const double* q, const double* sa, const double* sb) {
+    static double weno(int N, const double* q, const double* sa, const double* sb, bool ref_arith = false) {
         if (N == 1) return q[0];  // UpwindBiased(order = 1)
+        if (ref_arith) return weno_ref(N, q, sa, sb);
         double beta[5], alpha[5], asum = 0.0, r = 0.0;
         for (int s = 0; s < N; s++) {
             int off = N - 1 - s;
@@ -572,7 +648,7 @@ struct Oracle {
         double dxv = (inactive_cfc(i - 1, j, k) || inactive_cfc(i, j, k)) ? 0.0 : dy * v(i, j, k) - dy * v(i - 1, j, k);
         double dyu = (inactive_fcc(i, j - 1, k) || inactive_fcc(i, j, k)) ? 0.0
                                                                           : dxfc(j) * u(i, j, k) - dxfc(j - 1) * u(i, j - 1, k);
-        return (dxv - dyu) * razcf(j);
+        return mdiv(dxv - dyu, azcf(j), razcf(j));
     }
     inline double dxU(int i, int j, int k) const { return dy * dzc(k) * u(i + 1, j, k) - dy * dzc(k) * u(i, j, k); }
     inline double dyV(int i, int j, int k) const {
@@ -587,7 +663,7 @@ struct Oracle {
         // (1) vorticity flux: - upwind(vhat, zetaL, zetaR), WENO(order_vorticity) in y, VelocityStencil
         double qv[2][2];
         for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) qv[a][b] = dxcf(j + b) * v(i - 1 + a, j + b, k);
-        double vhat = 0.5 * (0.5 * (qv[0][0] + qv[0][1]) + 0.5 * (qv[1][0] + qv[1][1])) * rdxfc(j);
+        double vhat = mdiv(0.5 * (0.5 * (qv[0][0] + qv[0][1]) + 0.5 * (qv[1][0] + qv[1][1])), dxfc(j), rdxfc(j));
         int N = order_faces_y(i, j, k, (c.order_vorticity + 1) / 2);
         double zq[9], us[9], vs[9], zL, zR;
         for (int side = 0; side < 2; side++) {
@@ -597,7 +673,7 @@ struct Oracle {
                 us[m] = 0.5 * (u(i, jj - 1, k) + u(i, jj, k));
                 vs[m] = 0.5 * (v(i - 1, jj, k) + v(i, jj, k));
             }
-            (side == 0 ? zL : zR) = weno(N, zq, us, vs);
+            (side == 0 ? zL : zR) = weno(N, zq, us, vs, refar && (refbits & 2));
         }
         double G = upwind(vhat, zL, zR);
         // (2) vertical advection + upwinded horizontal-divergence flux (OnlySelfUpwinding, cross = Centered)
@@ -609,7 +685,7 @@ struct Oracle {
                 dq[m] = dxU(ii, j, k);
                 ds[m] = dxU(ii, j, k) + dyV(ii, j, k);
             }
-            (side == 0 ? dL : dR) = weno(Nd, dq, ds, nullptr);
+            (side == 0 ? dL : dR) = weno(Nd, dq, ds, nullptr, refar && (refbits & 2));
         }
         double uh = u(i, j, k);
         double Phi = upwind(uh, dL, dR) + uh * 0.5 * (dyV(i - 1, j, k) + dyV(i, j, k));
@@ -618,35 +694,35 @@ struct Oracle {
             double W = 0.5 * (azcc(j) * w(i - 1, j, kf) + azcc(j) * w(i, j, kf));
             return W * 0.5 * (u(i, j, kf - 1) + u(i, j, kf));
         };
-        G -= (Phi + wflux(k + 1) - wflux(k)) * (razcc(j) * rdzc(k));
+        G -= (Phi + wflux(k + 1) - wflux(k)) * rvol(azcc(j), razcc(j), k);
         // (3) Bernoulli head, centred
-        G -= (Kh(i, j, k) - Kh(i - 1, j, k)) * rdxfc(j);
+        G -= mdiv(Kh(i, j, k) - Kh(i - 1, j, k), dxfc(j), rdxfc(j));
         // (4) Coriolis, ActiveCellEnstrophyConserving: x_f_cross_U = -f * <dx v>_active / dx
         int nact = 0;
         for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) nact += peripheral_cfc(i - 1 + a, j + b, k) ? 0 : 1;
         double fbar = 0.5 * (fff(j) + fff(j + 1));
         double vavg = 0.5 * (0.5 * (qv[0][0] + qv[0][1]) + 0.5 * (qv[1][0] + qv[1][1]));
         double cor = nact == 0 ? 0.0 : nact == 4 ? vavg : vavg / (0.25 * nact);
-        G += fbar * cor * rdxfc(j);
+        G += mdiv(fbar * cor, dxfc(j), rdxfc(j));
         // (5) hydrostatic pressure gradient
-        G -= (p(i, j, k) - p(i - 1, j, k)) * rdxfc(j);
+        G -= mdiv(p(i, j, k) - p(i - 1, j, k), dxfc(j), rdxfc(j));
         // (6) optional QG-Leith horizontal viscosity, vector-invariant form
         if (c.qgleith_enabled) G -= leith_div_tau_u(i, j, k);
         // (7) flux boundary conditions (_apply_z_bcs!)
-        if (k == Nz - 1) G -= top_flux_u(i, j) * rdzc(k);
-        if (k == 0) G += bottom_flux_u(i, j) * rdzc(k);
+        if (k == Nz - 1) G -= mdiv(top_flux_u(i, j), dzc(k), rdzc(k));
+        if (k == 0) G += mdiv(bottom_flux_u(i, j), dzc(k), rdzc(k));
         // ImmersedBoundaryCondition(bottom = u_immersed_quadratic_bottom_drag) (boundary_and_initial_conditions.jl:124-134,
         // bathymetry_and_forcings.jl:138): the same drag law where the sea floor lies above level 0, i.e. on the first
         // non-peripheral node above a peripheral one [OCN-recall for where the immersed flux is applied]
         if (c.bc_kind == OB200_BC_REALISTIC && k > 0 && peripheral_fcc(i, j, k - 1))
-            G += -c.drag_mu * u(i, j, k) * speed_fcc(i, j, k) * rdzc(k);
+            G += mdiv(-c.drag_mu * u(i, j, k) * speed_fcc(i, j, k), dzc(k), rdzc(k));
         return G;
     }
 
     double tendency_v(int i, int j, int k) const {
         double qu[2][2];
         for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) qu[a][b] = dy * u(i + a, j - 1 + b, k);
-        double uhat = 0.5 * (0.5 * (qu[0][0] + qu[1][0]) + 0.5 * (qu[0][1] + qu[1][1])) * rdy;
+        double uhat = mdiv(0.5 * (0.5 * (qu[0][0] + qu[1][0]) + 0.5 * (qu[0][1] + qu[1][1])), dy, rdy);
         int N = order_faces_x(i, j, k, (c.order_vorticity + 1) / 2);
         double zq[9], us[9], vs[9], zL, zR;
         for (int side = 0; side < 2; side++) {
@@ -656,7 +732,7 @@ struct Oracle {
                 us[m] = 0.5 * (u(ii, j - 1, k) + u(ii, j, k));
                 vs[m] = 0.5 * (v(ii - 1, j, k) + v(ii, j, k));
             }
-            (side == 0 ? zL : zR) = weno(N, zq, us, vs);
+            (side == 0 ? zL : zR) = weno(N, zq, us, vs, refar && (refbits & 2));
         }
         double G = -upwind(uhat, zL, zR);
         int Nd = order_cells_y(i, j, k, (c.order_divergence + 1) / 2);
@@ -667,7 +743,7 @@ struct Oracle {
                 dq[m] = dyV(i, jj, k);
                 ds[m] = dxU(i, jj, k) + dyV(i, jj, k);
             }
-            (side == 0 ? dL : dR) = weno(Nd, dq, ds, nullptr);
+            (side == 0 ? dL : dR) = weno(Nd, dq, ds, nullptr, refar && (refbits & 2));
         }
         double vh = v(i, j, k);
         double Phi = upwind(vh, dL, dR) + vh * 0.5 * (dxU(i, j - 1, k) + dxU(i, j, k));
@@ -676,20 +752,20 @@ struct Oracle {
             double W = 0.5 * (azcc(j - 1) * w(i, j - 1, kf) + azcc(j) * w(i, j, kf));
             return W * 0.5 * (v(i, j, kf - 1) + v(i, j, kf));
         };
-        G -= (Phi + wflux(k + 1) - wflux(k)) * (razcf(j) * rdzc(k));
-        G -= (Kh(i, j, k) - Kh(i, j - 1, k)) * rdy;
+        G -= (Phi + wflux(k + 1) - wflux(k)) * rvol(azcf(j), razcf(j), k);
+        G -= mdiv(Kh(i, j, k) - Kh(i, j - 1, k), dy, rdy);
         int nact = 0;
         for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) nact += peripheral_fcc(i + a, j - 1 + b, k) ? 0 : 1;
         double fbar = 0.5 * (fff(j) + fff(j));
         double uavg = 0.5 * (0.5 * (qu[0][0] + qu[1][0]) + 0.5 * (qu[0][1] + qu[1][1]));
         double cor = nact == 0 ? 0.0 : nact == 4 ? uavg : uavg / (0.25 * nact);
-        G -= fbar * cor * rdy;
-        G -= (p(i, j, k) - p(i, j - 1, k)) * rdy;
+        G -= mdiv(fbar * cor, dy, rdy);
+        G -= mdiv(p(i, j, k) - p(i, j - 1, k), dy, rdy);
         if (c.qgleith_enabled) G -= leith_div_tau_v(i, j, k);
-        if (k == Nz - 1) G -= top_flux_v(i, j) * rdzc(k);
-        if (k == 0) G += bottom_flux_v(i, j) * rdzc(k);
+        if (k == Nz - 1) G -= mdiv(top_flux_v(i, j), dzc(k), rdzc(k));
+        if (k == 0) G += mdiv(bottom_flux_v(i, j), dzc(k), rdzc(k));
         if (c.bc_kind == OB200_BC_REALISTIC && k > 0 && peripheral_cfc(i, j, k - 1))
-            G += -c.drag_mu * v(i, j, k) * speed_cfc(i, j, k) * rdzc(k);
+            G += mdiv(-c.drag_mu * v(i, j, k) * speed_cfc(i, j, k), dzc(k), rdzc(k));
         return G;
     }
 
@@ -729,9 +805,9 @@ struct Oracle {
             if (N == 0) return 0.0;
             double q[7], L, R;
             for (int m = 0; m < 2 * N - 1; m++) q[m] = cfld(ii - N + m, j, k);
-            L = weno(N, q, q, nullptr);
+            L = weno(N, q, q, nullptr, refar && (refbits & 2));
             for (int m = 0; m < 2 * N - 1; m++) q[m] = cfld(ii + N - 1 - m, j, k);
-            R = weno(N, q, q, nullptr);
+            R = weno(N, q, q, nullptr, refar && (refbits & 2));
             return dy * dzc(k) * upwind(u(ii, j, k), L, R);
         };
         auto flux_y = [&](int jj) {
@@ -740,9 +816,9 @@ struct Oracle {
             if (N == 0) return 0.0;  // wall face: v = 0
             double q[7], L, R;
             for (int m = 0; m < 2 * N - 1; m++) q[m] = cfld(i, jj - N + m, k);
-            L = weno(N, q, q, nullptr);
+            L = weno(N, q, q, nullptr, refar && (refbits & 2));
             for (int m = 0; m < 2 * N - 1; m++) q[m] = cfld(i, jj + N - 1 - m, k);
-            R = weno(N, q, q, nullptr);
+            R = weno(N, q, q, nullptr, refar && (refbits & 2));
             return dxcf(jj) * dzc(k) * upwind(v(i, jj, k), L, R);
         };
         auto flux_z = [&](int kf) {
@@ -750,8 +826,8 @@ struct Oracle {
             return azcc(j) * w(i, j, kf) * 0.5 * (cfld(i, j, kf - 1) + cfld(i, j, kf));
         };
         double G = -((flux_x(i + 1) - flux_x(i)) + (flux_y(j + 1) - flux_y(j)) + (flux_z(k + 1) - flux_z(k))) *
-                   (razcc(j) * rdzc(k));
-        if (k == Nz - 1) G -= top_flux * rdzc(k);
+                   rvol(azcc(j), razcc(j), k);
+        if (k == Nz - 1) G -= mdiv(top_flux, dzc(k), rdzc(k));
         return G;
     }
 
@@ -887,8 +963,9 @@ struct Oracle {
     void implicit_column(F3& f, int i, int j, double dt, KF Kface) {
         std::vector<double> t(Nz + 1), lo(Nz + 1), up(Nz + 1);
         for (int k = 0; k < Nz; k++) {
-            up[k] = (k < Nz - 1) ? -dt * Kface(k + 1) * rupz_[k] : 0.0;
-            lo[k] = (k > 0) ? -dt * Kface(k) * rloz_[k] : 0.0;  // coupling of row k to k-1
+            // reference: -Δt * κ_Δz²  with  κ_Δz² = κ / Δzᶜ(k) / Δzᶠ(face)  (two successive divisions)
+            up[k] = (k < Nz - 1) ? ((refar && (refbits & 1)) ? -dt * (Kface(k + 1) / dzc(k) / dzf(k + 1)) : -dt * Kface(k + 1) * rupz_[k]) : 0.0;
+            lo[k] = (k > 0) ? ((refar && (refbits & 1)) ? -dt * (Kface(k) / dzc(k) / dzf(k)) : -dt * Kface(k) * rloz_[k]) : 0.0;  // coupling of row k to k-1
         }
         double beta = 1.0 - up[0] - lo[0];
         f(i, j, 0) = f(i, j, 0) / beta;
@@ -1115,6 +1192,8 @@ int oracle_get_field(void* h, int id, double* buf, int hx, int hy, int hz) {
 }
 int oracle_set_option(void* h, const char* name, int value) {
     if (!std::strcmp(name, "transfer_x_halo")) { ((Oracle*)h)->xfer_halo = value; return OB200_OK; }
+    if (!std::strcmp(name, "reference_arithmetic")) { ((Oracle*)h)->refar = value != 0; return OB200_OK; }
+    if (!std::strcmp(name, "reference_arithmetic_mask")) { ((Oracle*)h)->refbits = value; return OB200_OK; }
     return OB200_EINVAL;
 }
 int oracle_get_strip(void* h, int id, double* buf, int side, int width, int interior_edge) {
@@ -1150,6 +1229,20 @@ int oracle_zero_prev_tendencies(void* h) {
 }
 // standalone WENO entry point for unit tests: biased reconstruction from 2N-1 values
 double oracle_weno(int N, const double* q, const double* sa, const double* sb) { return Oracle::weno(N, q, sa, sb); }
+double oracle_weno_ref(int N, const double* q, const double* sa, const double* sb) { return Oracle::weno(N, q, sa, sb, true); }
 double oracle_teos10_rprime(double Th, double SA, double Z) { static Teos t; return t.rprime(Th, SA, Z); }
 double oracle_det_tanh(double x) { return det_tanh(x); }
+// OpenMP team size: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would silently turn the
+// reference arm of bench.py into a single-threaded run
+void oracle_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_get_max_threads(void) { return omp_get_max_threads(); }
+int oracle_threads_in_parallel_region(void) {
+    int n = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        n = omp_get_num_threads();
+    }
+    return n;
+}
 }

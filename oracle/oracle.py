@@ -63,6 +63,10 @@ def load():
     lib.oracle_teos10_rprime.restype = C.c_double
     lib.oracle_det_tanh.argtypes = [C.c_double]
     lib.oracle_det_tanh.restype = C.c_double
+    lib.oracle_set_num_threads.argtypes = [C.c_int]
+    lib.oracle_set_num_threads.restype = None
+    lib.oracle_get_max_threads.restype = C.c_int
+    lib.oracle_threads_in_parallel_region.restype = C.c_int
     _lib = lib
     return lib
 
@@ -179,3 +183,11 @@ def weno(N, q, sa=None, sb=None) -> float:
     sa = q if sa is None else np.ascontiguousarray(sa, dtype=np.float64)
     sbp = None if sb is None else np.ascontiguousarray(sb, dtype=np.float64).ctypes.data
     return lib.oracle_weno(N, q.ctypes.data, sa.ctypes.data, sbp)
+
+
+def set_num_threads(n: int) -> int:
+    """Size of the oracle's OpenMP team (overrides an inherited OMP_NUM_THREADS); returns the threads a parallel region
+    actually gets."""
+    lib = load()
+    lib.oracle_set_num_threads(int(n))
+    return int(lib.oracle_threads_in_parallel_region())

@@ -28,10 +28,23 @@ class Case:
     bathymetry: str = "experiment"    # "experiment" | "bumpy" (k-dependent masks)
     ranks: int = 1
     balance: str = "equal"            # "equal" (reference: Partition(ranks...)) | "cost" (kernel-cost-balanced slabs)
+    # a periodic SECTOR of a larger grid: Nx columns starting at `sector_start` of a grid with `sector_of` columns (same
+    # spacing, levels, bathymetry rule and forcing as the full grid) -- BASELINE shapes at a size the oracle finishes
+    sector_of: int = 0
+    sector_start: int = 0
+    uniform_TS: tuple = ()            # (T, S): a fixed T, S everywhere (TEOS-10 N^2 = 0 check)
 
     def grid(self, pkg, rank=0, ranks=None):
         ranks = ranks or self.ranks
         zf = pkg.exponential_z_faces(self.Nz, self.depth)
+        if self.sector_of:
+            P = self.sector_of
+            g0 = pkg.LatitudeLongitudeGrid(P, self.Ny, self.Nz, zf)
+            bottom = pkg.double_drake_bathymetry(g0.lam_c()[None, :], g0.phi_c()[:, None])
+            bottom = np.ascontiguousarray(bottom[:, self.sector_start:self.sector_start + self.Nx])
+            lon0 = -180.0 + 360.0 * self.sector_start / P
+            return pkg.LatitudeLongitudeGrid(self.Nx, self.Ny, self.Nz, zf, longitude=(lon0, lon0 + 360.0 * self.Nx / P),
+                                             rank=rank, partition=pkg.Partition.equal(self.Nx, ranks), bottom_height_global=bottom)
         g0 = pkg.LatitudeLongitudeGrid(self.Nx, self.Ny, self.Nz, zf)
         lam, phi = g0.lam_c()[None, :], g0.phi_c()[:, None]
         if self.experiment == "Quiescent" and self.bathymetry == "experiment":
@@ -55,9 +68,11 @@ class Case:
 
     def make_model(self, pkg, backend_factory, rank=0, ranks=None, device=0, initialize=True, comm=None):
         grid = self.grid(pkg, rank, ranks)
-        res = self.Nx / 360.0
+        res = (self.sector_of or self.Nx) / 360.0
         max_dt = 3240.0 / res
-        nsub = pkg.barotropic_substeps(max_dt, grid)
+        # the substep count follows the FULL grid's spacing (near_global_simulation.jl:11-19 reduces over all ranks)
+        g_sub = pkg.LatitudeLongitudeGrid(self.sector_of, self.Ny, self.Nz, grid.z_faces) if self.sector_of else grid
+        nsub = pkg.barotropic_substeps(max_dt, g_sub)
         fs = pkg.SplitExplicitFreeSurface(substeps=nsub)
         if self.experiment == "RealisticOcean":
             bcs = pkg.set_boundary_conditions("RealisticOcean", grid, forcing_arrays=pkg.synthetic.forcing_arrays(grid))
@@ -75,6 +90,9 @@ class Case:
         return model
 
     def initialize(self, pkg, model):
+        if self.uniform_TS:
+            pkg.set_model(model, T=self.uniform_TS[0], S=self.uniform_TS[1])
+            return
         if self.experiment == "RealisticOcean":
             T0, S0 = pkg.synthetic.initial_T_S(model.grid)
             r = math.pi / 180.0
@@ -122,6 +140,17 @@ CASES = {
     "quiescent": Case("quiescent", 90, 40, 8, experiment="Quiescent", dt=3240.0, perturb=False),
     # C1: BASELINE.json configs[0]
     "c1": Case("c1", 360, 150, 10, experiment="Quiescent", dt=3240.0, perturb=False),
+    # ---- BASELINE shapes at sizes the oracle finishes in seconds (parity only on toy grids) ----
+    # configs[2] DoubleDrake 1/6 deg NZ = 120: a 37-column periodic sector around the ridge at 0..1 deg E (the sample
+    # bench.py's CPU legs time): full Ny = 900 (57 tile rows), 15 level chunks of the tendency kernels, 1/6 deg metrics
+    "c3_sector": Case("c3_sector", 37, 900, 120, dt=540.0, sector_of=2160, sector_start=1072),
+    # the same grid at the width of ONE x-slab of the 8-GPU partition (270 columns: 17 tile columns, 32 x 4 column blocks)
+    "c3_slab270": Case("c3_slab270", 270, 900, 120, dt=540.0, sector_of=2160, sector_start=1000),
+    # configs[3] RealisticOcean-shaped 1/4 deg per GPU, NZ = 100: a 1440-wide TEOS-10 strip with synthetic continents,
+    # time-interpolated fluxes + restoring, quadratic + immersed drag
+    "c4_strip": Case("c4_strip", 1440, 48, 100, experiment="RealisticOcean", dt=810.0, depth=5244.5),
+    # TEOS-10 with a fixed T, S over depth: N^2 must be exactly 0 (no compressibility term in d b / dz)
+    "teos_uniform": Case("teos_uniform", 96, 48, 12, experiment="Quiescent", dt=900.0, bathymetry="bumpy", uniform_TS=(10.0, 35.0)),
 }
 
 

@@ -130,3 +130,45 @@ def test_slab_checkpoint_restart_is_bit_reproducible(pkg, orc, tmp_path):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert got == [(0, True, "DoubleDrake_checkpoint_0_iteration3.npz"), (1, True, "DoubleDrake_checkpoint_1_iteration3.npz")]
+
+
+def _wizard_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import __graft_entry__ as ge
+    import cases
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg, orc = ge.package(), ge.oracle_module()
+    c = cases.build_case("dd_small")
+    m = c.make_model(pkg, orc.OracleBackend, rank=rank, ranks=world, initialize=False)
+    m.backend.grid_for_diagnostics = m.grid
+    # asymmetric flow: the CFL limit binds on rank 1 only (set fields directly: update_state! on a slab needs the exchange)
+    m.set("U", 0.05 if rank == 0 else 100.0)
+    sim = pkg.Simulation(m, dt=1000.0, stop_time=1e9, max_dt=5000.0, min_dt=5.0, comm=pkg.Comm())
+    _, local_cfl = m.backend.diagnostics()
+    pkg.near_global_simulation.time_step_wizard(sim)
+    q.put((rank, float(local_cfl), float(sim.dt)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_time_step_wizard_agrees_across_ranks(pkg, orc):
+    """the wizard's advective time scale is min-reduced over the x-slabs, so every rank takes the same dt."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 11
+    procs = [ctx.Process(target=_wizard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    (_, cfl0, dt0), (_, cfl1, dt1) = got
+    assert cfl1 < 0.1 * cfl0                      # the local time scales differ by more than 10x ...
+    assert dt0 == dt1                             # ... but both ranks take the same step,
+    assert dt0 == max(0.5 * 1000.0, min(1.1 * 1000.0, 0.35 * cfl1)) and dt0 < 1000.0   # the tighter rank dictates it

@@ -289,3 +289,63 @@ def test_free_surface_volume_is_conserved(pkg, orc):
         pkg.time_step(m, c.dt)
     vol1 = float(np.sum(m.get("ETA") * az[:, None]))
     assert abs(vol1 - vol0) / ref < 1e-12
+
+
+# ---- the two arithmetic modes of the oracle (oracle/ocean_oracle.cpp header) ----------------------------------------
+def test_reference_arithmetic_weno_equals_product_arithmetic_to_rounding(orc):
+    """alpha_s = C_s (1 + (tau / (beta_s + eps))^2), w = alpha / sum(alpha) (reference) against the division-free
+    fma form (product): the same numbers up to rounding, on smooth and on kinked stencils, with and without a large mean."""
+    import ctypes as C
+    lib = orc.load()
+    lib.oracle_weno_ref.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_weno_ref.restype = C.c_double
+    rng = np.random.default_rng(20240611)
+    worst = 0.0
+    for N in (2, 3, 4, 5):
+        for mean in (0.0, 35.0):
+            for kind in ("smooth", "kink"):
+                for _ in range(20):
+                    x = np.arange(2 * N - 1, dtype=np.float64)
+                    q = mean + (np.sin(0.3 * x + rng.uniform(0, 6)) if kind == "smooth" else np.where(x < N - 1, 0.0, 1.0) + 0.01 * rng.standard_normal(2 * N - 1))
+                    q = np.ascontiguousarray(q)
+                    a = lib.oracle_weno(N, q.ctypes.data, q.ctypes.data, None)
+                    b = lib.oracle_weno_ref(N, q.ctypes.data, q.ctypes.data, None)
+                    worst = max(worst, abs(a - b) / max(abs(b), 1.0))
+    # beta of a field with mean 35 cancels ~ 35^2 / (range^2): the weights are only reproducible to ~1e-8 relative between
+    # two evaluation orders, the reconstruction (a convex combination of nearby values) to ~1e-10 of the range
+    assert worst < 1e-9, worst
+
+
+def test_reference_arithmetic_mode_is_the_same_algorithm(pkg, orc):
+    """One step in both modes: every field agrees to rounding (1e-13); 20 steps: still within 1e-11 for u, v, eta, T, S."""
+    c = cases.build_case("bumpy")
+    ma = c.make_model(pkg, orc.OracleBackend)
+    mb = c.make_model(pkg, orc.OracleBackend, initialize=False)
+    mb.backend.set_option("reference_arithmetic", 1)
+    c.initialize(pkg, mb)
+    for n, tol in ((1, 1e-13), (20, 1e-11)):
+        while ma.clock["iteration"] < n:
+            pkg.time_step(ma, c.dt)
+            pkg.time_step(mb, c.dt)
+        for f in ("U", "V", "ETA", "T", "S"):
+            a, b = ma.get(f), mb.get(f)
+            assert np.max(np.abs(a - b)) <= tol * np.max(np.abs(b)), (n, f)
+        assert not np.array_equal(ma.get("U"), mb.get("U")) or n == 0      # the modes do differ in the last bits
+
+
+def test_teos10_fixed_TS_column_has_zero_N2_oracle(pkg, orc):
+    """N^2 = g (alpha dT/dz - beta dS/dz), alpha / beta at the face (Oceananigans' ∂z_b): zero for a fixed T, S column even
+    though the in-situ buoyancy varies with depth (TEOS-10 compressibility) -> kappa takes its Ri = 0 value."""
+    c = cases.build_case("teos_uniform")
+    m = c.make_model(pkg, orc.OracleBackend)
+    kc = m.get("KAPPA_C")
+    ri = pkg.RiBasedVerticalDiffusivity()
+    tau0 = 0.5 * (1.0 - np.tanh((0.0 - ri.Ri0) / ri.Ridelta))
+    f = 1.0 / (1.0 + ri.Cav)
+    wet = kc[1:-1][kc[1:-1] > 0]
+    assert wet.size > 0.5 * kc[1:-1].size
+    assert np.allclose(wet, ri.kappa0 * tau0 * (f + ri.Cav * f * f), rtol=1e-12)
+    # in-situ buoyancy DOES vary with depth for this column (what the old finite difference picked up)
+    b_top = orc.load().oracle_teos10_rprime(10.0, 35.0, -5.0)
+    b_deep = orc.load().oracle_teos10_rprime(10.0, 35.0, -4000.0)
+    assert abs(b_deep - b_top) > 0.1
