@@ -14,6 +14,7 @@ struct Fields {
     double *nuL, *qx, *qy;
     // 2-D
     double *eta, *U, *V, *etab, *Ub, *Vb, *GU, *GV, *Hfc, *Hcf, *Ld;
+    double *Usum, *Vsum;   // sum_k dz u, sum_k dz v of the freshly solved u, v (barotropic layout), produced by the implicit solve
     // RealisticOcean forcing (Nx x Ny(+1) x 6, compact), may be null
     double* forcing[6];
 };
@@ -37,8 +38,11 @@ void launch_w_p(const Geom& G, const Fields& F, int a0, int n0, int a1, int n1, 
 void launch_ri_kappa(const Geom& G, const Fields& F, double time, int a0, int n0, int a1, int n1, cudaStream_t st);
 void launch_barotropic_forcing(const Geom& G, const Fields& F, double chi, cudaStream_t st);
 // momentum (u, v: also G^U, G^V) and tracer (T, S) solves can run on different streams (separate scratch arrays)
-void launch_ab2_implicit_uv(const Geom& G, const Fields& F, double dt, double chi, cudaStream_t st);
-void launch_ab2_implicit_ts(const Geom& G, const Fields& F, double dt, double chi, cudaStream_t st);
+// `onchip`: eliminated coefficients and forward values in shared memory (every array crosses HBM once); needs
+// ab2_onchip_fits(G), otherwise the variant with an HBM scratch array.  Same arithmetic, same bits.
+bool ab2_onchip_fits(const Geom& G);
+void launch_ab2_implicit_uv(const Geom& G, const Fields& F, double dt, double chi, bool onchip, cudaStream_t st);
+void launch_ab2_implicit_ts(const Geom& G, const Fields& F, double dt, double chi, bool onchip, cudaStream_t st);
 void launch_correct(const Geom& G, const Fields& F, cudaStream_t st);
 
 // kernels_baro.cu

@@ -37,7 +37,8 @@ struct ob200_handle {
     cudaStream_t stream2 = nullptr;            // tracer work that can overlap the momentum / barotropic chain
     cudaStream_t stream3 = nullptr;            // masked tendency tiles beside the full-order tiles
     cudaEvent_t ev_tend[2] = {nullptr, nullptr};   // auxiliaries done (fork), masked tiles done (join)
-    bool concurrent_masked = true;             // option "concurrent_masked_tiles"
+    bool concurrent_masked = false;            // option "concurrent_masked_tiles" (measured: no gain, 53.0 vs 52.9 ms at C3)
+    bool onchip_solve = false;                 // option "onchip_solve": implicit solve with t, f' in shared memory
     cudaEvent_t ev_join[4];                    // step start, T/S solved, w ready, tracer tendencies done
     cudaEvent_t ev2[4];                        // timing events on stream2
     int n_timed = 0;
@@ -302,7 +303,7 @@ int alloc_fields(ob200_handle* h) {
         for (double** p : {&F.nuL, &F.qx, &F.qy})
             if (int rc = dev_alloc(h, p, n3)) return rc;
     const size_t n2b = (size_t)G.pitch2 * G.NyP;
-    double** f2[] = {&F.eta, &F.U, &F.V, &F.etab, &F.Ub, &F.Vb, &F.GU, &F.GV};
+    double** f2[] = {&F.eta, &F.U, &F.V, &F.etab, &F.Ub, &F.Vb, &F.GU, &F.GV, &F.Usum, &F.Vsum};
     for (double** p : f2)
         if (int rc = dev_alloc(h, p, n2b)) return rc;
     F.Hfc = h->F_Hfc; F.Hcf = h->F_Hcf;
@@ -542,12 +543,12 @@ int step_body(ob200_handle* h, double dt, bool euler) {
     auto mark = [&]() { if (h->timing) cudaEventRecord(h->ev[e++], s1); };
     auto mark2 = [&](int q) { if (h->timing) cudaEventRecord(h->ev2[q], s2); };
     mark();
-    launch_ab2_implicit_uv(G, h->F, dt, chi, s1);   // also produces G^U, G^V (barotropic forcing)
+    launch_ab2_implicit_uv(G, h->F, dt, chi, h->onchip_solve, s1);   // also produces G^U, G^V (barotropic forcing)
     mark();
     // the T, S solve (HBM-bound) runs beside the barotropic substeps (launch-latency-bound, SMs mostly idle)
     cudaEventRecord(h->ev_join[0], s1); cudaStreamWaitEvent(s2, h->ev_join[0], 0);
     mark2(0);
-    launch_ab2_implicit_ts(G, h->F, dt, chi, s2);
+    launch_ab2_implicit_ts(G, h->F, dt, chi, h->onchip_solve, s2);
     mark2(1);
     cudaEventRecord(h->ev_join[1], s2);
     if (int rc = barotropic_loop(h, dt)) return rc;
@@ -582,10 +583,10 @@ int step_body_serial(ob200_handle* h, double dt, bool euler) {
     int e = 0;
     auto mark = [&]() { if (h->timing) cudaEventRecord(h->ev[e++], s1); };
     if (h->timing) cudaEventRecord(h->ev2[0], s1);
-    launch_ab2_implicit_ts(G, h->F, dt, chi, s1);
+    launch_ab2_implicit_ts(G, h->F, dt, chi, h->onchip_solve, s1);
     if (h->timing) cudaEventRecord(h->ev2[1], s1);
     mark();
-    launch_ab2_implicit_uv(G, h->F, dt, chi, s1);   // also produces G^U, G^V (barotropic forcing)
+    launch_ab2_implicit_uv(G, h->F, dt, chi, h->onchip_solve, s1);   // also produces G^U, G^V (barotropic forcing)
     mark();
     if (int rc = barotropic_loop(h, dt)) return rc;
     mark();
@@ -639,6 +640,10 @@ int ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out) {
     if (rc) { g_last_error = h->err; ob200_destroy(h); return rc; }
     cudaMemcpy(h->d_weights, h->weights.data(), cfg->n_substeps * sizeof(double), cudaMemcpyHostToDevice);
     h->cfg.z_faces = nullptr; h->cfg.bottom_height = nullptr; h->cfg.averaging_weights = nullptr;  // borrowed only during create
+    {   // the shared-memory solve is an OPTION: measured slower than the HBM-scratch sweep
+        const char* e = getenv("OB200_ONCHIP_SOLVE");
+        h->onchip_solve = ab2_onchip_fits(h->G) && (e && e[0] == '1');
+    }
     cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking);
@@ -766,8 +771,8 @@ int ob200_run_stage(ob200_handle* h, int32_t stage, double dt, int32_t arg) {
     switch (stage) {
         case OB200_ST_BAROTROPIC_FORCING: launch_barotropic_forcing(h->G, h->F, chi, h->stream); break;
         case OB200_ST_AB2_IMPLICIT:
-            launch_ab2_implicit_uv(h->G, h->F, dt, chi, h->stream);
-            launch_ab2_implicit_ts(h->G, h->F, dt, chi, h->stream);
+            launch_ab2_implicit_uv(h->G, h->F, dt, chi, h->onchip_solve, h->stream);
+            launch_ab2_implicit_ts(h->G, h->F, dt, chi, h->onchip_solve, h->stream);
             break;
         case OB200_ST_BAROTROPIC_INIT: launch_baro_init(h->G, h->F, h->periodic_local, 0, h->stream); break;
         case OB200_ST_BAROTROPIC_ETA: launch_baro_eta(h->G, h->F, dtau, h->periodic_local, 0, h->stream); break;
@@ -861,6 +866,10 @@ int ob200_set_option(ob200_handle* h, const char* name, int32_t value) {
     else if (!std::strcmp(name, "barotropic_graph")) h->use_graph = value != 0;
     else if (!std::strcmp(name, "overlap_exchange")) h->overlap_exchange = value != 0;
     else if (!std::strcmp(name, "concurrent_masked_tiles")) h->concurrent_masked = value != 0;
+    else if (!std::strcmp(name, "onchip_solve")) {
+        if (value && !ab2_onchip_fits(h->G)) return h->fail(OB200_EINVAL, "onchip_solve", "Nz too large for the shared-memory solve");
+        h->onchip_solve = value != 0;
+    }
     else if (!std::strcmp(name, "transfer_x_halo")) h->transfer_x_halo = value < 0 ? 0 : value;
     else return h->fail(OB200_EINVAL, "option", name);
     return OB200_OK;

@@ -968,12 +968,24 @@ struct Oracle {
             lo[k] = (k > 0) ? ((refar && (refbits & 1)) ? -dt * (Kface(k) / dzc(k) / dzf(k)) : -dt * Kface(k) * rloz_[k]) : 0.0;  // coupling of row k to k-1
         }
         double beta = 1.0 - up[0] - lo[0];
-        f(i, j, 0) = f(i, j, 0) / beta;
-        for (int k = 1; k < Nz; k++) {
-            t[k] = up[k - 1] / beta;
-            beta = (1.0 - up[k] - lo[k]) - lo[k] * t[k];
-            if (!(std::fabs(beta) > 10 * 2.220446049250313e-16)) break;
-            f(i, j, k) = (f(i, j, k) - lo[k] * f(i, j, k - 1)) / beta;
+        if (!refar) {
+            // product arithmetic: ONE reciprocal per level, r_k = 1 / beta_k, t_k = up_{k-1} r_{k-1}, f'_k = (...) r_k
+            double r = 1.0 / beta;
+            f(i, j, 0) = f(i, j, 0) * r;
+            for (int k = 1; k < Nz; k++) {
+                t[k] = up[k - 1] * r;
+                r = 1.0 / ((1.0 - up[k] - lo[k]) - lo[k] * t[k]);
+                f(i, j, k) = (f(i, j, k) - lo[k] * f(i, j, k - 1)) * r;
+            }
+        } else {
+            // reference: solve_batched_tridiagonal_system_kernel! -- two divisions by beta per level
+            f(i, j, 0) = f(i, j, 0) / beta;
+            for (int k = 1; k < Nz; k++) {
+                t[k] = up[k - 1] / beta;
+                beta = (1.0 - up[k] - lo[k]) - lo[k] * t[k];
+                if (!(std::fabs(beta) > 10 * 2.220446049250313e-16)) break;
+                f(i, j, k) = (f(i, j, k) - lo[k] * f(i, j, k - 1)) / beta;
+            }
         }
         for (int k = Nz - 2; k >= 0; k--) f(i, j, k) -= t[k + 1] * f(i, j, k + 1);
     }
@@ -1063,7 +1075,11 @@ struct Oracle {
         for (int j = 0; j <= Ny; j++)
             for (int i = 0; i < Nx; i++) {
                 double a = 0, b = 0;
-                for (int k = 0; k < Nz; k++) { if (j < Ny) a += dzc(k) * u(i, j, k); b += dzc(k) * v(i, j, k); }
+                if (refar) {   // barotropic_mode_kernel!: bottom-up
+                    for (int k = 0; k < Nz; k++) { if (j < Ny) a += dzc(k) * u(i, j, k); b += dzc(k) * v(i, j, k); }
+                } else {       // product: accumulated in the back-substitution of the implicit solve, i.e. top-down
+                    for (int k = Nz - 1; k >= 0; k--) { if (j < Ny) a += dzc(k) * u(i, j, k); b += dzc(k) * v(i, j, k); }
+                }
                 if (j < Ny) U(i, j) = a;
                 V(i, j) = b;
                 for (int k = 0; k < Nz; k++) {

@@ -202,6 +202,21 @@ def test_persistent_barotropic_matches_launch_loop(pkg, gpu_lib):
         assert np.array_equal(m1.get(n), m2.get(n)), n
 
 
+def test_onchip_solve_matches_hbm_scratch_solve(pkg, gpu_lib):
+    """The implicit solve with t, f' in shared memory (default when Nz fits) against the variant that streams them
+    through an HBM scratch array: same arithmetic, same bits -- incl. the column sums the corrector consumes."""
+    for name in ("bumpy", "realistic"):
+        c = cases.build_case(name)
+        m1, m2 = c.make_model(pkg, None), c.make_model(pkg, None)
+        m1.backend.set_option("onchip_solve", 1)
+        m2.backend.set_option("onchip_solve", 0)
+        for _ in range(6):
+            pkg.time_step(m1, c.dt)
+            pkg.time_step(m2, c.dt)
+        for n in PROG + ("GUBT", "GVBT", "UTRANS", "VTRANS", "KAPPA_C"):
+            assert np.array_equal(m1.get(n), m2.get(n)), (name, n)
+
+
 def test_two_stream_overlap_matches_serial_order(pkg, gpu_lib):
     """Option "overlap": the T, S solve runs on a second stream beside the barotropic substeps; same bits."""
     c = cases.build_case("bumpy")
