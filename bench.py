@@ -42,8 +42,13 @@ WORKLOADS = {
     # BASELINE configs[3] starting point: RealisticOcean-shaped 1/4 deg NZ=100 per GPU (TEOS-10, synthetic continents,
     # time-interpolated fluxes + restoring, quadratic + immersed bottom drag); not the metric's configuration
     "c4quarter": (1440, 600, 100, 810.0),
+    # BASELINE configs[3]: RealisticOcean-shaped 1/12 deg NZ=100 on 8 GPUs, and the 1/8 deg step of its weak-scaling series
+    # (1/4 deg on 1 GPU -> 1/8 deg on 4 -> 1/12 deg on 8: 86.4 / 86.4 / 97.2 M cells per GPU); dt = 3240 / RESOLUTION
+    "c4eighth": (2880, 1200, 100, 405.0),
+    "c4": (4320, 1800, 100, 270.0),
 }
-REALISTIC = {"c4quarter"}
+REALISTIC = {"c4quarter", "c4eighth", "c4"}
+BIG = {"c4eighth", "c4"}     # host-side fields are generated and uploaded one at a time; no pinned end-to-end leg
 # algorithmic bytes per cell (SURVEY 8d / DESIGN.md): momentum kernel reads u,v,w,p and writes Gu,Gv
 MOMENTUM_BYTES_PER_CELL = 48.0
 # stage groups of ob200_timing (include/ocean_b200.h); group 8 is the T,S part of group 0
@@ -148,16 +153,25 @@ def make_case(workload: str, ranks: int, balance: str = "equal") -> cases.Case:
     return cases.Case(workload, Nx, Ny, Nz, experiment="DoubleDrake", dt=dt, perturb=True, ranks=ranks, balance=balance)
 
 
+def realistic_field(pkg, grid, name):
+    """One field of the RealisticOcean-shaped initial state (generated separately: a 1/12-degree slab field is 0.8 GB)."""
+    r = np.pi / 180.0
+    lam, lamf = grid.lam_c()[None, None, :], (grid.lam_c() - 0.5 * grid.dlam)[None, None, :]
+    phi, phif, z = grid.phi_c()[None, :, None], grid.phi_f()[None, :, None], grid.z_c()[:, None, None]
+    if name in ("T", "S"):
+        return pkg.synthetic.initial_T_S(grid)[0 if name == "T" else 1]
+    if name == "U":
+        return 0.05 * np.sin(2 * lamf * r) * np.cos(phi * r) * np.exp(z / 2000.0)
+    if name == "V":
+        return 0.03 * np.cos(3 * lam * r) * np.sin(2 * phif * r) * np.exp(z / 1000.0)
+    return np.zeros((grid.Ny, grid.Nx))
+
+
 def initial_state(pkg, case, grid):
     """Closed-form initial state as host arrays (the same formulas as tests/cases.py)."""
     D, r = case.depth, np.pi / 180.0
     if case.experiment == "RealisticOcean":
-        T, S = pkg.synthetic.initial_T_S(grid)
-        lam, lamf = grid.lam_c()[None, None, :], (grid.lam_c() - 0.5 * grid.dlam)[None, None, :]
-        phi, phif, z = grid.phi_c()[None, :, None], grid.phi_f()[None, :, None], grid.z_c()[:, None, None]
-        u = 0.05 * np.sin(2 * lamf * r) * np.cos(phi * r) * np.exp(z / 2000.0)
-        v = 0.03 * np.cos(3 * lam * r) * np.sin(2 * phif * r) * np.exp(z / 1000.0)
-        return {"T": T, "S": S, "U": u, "V": v, "ETA": np.zeros((grid.Ny, grid.Nx))}
+        return {n: realistic_field(pkg, grid, n) for n in ("T", "S", "U", "V", "ETA")}
     lam, lamf = grid.lam_c()[None, None, :], (grid.lam_c() - 0.5 * grid.dlam)[None, None, :]
     phi, phif = grid.phi_c()[None, :, None], grid.phi_f()[None, :, None]
     z = grid.z_c()[:, None, None]
@@ -254,8 +268,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("OB200_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-columns", type=int, default=72)
-    ap.add_argument("--balance", default=os.environ.get("OB200_BALANCE", "equal"), choices=["equal", "cost"],
-                    help="x-slab widths: equal (reference default for DoubleDrake) or balanced by kernel cost")
+    ap.add_argument("--balance", default=os.environ.get("OB200_BALANCE", "equal"), choices=["equal", "cost", "wet"],
+                    help="x-slab widths: equal (reference default for DoubleDrake), balanced by kernel cost, or by wet-cell count "
+                         "(the reference's LOADBALANCE=1 for RealisticOcean, grid_load_balance.jl:35-75)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--persistent-barotropic", type=int, default=int(os.environ.get("OB200_PERSISTENT_BARO", "0")))
@@ -299,20 +314,33 @@ def main():
         model.backend.set_option("barotropic_graph", 0)
     if os.environ.get("OB200_OVERLAP", "0") == "1":
         model.backend.set_option("overlap", 1)
-    for env, opt in (("OB200_CONCURRENT_MASKED", "concurrent_masked_tiles"), ("OB200_OVERLAP_EXCHANGE", "overlap_exchange")):
+    for env, opt in (("OB200_CONCURRENT_MASKED", "concurrent_masked_tiles"), ("OB200_OVERLAP_EXCHANGE", "overlap_exchange"),
+                     ("OB200_EARLY_TS", "early_ts_exchange")):
         if env in os.environ:
             model.backend.set_option(opt, int(os.environ[env]))
-    state = initial_state(pkg, case, grid)
-    # pinned host copies of the initial state (what a host application owns)
-    pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in state.items()}
+    big = args.workload in BIG
+    if big:
+        args.no_e2e = True
+        pinned = {}
 
-    def upload():
-        for k, t in pinned.items():
-            model.backend.lib.ob200_set_field(model.backend.h, pkg._abi.FIELD_ID[k], t.data_ptr(), 0, 0, 0, 0)
-        model.backend.update_state()
+        def upload():      # one field at a time from pageable memory
+            for k in ("T", "S", "U", "V", "ETA"):
+                a = np.ascontiguousarray(realistic_field(pkg, grid, k), dtype=np.float64)
+                model.backend.lib.ob200_set_field(model.backend.h, pkg._abi.FIELD_ID[k], a.ctypes.data, 0, 0, 0, 0)
+                del a
+            model.backend.update_state()
+    else:
+        state = initial_state(pkg, case, grid)
+        # pinned host copies of the initial state (what a host application owns)
+        pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in state.items()}
+
+        def upload():
+            for k, t in pinned.items():
+                model.backend.lib.ob200_set_field(model.backend.h, pkg._abi.FIELD_ID[k], t.data_ptr(), 0, 0, 0, 0)
+            model.backend.update_state()
 
     out_names = ("U", "V", "W", "ETA", "T", "S")
-    out_pinned = {k: torch.empty(pkg._abi.field_shape(k, *grid.size()), dtype=torch.float64).pin_memory() for k in out_names}
+    out_pinned = {} if big else {k: torch.empty(pkg._abi.field_shape(k, *grid.size()), dtype=torch.float64).pin_memory() for k in out_names}
 
     def download():
         for k, t in out_pinned.items():
@@ -451,6 +479,11 @@ def main():
         out["ncu"] = {k: prof[k] for k in prof if k not in ("workload", "n_gpus")}
     if per_rank_groups is not None:
         out["stage_ms_per_rank"] = [[round(x, 3) for x in r] for r in per_rank_groups]
+    if case.experiment == "RealisticOcean" and grid.bottom_height_global is not None:
+        load = pkg.assess_x_load_from_bottom(grid.z_c(), grid.bottom_height_global)
+        off = np.cumsum((0,) + tuple(grid.partition.sizes))
+        out["wet_cells_per_rank"] = [int(load[off[r]:off[r + 1]].sum()) for r in range(world)]
+        out["wet_fraction"] = float(load.sum()) / float(Nx * Ny * Nz)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample(pkg, args)
     print(json.dumps(out), flush=True)

@@ -46,6 +46,10 @@ extern "C" {
 #define OB200_BC_DOUBLEDRAKE  1 /* cubic wind/salt, T restoring, linear drag (:58-81) */
 #define OB200_BC_REALISTIC    2 /* time-interpolated flux arrays, quadratic drag (:83-137) */
 
+#define OB200_BAROX_AUTO      0
+#define OB200_BAROX_WIDE      1
+#define OB200_BAROX_SUBSTEP   2
+
 /* Field identifiers for ob200_set_field / ob200_get_field.
  * Interior extents (i fastest, then j, then k):
  *   U,T,S,P,GU,GT,GS,..  Nx x Ny     x Nz
@@ -120,8 +124,16 @@ typedef struct ob200_config {
     int32_t qgleith_enabled;
     double  leith_C, leith_min_N2, leith_Vscale;
     /* host arrays, copied during ob200_create */
-    int32_t bottom_halo_columns;     /* x-halo columns carried by bottom_height: >= OB200_HALO, and
-                                        >= n_substeps + 1 when nranks > 1 (wide barotropic halo) */
+    int32_t bottom_halo_columns;     /* x-halo columns carried by bottom_height: >= OB200_HALO; the wide barotropic
+                                        halo (below) needs >= n_substeps + 1                                      */
+    /* x-slabs only: how the barotropic substeps see their neighbours (BASELINE configs[4]).
+     * OB200_BAROX_WIDE: halo of n_substeps + 1 columns exchanged ONCE per step, no communication inside the loop
+     *   (what Oceananigans' distributed solver does; src/simulation_outputs.jl:70-80); needs Nx and
+     *   bottom_halo_columns >= n_substeps + 1.
+     * OB200_BAROX_SUBSTEP: one-column exchanges of eta / U every half substep; works on slabs as narrow as the
+     *   reference's 20-column clamp (src/grid_load_balance.jl:132-145).
+     * OB200_BAROX_AUTO: wide when the slab allows it, per-substep otherwise.                                      */
+    int32_t barotropic_exchange;
     const double* z_faces;           /* Nz+1, bottom to top (bathymetry_and_forcings.jl:47-58) */
     const double* bottom_height;     /* Ny rows x (Nx + 2*bottom_halo_columns) columns incl. x-halos */
     const double* averaging_weights; /* n_substeps                                             */

@@ -12,7 +12,7 @@ from .bathymetry_and_forcings import (T_reference, cubic_profile, double_drake_b
 from .boundary_and_initial_conditions import (flux_filenum, initialize_model, load_fluxes, load_restoring,
                                               partition_global_array, restoring_filenum, set_boundary_conditions,
                                               update_fluxes, update_restoring)
-from .grid_load_balance import (LatitudeLongitudeGrid, Partition, assess_x_load, assess_y_load, calculate_local_N,
+from .grid_load_balance import (LatitudeLongitudeGrid, Partition, assess_x_load, assess_x_load_from_bottom, assess_y_load, calculate_local_N,
                                 kernel_cost_per_column, load_balanced_grid, redistribute_size_to_fulfill_memory_limitation)
 from .model import (B200Backend, BoundaryConditions, HydrostaticFreeSurfaceModel, QGLeith,
                     RiBasedVerticalDiffusivity, SplitExplicitFreeSurface, VerticalScalarDiffusivity,

@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("OB200_LIB", os.path.join(HERE, "csrc", "libocean_b200
 OB200_HALO = 7
 OB200_EOS_LINEAR, OB200_EOS_TEOS10 = 0, 1
 OB200_BC_QUIESCENT, OB200_BC_DOUBLEDRAKE, OB200_BC_REALISTIC = 0, 1, 2
+OB200_BAROX_AUTO, OB200_BAROX_WIDE, OB200_BAROX_SUBSTEP = 0, 1, 2
 
 FIELDS = ["U", "V", "W", "T", "S", "P", "KAPPA_C", "KAPPA_U", "GU", "GV", "GT", "GS",
           "GU_PREV", "GV_PREV", "GT_PREV", "GS_PREV", "ETA", "UBAR", "VBAR", "UTRANS", "VTRANS",
@@ -65,6 +66,7 @@ class ob200_config(C.Structure):
         ("qgleith_enabled", C.c_int32),
         ("leith_C", C.c_double), ("leith_min_N2", C.c_double), ("leith_Vscale", C.c_double),
         ("bottom_halo_columns", C.c_int32),
+        ("barotropic_exchange", C.c_int32),
         ("z_faces", C.POINTER(C.c_double)),
         ("bottom_height", C.POINTER(C.c_double)),
         ("averaging_weights", C.POINTER(C.c_double)),

@@ -25,9 +25,12 @@ void launch_mask_fields(const Geom& G, const Fields& F, cudaStream_t st);
 // layout: 0 = 3-D field, 1 = 2-D in the 3-D plane layout (Ld), 2 = 2-D barotropic layout
 void launch_copy_field(const Geom& G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, int layout,
                        bool to_field, int ex, cudaStream_t st);
-void launch_pack_x(const Geom& G, const Fields& F, double* sendW, double* sendE, cudaStream_t st);
-void launch_unpack_x(const Geom& G, const Fields& F, const double* recvW, const double* recvE, cudaStream_t st);
-size_t pack_x_count(const Geom& G);
+// exchange groups of the 7-column x-halos: u, v, eta (final after the corrector) | T, S (final after their implicit solve)
+#define OB_XG_UVETA 0
+#define OB_XG_TS 1
+void launch_pack_x(const Geom& G, const Fields& F, double* sendW, double* sendE, int group, cudaStream_t st);
+void launch_unpack_x(const Geom& G, const Fields& F, const double* recvW, const double* recvE, int group, cudaStream_t st);
+size_t pack_x_count(const Geom& G, int group);
 void launch_diagnostics(const Geom& G, const Fields& F, double* out8, cudaStream_t st);
 
 // kernels_column.cu
@@ -51,6 +54,12 @@ void launch_baro_init(const Geom& G, const Fields& F, bool periodic_x, int ex, c
 void launch_baro_eta(const Geom& G, const Fields& F, double dtau, bool periodic_x, int ex, cudaStream_t st);
 void launch_baro_vel(const Geom& G, const Fields& F, double dtau, double wgt, bool periodic_x, int ex, cudaStream_t st);
 void launch_baro_finish(const Geom& G, const Fields& F, cudaStream_t st);
+// per-substep slab exchange: interior columns only; edge columns through contiguous buffers of Ny doubles (kernels_baro.cu)
+void launch_baro_eta_edge(const Geom& G, const Fields& F, double dtau, double* send_eta, const double* recv_eta, double* send_U,
+                          const double* recv_U, cudaStream_t st);
+void launch_baro_vel_edge(const Geom& G, const Fields& F, double dtau, double wgt, double* send_eta, const double* recv_eta,
+                          double* send_U, const double* recv_U, cudaStream_t st);
+void launch_baro_edge_first(const Geom& G, const Fields& F, double* send_U, cudaStream_t st);
 int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const double* weights_dev, int M, bool periodic_x,
                            int ex, cudaStream_t st);
 size_t pack_baro_count(const Geom& G, int W);

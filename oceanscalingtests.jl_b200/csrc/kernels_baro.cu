@@ -26,23 +26,37 @@ __global__ void k_baro_init(Geom G, Fields F, bool periodic, int ex) {
     F.etab[c] = 0.0; F.Ub[c] = 0.0; F.Vb[c] = 0.0;
 }
 
-__device__ __forceinline__ void eta_update(const Geom& G, const Fields& F, int i, int j, double dtau, bool periodic) {
+// Per-substep slab exchange (x-slabs narrower than the wide halo, and the microbenchmark of BASELINE configs[4]): the one
+// column a neighbour needs travels through contiguous edge buffers -- the producer writes its edge value there as well,
+// the consumer reads the neighbour's from there -- so there are no pack / unpack launches between the NCCL calls.
+struct BaroEdge {
+    double* send_eta;         // my eta(Nx - 1, j)      -> east neighbour's eta(-1, j)
+    const double* recv_eta;   // west neighbour's eta(Nx - 1, j)
+    double* send_U;           // my U(0, j)             -> west neighbour's U(Nx, j)
+    const double* recv_U;     // east neighbour's U(0, j)
+};
+
+__device__ __forceinline__ void eta_update(const Geom& G, const Fields& F, int i, int j, double dtau, bool periodic,
+                                           const BaroEdge* E = nullptr) {
     const int c = idx2b(G, i, j);
     const double Vn = (j + 1 == G.Ny) ? 0.0 : F.V[c + G.pitch2];
     const double Vs = (j == 0) ? 0.0 : F.V[c];
-    const double e = F.eta[c] - dtau * ((G.dy * F.U[c + 1] - G.dy * F.U[c]) + (G.dxcf[j + 1] * Vn - G.dxcf[j] * Vs)) / G.azcc[j];
+    const double Ue = (E && i == G.Nx - 1) ? E->recv_U[j] : F.U[c + 1];
+    const double e = F.eta[c] - dtau * ((G.dy * Ue - G.dy * F.U[c]) + (G.dxcf[j + 1] * Vn - G.dxcf[j] * Vs)) / G.azcc[j];
     F.eta[c] = e;
     if (periodic) {
         if (i == G.Nx - 1) F.eta[c - G.Nx] = e;   // west halo column i = -1
         if (i == 0) F.eta[c + G.Nx] = e;          // east halo column i = Nx
     }
+    if (E && i == G.Nx - 1) E->send_eta[j] = e;
 }
 
 __device__ __forceinline__ void vel_update(const Geom& G, const Fields& F, int i, int j, double dtau, double wgt,
-                                           bool periodic) {
+                                           bool periodic, const BaroEdge* E = nullptr) {
     const int c = idx2b(G, i, j);
     const double e = F.eta[c];
-    const double detax = (e - F.eta[c - 1]) / G.dxfc[j];
+    const double ew = (E && i == 0) ? E->recv_eta[j] : F.eta[c - 1];
+    const double detax = (e - ew) / G.dxfc[j];
     const double detay = (j == 0) ? 0.0 : (e - F.eta[c - G.pitch2]) / G.dy;
     const double Un = F.U[c] + dtau * (-G.g * F.Hfc[c] * detax + F.GU[c]);
     const double Vn = F.V[c] + dtau * (-G.g * F.Hcf[c] * detay + F.GV[c]);
@@ -54,6 +68,7 @@ __device__ __forceinline__ void vel_update(const Geom& G, const Fields& F, int i
         if (i == 0) { F.U[c + G.Nx] = Un; F.V[c + G.Nx] = Vn; }
         if (i == G.Nx - 1) { F.U[c - G.Nx] = Un; F.V[c - G.Nx] = Vn; }
     }
+    if (E && i == 0) E->send_U[j] = Un;
 }
 
 __global__ void __launch_bounds__(128) k_baro_eta(Geom G, Fields F, double dtau, bool periodic, int ex) {
@@ -65,6 +80,21 @@ __global__ void __launch_bounds__(128) k_baro_vel(Geom G, Fields F, double dtau,
     const int i = blockIdx.x * blockDim.x + threadIdx.x - ex;
     if (i >= G.Nx + ex) return;
     vel_update(G, F, i, blockIdx.y, dtau, wgt, periodic);
+}
+__global__ void __launch_bounds__(128) k_baro_eta_edge(Geom G, Fields F, double dtau, BaroEdge E) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.Nx) return;
+    eta_update(G, F, i, blockIdx.y, dtau, false, &E);
+}
+__global__ void __launch_bounds__(128) k_baro_vel_edge(Geom G, Fields F, double dtau, double wgt, BaroEdge E) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.Nx) return;
+    vel_update(G, F, i, blockIdx.y, dtau, wgt, false, &E);
+}
+// after baro_init: the first eta substep needs U(Nx) = the east neighbour's U(0)
+__global__ void k_baro_edge_first(Geom G, Fields F, BaroEdge E) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < G.Ny) E.send_U[j] = F.U[idx2b(G, 0, j)];
 }
 __global__ void k_baro_finish(Geom G, Fields F) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,6 +117,22 @@ void launch_baro_eta(const Geom& G, const Fields& F, double dtau, bool periodic,
 void launch_baro_vel(const Geom& G, const Fields& F, double dtau, double wgt, bool periodic, int ex, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 2 * ex + 127) / 128, G.Ny);
     k_baro_vel<<<g, b, 0, st>>>(G, F, dtau, wgt, periodic, ex);
+    OB_COUNT_LAUNCH(1);
+}
+void launch_baro_eta_edge(const Geom& G, const Fields& F, double dtau, double* send_eta, const double* recv_eta, double* send_U,
+                          const double* recv_U, cudaStream_t st) {
+    dim3 b(128), g((G.Nx + 127) / 128, G.Ny);
+    k_baro_eta_edge<<<g, b, 0, st>>>(G, F, dtau, BaroEdge{send_eta, recv_eta, send_U, recv_U});
+    OB_COUNT_LAUNCH(1);
+}
+void launch_baro_vel_edge(const Geom& G, const Fields& F, double dtau, double wgt, double* send_eta, const double* recv_eta,
+                          double* send_U, const double* recv_U, cudaStream_t st) {
+    dim3 b(128), g((G.Nx + 127) / 128, G.Ny);
+    k_baro_vel_edge<<<g, b, 0, st>>>(G, F, dtau, wgt, BaroEdge{send_eta, recv_eta, send_U, recv_U});
+    OB_COUNT_LAUNCH(1);
+}
+void launch_baro_edge_first(const Geom& G, const Fields& F, double* send_U, cudaStream_t st) {
+    k_baro_edge_first<<<(G.Ny + 127) / 128, 128, 0, st>>>(G, F, BaroEdge{nullptr, nullptr, send_U, nullptr});
     OB_COUNT_LAUNCH(1);
 }
 void launch_baro_finish(const Geom& G, const Fields& F, cudaStream_t st) {

@@ -96,41 +96,45 @@ void launch_copy_field(const Geom& G, double* field, double* buf, int ny, int nz
     OB_COUNT_LAUNCH(1);
 }
 
-// ---- x-slab exchange buffers: [u | v | T | S] x (Nz planes x (Ny+1) rows x OB_H cols) + eta ((Ny+1) x OB_H)
-size_t pack_x_count(const Geom& G) { return (size_t)OB_H * (G.Ny + 1) * (4 * (size_t)G.Nz + 1); }
+// ---- x-slab exchange buffers: per field Nz planes x (Ny+1) rows x OB_H cols; eta ((Ny+1) x OB_H) rides with u, v.
+// Two groups with their own buffers so that they can travel at different times: T, S are final after their implicit solve
+// (their exchange hides behind the u, v solve and the barotropic loop), u, v, eta only after the corrector.
+size_t pack_x_count(const Geom& G, int group) {
+    return (size_t)OB_H * (G.Ny + 1) * (2 * (size_t)G.Nz + (group == OB_XG_UVETA ? 1 : 0));
+}
 
-__global__ void k_pack_x(Geom G, Fields F, double* sendW, double* sendE, bool unpack) {
+__global__ void k_pack_x(Geom G, Fields F, double* sendW, double* sendE, bool unpack, int group) {
     const int h = threadIdx.x;
     const int j = blockIdx.x * blockDim.y + threadIdx.y;
-    const int k = blockIdx.y;   // 0..Nz (Nz = eta)
+    const int k = blockIdx.y;   // 0..Nz (Nz = eta, group u, v, eta only)
     if (h >= OB_H || j > G.Ny) return;
     const size_t per = (size_t)OB_H * (G.Ny + 1);
     const size_t o = (size_t)j * OB_H + h;
     if (k < G.Nz) {
-        double* fs[4] = {F.u, F.v, F.T, F.S};
+        double* fs[2] = {group == OB_XG_UVETA ? F.u : F.T, group == OB_XG_UVETA ? F.v : F.S};
         const long long c = idx3(G, 0, j, k);
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < 2; q++) {
             const size_t b = ((size_t)q * G.Nz + k) * per + o;
             if (!unpack) { sendW[b] = fs[q][c + h]; sendE[b] = fs[q][c + G.Nx - OB_H + h]; }
             else { fs[q][c - OB_H + h] = sendW[b]; fs[q][c + G.Nx + h] = sendE[b]; }
         }
     } else {
-        const size_t b = (size_t)4 * G.Nz * per + o;
+        const size_t b = (size_t)2 * G.Nz * per + o;
         const int c = idx2b(G, 0, j);
         if (!unpack) { sendW[b] = F.eta[c + h]; sendE[b] = F.eta[c + G.Nx - OB_H + h]; }
         else { F.eta[c - OB_H + h] = sendW[b]; F.eta[c + G.Nx + h] = sendE[b]; }
     }
 }
-void launch_pack_x(const Geom& G, const Fields& F, double* sendW, double* sendE, cudaStream_t st) {
-    dim3 b(8, 16), g((G.Ny + 1 + 15) / 16, G.Nz + 1);
-    k_pack_x<<<g, b, 0, st>>>(G, F, sendW, sendE, false);
+void launch_pack_x(const Geom& G, const Fields& F, double* sendW, double* sendE, int group, cudaStream_t st) {
+    dim3 b(8, 16), g((G.Ny + 1 + 15) / 16, G.Nz + (group == OB_XG_UVETA ? 1 : 0));
+    k_pack_x<<<g, b, 0, st>>>(G, F, sendW, sendE, false, group);
     OB_COUNT_LAUNCH(1);
 }
 // recvW = data for the west halo (from the west neighbour's east edge), recvE likewise
-void launch_unpack_x(const Geom& G, const Fields& F, const double* recvW, const double* recvE, cudaStream_t st) {
-    dim3 b(8, 16), g((G.Ny + 1 + 15) / 16, G.Nz + 1);
-    k_pack_x<<<g, b, 0, st>>>(G, F, const_cast<double*>(recvW), const_cast<double*>(recvE), true);
+void launch_unpack_x(const Geom& G, const Fields& F, const double* recvW, const double* recvE, int group, cudaStream_t st) {
+    dim3 b(8, 16), g((G.Ny + 1 + 15) / 16, G.Nz + (group == OB_XG_UVETA ? 1 : 0));
+    k_pack_x<<<g, b, 0, st>>>(G, F, const_cast<double*>(recvW), const_cast<double*>(recvE), true, group);
     OB_COUNT_LAUNCH(1);
 }
 

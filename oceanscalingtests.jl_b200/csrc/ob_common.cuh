@@ -120,24 +120,34 @@ __device__ __forceinline__ double teos_rprime(double Th, double SA, double Z, do
     return r;
 }
 
-__device__ __forceinline__ double buoyancy_of(const Geom& G, double T, double S, int k) {
-    if (G.eos == OB200_EOS_LINEAR) return G.g * (G.alpha * T - G.beta_s * S);
+// compile-time equation of state (the column sweeps are instantiated per EOS: the TEOS-10 polynomial costs registers the
+// linear instance does not have under its 32-register occupancy bound)
+template <bool TEOS>
+__device__ __forceinline__ double buoyancy_t(const Geom& G, double T, double S, int k) {
+    if (!TEOS) return G.g * (G.alpha * T - G.beta_s * S);
     return -G.g * teos_rprime<false>(T, S, G.zc[k], nullptr, nullptr) / G.rho0;
+}
+__device__ __forceinline__ double buoyancy_of(const Geom& G, double T, double S, int k) {
+    return G.eos == OB200_EOS_LINEAR ? buoyancy_t<false>(G, T, S, k) : buoyancy_t<true>(G, T, S, k);
 }
 
 // N^2 on the (c,c,f) face kf between the cells kf - 1 (Tm, Sm) and kf (Tk, Sk): Oceananigans' `∂z_b` for SeawaterBuoyancy,
 //     g (alpha ∂z T - beta ∂z S),   alpha, beta evaluated AT THE FACE from the z-averaged T, S and the face depth
 // -- not a difference of in-situ buoyancies, which for TEOS-10 would add the compressibility term ∂rho'/∂z at fixed T, S.
 // The caller applies the immersed conditional (zero when either cell is inactive).
-__device__ __forceinline__ double n2_face(const Geom& G, double Tm, double Sm, double Tk, double Sk, int kf) {
+template <bool TEOS>
+__device__ __forceinline__ double n2_face_t(const Geom& G, double Tm, double Sm, double Tk, double Sk, int kf) {
     double al = G.alpha, be = G.beta_s;
-    if (G.eos != OB200_EOS_LINEAR) {
+    if (TEOS) {
         double dTh, dSA;
         teos_rprime<true>(0.5 * (Tm + Tk), 0.5 * (Sm + Sk), G.zfa[kf], &dTh, &dSA);
         al = -dTh / G.rho0; be = dSA / G.rho0;
     }
     const double rdzf = G.rdzf[kf];
     return G.g * (al * ((Tk - Tm) * rdzf) - be * ((Sk - Sm) * rdzf));
+}
+__device__ __forceinline__ double n2_face(const Geom& G, double Tm, double Sm, double Tk, double Sk, int kf) {
+    return G.eos == OB200_EOS_LINEAR ? n2_face_t<false>(G, Tm, Sm, Tk, Sk, kf) : n2_face_t<true>(G, Tm, Sm, Tk, Sk, kf);
 }
 
 // Deterministic tanh from +,-,*,/ only (the library is compiled with -fmad=false): the same operation

@@ -27,6 +27,8 @@ struct ob200_handle {
     double *F_Hfc = nullptr, *F_Hcf = nullptr;
     double *bsendW = nullptr, *bsendE = nullptr, *brecvW = nullptr, *brecvE = nullptr;
     size_t bcount = 0;
+    bool substep_exchange = false;   // x-slabs: one-column eta / U exchanges every half substep instead of the wide halo
+    double *e_send_eta = nullptr, *e_recv_eta = nullptr, *e_send_U = nullptr, *e_recv_U = nullptr;   // Ny doubles each
     bool periodic_local = true;
     bool own_stream = true;
     cudaStream_t stream = nullptr;
@@ -52,8 +54,10 @@ struct ob200_handle {
     bool fields_dirty = true;   // set_field since the last mask
     // NCCL ring
     ncclComm_t comm = nullptr;
-    double *sendW = nullptr, *sendE = nullptr, *recvW = nullptr, *recvE = nullptr;
-    size_t xcount = 0;
+    double *sendW[2] = {nullptr, nullptr}, *sendE[2] = {nullptr, nullptr}, *recvW[2] = {nullptr, nullptr}, *recvE[2] = {nullptr, nullptr};
+    size_t xcount[2] = {0, 0};      // per exchange group (OB_XG_UVETA, OB_XG_TS)
+    bool early_ts_exchange = true;  // option "early_ts_exchange": T, S halos travel right after their solve, on stream2
+    cudaEvent_t ev_ts[2] = {nullptr, nullptr};   // T, S solved (fork) / their halos unpacked (join)
     // CUDA graph of the barotropic substep launches at fixed dt
     cudaGraphExec_t graph_exec = nullptr;
     double graph_dt = NAN;
@@ -98,7 +102,7 @@ int setup_geometry(ob200_handle* h) {
     G.NyP = c.Ny + 1 + 2 * OB_H;
     G.sz = (long long)G.pitch * G.NyP;
     // barotropic arrays: halo of Wb columns (M + 1 on x-slabs: exchanged once, then no communication in the loop)
-    G.Wb = h->periodic_local ? OB_H : std::max(OB_H, c.n_substeps + 1);
+    G.Wb = (h->periodic_local || h->substep_exchange) ? OB_H : std::max(OB_H, c.n_substeps + 1);
     G.X0b = ((G.Wb + 15) / 16) * 16;
     G.pitch2 = G.X0b + ((c.Nx + G.Wb + 15) / 16) * 16;
     const double pi = M_PI;
@@ -362,32 +366,49 @@ FieldRef field_ref(ob200_handle* h, int id) {
 }
 
 // ---- stages ------------------------------------------------------------------------------------------
-int exchange_halos(ob200_handle* h, cudaStream_t st = nullptr) {
+// groups: bit 0 = u, v, eta; bit 1 = T, S
+int exchange_halos(ob200_handle* h, cudaStream_t st = nullptr, int groups = 3) {
     if (h->periodic_local) return OB200_OK;
     if (!st) st = h->stream;
     if (!h->comm) return h->fail(OB200_ESTATE, "exchange_halos", "nranks > 1 but ob200_comm_init was not called");
     const int r = h->cfg.rank, n = h->cfg.nranks;
     const int west = (r + n - 1) % n, east = (r + 1) % n;
-    launch_pack_x(h->G, h->F, h->sendW, h->sendE, st);
+    for (int g = 0; g < 2; g++)
+        if (groups & (1 << g)) launch_pack_x(h->G, h->F, h->sendW[g], h->sendE[g], g, st);
     // order matters on a 2-rank ring (west == east == the same peer): NCCL pairs sends and receives between two
     // ranks in issue order, and my west halo must receive the peer's EAST edge -> east-bound message first
     ncclGroupStart();
-    ncclSend(h->sendE, h->xcount, ncclDouble, east, h->comm, st);
-    ncclSend(h->sendW, h->xcount, ncclDouble, west, h->comm, st);
-    ncclRecv(h->recvW, h->xcount, ncclDouble, west, h->comm, st);
-    ncclRecv(h->recvE, h->xcount, ncclDouble, east, h->comm, st);
+    for (int g = 0; g < 2; g++)
+        if (groups & (1 << g)) {
+            ncclSend(h->sendE[g], h->xcount[g], ncclDouble, east, h->comm, st);
+            ncclSend(h->sendW[g], h->xcount[g], ncclDouble, west, h->comm, st);
+            ncclRecv(h->recvW[g], h->xcount[g], ncclDouble, west, h->comm, st);
+            ncclRecv(h->recvE[g], h->xcount[g], ncclDouble, east, h->comm, st);
+        }
     ncclResult_t rc = ncclGroupEnd();
     if (rc != ncclSuccess) return h->fail(OB200_ENCCL, "halo exchange", ncclGetErrorString(rc));
-    launch_unpack_x(h->G, h->F, h->recvW, h->recvE, st);
+    for (int g = 0; g < 2; g++)
+        if (groups & (1 << g)) launch_unpack_x(h->G, h->F, h->recvW[g], h->recvE[g], g, st);
     return OB200_OK;
 }
 
 int barotropic_loop(ob200_handle* h, double dt);
 
-int mask_and_halos(ob200_handle* h) {
+// `ts_in_flight`: the T, S halos were sent on stream2 right after their solve (ev_ts[1] marks their arrival)
+int mask_and_halos(ob200_handle* h, bool ts_in_flight = false) {
     if (h->fields_dirty) { launch_mask_fields(h->G, h->F, h->stream); h->fields_dirty = false; }
-    if (int rc = exchange_halos(h)) return rc;
+    if (int rc = exchange_halos(h, nullptr, ts_in_flight ? 1 : 3)) return rc;
+    if (ts_in_flight) cudaStreamWaitEvent(h->stream, h->ev_ts[1], 0);
     launch_fill_halos(h->G, h->F, h->periodic_local, h->stream);
+    return OB200_OK;
+}
+// T, S are final once their implicit solve is done: their x-halos travel on stream2 while the main stream goes on with the
+// u, v solve, the barotropic loop and the corrector (half of the exchange payload off the critical path)
+int early_ts_exchange(ob200_handle* h) {
+    cudaEventRecord(h->ev_ts[0], h->stream);
+    cudaStreamWaitEvent(h->stream2, h->ev_ts[0], 0);
+    if (int rc = exchange_halos(h, h->stream2, 2)) return rc;
+    cudaEventRecord(h->ev_ts[1], h->stream2);
     return OB200_OK;
 }
 void auxiliaries(ob200_handle* h) {
@@ -424,12 +445,12 @@ void tendencies(ob200_handle* h, cudaEvent_t mid = nullptr, cudaEvent_t end = nu
 // Option "overlap_exchange", off by default: bit-identical, but measured SLOWER on 2 B200 at C3 (halo + sweeps 3.89 vs
 // 3.58 ms): a column sweep is latency-bound (one thread marches 120 levels), so the extra launches for the few
 // halo-dependent columns cost a full sweep latency each (~0.35 ms), more than the 0.17 ms of exchange they hide.
-int halos_and_auxiliaries(ob200_handle* h, cudaEvent_t* ev) {
+int halos_and_auxiliaries(ob200_handle* h, cudaEvent_t* ev, bool ts_in_flight = false) {
     const Geom& G = h->G;
     cudaStream_t s1 = h->stream, s2 = h->stream2;
     const int Nx = G.Nx;
     if (h->periodic_local || !h->overlap_exchange) {
-        if (int rc = mask_and_halos(h)) return rc;
+        if (int rc = mask_and_halos(h, ts_in_flight)) return rc;
         if (ev) cudaEventRecord(ev[0], s1);
         launch_w_p(G, h->F, s1);
         if (ev) cudaEventRecord(ev[1], s1);
@@ -482,10 +503,58 @@ int barotropic_wide_exchange(ob200_handle* h) {
     return OB200_OK;
 }
 
+// one-column ring exchange: my `send` goes to `to`, `recv` comes from the opposite neighbour
+int edge_exchange(ob200_handle* h, const double* send, double* recv, int to, int from) {
+    ncclGroupStart();
+    ncclSend(send, h->G.Ny, ncclDouble, to, h->comm, h->stream);
+    ncclRecv(recv, h->G.Ny, ncclDouble, from, h->comm, h->stream);
+    ncclResult_t rc = ncclGroupEnd();
+    if (rc != ncclSuccess) return h->fail(OB200_ENCCL, "barotropic edge exchange", ncclGetErrorString(rc));
+    return OB200_OK;
+}
+// substeps with one-column exchanges: eta(Nx - 1) travels east after every eta half step, U(0) west after every velocity
+// half step (2 M - 1 + 1 NCCL groups per baroclinic step; the loop is captured in a CUDA graph like the wide-halo loop)
+int barotropic_substeps_edge(ob200_handle* h, double dtau) {
+    const int r = h->cfg.rank, n = h->cfg.nranks, west = (r + n - 1) % n, east = (r + 1) % n, M = h->cfg.n_substeps;
+    launch_baro_edge_first(h->G, h->F, h->e_send_U, h->stream);
+    if (int rc = edge_exchange(h, h->e_send_U, h->e_recv_U, west, east)) return rc;
+    for (int m = 0; m < M; m++) {
+        launch_baro_eta_edge(h->G, h->F, dtau, h->e_send_eta, h->e_recv_eta, h->e_send_U, h->e_recv_U, h->stream);
+        if (int rc = edge_exchange(h, h->e_send_eta, h->e_recv_eta, east, west)) return rc;
+        launch_baro_vel_edge(h->G, h->F, dtau, h->weights[m], h->e_send_eta, h->e_recv_eta, h->e_send_U, h->e_recv_U, h->stream);
+        if (m + 1 < M)
+            if (int rc = edge_exchange(h, h->e_send_U, h->e_recv_U, west, east)) return rc;
+    }
+    launch_baro_finish(h->G, h->F, h->stream);
+    return OB200_OK;
+}
+
 int barotropic_loop(ob200_handle* h, double dt) {
     const double dtau = h->cfg.frac_dtau * dt;
     const bool per = h->periodic_local;
     const int ex = per ? 0 : h->G.Wb - 1;
+    if (!per && h->substep_exchange) {
+        if (!h->comm) return h->fail(OB200_ESTATE, "barotropic_loop", "nranks > 1 but ob200_comm_init was not called");
+        launch_baro_init(h->G, h->F, false, 0, h->stream);
+        if (!h->use_graph) return barotropic_substeps_edge(h, dtau);
+        if (!h->graph_exec || h->graph_dt != dt) {
+            if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            const long long before = ob_launch_count;
+            OB_CUDA_CHECK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = barotropic_substeps_edge(h, dtau);
+            const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            ob_launch_count = before;
+            if (rc) return rc;
+            OB_CUDA_CHECK(h, ce);
+            OB_CUDA_CHECK(h, cudaGraphInstantiate(&h->graph_exec, graph, 0));
+            cudaGraphDestroy(graph);
+            h->graph_dt = dt;
+        }
+        OB_CUDA_CHECK(h, cudaGraphLaunch(h->graph_exec, h->stream));
+        OB_COUNT_LAUNCH(2 * h->cfg.n_substeps + 2);
+        return OB200_OK;
+    }
     if (!per)
         if (int rc = barotropic_wide_exchange(h)) return rc;
     launch_baro_init(h->G, h->F, per, ex, h->stream);
@@ -585,6 +654,10 @@ int step_body_serial(ob200_handle* h, double dt, bool euler) {
     if (h->timing) cudaEventRecord(h->ev2[0], s1);
     launch_ab2_implicit_ts(G, h->F, dt, chi, h->onchip_solve, s1);
     if (h->timing) cudaEventRecord(h->ev2[1], s1);
+    // set_field since the last step (fields_dirty): T, S still have to be masked before they travel -> regular exchange
+    const bool ts_early = !h->periodic_local && h->early_ts_exchange && !h->overlap_exchange && !h->fields_dirty;
+    if (ts_early)
+        if (int rc = early_ts_exchange(h)) return rc;
     mark();
     launch_ab2_implicit_uv(G, h->F, dt, chi, h->onchip_solve, s1);   // also produces G^U, G^V (barotropic forcing)
     mark();
@@ -594,7 +667,7 @@ int step_body_serial(ob200_handle* h, double dt, bool euler) {
     swap_tendencies(h);
     mark();
     h->time += dt; h->iteration += 1; h->last_dt = dt;
-    if (int rc = halos_and_auxiliaries(h, h->timing ? &h->ev[e] : nullptr)) return rc;
+    if (int rc = halos_and_auxiliaries(h, h->timing ? &h->ev[e] : nullptr, ts_early)) return rc;
     if (h->timing) e += 3;
     if (h->timing) { tendencies(h, h->ev[e], h->ev2[3]); e++; }   // ev[e]: momentum done; ev2[3]: tracers + masked tiles done
     else tendencies(h);
@@ -614,10 +687,17 @@ int ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out) {
     if (!cfg || !out) { g_last_error = "null argument"; return OB200_EINVAL; }
     if (cfg->struct_bytes != (int32_t)sizeof(ob200_config)) { g_last_error = "ob200_config size mismatch (ABI)"; return OB200_EINVAL; }
     if (cfg->Nx < 2 * OB_H || cfg->Ny < 2 || cfg->Nz < 2 || cfg->Nz > 32767 || cfg->n_substeps < 1 || cfg->n_substeps > OB200_MAX_SUBSTEPS ||
-        !cfg->z_faces || !cfg->bottom_height || !cfg->averaging_weights || cfg->nranks < 1 ||
-        cfg->bottom_halo_columns < OB_H || (cfg->nranks > 1 && cfg->bottom_halo_columns < cfg->n_substeps + 1) ||
-        (cfg->nranks > 1 && cfg->Nx < cfg->n_substeps + 1)) {
-        g_last_error = "invalid ob200_config (sizes / null arrays; Nx >= 14; Nz <= 32767; x-slabs need Nx and bottom_halo_columns >= n_substeps + 1)";
+        !cfg->z_faces || !cfg->bottom_height || !cfg->averaging_weights || cfg->nranks < 1 || cfg->bottom_halo_columns < OB_H ||
+        cfg->barotropic_exchange < OB200_BAROX_AUTO || cfg->barotropic_exchange > OB200_BAROX_SUBSTEP) {
+        g_last_error = "invalid ob200_config (sizes / null arrays; Nx >= 14; Nz <= 32767; bottom_halo_columns >= 7)";
+        return OB200_EINVAL;
+    }
+    const bool wide_ok = cfg->Nx >= cfg->n_substeps + 1 && cfg->bottom_halo_columns >= cfg->n_substeps + 1;
+    if (cfg->nranks > 1 && cfg->barotropic_exchange == OB200_BAROX_WIDE && !wide_ok) {
+        char msg[256];
+        std::snprintf(msg, sizeof msg, "x-slab of %d columns (bathymetry halo %d) is narrower than the wide barotropic halo of n_substeps + 1 = %d "
+                      "columns: use barotropic_exchange = OB200_BAROX_SUBSTEP (or AUTO)", cfg->Nx, cfg->bottom_halo_columns, cfg->n_substeps + 1);
+        g_last_error = msg;
         return OB200_EINVAL;
     }
     int ndev = 0;
@@ -633,6 +713,13 @@ int ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out) {
     cudaSetDevice(device);
     h->weights.assign(cfg->averaging_weights, cfg->averaging_weights + cfg->n_substeps);
     h->periodic_local = cfg->nranks <= 1;
+    {
+        int mode = cfg->barotropic_exchange;
+        const char* e = getenv("OB200_BARO_EXCHANGE");      // tuning / microbenchmark override: "wide" | "substep"
+        if (e && !std::strcmp(e, "substep")) mode = OB200_BAROX_SUBSTEP;
+        if (e && !std::strcmp(e, "wide") && wide_ok) mode = OB200_BAROX_WIDE;
+        h->substep_exchange = cfg->nranks > 1 && (mode == OB200_BAROX_SUBSTEP || (mode == OB200_BAROX_AUTO && !wide_ok));
+    }
     int rc = setup_geometry(h);
     if (!rc) rc = alloc_fields(h);
     if (!rc) rc = dev_alloc(h, &h->d_weights, cfg->n_substeps, false);
@@ -648,6 +735,7 @@ int ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out) {
     cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking);
     for (auto& ev : h->ev_tend) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto& ev : h->ev_ts) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : h->ev) cudaEventCreate(&ev);
     for (auto& ev : h->ev2) cudaEventCreate(&ev);
     for (auto& ev : h->ev_join) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -668,6 +756,7 @@ void ob200_destroy(ob200_handle* h) {
     for (auto& ev : h->ev2) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->ev_join) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->ev_tend) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->ev_ts) if (ev) cudaEventDestroy(ev);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
@@ -866,6 +955,7 @@ int ob200_set_option(ob200_handle* h, const char* name, int32_t value) {
     else if (!std::strcmp(name, "barotropic_graph")) h->use_graph = value != 0;
     else if (!std::strcmp(name, "overlap_exchange")) h->overlap_exchange = value != 0;
     else if (!std::strcmp(name, "concurrent_masked_tiles")) h->concurrent_masked = value != 0;
+    else if (!std::strcmp(name, "early_ts_exchange")) h->early_ts_exchange = value != 0;
     else if (!std::strcmp(name, "onchip_solve")) {
         if (value && !ab2_onchip_fits(h->G)) return h->fail(OB200_EINVAL, "onchip_solve", "Nz too large for the shared-memory solve");
         h->onchip_solve = value != 0;
@@ -892,12 +982,16 @@ int ob200_comm_init(ob200_handle* h, const void* id128) {
     std::memcpy(&id, id128, sizeof(id));
     ncclResult_t rc = ncclCommInitRank(&h->comm, h->cfg.nranks, id, h->cfg.rank);
     if (rc != ncclSuccess) return h->fail(OB200_ENCCL, "ncclCommInitRank", ncclGetErrorString(rc));
-    h->xcount = pack_x_count(h->G);
-    for (double** p : {&h->sendW, &h->sendE, &h->recvW, &h->recvE})
-        if (int r2 = dev_alloc(h, p, h->xcount)) return r2;
+    for (int g = 0; g < 2; g++) {
+        h->xcount[g] = pack_x_count(h->G, g);
+        for (double** p : {&h->sendW[g], &h->sendE[g], &h->recvW[g], &h->recvE[g]})
+            if (int r2 = dev_alloc(h, p, h->xcount[g])) return r2;
+    }
     h->bcount = pack_baro_count(h->G, h->G.Wb);
     for (double** p : {&h->bsendW, &h->bsendE, &h->brecvW, &h->brecvE})
         if (int r2 = dev_alloc(h, p, h->bcount)) return r2;
+    for (double** p : {&h->e_send_eta, &h->e_recv_eta, &h->e_send_U, &h->e_recv_U})
+        if (int r2 = dev_alloc(h, p, (size_t)h->G.Ny + 1)) return r2;
     return OB200_OK;
 }
 

@@ -120,7 +120,7 @@ class BoundaryConditions:
 
 def build_config(grid: LatitudeLongitudeGrid, free_surface: SplitExplicitFreeSurface, *, eos: str,
                  closure, boundary_conditions: BoundaryConditions, advection_orders=(9, 5, 7), chi: float = 0.1,
-                 rotation_rate: float = Omega_Earth):
+                 rotation_rate: float = Omega_Earth, barotropic_exchange: str = "auto"):
     """Assemble `ob200_config` (include/ocean_b200.h).  Returns (config, keepalive arrays)."""
     cfg = _abi.ob200_config()
     cfg.struct_bytes = C.sizeof(_abi.ob200_config)
@@ -171,6 +171,10 @@ def build_config(grid: LatitudeLongitudeGrid, free_surface: SplitExplicitFreeSur
     # x-slabs carry a barotropic halo of M + 1 columns, exchanged once per step
     halo_b = grid.halo if grid.nranks == 1 else max(grid.halo, len(w) + 1)
     cfg.bottom_halo_columns = halo_b
+    # x-slabs: wide halo exchanged once per step, or one-column exchanges every half substep (narrow slabs: the reference
+    # clamps wet-cell-balanced slabs at >= 20 columns, grid_load_balance.jl:132-145, fewer than the M + 1 a wide halo needs)
+    cfg.barotropic_exchange = {"auto": _abi.OB200_BAROX_AUTO, "wide": _abi.OB200_BAROX_WIDE,
+                               "substep": _abi.OB200_BAROX_SUBSTEP}[barotropic_exchange]
     bh = np.ascontiguousarray(grid.bottom_height_local(halo_b), dtype=np.float64)
     cfg.z_faces = _abi.as_double_ptr(zf)
     cfg.bottom_height = _abi.as_double_ptr(bh)
@@ -297,7 +301,7 @@ class HydrostaticFreeSurfaceModel:
     def __init__(self, *, grid: LatitudeLongitudeGrid, free_surface: SplitExplicitFreeSurface, eos: str = "linear",
                  closure=(VerticalScalarDiffusivity(), RiBasedVerticalDiffusivity()),
                  boundary_conditions: Optional[BoundaryConditions] = None, advection_orders=(9, 5, 7),
-                 device: int = 0, backend_factory=None, comm=None):
+                 device: int = 0, backend_factory=None, comm=None, barotropic_exchange: str = "auto"):
         self.grid = grid
         self.free_surface = free_surface
         self.closure = tuple(closure)
@@ -305,7 +309,7 @@ class HydrostaticFreeSurfaceModel:
         self.eos = eos
         self.cfg, self._keep = build_config(grid, free_surface, eos=eos, closure=self.closure,
                                             boundary_conditions=self.boundary_conditions,
-                                            advection_orders=advection_orders)
+                                            advection_orders=advection_orders, barotropic_exchange=barotropic_exchange)
         factory = backend_factory or B200Backend
         self.backend = factory(self.cfg, device) if factory is B200Backend else factory(self.cfg)
         if grid.nranks > 1 and hasattr(self.backend, "comm_init"):

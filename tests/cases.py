@@ -61,6 +61,12 @@ class Case:
             bottom = pkg.double_drake_bathymetry(lam, phi)
         if self.balance == "cost" and ranks > 1:
             part = pkg.Partition.balanced(pkg.kernel_cost_per_column(bottom, self.Nx, self.Ny), ranks, min_columns=40)
+        elif self.balance == "wet" and ranks > 1 and bottom is not None:
+            # LOADBALANCE=1: the reference's wet-cell prefix split + memory clamp (grid_load_balance.jl:49-62,97-146)
+            load = pkg.assess_x_load_from_bottom(g0.z_c(), bottom)
+            local_Nx = pkg.calculate_local_N(load, self.Nx, ranks)
+            pkg.redistribute_size_to_fulfill_memory_limitation(local_Nx, 1150)
+            part = pkg.Partition(tuple(int(n) for n in local_Nx))
         else:
             part = pkg.Partition.equal(self.Nx, ranks)
         return pkg.LatitudeLongitudeGrid(self.Nx, self.Ny, self.Nz, zf, rank=rank, partition=part,
@@ -132,6 +138,8 @@ CASES = {
     "ref_test": Case("ref_test", 72, 30, 10, dt=600.0),
     "dd_small": Case("dd_small", 90, 40, 8, dt=1200.0),
     "dd_mid": Case("dd_mid", 180, 75, 12, dt=1200.0),
+    # 2 x-slabs of 30 columns: narrower than the wide barotropic halo (M + 1 = 38) -> per-substep one-column exchanges
+    "dd_narrow": Case("dd_narrow", 60, 40, 8, dt=1200.0),
     "dd_leith": Case("dd_leith", 90, 40, 8, dt=1200.0, qgleith=True),
     "bumpy": Case("bumpy", 96, 48, 12, dt=900.0, bathymetry="bumpy"),
     # RealisticOcean-shaped (BASELINE configs[3]): TEOS-10, synthetic continents, time-interpolated fluxes +

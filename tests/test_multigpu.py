@@ -45,3 +45,18 @@ def test_overlapped_exchange_option_matches_single_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, OB200_OVERLAP_EXCHANGE="1"))
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("case_name,env", [("dd_mid", {"OB200_BARO_EXCHANGE": "substep"}), ("dd_narrow", {}),
+                                           ("dd_mid", {"OB200_BARO_EXCHANGE": "substep", "OB200_BARO_GRAPH": "0"})])
+def test_per_substep_barotropic_exchange_matches_single_gpu(case_name, env):
+    """One-column eta / U exchanges every half substep (BASELINE configs[4]'s second strategy; the only one possible on
+    slabs narrower than the wide halo, e.g. the reference's 20-column clamp): same bits as one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29737", os.path.join(HERE, "mgpu_worker.py"), case_name, "6"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, **env))
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
