@@ -174,6 +174,20 @@ int ob200_get_field(ob200_handle* h, int32_t field, double* buf, int32_t buf_on_
  * `Field(model.velocities.u; indices = (:, :, Nz))` views read (src/simulation_outputs.jl:17-25).                  */
 int ob200_get_level(ob200_handle* h, int32_t field, int32_t k, double* buf, int32_t buf_on_device,
                     int32_t hx, int32_t hy);
+/* --- borrowed arrays ("Julia owns, library borrows": SURVEY 8b) -------------------------------------------------
+ * The reference's callbacks and writers read `model.velocities`, `model.tracers`, `model.free_surface.η` and
+ * `model.timestepper.Gⁿ / G⁻` directly (src/near_global_simulation.jl:138-162, src/simulation_outputs.jl:14-37,47-64).
+ * ob200_bind registers the caller-owned DEVICE parent array of a field (Oceananigans layout, halos (hx, hy, hz); the
+ * library keeps its own 128-byte-aligned, pitched working copy, which TMA needs) for the lifetime of the handle or until
+ * ob200_unbind; nothing is copied by the call itself.  ob200_sync_outputs refreshes every bound array from the library
+ * (one device-to-device pass per bound field: u, v, w, eta, T, S at 1/6 degree = 3.5 ms, so the Julia glue calls it on
+ * the schedule of the callbacks, not every step); ob200_sync_inputs goes the other way (after `set!(model, ...)`) and
+ * ends with update_state!.  Both are ordered on the handle's stream; ob200_sync_outputs returns after the copies are done. */
+int ob200_bind(ob200_handle* h, int32_t field, double* dev_ptr, int32_t hx, int32_t hy, int32_t hz);
+int ob200_unbind(ob200_handle* h, int32_t field);
+int ob200_sync_outputs(ob200_handle* h);
+int ob200_sync_inputs(ob200_handle* h);
+
 /* RealisticOcean forcing arrays (src/boundary_and_initial_conditions.jl:90-105):
  * which = 0 taux, 1 tauy, 2 Qs, 3 Fs, 4 Tr, 5 Sr; Nx x Ny(+1 for tauy) x 6.   */
 int ob200_set_forcing(ob200_handle* h, int32_t which, const double* buf, int32_t buf_on_device);

@@ -1,11 +1,19 @@
 # OceanB200.jl -- Julia glue that makes libocean_b200.so a drop-in for Oceananigans' `time_step!` on the model
 # OceanScalingTests.jl builds (src/near_global_simulation.jl:105-113).  NOT executed in this repository's image
 # (no Julia here); kept small and literal.  See INTEGRATION.md.
+#
+# After `OceanB200.attach(model; ...)` the reference's own call sites -- `time_step!(model, Δt)` at
+# src/near_global_simulation.jl:181,196 and Oceananigans' `run!` (experiments/run.jl:60) -- dispatch to the library
+# through the method defined at the bottom of this file; a model that was not attached falls through to Oceananigans.
 module OceanB200
 
 using Oceananigans
 using Oceananigans.Grids: halo_size
+using Oceananigans.Models.HydrostaticFreeSurfaceModels: HydrostaticFreeSurfaceModel
+using Oceananigans.TimeSteppers: QuasiAdamsBashforth2TimeStepper
+using Oceananigans: AbstractModel
 using CUDA
+import Oceananigans.TimeSteppers: time_step!
 
 const LIB = get(ENV, "OCEAN_B200_LIB", "libocean_b200.so")
 const HALO = 7
@@ -31,12 +39,17 @@ Base.@kwdef mutable struct Config
     T_restoring_lambda::Float64 = 0; drag_mu::Float64 = 0
     qgleith_enabled::Int32 = 0; leith_C::Float64 = 2; leith_min_N2::Float64 = 1e-20; leith_Vscale::Float64 = 1
     bottom_halo_columns::Int32 = 7
+    barotropic_exchange::Int32 = 0      # OB200_BAROX_AUTO: wide halo when the slab allows it, per-substep exchange otherwise
     z_faces::Ptr{Float64} = C_NULL; bottom_height::Ptr{Float64} = C_NULL; averaging_weights::Ptr{Float64} = C_NULL
 end
 
 mutable struct Handle
     ptr::Ptr{Cvoid}
+    sync_every::Int          # refresh the Julia-owned arrays every n iterations (0 = only on request)
 end
+
+"models that were attached: `time_step!(model, Δt)` looks its handle up here"
+const ATTACHED = IdDict{Any, Handle}()
 
 check(h, rc) = rc == 0 || error("libocean_b200: " * unsafe_string(ccall((:ob200_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))
 
@@ -46,19 +59,43 @@ const F_GU, F_GV, F_GT, F_GS = Int32(8), Int32(9), Int32(10), Int32(11)
 const F_GU_PREV, F_GV_PREV, F_GT_PREV, F_GS_PREV = Int32(12), Int32(13), Int32(14), Int32(15)
 const F_ETA, F_UBAR, F_VBAR = Int32(16), Int32(17), Int32(18)
 
-"Create the native model from an Oceananigans model and copy its state in (replaces device allocation)."
-function attach(model; device = CUDA.deviceid(), bottom_height, bc_kind, wind_coeffs, salt_coeffs, λ, μ)
+# x-slab geometry from the Distributed architecture: equal `Partition(Rx)` or `Partition(x = Sizes(local_Nx...))`
+# (src/grid_load_balance.jl:62 with LOADBALANCE=1) -- the offset is the sum of the slabs to the west, not rank * Nx
+function slab_geometry(arch, Nx)
+    arch isa Oceananigans.DistributedComputations.Distributed || return (Nx, 0, 0, 1)
+    R, r = arch.ranks[1], arch.local_index[1] - 1
+    px = arch.partition.x
+    sizes = px isa Oceananigans.DistributedComputations.Sizes ? collect(Int, px.sizes) : fill(Nx, R)
+    return (sum(sizes), sum(sizes[1:r]), r, R)
+end
+
+"""
+    attach(model; bottom_height, bc_kind, wind_coeffs, salt_coeffs, λ, μ, comm = nothing, MPI = nothing, sync_every = 10)
+
+Create the native model for `model`, register the Julia-owned arrays the reference's callbacks and writers read
+(`ob200_bind`: u, v, w, η, T, S, Gⁿ, G⁻ -- src/near_global_simulation.jl:138-162, src/simulation_outputs.jl:14-37,47-64),
+copy the state in and remember the handle, so that `time_step!(model, Δt)` runs on the library from now on.
+
+`bottom_height` is the rank's host `Array{Float64}(Nx + 2 h, Ny)` (i fastest) INCLUDING `h = bottom_halo_columns(model)` x-halo columns
+(`partition_global_array` plus periodic / neighbour columns; h = max(7, substeps + 1) on x-slabs, where the barotropic
+solver carries a wide halo).  `sync_every` = 10 matches the reference's callback schedules (wizard every 10 iterations,
+progress every 100, near_global_simulation.jl:160-162); use 0 in profile mode and call `sync_outputs!` yourself.
+"""
+function attach(model; device = CUDA.deviceid(), bottom_height, bc_kind, wind_coeffs, salt_coeffs, λ, μ,
+                comm = nothing, MPI = nothing, sync_every = 10)
     grid = model.grid
     arch = Oceananigans.architecture(grid)
     Nx, Ny, Nz = size(grid)
     fs = model.free_surface
     w = collect(Float64, fs.settings.substepping.averaging_weights)
     zf = collect(Float64, Array(grid.underlying_grid.zᵃᵃᶠ[1:Nz+1]))
-    cfg = Config(; Nx, Ny, Nz, Nx_global = Nx * arch.ranks[1], i_offset = (arch.local_index[1] - 1) * Nx,
-                 rank = arch.local_rank, nranks = arch.ranks[1],
+    Nx_global, i_offset, rank, nranks = slab_geometry(arch, Nx)
+    hb = bottom_halo_columns(model)
+    size(bottom_height) == (Nx + 2hb, Ny) || error("bottom_height must be (Nx + 2*$hb, Ny) = ($(Nx + 2hb), $Ny), got $(size(bottom_height))")
+    cfg = Config(; Nx, Ny, Nz, Nx_global, i_offset, rank, nranks,
                  eos_kind = model.buoyancy.model.equation_of_state isa LinearEquationOfState ? 0 : 1,
                  n_substeps = length(w), frac_dtau = fs.settings.substepping.fractional_step_size,
-                 bc_kind, wind_coeffs, salt_coeffs, T_restoring_lambda = λ, drag_mu = μ)
+                 bc_kind, wind_coeffs, salt_coeffs, T_restoring_lambda = λ, drag_mu = μ, bottom_halo_columns = hb)
     cfg.struct_bytes = sizeof(Config)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve w zf bottom_height begin
@@ -66,10 +103,44 @@ function attach(model; device = CUDA.deviceid(), bottom_height, bc_kind, wind_co
         rc = ccall((:ob200_create, LIB), Cint, (Ref{Config}, Int32, Ref{Ptr{Cvoid}}), cfg, device, h)
         rc == 0 || error("ob200_create failed: " * unsafe_string(ccall((:ob200_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
     end
-    handle = Handle(h[])
-    push_state!(handle, model)
+    handle = Handle(h[], sync_every)
+    nranks > 1 && comm_init!(handle, comm, MPI)
+    bind_model!(handle, model)
+    sync_inputs!(handle)                 # the state `set!` / `initialize_model!` left in the Julia arrays, + update_state!
+    ATTACHED[model] = handle
     return handle
 end
+
+"x-halo columns the bottom-height array must carry: 7, or substeps + 1 on x-slabs (wide barotropic halo, SURVEY F9)"
+function bottom_halo_columns(model)
+    arch = Oceananigans.architecture(model.grid)
+    M = length(model.free_surface.settings.substepping.averaging_weights)
+    return arch isa Oceananigans.DistributedComputations.Distributed && arch.ranks[1] > 1 ? max(HALO, M + 1) : HALO
+end
+
+"ob200_bind: the library borrows the parent arrays for the lifetime of the handle (the model must outlive it)"
+function bind!(h::Handle, id, field)
+    Hx, Hy, Hz = halo_size(field.grid)
+    check(h.ptr, ccall((:ob200_bind, LIB), Cint, (Ptr{Cvoid}, Int32, CuPtr{Float64}, Int32, Int32, Int32),
+                       h.ptr, id, pointer(parent(field)), Hx, Hy, size(parent(field), 3) == 1 ? 0 : Hz))
+end
+function bind_model!(h::Handle, model)
+    u, v, w = model.velocities
+    bind!(h, F_U, u); bind!(h, F_V, v); bind!(h, F_W, w)
+    bind!(h, F_T, model.tracers.T); bind!(h, F_S, model.tracers.S); bind!(h, F_ETA, model.free_surface.η)
+    G⁻, Gⁿ = model.timestepper.G⁻, model.timestepper.Gⁿ
+    bind!(h, F_GU, Gⁿ.u); bind!(h, F_GV, Gⁿ.v); bind!(h, F_GT, Gⁿ.T); bind!(h, F_GS, Gⁿ.S)
+    bind!(h, F_GU_PREV, G⁻.u); bind!(h, F_GV_PREV, G⁻.v); bind!(h, F_GT_PREV, G⁻.T); bind!(h, F_GS_PREV, G⁻.S)
+end
+"Refresh every bound Julia array from the library (what callbacks / writers / the checkpointer read)."
+sync_outputs!(h::Handle) = check(h.ptr, ccall((:ob200_sync_outputs, LIB), Cint, (Ptr{Cvoid},), h.ptr))
+sync_outputs!(model) = sync_outputs!(ATTACHED[model])
+"Take the bound Julia arrays into the library (after `set!(model, ...)` or a restore) and run update_state!."
+function sync_inputs!(h::Handle)
+    CUDA.synchronize()
+    check(h.ptr, ccall((:ob200_sync_inputs, LIB), Cint, (Ptr{Cvoid},), h.ptr))
+end
+sync_inputs!(model) = sync_inputs!(ATTACHED[model])
 
 "Copy a Julia-owned field (parent array, any halo) into / out of the library: device-to-device."
 function set_field!(h::Handle, id, field)
@@ -111,12 +182,32 @@ function pull_state!(model, h::Handle)
     check(h.ptr, ccall((:ob200_sync, LIB), Cint, (Ptr{Cvoid},), h.ptr))
 end
 
-"The replacement for Oceananigans.TimeSteppers.time_step!(model, Δt) (near_global_simulation.jl:181,196)."
+"The native step: ob200_time_step, then the Julia clock (the reference's callbacks and schedules read `model.clock`)."
 function time_step!(h::Handle, model, Δt)
     check(h.ptr, ccall((:ob200_time_step, LIB), Cint, (Ptr{Cvoid}, Float64), h.ptr, Δt))
     Oceananigans.TimeSteppers.tick!(model.clock, Δt)
     model.clock.last_Δt = Δt
+    h.sync_every > 0 && model.clock.iteration % h.sync_every == 0 && sync_outputs!(h)
     return nothing
+end
+
+# THE DROP-IN: a method of Oceananigans' own `time_step!`, more specific than its
+# `time_step!(::AbstractModel{<:QuasiAdamsBashforth2TimeStepper}, Δt; ...)`, so `time_step!(model, Δt)` at
+# src/near_global_simulation.jl:181,196 and inside `run!` (experiments/run.jl:60) needs NO edit.  Attached models step on
+# the library (the `euler` decision is the library's: a Δt that differs from the previous one takes a forward-Euler step,
+# exactly Oceananigans' rule); any other model is handed to the method this one shadows.
+function time_step!(model::HydrostaticFreeSurfaceModel{<:QuasiAdamsBashforth2TimeStepper}, Δt; callbacks = [], kw...)
+    h = get(ATTACHED, model, nothing)
+    h === nothing && return invoke(time_step!, Tuple{AbstractModel{<:QuasiAdamsBashforth2TimeStepper}, Any}, model, Δt; callbacks, kw...)
+    time_step!(h, model, Δt)
+    isempty(callbacks) || (sync_outputs!(h); foreach(cb -> cb(model), callbacks))    # state callbacks of Oceananigans' run!
+    return nothing
+end
+
+"Release the native model (the Julia arrays stay with Julia)."
+function detach!(model)
+    h = pop!(ATTACHED, model)
+    ccall((:ob200_destroy, LIB), Cvoid, (Ptr{Cvoid},), h.ptr)
 end
 
 "NCCL ring bootstrap over the MPI communicator the reference already has (experiments/run.jl:9-27)."

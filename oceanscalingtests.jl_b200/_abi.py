@@ -89,6 +89,7 @@ EXPORTED_SYMBOLS = [
     "ob200_update_state", "ob200_time_step", "ob200_time_steps", "ob200_run_stage", "ob200_sync",
     "ob200_get_clock", "ob200_set_clock", "ob200_diagnostics", "ob200_get_timing", "ob200_set_stream",
     "ob200_set_option", "ob200_comm_unique_id", "ob200_comm_init",
+    "ob200_bind", "ob200_unbind", "ob200_sync_outputs", "ob200_sync_inputs",
 ]
 
 _lib = None
@@ -148,6 +149,14 @@ def load_library(path: str | None = None):
     lib.ob200_set_stream.restype = C.c_int
     lib.ob200_set_option.argtypes = [H, C.c_char_p, C.c_int32]
     lib.ob200_set_option.restype = C.c_int
+    lib.ob200_bind.argtypes = [H, C.c_int32, dp, C.c_int32, C.c_int32, C.c_int32]
+    lib.ob200_bind.restype = C.c_int
+    lib.ob200_unbind.argtypes = [H, C.c_int32]
+    lib.ob200_unbind.restype = C.c_int
+    lib.ob200_sync_outputs.argtypes = [H]
+    lib.ob200_sync_outputs.restype = C.c_int
+    lib.ob200_sync_inputs.argtypes = [H]
+    lib.ob200_sync_inputs.restype = C.c_int
     lib.ob200_comm_unique_id.argtypes = [C.c_void_p]
     lib.ob200_comm_unique_id.restype = C.c_int
     lib.ob200_comm_init.argtypes = [H, C.c_void_p]

@@ -139,9 +139,12 @@ void launch_unpack_x(const Geom& G, const Fields& F, const double* recvW, const 
 }
 
 // ---- diagnostics: max |u|,|v|,|w|,|eta|,|T|,|S| and the advective CFL time scale (TimeStepWizard) ----------
-__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {   // v >= 0
-    atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
+__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {   // v >= 0 or the canonical (positive) NaN,
+    atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));   // whose bit pattern tops every finite one
 }
+// max that PROPAGATES NaN like Julia's `maximum(abs, u)` (fmax drops it): after a blow-up the progress line and the wizard
+// must see NaN, not the maximum over the cells that are still finite
+__device__ __forceinline__ double max_nan(double a, double b) { return (a != a || b != b) ? nan("") : fmax(a, b); }
 __global__ void __launch_bounds__(256) k_diag(Geom G, Fields F, double* out) {
     // one block per (row j, level-chunk): threads stride over i and 8 levels, then one atomic per block and quantity
     __shared__ double red[7][8];
@@ -151,24 +154,24 @@ __global__ void __launch_bounds__(256) k_diag(Geom G, Fields F, double* out) {
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < G.Nx; i += gridDim.x * blockDim.x) {
             const long long c = idx3(G, i, j, k);
             const double au = fabs(F.u[c]), av = fabs(F.v[c]), aw = fabs(F.w[c]);
-            m[0] = fmax(m[0], au); m[1] = fmax(m[1], av);
-            m[2] = fmax(m[2], fmax(aw, k == G.Nz - 1 ? fabs(F.w[c + G.sz]) : 0.0));
-            if (k == 0) m[3] = fmax(m[3], fabs(F.eta[idx2b(G, i, j)]));
-            m[4] = fmax(m[4], fabs(F.T[c])); m[5] = fmax(m[5], fabs(F.S[c]));
+            m[0] = max_nan(m[0], au); m[1] = max_nan(m[1], av);
+            m[2] = max_nan(m[2], max_nan(aw, k == G.Nz - 1 ? fabs(F.w[c + G.sz]) : 0.0));
+            if (k == 0) m[3] = max_nan(m[3], fabs(F.eta[idx2b(G, i, j)]));
+            m[4] = max_nan(m[4], fabs(F.T[c])); m[5] = max_nan(m[5], fabs(F.S[c]));
             // 1 / cell advection time scale: |u|/dx + |v|/dy + |w|/dz
-            m[6] = fmax(m[6], au / G.dxfc[j] + av / G.dy + aw / G.dzc[k]);
+            m[6] = max_nan(m[6], au / G.dxfc[j] + av / G.dy + aw / G.dzc[k]);
         }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int q = 0; q < 7; q++) {
         double v = m[q];
-        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        for (int o = 16; o > 0; o >>= 1) v = max_nan(v, __shfl_xor_sync(0xffffffffu, v, o));
         if (lane == 0) red[q][warp] = v;
     }
     __syncthreads();
     if (threadIdx.x < 7) {
         double v = 0.0;
-        for (int w = 0; w < 8; w++) v = fmax(v, red[threadIdx.x][w]);
-        if (v > 0.0) atomic_max_pos(out + threadIdx.x, v);
+        for (int w = 0; w < 8; w++) v = max_nan(v, red[threadIdx.x][w]);
+        if (v > 0.0 || v != v) atomic_max_pos(out + threadIdx.x, v);
     }
 }
 void launch_diagnostics(const Geom& G, const Fields& F, double* out8, cudaStream_t st) {

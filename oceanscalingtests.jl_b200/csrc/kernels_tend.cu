@@ -81,6 +81,24 @@ struct MomG {
     }
 };
 
+// per-latitude metrics of a tile's rows in shared memory: [metric][row], row r <-> j = j0 - MT_J0 + r.  One LDS with an
+// immediate offset replaces the constant-bank pointer load + address arithmetic + global load of `G.metric[j]`.
+enum { MT_DXFC = 0, MT_DXCF, MT_RAZCF, MT_RDXFC, MT_AZCC, MT_RAZCC, MT_FFF, MT_TAUX, MT_N };
+#define MT_ROWS 32
+#define MT_J0 6
+__device__ __forceinline__ void load_metric_table(const Geom& G, double* smt, int j0, int tid, int nt) {
+    const double* src[MT_N] = {G.dxfc, G.dxcf, G.razcf, G.rdxfc, G.azcc, G.razcc, G.fff, G.taux};
+    for (int e = tid; e < MT_N * MT_ROWS; e += nt) {
+        const int m = e / MT_ROWS, r = e % MT_ROWS;
+        const int j = min(j0 - MT_J0 + r, G.Ny + OB_H + 1);   // the arrays are indexable for j = -8 .. Ny + 8
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < MT_N; q++) if (q == m) v = src[q][j];
+        smt[e] = v;
+    }
+}
+#define MET(mrow, name, dj) ((mrow)[MT_##name * MT_ROWS + (dj)])
+
 // shared-memory tile geometry for the fast path (TX x TY cells per block)
 template <int TX, int TY>
 struct TileDims {
@@ -97,7 +115,7 @@ struct TileDims {
     static constexpr int PK = TX + 1, RK = TY + 1;       // K: [i0-1, i0+TX-1]
     static constexpr int NU = PU * RU, NZ = PZ * RZ, ND = PD * RD, NK = PK * RK;
     static constexpr int NUP = (NU + 15) / 16 * 16;      // tile slot padded to 128 bytes (TMA destination alignment)
-    static constexpr int TOTAL = 4 * NUP + 3 * NZ + 2 * ND + NK;   // doubles: u, v double-buffered + derived fields
+    static constexpr int TOTAL = 4 * NUP + 3 * NZ + 2 * ND + NK + MT_N * MT_ROWS;   // doubles: u, v double-buffered + derived fields + metrics
 };
 
 template <int TX, int TY>
@@ -268,13 +286,14 @@ __device__ __forceinline__ int order_from(const int* thr, int Nmax, int k) {
 // ================================================================================================
 template <bool GEN, class A>
 __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A& M, int i, int j, int k, int NV, int ND,
-                                         double time, const GenThr& T) {
+                                         double time, const GenThr& T, const double* __restrict__ mrow) {
     const long long c = idx3(G, i, j, k);
     // (1) vorticity flux
-    const double q00 = G.dxcf[j] * M.V(i - 1, j, k), q01 = G.dxcf[j + 1] * M.V(i - 1, j + 1, k);
-    const double q10 = G.dxcf[j] * M.V(i, j, k), q11 = G.dxcf[j + 1] * M.V(i, j + 1, k);
+    const double dxcf0 = MET(mrow, DXCF, 0), dxcf1 = MET(mrow, DXCF, 1), rdxfc = MET(mrow, RDXFC, 0);
+    const double q00 = dxcf0 * M.V(i - 1, j, k), q01 = dxcf1 * M.V(i - 1, j + 1, k);
+    const double q10 = dxcf0 * M.V(i, j, k), q11 = dxcf1 * M.V(i, j + 1, k);
     const double vavg = 0.5 * (0.5 * (q00 + q01) + 0.5 * (q10 + q11));
-    const double vhat = vavg * G.rdxfc[j];
+    const double vhat = vavg * rdxfc;
     double Gt = 0.0;
     if (vhat != 0.0) {
         const bool left = vhat > 0.0;
@@ -303,7 +322,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
         }
         Phi = uh * d + uh * 0.5 * (M.dyV(i - 1, j, k) + M.dyV(i, j, k));
     }
-    const double az = G.azcc[j];
+    const double az = MET(mrow, AZCC, 0);
     const int km = max(k - 1, 0), kp = min(k + 1, G.Nz - 1);
     double fl_lo, fl_hi;
     {
@@ -317,19 +336,19 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
             // (the node above an active node is active for a grid-fitted bottom; the top face is a domain boundary)
         }
     }
-    Gt -= (Phi + fl_hi - fl_lo) * (G.razcc[j] * G.rdzc[k]);
+    Gt -= (Phi + fl_hi - fl_lo) * (MET(mrow, RAZCC, 0) * G.rdzc[k]);
     // (3) Bernoulli head  (4) Coriolis  (5) pressure gradient
-    Gt -= (M.Kh(i, j, k) - M.Kh(i - 1, j, k)) * G.rdxfc[j];
+    Gt -= (M.Kh(i, j, k) - M.Kh(i - 1, j, k)) * rdxfc;
     int nact = 4;
     if (GEN) {
         nact = 0;
 #pragma unroll
         for (int n = 0; n < 4; n++) nact += k >= T.cu[n] ? 1 : 0;
     }
-    const double fbar = 0.5 * (G.fff[j] + G.fff[j + 1]);
+    const double fbar = 0.5 * (MET(mrow, FFF, 0) + MET(mrow, FFF, 1));
     const double cor = nact == 0 ? 0.0 : nact == 4 ? vavg : vavg / (0.25 * nact);
-    Gt += fbar * cor * G.rdxfc[j];
-    Gt -= (F.p[c] - F.p[c - 1]) * G.rdxfc[j];
+    Gt += fbar * cor * rdxfc;
+    Gt -= (F.p[c] - F.p[c - 1]) * rdxfc;
     // (6) QG-Leith stress divergence
     if (G.qgleith) {
         const MomG Mg{G, F.u, F.v};
@@ -349,7 +368,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
     // (7) flux boundary conditions
     if (k == G.Nz - 1) {
         double J = 0.0;
-        if (G.bc_kind == OB200_BC_DOUBLEDRAKE) J = G.taux[j];
+        if (G.bc_kind == OB200_BC_DOUBLEDRAKE) J = MET(mrow, TAUX, 0);
         else if (G.bc_kind == OB200_BC_REALISTIC) J = interp_flux(G, F.forcing[0], i, j, G.Ny, time, false);
         Gt -= J * G.rdzc[k];
     }
@@ -372,7 +391,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
 
 template <bool GEN, class A>
 __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A& M, int i, int j, int k, int NV, int ND,
-                                         double time, const GenThr& T) {
+                                         double time, const GenThr& T, const double* __restrict__ mrow) {
     const long long c = idx3(G, i, j, k);
     const double dy = G.dy;
     const double q00 = dy * M.U(i, j - 1, k), q10 = dy * M.U(i + 1, j - 1, k);
@@ -407,14 +426,15 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
         Phi = vh * d + vh * 0.5 * (M.dxU(i, j - 1, k) + M.dxU(i, j, k));
     }
     const int km = max(k - 1, 0), kp = min(k + 1, G.Nz - 1);
-    const double Wlo = 0.5 * (G.azcc[j - 1] * F.w[c - G.pitch] + G.azcc[j] * F.w[c]);
-    const double Whi = 0.5 * (G.azcc[j - 1] * F.w[c - G.pitch + G.sz] + G.azcc[j] * F.w[c + G.sz]);
+    const double azm = MET(mrow, AZCC, -1), az0 = MET(mrow, AZCC, 0);
+    const double Wlo = 0.5 * (azm * F.w[c - G.pitch] + az0 * F.w[c]);
+    const double Whi = 0.5 * (azm * F.w[c - G.pitch + G.sz] + az0 * F.w[c + G.sz]);
     double fl_lo = Wlo * 0.5 * (F.v[idx3(G, i, j, km)] + vh);
     const double fl_hi = Whi * 0.5 * (vh + F.v[idx3(G, i, j, kp)]);
     if (GEN) {
         if (k > 0 && k <= T.per_v) fl_lo = 0.0;
     }
-    Gt -= (Phi + fl_hi - fl_lo) * (G.razcf[j] * G.rdzc[k]);
+    Gt -= (Phi + fl_hi - fl_lo) * (MET(mrow, RAZCF, 0) * G.rdzc[k]);
     Gt -= (M.Kh(i, j, k) - M.Kh(i, j - 1, k)) * G.rdy;
     int nact = 4;
     if (GEN) {
@@ -422,7 +442,8 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
 #pragma unroll
         for (int n = 0; n < 4; n++) nact += k >= T.cv[n] ? 1 : 0;
     }
-    const double fbar = 0.5 * (G.fff[j] + G.fff[j]);
+    const double f0 = MET(mrow, FFF, 0);
+    const double fbar = 0.5 * (f0 + f0);
     const double cor = nact == 0 ? 0.0 : nact == 4 ? uavg : uavg / (0.25 * nact);
     Gt -= fbar * cor * G.rdy;
     Gt -= (F.p[c] - F.p[c - G.pitch]) * G.rdy;
@@ -492,6 +513,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
     double* sdx = svs + D::NZ;
     double* sdy = sdx + D::ND;
     double* sK = sdy + D::ND;
+    double* smt = sK + D::NK;       // metrics table [MT_N][MT_ROWS]
     int tile, kf;
     int kskip = 0;   // masked tiles: levels below the shallowest sea floor of the tile are all solid -> G stays 0 (never written)
     if (GEN) { tile = slow_tiles[3 * blockIdx.x]; kf = slow_tiles[3 * blockIdx.x + 1]; kskip = slow_tiles[3 * blockIdx.x + 2]; }
@@ -506,6 +528,17 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
     const bool mine = i < G.Nx && j < G.Ny;
     const int tx0 = i0 - D::HUX + OB_X0, ty0 = j0 - D::HU + OB_H;   // tile origin in array coordinates (even column)
     constexpr unsigned TILE_BYTES = D::NU * sizeof(double);
+    load_metric_table(G, smt, j0, tid, NT);
+    const double* mrow = smt + (threadIdx.y + MT_J0);               // this thread's row j: MET(mrow, X, dj) = X[j + dj]
+    // staging map: thread (tx, ty) stages the tile points (tx + TX p, ty + TY r) -- every smem offset below is this
+    // thread's base plus a compile-time constant (no div / mod, no per-element index arithmetic in the level loop)
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int ez0 = ty * D::PZ + tx, qz0 = (ty + D::HU - D::HZ) * D::PU + (tx + D::HUX - D::HZ);
+    const int ed0 = ty * D::PD + tx, qd0 = (ty + D::HU - D::HD) * D::PU + (tx + D::HUX - D::HD);
+    const int ek0 = ty * D::PK + tx, qk0 = (ty + D::HU - 1) * D::PU + (tx + D::HUX - 1);
+    constexpr int NRXZ = (D::PZ + TX - 1) / TX, NRYZ = (D::RZ + TY - 1) / TY;
+    constexpr int NRXD = (D::PD + TX - 1) / TX, NRYD = (D::RD + TY - 1) / TY;
+    constexpr int NRXK = (D::PK + TX - 1) / TX, NRYK = (D::RK + TY - 1) / TY;
     int offu[TMA ? 1 : RU];
     double ru[TMA ? 1 : RU], rv[TMA ? 1 : RU];
     auto prefetch = [&](int k) {
@@ -531,15 +564,13 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
         prefetch(k_begin);
     }
     // masked tiles: level thresholds of this thread's column and of the zeta points it stages (k independent)
-    constexpr int RZE = (D::NZ + NT - 1) / NT;
     GenThr T;
-    int zthr[GEN ? RZE : 1];
+    int zthr[GEN ? NRXZ * NRYZ : 1];
     if (GEN) {
         if (mine) gen_thresholds(G, i, j, NV, ND, T);
 #pragma unroll
-        for (int r = 0; r < RZE; r++) {
-            const int e = min(tid + r * NT, D::NZ - 1);
-            const int a = e % D::PZ, b = e / D::PZ;
+        for (int r = 0; r < NRXZ * NRYZ; r++) {
+            const int a = min(tx + TX * (r % NRXZ), D::PZ - 1), b = min(ty + TY * (r / NRXZ), D::RZ - 1);
             const int ic = min(i0 - D::HZ + a, G.Nx + OB_H - 1), jc = min(j0 - D::HZ + b, G.Ny + OB_H);
             const int k00 = kb_at(G, ic - 1, jc - 1), k10 = kb_at(G, ic, jc - 1), k01 = kb_at(G, ic - 1, jc), k11 = kb_at(G, ic, jc);
             const int kzx = max(min(k00, k01), min(k10, k11));   // delta_x v touches an inactive (c,f,c) node below this level
@@ -573,56 +604,63 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
             if (k + 1 < k_end) prefetch(k + 1);
         }
         const double dzk = G.dzc[k];
-        auto stage_zeta = [&](int e, int kzx, int kzy) {
-            const int a = e % D::PZ, b = e / D::PZ;
-            const int jj = j0 - D::HZ + b;
-            const int q = (b + D::HU - D::HZ) * D::PU + (a + D::HUX - D::HZ);   // same point in the u/v tiles
-            double dxv = G.dy * sv[q] - G.dy * sv[q - 1];
-            double dyu = G.dxfc[jj] * su[q] - G.dxfc[jj - 1] * su[q - D::PU];
-            if (GEN) {   // conditional differences: a difference that touches an inactive node is zero
-                if (k < kzx) dxv = 0.0;
-                if (k < kzy) dyu = 0.0;
-            }
-            sz[e] = (dxv - dyu) * G.razcf[jj];
-            sus[e] = 0.5 * (su[q - D::PU] + su[q]);
-            svs[e] = 0.5 * (sv[q - 1] + sv[q]);
-        };
-        if (GEN) {
+        // zeta, I_y u, I_x v on [i0 - 4, i0 + TX + 4] x [j0 - 4, j0 + TY + 4]
 #pragma unroll
-            for (int r = 0; r < RZE; r++) {
-                const int e = tid + r * NT;
-                if (e < D::NZ) stage_zeta(e, zthr[r] >> 16, zthr[r] & 0xffff);
+        for (int r = 0; r < NRYZ; r++)
+#pragma unroll
+            for (int p = 0; p < NRXZ; p++) {
+                if ((p == 0 || tx + TX * p < D::PZ) && (r == 0 || ty + TY * r < D::RZ)) {
+                    const int e = ez0 + TX * p + TY * r * D::PZ, q = qz0 + TX * p + TY * r * D::PU;
+                    const double* mz = smt + (ty + TY * r + MT_J0 - D::HZ);     // row jj = j0 - HZ + b
+                    double dxv = G.dy * sv[q] - G.dy * sv[q - 1];
+                    double dyu = MET(mz, DXFC, 0) * su[q] - MET(mz, DXFC, -1) * su[q - D::PU];
+                    if (GEN) {   // conditional differences: a difference that touches an inactive node is zero
+                        const int th = zthr[r * NRXZ + p];
+                        if (k < (th >> 16)) dxv = 0.0;
+                        if (k < (th & 0xffff)) dyu = 0.0;
+                    }
+                    sz[e] = (dxv - dyu) * MET(mz, RAZCF, 0);
+                    sus[e] = 0.5 * (su[q - D::PU] + su[q]);
+                    svs[e] = 0.5 * (sv[q - 1] + sv[q]);
+                }
             }
-        } else {
-            for (int e = tid; e < D::NZ; e += NT) stage_zeta(e, 0, 0);
-        }
-        for (int e = tid; e < D::ND; e += NT) {
-            const int a = e % D::PD, b = e / D::PD;
-            const int jj = j0 - D::HD + b;
-            const int q = (b + D::HU - D::HD) * D::PU + (a + D::HUX - D::HD);
-            const double ax = G.dy * dzk;
-            sdx[e] = ax * su[q + 1] - ax * su[q];
-            sdy[e] = G.dxcf[jj + 1] * dzk * sv[q + D::PU] - G.dxcf[jj] * dzk * sv[q];
-        }
-        for (int e = tid; e < D::NK; e += NT) {
-            const int a = e % D::PK, b = e / D::PK;
-            const int q = (b + D::HU - 1) * D::PU + (a + D::HUX - 1);
-            const double ua = su[q], ub = su[q + 1], va = sv[q], vb = sv[q + D::PU];
-            sK[e] = (0.5 * (ua * ua + ub * ub) + 0.5 * (va * va + vb * vb)) / 2.0;
-        }
+        // dx(Ax u), dy(Ay v) on [i0 - 3, i0 + TX + 2] x [j0 - 3, j0 + TY + 2]
+#pragma unroll
+        for (int r = 0; r < NRYD; r++)
+#pragma unroll
+            for (int p = 0; p < NRXD; p++) {
+                if ((p == 0 || tx + TX * p < D::PD) && (r == 0 || ty + TY * r < D::RD)) {
+                    const int e = ed0 + TX * p + TY * r * D::PD, q = qd0 + TX * p + TY * r * D::PU;
+                    const double* md = smt + (ty + TY * r + MT_J0 - D::HD);     // row jj = j0 - HD + b
+                    const double ax = G.dy * dzk;
+                    sdx[e] = ax * su[q + 1] - ax * su[q];
+                    sdy[e] = MET(md, DXCF, 1) * dzk * sv[q + D::PU] - MET(md, DXCF, 0) * dzk * sv[q];
+                }
+            }
+        // K on [i0 - 1, i0 + TX - 1] x [j0 - 1, j0 + TY - 1]
+#pragma unroll
+        for (int r = 0; r < NRYK; r++)
+#pragma unroll
+            for (int p = 0; p < NRXK; p++) {
+                if ((p == 0 || tx + TX * p < D::PK) && (r == 0 || ty + TY * r < D::RK)) {
+                    const int e = ek0 + TX * p + TY * r * D::PK, q = qk0 + TX * p + TY * r * D::PU;
+                    const double ua = su[q], ub = su[q + 1], va = sv[q], vb = sv[q + D::PU];
+                    sK[e] = (0.5 * (ua * ua + ub * ub) + 0.5 * (va * va + vb * vb)) / 2.0;
+                }
+            }
         __syncthreads();
         if (mine) {
             const long long c = idx3(G, i, j, k);
             if (!GEN) {
-                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time, T);
-                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time, T);
+                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time, T, mrow);
+                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time, T, mrow);
             } else if (k >= T.kfast) {
                 // most cells of a masked tile are still far from any boundary: full-order, check-free path
-                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time, T);
-                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time, T);
+                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time, T, mrow);
+                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time, T, mrow);
             } else {
-                F.Gu[c] = k < T.per_u ? 0.0 : tend_u<true>(G, F, M, i, j, k, NV, ND, time, T);
-                F.Gv[c] = k < T.per_v ? 0.0 : tend_v<true>(G, F, M, i, j, k, NV, ND, time, T);
+                F.Gu[c] = k < T.per_u ? 0.0 : tend_u<true>(G, F, M, i, j, k, NV, ND, time, T, mrow);
+                F.Gv[c] = k < T.per_v ? 0.0 : tend_v<true>(G, F, M, i, j, k, NV, ND, time, T, mrow);
             }
         }
         __syncthreads();
@@ -884,7 +922,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
 #define MOM_TY 16
 #endif
 #ifndef TEND_KLEV
-#define TEND_KLEV 8
+#define TEND_KLEV 20   // levels marched by one block (measured at C3: 8 -> 18.85 + 11.62 ms, 20 -> 18.44 + 11.39, 60 -> 18.66 + 11.78)
 #endif
 // `which`: bit 0 = the full-order tiles, bit 1 = the masked tiles (disjoint (tile, level) sets of G: the two instances may
 // run concurrently on different streams)

@@ -45,6 +45,8 @@ struct ob200_handle {
     cudaEvent_t ev2[4];                        // timing events on stream2
     int n_timed = 0;
     std::vector<void*> allocs;
+    struct Bound { double* ptr = nullptr; int hx = 0, hy = 0, hz = 0; };
+    Bound bound[OB200_F_COUNT];   // caller-owned device parent arrays (ob200_bind)
     std::vector<double> weights;
     double* d_weights = nullptr;
     double* d_diag = nullptr;
@@ -619,6 +621,11 @@ int step_body(ob200_handle* h, double dt, bool euler) {
     mark2(0);
     launch_ab2_implicit_ts(G, h->F, dt, chi, h->onchip_solve, s2);
     mark2(1);
+    const bool ts_early = !h->periodic_local && h->early_ts_exchange && !h->overlap_exchange && !h->fields_dirty;
+    if (ts_early) {   // the T, S halos follow their solve on the same side stream
+        if (int rc = exchange_halos(h, s2, 2)) return rc;
+        cudaEventRecord(h->ev_ts[1], s2);
+    }
     cudaEventRecord(h->ev_join[1], s2);
     if (int rc = barotropic_loop(h, dt)) return rc;
     mark();
@@ -627,7 +634,7 @@ int step_body(ob200_handle* h, double dt, bool euler) {
     mark();
     h->time += dt; h->iteration += 1; h->last_dt = dt;
     cudaStreamWaitEvent(s1, h->ev_join[1], 0);   // halos need the new T, S
-    if (int rc = mask_and_halos(h)) return rc;
+    if (int rc = mask_and_halos(h, ts_early)) return rc;
     mark();
     launch_w_p(G, h->F, s1);
     mark();
@@ -731,8 +738,12 @@ int ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out) {
         const char* e = getenv("OB200_ONCHIP_SOLVE");
         h->onchip_solve = ab2_onchip_fits(h->G) && (e && e[0] == '1');
     }
-    cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    {   // the main stream outranks the side streams: its (small, latency-bound) barotropic kernels get free SM slots first
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, hi);
+        cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, lo);
+    }
     cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking);
     for (auto& ev : h->ev_tend) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : h->ev_ts) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -804,6 +815,42 @@ int ob200_set_field(ob200_handle* h, int32_t field, const double* buf, int32_t o
 }
 int ob200_get_field(ob200_handle* h, int32_t field, double* buf, int32_t on_device, int32_t hx, int32_t hy, int32_t hz) {
     return copy_common(h, field, buf, on_device, hx, hy, hz, false);
+}
+
+int ob200_bind(ob200_handle* h, int32_t field, double* dev_ptr, int32_t hx, int32_t hy, int32_t hz) {
+    if (!h) return OB200_EINVAL;
+    if (field < 0 || field >= OB200_F_COUNT || !field_ref(h, field).p) return h->fail(OB200_EINVAL, "bind", "unknown or unallocated field id");
+    if (!dev_ptr || hx < 0 || hy < 0 || hz < 0) return h->fail(OB200_EINVAL, "bind", "null pointer or negative halo");
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, dev_ptr) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        return h->fail(OB200_EINVAL, "bind", "not a device pointer");
+    }
+    h->bound[field].ptr = dev_ptr; h->bound[field].hx = hx; h->bound[field].hy = hy; h->bound[field].hz = hz;
+    return OB200_OK;
+}
+int ob200_unbind(ob200_handle* h, int32_t field) {
+    if (!h || field < 0 || field >= OB200_F_COUNT) return OB200_EINVAL;
+    h->bound[field] = ob200_handle::Bound();
+    return OB200_OK;
+}
+int ob200_sync_outputs(ob200_handle* h) {
+    if (!h) return OB200_EINVAL;
+    for (int f = 0; f < OB200_F_COUNT; f++)
+        if (h->bound[f].ptr)
+            if (int rc = copy_common(h, f, h->bound[f].ptr, 1, h->bound[f].hx, h->bound[f].hy, h->bound[f].hz, false)) return rc;
+    OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    return OB200_OK;
+}
+int ob200_sync_inputs(ob200_handle* h) {
+    if (!h) return OB200_EINVAL;
+    bool any = false;
+    for (int f = 0; f < OB200_F_COUNT; f++)
+        if (h->bound[f].ptr) {
+            if (int rc = copy_common(h, f, h->bound[f].ptr, 1, h->bound[f].hx, h->bound[f].hy, h->bound[f].hz, true)) return rc;
+            any = true;
+        }
+    return any ? ob200_update_state(h) : OB200_OK;
 }
 
 int ob200_get_level(ob200_handle* h, int32_t field, int32_t k, double* buf, int32_t on_device, int32_t hx, int32_t hy) {
@@ -914,7 +961,7 @@ int ob200_diagnostics(ob200_handle* h, double maxabs[6], double* cfl_dt) {
     OB_CUDA_CHECK(h, cudaMemcpyAsync(out, h->d_diag, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
     OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
     if (maxabs) for (int q = 0; q < 6; q++) maxabs[q] = out[q];
-    if (cfl_dt) *cfl_dt = out[6] > 0.0 ? 1.0 / out[6] : INFINITY;
+    if (cfl_dt) *cfl_dt = out[6] != out[6] ? NAN : (out[6] > 0.0 ? 1.0 / out[6] : INFINITY);
     return OB200_OK;
 }
 

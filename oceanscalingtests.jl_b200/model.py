@@ -224,6 +224,19 @@ class B200Backend:
     def get_field_device(self, fid, ptr: int, halo=(0, 0, 0)):
         self._check(self.lib.ob200_get_field(self.h, fid, ptr, 1, *halo))
 
+    def bind(self, fid, ptr: int, halo=(0, 0, 0)):
+        """Register a caller-owned device parent array (what julia/OceanB200.jl does with `pointer(parent(field))`)."""
+        self._check(self.lib.ob200_bind(self.h, fid, ptr, *halo))
+
+    def unbind(self, fid):
+        self._check(self.lib.ob200_unbind(self.h, fid))
+
+    def sync_outputs(self):
+        self._check(self.lib.ob200_sync_outputs(self.h))
+
+    def sync_inputs(self):
+        self._check(self.lib.ob200_sync_inputs(self.h))
+
     def set_forcing(self, which, arr):
         arr = np.ascontiguousarray(arr, dtype=np.float64)
         self._check(self.lib.ob200_set_forcing(self.h, which, arr.ctypes.data, 0))

@@ -247,13 +247,15 @@ def set_from_checkpoint(model, filepath: str) -> None:
             if f"{name}/data" in file:            # "Test if variable exist in checkpoint"
                 model.set(fid, _interior(file[f"{name}/data"], _abi.field_shape(fid, *model.grid.size())))
         load_free_surface(model, file)
+        # the clock FIRST: update_state! evaluates the time-interpolated surface fluxes (forcing of the tendencies, Q_b of the
+        # Ri-based entrainment term) at the model time -- with the clock of a fresh model a checkpoint that carries no
+        # b200/* members (one converted from the reference) would restore a diffusivity filtered with the wrong Q_b
+        last_dt = float(file["b200/last_dt"]) if "b200/last_dt" in file else 0.0
+        model.backend.set_clock(float(file["clock/time"]), int(file["clock/iteration"]), last_dt)
         # auxiliaries (w, pHY', diffusivities) and halos of the restored state; then the stored tendencies and the
         # state Oceananigans does not checkpoint overwrite what update_state! recomputed
         model.backend.update_state()
         set_time_stepper_tendencies(model, file)
-        last_dt = 0.0
         if "b200/last_dt" in file:
             for fid in _EXTRA:
                 model.set_parent(fid, file[f"b200/{fid}/data"], x_halo_data=True)
-            last_dt = float(file["b200/last_dt"])
-        model.backend.set_clock(float(file["clock/time"]), int(file["clock/iteration"]), last_dt)

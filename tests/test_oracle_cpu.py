@@ -349,3 +349,17 @@ def test_teos10_fixed_TS_column_has_zero_N2_oracle(pkg, orc):
     b_top = orc.load().oracle_teos10_rprime(10.0, 35.0, -5.0)
     b_deep = orc.load().oracle_teos10_rprime(10.0, 35.0, -4000.0)
     assert abs(b_deep - b_top) > 0.1
+
+
+def test_compare_dump_tool_on_a_self_made_dump(pkg, orc, tmp_path):
+    """tests/compare_dump.py (the consumer of julia/compare_with_oceananigans.jl) on a dump written by the oracle itself
+    in the layout the Julia script writes: the reference-arithmetic row must read 0, the product-arithmetic row a few ulps."""
+    import compare_dump
+    steps = 5
+    fields = compare_dump.run_case(pkg, orc.OracleBackend, steps, 600.0, reference_arithmetic=True)
+    path = tmp_path / "dump.npz"
+    np.savez(path, steps=steps, dt=600.0, **fields)
+    assert compare_dump.main([str(path)]) == 0
+    prod = compare_dump.run_case(pkg, orc.OracleBackend, steps, 600.0)
+    d = compare_dump.distances(prod, np.load(path))
+    assert 0.0 < max(d.values()) < 1e-11

@@ -288,6 +288,67 @@ def test_parent_array_layout_round_trip(pkg, gpu_lib):
             assert lev.shape == (Ny + 2 * H, Nx + 2 * H) and np.array_equal(lev[H:-H, H:-H], ((ref + 1.0) + 2.0)[Nz - 1])
 
 
+def test_bound_caller_arrays_follow_the_model(pkg, gpu_lib):
+    """SURVEY 8b "Julia owns, library borrows": caller-owned DEVICE parent arrays (halo (7,7,7), what the Julia glue passes
+    as `pointer(parent(field))`) are registered once with ob200_bind; ob200_sync_outputs refreshes them in place -- what
+    the reference's progress / TimeStepWizard callbacks and writers read (near_global_simulation.jl:138-162) -- and
+    ob200_sync_inputs takes a `set!` done on the caller's arrays back into the library (ending with update_state!)."""
+    import torch
+    c = cases.build_case("bumpy")
+    m, ref = c.make_model(pkg, None), c.make_model(pkg, None)
+    Nx, Ny, Nz = m.grid.size()
+    H = 7
+    shapes = {"U": (Nz, Ny), "V": (Nz, Ny + 1), "W": (Nz + 1, Ny), "T": (Nz, Ny), "S": (Nz, Ny), "ETA": (1, Ny)}
+    owned = {}
+    for name, (nz, ny) in shapes.items():
+        hz = 0 if name == "ETA" else H
+        owned[name] = torch.full((nz + 2 * hz, ny + 2 * H, Nx + 2 * H), -3.0, dtype=torch.float64, device="cuda")
+        m.backend.bind(pkg._abi.FIELD_ID[name], owned[name].data_ptr(), (H, H, hz))
+
+    def interior(name):
+        nz, ny = shapes[name]
+        hz = 0 if name == "ETA" else H
+        a = owned[name][hz:hz + nz, H:H + ny, H:H + Nx].cpu().numpy()
+        return a[0] if name == "ETA" else a
+
+    for _ in range(4):
+        pkg.time_step(m, c.dt)
+        pkg.time_step(ref, c.dt)
+    assert float(owned["U"][H, H, H]) == -3.0          # nothing is copied until asked
+    m.backend.sync_outputs()
+    for name in shapes:
+        assert np.array_equal(interior(name), ref.get(name)), name
+        assert float(owned[name].flatten()[0]) == -3.0  # the caller's halo cells are left alone
+    # set! on the caller's arrays (here: T += 0.25 on the interior), then sync_inputs == set_model on the reference
+    Tnew = ref.get("T") + 0.25
+    owned["T"][H:H + Nz, H:H + Ny, H:H + Nx] = torch.from_numpy(Tnew).cuda()
+    m.backend.sync_inputs()
+    pkg.set_model(ref, T=Tnew)
+    for _ in range(2):
+        pkg.time_step(m, c.dt)
+        pkg.time_step(ref, c.dt)
+    m.backend.sync_outputs()
+    for name in shapes:
+        assert np.array_equal(interior(name), ref.get(name)), name
+    m.backend.unbind(pkg._abi.FIELD_ID["U"])
+    lib = m.backend.lib
+    assert lib.ob200_bind(m.backend.h, 999, owned["U"].data_ptr(), H, H, H) == -1
+    host = np.zeros(8)
+    assert lib.ob200_bind(m.backend.h, 0, host.ctypes.data, 0, 0, 0) == -1 and b"device" in lib.ob200_last_error(m.backend.h)
+
+
+def test_diagnostics_propagate_nan(pkg, gpu_lib):
+    """after a blow-up `maximum(abs, u)` is NaN in the reference; the device reduction must not drop it."""
+    c = cases.build_case("dd_small")
+    m = c.make_model(pkg, None)
+    u = m.get("U")
+    u[3, 10, 20] = np.nan
+    m.set("U", u)
+    mx, cfl_dt = m.backend.diagnostics()
+    assert np.isnan(mx[0]) and np.isnan(cfl_dt)
+    assert np.isfinite(mx[4]) and np.isfinite(mx[5])
+
+
 def test_abi_error_paths(pkg, gpu_lib):
     import ctypes as C
     lib = gpu_lib
