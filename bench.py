@@ -315,7 +315,7 @@ def main():
     if os.environ.get("OB200_OVERLAP", "0") == "1":
         model.backend.set_option("overlap", 1)
     for env, opt in (("OB200_CONCURRENT_MASKED", "concurrent_masked_tiles"), ("OB200_OVERLAP_EXCHANGE", "overlap_exchange"),
-                     ("OB200_EARLY_TS", "early_ts_exchange")):
+                     ("OB200_EARLY_TS", "early_ts_exchange"), ("OB200_ONCHIP_BARO", "onchip_barotropic")):
         if env in os.environ:
             model.backend.set_option(opt, int(os.environ[env]))
     big = args.workload in BIG

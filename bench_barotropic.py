@@ -5,8 +5,10 @@ The number of substeps M actually run per baroclinic step is swept over {10, 20,
 barotropic stage (wide exchange / per-substep exchanges + the substep loop) of one baroclinic step is timed with CUDA
 events on the library's stream, max over ranks, for every strategy the library has:
 
-  1 GPU     launch_loop | cuda_graph | persistent (cooperative, global memory)
-  x-slabs   wide_graph | wide_loop      halo of M + 1 columns exchanged once, no communication inside the loop
+  1 GPU     launch_loop | cuda_graph | persistent (cooperative, global memory) | onchip (cooperative, state in shared
+            memory; only when the domain fits the aggregate shared memory, else it falls back to the graph)
+  x-slabs   wide_graph | wide_loop | wide_persistent | wide_onchip
+                                        halo of M + 1 columns exchanged once, no communication inside the loop
             substep_graph | substep_loop  one-column eta / U exchanges (NCCL send/recv) every half substep
 
     python bench_barotropic.py                                   # 1 GPU
@@ -47,10 +49,11 @@ def main():
     Nx, Ny, Nz, dt = 2160, 900, 4, 540.0      # the 2-D problem of C3; a few levels only (the 3-D stages are not timed)
     steps = int(os.environ.get("OB200_BARO_STEPS", "10"))
     if world == 1:
-        modes = {"launch_loop": ("auto", 0, 0), "cuda_graph": ("auto", 1, 0), "persistent": ("auto", 0, 1)}
+        modes = {"launch_loop": ("auto", 0, 0), "cuda_graph": ("auto", 1, 0), "persistent": ("auto", 0, 1),
+                 "onchip": ("auto", 0, 2)}
     else:
-        modes = {"wide_graph": ("wide", 1, 0), "wide_loop": ("wide", 0, 0), "substep_graph": ("substep", 1, 0),
-                 "substep_loop": ("substep", 0, 0)}
+        modes = {"wide_graph": ("wide", 1, 0), "wide_loop": ("wide", 0, 0), "wide_persistent": ("wide", 0, 1),
+                 "wide_onchip": ("wide", 0, 2), "substep_graph": ("substep", 1, 0), "substep_loop": ("substep", 0, 0)}
     lines = []
     for M in (10, 20, 38, 51, 80, 160):
         case = cases.Case("baro", Nx, Ny, Nz, experiment="DoubleDrake", dt=dt, ranks=world)
@@ -66,7 +69,8 @@ def main():
                                                     device=local, comm=pkg.Comm(), barotropic_exchange=exchange)
             case.initialize(pkg, model)
             model.backend.set_option("barotropic_graph", graph)
-            model.backend.set_option("persistent_barotropic", persistent)
+            model.backend.set_option("persistent_barotropic", int(persistent == 1))
+            model.backend.set_option("onchip_barotropic", int(persistent == 2))      # falls back to the graph when it does not fit
             model.backend.set_option("timing", 1)
             for _ in range(3):
                 pkg.time_step(model, dt)

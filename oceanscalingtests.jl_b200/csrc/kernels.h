@@ -62,6 +62,10 @@ void launch_baro_vel_edge(const Geom& G, const Fields& F, double dtau, double wg
 void launch_baro_edge_first(const Geom& G, const Fields& F, double* send_U, cudaStream_t st);
 int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const double* weights_dev, int M, bool periodic_x,
                            int ex, cudaStream_t st);
+// persistent ON-CHIP variant: eta, U, V resident in shared memory for all M substeps (returns -2 when the slab does not fit)
+bool baro_onchip_fits(const Geom& G, int ex);
+int launch_baro_onchip(const Geom& G, const Fields& F, double dtau, const double* weights_dev, int M, bool periodic_x, int ex,
+                       cudaStream_t st);
 size_t pack_baro_count(const Geom& G, int W);
 void launch_pack_baro(const Geom& G, const Fields& F, double* bufW, double* bufE, int W, bool unpack, cudaStream_t st);
 

@@ -6,6 +6,10 @@
 // SURVEY F9); every substep is computed over [-ex, Nx + ex) and the invalid fringe, which grows by one column
 // per substep, never reaches the interior.
 // launch_baro_persistent: one cooperative launch for all M substeps (grid-wide barrier between half steps).
+#include <algorithm>
+#include <utility>
+#include <vector>
+
 #include <cooperative_groups.h>
 
 #include "kernels.h"
@@ -200,4 +204,205 @@ void launch_pack_baro(const Geom& G, const Fields& F, double* bufW, double* bufE
     dim3 b(64), g((W + 63) / 64, G.Ny + 1, 5);
     k_pack_baro<<<g, b, 0, st>>>(G, F, bufW, bufE, W, unpack);
     OB_COUNT_LAUNCH(1);
+}
+
+// ==========================================================================================================
+// Persistent ON-CHIP variant (BASELINE north_star (4)): the whole substep loop in ONE cooperative launch with the
+// stencil-coupled state (eta, U, V) of the slab RESIDENT IN SHARED MEMORY across all M substeps and the averages
+// (eta_bar, U_bar, V_bar) in registers; global memory is touched once at the start and once at the end, plus one halo
+// row per block and half step.  Decomposition: block b owns the rows [b R, (b + 1) R) at full slab width, so all
+// x-neighbours are on chip; the two y-neighbours a block needs (eta of the row below its first, V of the row above its
+// last) are published by their owners in global memory, made visible by ONE grid-wide barrier per half step, and
+// staged into the block's halo rows with a bulk async copy (cp.async.bulk, mbarrier completion).
+// Fits when (3 R + 2) rows x (Nx + 2 ex + 2) doubles <= 227 KB with R = ceil(Ny / #SMs): C3 slabs at 2, 4, 8 GPUs, not
+// the single-GPU grid (1.94 M columns x 24 B = 47 MB > 148 x 227 KB).  Same operations per column as k_baro_eta / _vel.
+// ==========================================================================================================
+__device__ __forceinline__ unsigned bsm_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_row_load(double* dst, const double* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bsm_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(bsm_u32(dst)), "l"(src), "r"(bytes), "r"(bsm_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "OBB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra OBB_DONE;\n"
+        "bra OBB_WAIT;\n"
+        "OBB_DONE:\n"
+        "}\n" ::"r"(bsm_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int MAXC>
+__global__ void __launch_bounds__(1024, 1) k_baro_onchip(Geom G, Fields F, double dtau, const double* __restrict__ wts, int M,
+                                                         bool periodic, int ex, int R, int Wp, int a0) {
+    // Wp = padded row length in shared memory (even, covers array columns [a0, a0 + Wp) of a barotropic row: the slab's
+    // columns [-ex - 1, Nx + ex] plus alignment padding, a0 even so that bulk copies are 16-byte aligned)
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(128) double bsm[];
+    __shared__ unsigned long long bar[2];
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int j0 = blockIdx.x * R, j1 = min(j0 + R, G.Ny), nr = max(j1 - j0, 0);
+    double* sE = bsm;                       // (R + 1) rows: row 0 = eta(j0 - 1), row 1 + r = eta(j0 + r)
+    double* sU = sE + (size_t)(R + 1) * Wp;  // R rows
+    double* sV = sU + (size_t)R * Wp;        // (R + 1) rows: row r = V(j0 + r), row R(=nr) = V(j1) halo
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bsm_u32(&bar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bsm_u32(&bar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int ncol = G.Nx + 2 * ex;          // columns updated per row: i in [-ex, Nx + ex)
+    const int nwork = nr * ncol;
+    const int xo = G.X0b - a0;               // shared-memory column of array column X0b (i = 0)
+    // load the block's rows (+ the two halo rows) once
+    for (int r = -1; r <= nr; r++) {
+        const int j = j0 + r;
+        if (j < 0 || j > G.Ny) continue;
+        const double* ge = F.eta + (size_t)(j + OB_H) * G.pitch2 + a0;
+        const double* gu = F.U + (size_t)(j + OB_H) * G.pitch2 + a0;
+        const double* gv = F.V + (size_t)(j + OB_H) * G.pitch2 + a0;
+        for (int x = tid; x < Wp; x += NT) {
+            if (r < nr) sE[(size_t)(r + 1) * Wp + x] = ge[x];
+            if (r >= 0 && r < nr) sU[(size_t)r * Wp + x] = gu[x];
+            if (r >= 0) sV[(size_t)r * Wp + x] = gv[x];
+        }
+    }
+    double aE[MAXC], aU[MAXC], aV[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; c++) { aE[c] = 0.0; aU[c] = 0.0; aV[c] = 0.0; }
+    __syncthreads();
+    unsigned ph0 = 0, ph1 = 0;
+    const unsigned row_bytes = (unsigned)Wp * sizeof(double);
+    for (int m = 0; m < M; m++) {
+        // ---- eta half step: eta -= dtau * div(U, V) / Az
+#pragma unroll
+        for (int c = 0; c < MAXC; c++) {
+            const int wi = tid + c * NT;
+            if (wi < nwork) {
+                const int r = wi / ncol, i = wi - r * ncol - ex, j = j0 + r;
+                const int x = xo + i;
+                const double Vn = (j + 1 == G.Ny) ? 0.0 : sV[(size_t)(r + 1) * Wp + x];
+                const double Vs = (j == 0) ? 0.0 : sV[(size_t)r * Wp + x];
+                const double* u = sU + (size_t)r * Wp + x;
+                double* e = sE + (size_t)(r + 1) * Wp + x;
+                const double en = e[0] - dtau * ((G.dy * u[1] - G.dy * u[0]) + (G.dxcf[j + 1] * Vn - G.dxcf[j] * Vs)) / G.azcc[j];
+                e[0] = en;
+                if (periodic) {
+                    if (i == G.Nx - 1) e[-G.Nx] = en;   // west halo column i = -1
+                    if (i == 0) e[G.Nx] = en;           // east halo column i = Nx
+                }
+            }
+        }
+        __syncthreads();
+        // publish my LAST row of eta for the block above, barrier, stage the row below my first
+        if (nr > 0 && j1 < G.Ny) {
+            double* ge = F.eta + (size_t)(j1 - 1 + OB_H) * G.pitch2 + a0;
+            const double* se = sE + (size_t)nr * Wp;
+            for (int x = tid; x < Wp; x += NT) ge[x] = se[x];
+        }
+        grid.sync();
+        if (nr > 0 && j0 > 0) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async;" ::: "memory");
+                bulk_row_load(sE, F.eta + (size_t)(j0 - 1 + OB_H) * G.pitch2 + a0, row_bytes, &bar[0]);
+            }
+            bar_wait(&bar[0], ph0); ph0 ^= 1;
+        }
+        // ---- velocity half step + averaging
+        const double wgt = wts[m];
+#pragma unroll
+        for (int c = 0; c < MAXC; c++) {
+            const int wi = tid + c * NT;
+            if (wi < nwork) {
+                const int r = wi / ncol, i = wi - r * ncol - ex, j = j0 + r;
+                const int x = xo + i;
+                const int cg2 = idx2b(G, i, j);
+                const double* e = sE + (size_t)(r + 1) * Wp + x;
+                const double en = e[0];
+                const double detax = (en - e[-1]) / G.dxfc[j];
+                const double detay = (j == 0) ? 0.0 : (en - e[-Wp]) / G.dy;
+                double* u = sU + (size_t)r * Wp + x;
+                double* v = sV + (size_t)r * Wp + x;
+                const double Un = u[0] + dtau * (-G.g * F.Hfc[cg2] * detax + F.GU[cg2]);
+                const double Vn = v[0] + dtau * (-G.g * F.Hcf[cg2] * detay + F.GV[cg2]);
+                u[0] = Un; v[0] = Vn;
+                aE[c] += wgt * en; aU[c] += wgt * Un; aV[c] += wgt * Vn;
+                if (periodic) {
+                    if (i == 0) { u[G.Nx] = Un; v[G.Nx] = Vn; }
+                    if (i == G.Nx - 1) { u[-G.Nx] = Un; v[-G.Nx] = Vn; }
+                }
+            }
+        }
+        __syncthreads();
+        if (m + 1 < M) {
+            // publish my FIRST row of V for the block below, barrier, stage the row above my last
+            if (nr > 0 && j0 > 0) {
+                double* gv = F.V + (size_t)(j0 + OB_H) * G.pitch2 + a0;
+                for (int x = tid; x < Wp; x += NT) gv[x] = sV[x];
+            }
+            grid.sync();
+            if (nr > 0 && j1 < G.Ny) {
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    bulk_row_load(sV + (size_t)nr * Wp, F.V + (size_t)(j1 + OB_H) * G.pitch2 + a0, row_bytes, &bar[1]);
+                }
+                bar_wait(&bar[1], ph1); ph1 ^= 1;
+            }
+        }
+    }
+    // write back: eta <- eta_bar (interior columns, as k_baro_finish), the averages, the final transports
+#pragma unroll
+    for (int c = 0; c < MAXC; c++) {
+        const int wi = tid + c * NT;
+        if (wi < nwork) {
+            const int r = wi / ncol, i = wi - r * ncol - ex, j = j0 + r;
+            const int cg2 = idx2b(G, i, j);
+            F.etab[cg2] = aE[c]; F.Ub[cg2] = aU[c]; F.Vb[cg2] = aV[c];
+            F.U[cg2] = sU[(size_t)r * Wp + xo + i];
+            F.V[cg2] = sV[(size_t)r * Wp + xo + i];
+            F.eta[cg2] = ((unsigned)i < (unsigned)G.Nx) ? aE[c] : sE[(size_t)(r + 1) * Wp + xo + i];
+        }
+    }
+}
+
+// geometry of the on-chip variant; returns false when the slab does not fit one block per row band
+static bool onchip_plan(const Geom& G, int ex, int* R, int* Wp, int* a0, int* nblk, int* maxc, size_t* smem) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    *R = (G.Ny + sms - 1) / sms;
+    *nblk = (G.Ny + *R - 1) / *R;
+    const int lo = G.X0b - ex - 1;                  // first array column needed (i = -ex - 1)
+    *a0 = lo & ~1;                                  // even -> 16-byte aligned bulk copies
+    const int hi = G.X0b + G.Nx + ex + 1;           // one past the last (i = Nx + ex)
+    *Wp = ((hi - *a0) + 1) & ~1;
+    if (*a0 < 0 || *a0 + *Wp > G.pitch2) return false;
+    *smem = (size_t)(3 * *R + 2) * *Wp * sizeof(double);
+    const int per_thread = ((*R) * (G.Nx + 2 * ex) + 1023) / 1024;
+    *maxc = per_thread <= 3 ? 3 : per_thread <= 6 ? 6 : per_thread <= 10 ? 10 : 0;
+    return *smem <= 220 * 1024 && *maxc > 0;
+}
+bool baro_onchip_fits(const Geom& G, int ex) {
+    int R, Wp, a0, nblk, maxc; size_t smem;
+    return onchip_plan(G, ex, &R, &Wp, &a0, &nblk, &maxc, &smem);
+}
+int launch_baro_onchip(const Geom& G, const Fields& F, double dtau, const double* wts, int M, bool periodic, int ex, cudaStream_t st) {
+    int R, Wp, a0, nblk, maxc; size_t smem;
+    if (!onchip_plan(G, ex, &R, &Wp, &a0, &nblk, &maxc, &smem)) return -2;
+    void* kern = maxc == 3 ? (void*)k_baro_onchip<3> : maxc == 6 ? (void*)k_baro_onchip<6> : (void*)k_baro_onchip<10>;
+    static std::vector<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const std::pair<const void*, int> key(kern, dev);
+    if (std::find(done.begin(), done.end(), key) == done.end()) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);   // 227 KB minus the static mbarriers
+        done.push_back(key);
+    }
+    Geom g = G; Fields f = F;
+    void* args[] = {&g, &f, &dtau, &wts, &M, &periodic, &ex, &R, &Wp, &a0};
+    cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(nblk), dim3(1024), args, smem, st);
+    OB_COUNT_LAUNCH(1);
+    return e == cudaSuccess ? 0 : -1;
 }

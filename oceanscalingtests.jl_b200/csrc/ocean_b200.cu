@@ -34,6 +34,7 @@ struct ob200_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[20];
     bool timing = false, use_graph = true, persistent_baro = false, overlap = false;
+    bool onchip_baro = false;   // option "onchip_barotropic": persistent kernel with eta, U, V resident in shared memory
     bool overlap_exchange = false;  // x-slabs: halo exchange on stream2 beside the interior columns of the auxiliary sweeps (option)
     int transfer_x_halo = 0;   // x-halo columns copied by set/get_field besides the interior (checkpoint of halo-carrying state)
     cudaStream_t stream2 = nullptr;            // tracer work that can overlap the momentum / barotropic chain
@@ -560,6 +561,12 @@ int barotropic_loop(ob200_handle* h, double dt) {
     if (!per)
         if (int rc = barotropic_wide_exchange(h)) return rc;
     launch_baro_init(h->G, h->F, per, ex, h->stream);
+    if (h->onchip_baro && baro_onchip_fits(h->G, ex)) {
+        // one cooperative launch, state in shared memory; writes eta <- eta_bar itself (no k_baro_finish)
+        if (launch_baro_onchip(h->G, h->F, dtau, h->d_weights, h->cfg.n_substeps, per, ex, h->stream) != 0)
+            return h->fail(OB200_ECUDA, "cooperative launch (on-chip barotropic)", cudaGetErrorString(cudaGetLastError()));
+        return OB200_OK;
+    }
     if (h->persistent_baro) {
         if (launch_baro_persistent(h->G, h->F, dtau, h->d_weights, h->cfg.n_substeps, per, ex, h->stream) != 0)
             return h->fail(OB200_ECUDA, "cooperative launch", cudaGetErrorString(cudaGetLastError()));
@@ -998,6 +1005,7 @@ int ob200_set_option(ob200_handle* h, const char* name, int32_t value) {
     if (!h || !name) return OB200_EINVAL;
     if (!std::strcmp(name, "timing")) h->timing = value != 0;
     else if (!std::strcmp(name, "persistent_barotropic")) h->persistent_baro = value != 0;
+    else if (!std::strcmp(name, "onchip_barotropic")) h->onchip_baro = value != 0;
     else if (!std::strcmp(name, "overlap")) h->overlap = value != 0;
     else if (!std::strcmp(name, "barotropic_graph")) h->use_graph = value != 0;
     else if (!std::strcmp(name, "overlap_exchange")) h->overlap_exchange = value != 0;

@@ -25,6 +25,8 @@ def main():
     if os.environ.get("OB200_OVERLAP_EXCHANGE") == "1":
         # halo exchange on a second stream beside the interior columns of the auxiliary sweeps (option, same bits)
         m.backend.set_option("overlap_exchange", 1)
+    if os.environ.get("OB200_ONCHIP_BARO") == "1":
+        m.backend.set_option("onchip_barotropic", 1)
     if os.environ.get("OB200_BARO_GRAPH") == "0":
         m.backend.set_option("barotropic_graph", 0)
     restart = len(sys.argv) > 3 and sys.argv[3] == "restart"

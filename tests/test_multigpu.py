@@ -48,10 +48,12 @@ def test_overlapped_exchange_option_matches_single_gpu():
 
 
 @pytest.mark.parametrize("case_name,env", [("dd_mid", {"OB200_BARO_EXCHANGE": "substep"}), ("dd_narrow", {}),
-                                           ("dd_mid", {"OB200_BARO_EXCHANGE": "substep", "OB200_BARO_GRAPH": "0"})])
+                                           ("dd_mid", {"OB200_BARO_EXCHANGE": "substep", "OB200_BARO_GRAPH": "0"}),
+                                           ("dd_mid", {"OB200_ONCHIP_BARO": "1"}), ("bumpy", {"OB200_ONCHIP_BARO": "1"})])
 def test_per_substep_barotropic_exchange_matches_single_gpu(case_name, env):
-    """One-column eta / U exchanges every half substep (BASELINE configs[4]'s second strategy; the only one possible on
-    slabs narrower than the wide halo, e.g. the reference's 20-column clamp): same bits as one GPU."""
+    """The other barotropic strategies on x-slabs: one-column eta / U exchanges every half substep (BASELINE configs[4]'s
+    second strategy; the only one possible on slabs narrower than the wide halo, e.g. the reference's 20-column clamp) and
+    the persistent on-chip kernel over the wide-halo slab: same bits as one GPU."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")

@@ -217,6 +217,21 @@ def test_onchip_solve_matches_hbm_scratch_solve(pkg, gpu_lib):
             assert np.array_equal(m1.get(n), m2.get(n)), (name, n)
 
 
+def test_onchip_persistent_barotropic_matches_graph_replay(pkg, gpu_lib):
+    """Option "onchip_barotropic": ONE cooperative launch for all substeps with eta, U, V resident in shared memory, the
+    averages in registers, halo rows staged by bulk async copies after one grid barrier per half step -- same bits as the
+    graph-replayed launch loop (periodic single-GPU domains that fit: these small cases; x-slabs: tests/test_multigpu.py)."""
+    for name in ("dd_small", "bumpy", "realistic"):
+        c = cases.build_case(name)
+        m1, m2 = c.make_model(pkg, None), c.make_model(pkg, None)
+        m2.backend.set_option("onchip_barotropic", 1)
+        for _ in range(5):
+            pkg.time_step(m1, c.dt)
+            pkg.time_step(m2, c.dt)
+        for n in PROG + ("UBAR", "VBAR", "GU", "GT"):
+            assert np.array_equal(m1.get(n), m2.get(n)), (name, n)
+
+
 def test_two_stream_overlap_matches_serial_order(pkg, gpu_lib):
     """Option "overlap": the T, S solve runs on a second stream beside the barotropic substeps; same bits."""
     c = cases.build_case("bumpy")
