@@ -84,7 +84,7 @@ struct MomG {
 // per-latitude metrics of a tile's rows in shared memory: [metric][row], row r <-> j = j0 - MT_J0 + r.  One LDS with an
 // immediate offset replaces the constant-bank pointer load + address arithmetic + global load of `G.metric[j]`.
 enum { MT_DXFC = 0, MT_DXCF, MT_RAZCF, MT_RDXFC, MT_AZCC, MT_RAZCC, MT_FFF, MT_TAUX, MT_N };
-#define MT_ROWS 32
+#define MT_ROWS 28
 #define MT_J0 6
 __device__ __forceinline__ void load_metric_table(const Geom& G, double* smt, int j0, int tid, int nt) {
     const double* src[MT_N] = {G.dxfc, G.dxcf, G.razcf, G.rdxfc, G.azcc, G.razcc, G.fff, G.taux};
@@ -99,6 +99,14 @@ __device__ __forceinline__ void load_metric_table(const Geom& G, double* smt, in
 }
 #define MET(mrow, name, dj) ((mrow)[MT_##name * MT_ROWS + (dj)])
 
+// MOM_DB = 1: the derived fields of consecutive levels alternate between two shared-memory buffers, so the barrier that
+// used to end a level (protecting them from the next level's staging) goes away: warps that finish a level early stage the
+// next one while the slow ones still compute.  77 KB per block -> 3 resident blocks (was 4 with 2 barriers per level).
+// Measured at C3 on one B200: 19.01 ms against 18.41 ms for the single-buffered kernel with 4 resident blocks -- the
+// occupancy is worth more than the barrier -- so it is OFF by default.
+#ifndef MOM_DB
+#define MOM_DB 0
+#endif
 // shared-memory tile geometry for the fast path (TX x TY cells per block)
 template <int TX, int TY>
 struct TileDims {
@@ -115,7 +123,9 @@ struct TileDims {
     static constexpr int PK = TX + 1, RK = TY + 1;       // K: [i0-1, i0+TX-1]
     static constexpr int NU = PU * RU, NZ = PZ * RZ, ND = PD * RD, NK = PK * RK;
     static constexpr int NUP = (NU + 15) / 16 * 16;      // tile slot padded to 128 bytes (TMA destination alignment)
-    static constexpr int TOTAL = 4 * NUP + 3 * NZ + 2 * ND + NK + MT_N * MT_ROWS;   // doubles: u, v double-buffered + derived fields + metrics
+    static constexpr int NDER = 3 * NZ + 2 * ND + NK;     // derived fields of one level: zeta, I_y u, I_x v, dxU, dyV, K
+    // doubles: u, v double-buffered (TMA) + derived fields (double-buffered when MOM_DB: ONE block barrier per level) + metrics
+    static constexpr int TOTAL = 4 * NUP + (MOM_DB ? 2 : 1) * NDER + MT_N * MT_ROWS;
 };
 
 template <int TX, int TY>
@@ -487,7 +497,7 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
 //   GEN = true : the remaining (tile, level) pairs near ridges, walls and the sea floor: conditional zeta,
 //                per-reconstruction order reduction, masked outputs.
 #ifndef MOM_MINB
-#define MOM_MINB 4
+#define MOM_MINB (MOM_DB ? 3 : 4)
 #endif
 #ifndef TRC_MINB
 #define TRC_MINB 4
@@ -507,13 +517,9 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
     constexpr int RU = (D::NU + NT - 1) / NT;
     extern __shared__ __align__(128) double sm[];
     __shared__ unsigned long long bar[2];
-    double* sz = sm + 4 * D::NUP;   // [u0 | v0 | u1 | v1] tile buffers first (128-byte aligned slots)
-    double* sus = sz + D::NZ;
-    double* svs = sus + D::NZ;
-    double* sdx = svs + D::NZ;
-    double* sdy = sdx + D::ND;
-    double* sK = sdy + D::ND;
-    double* smt = sK + D::NK;       // metrics table [MT_N][MT_ROWS]
+    constexpr bool DB = MOM_DB && TMA;          // one barrier per level (derived fields double-buffered)
+    double* der = sm + 4 * D::NUP;  // [u0 | v0 | u1 | v1] tile buffers first (128-byte aligned slots), then the derived fields
+    double* smt = der + (MOM_DB ? 2 : 1) * D::NDER;       // metrics table [MT_N][MT_ROWS]
     int tile, kf;
     int kskip = 0;   // masked tiles: levels below the shallowest sea floor of the tile are all solid -> G stays 0 (never written)
     if (GEN) { tile = slow_tiles[3 * blockIdx.x]; kf = slow_tiles[3 * blockIdx.x + 1]; kskip = slow_tiles[3 * blockIdx.x + 2]; }
@@ -553,6 +559,11 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
             mbar_expect_tx(&bar[0], 2 * TILE_BYTES);
             tma_load_tile(sm, &tmu, &bar[0], tx0, ty0, k_begin);
             tma_load_tile(sm + D::NUP, &tmv, &bar[0], tx0, ty0, k_begin);
+            if (DB && k_begin + 1 < k_end) {      // both tile buffers are free at the start: the second level follows at once
+                mbar_expect_tx(&bar[1], 2 * TILE_BYTES);
+                tma_load_tile(sm + 2 * D::NUP, &tmu, &bar[1], tx0, ty0, k_begin + 1);
+                tma_load_tile(sm + 3 * D::NUP, &tmv, &bar[1], tx0, ty0, k_begin + 1);
+            }
         }
     } else {
 #pragma unroll
@@ -583,10 +594,16 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
         const int buf = TMA ? (it & 1) : 0;
         double* su = sm + buf * 2 * D::NUP;
         double* sv = su + D::NUP;
+        double* sz = der + (DB ? buf : 0) * D::NDER;
+        double* sus = sz + D::NZ;
+        double* svs = sus + D::NZ;
+        double* sdx = svs + D::NZ;
+        double* sdy = sdx + D::ND;
+        double* sK = sdy + D::ND;
         const MomS<TX, TY> M{su, sv, sz, sus, svs, sdx, sdy, sK, i0, j0};
         if (TMA) {
             // the other buffer was last read in the previous iteration, which ended with a block barrier
-            if (tid == 0 && k + 1 < k_end) {
+            if (!DB && tid == 0 && k + 1 < k_end) {
                 fence_proxy_async();
                 double* nu = sm + (buf ^ 1) * 2 * D::NUP;
                 mbar_expect_tx(&bar[buf ^ 1], 2 * TILE_BYTES);
@@ -649,6 +666,14 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
                 }
             }
         __syncthreads();
+        if (DB && tid == 0 && it >= 1 && k + 1 < k_end) {
+            // every warp is past the compute phase of level k - 1, the last reader of the other tile buffer: refill it
+            fence_proxy_async();
+            double* nu = sm + (buf ^ 1) * 2 * D::NUP;
+            mbar_expect_tx(&bar[buf ^ 1], 2 * TILE_BYTES);
+            tma_load_tile(nu, &tmu, &bar[buf ^ 1], tx0, ty0, k + 1);
+            tma_load_tile(nu + D::NUP, &tmv, &bar[buf ^ 1], tx0, ty0, k + 1);
+        }
         if (mine) {
             const long long c = idx3(G, i, j, k);
             if (!GEN) {
@@ -663,7 +688,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
                 F.Gv[c] = k < T.per_v ? 0.0 : tend_v<true>(G, F, M, i, j, k, NV, ND, time, T, mrow);
             }
         }
-        __syncthreads();
+        if (!DB) __syncthreads();
     }
 }
 
