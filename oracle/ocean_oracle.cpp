@@ -961,7 +961,9 @@ struct Oracle {
     // solve (I + L) phi+ = phi* on one column; Kf(k) = diffusivity on the face below level k (k = 1..Nz-1)
     template <class KF>
     void implicit_column(F3& f, int i, int j, double dt, KF Kface) {
-        std::vector<double> t(Nz + 1), lo(Nz + 1), up(Nz + 1);
+        // scratch of the column solve: per-thread, allocated once (the reference's solver owns a scratch field `t`)
+        static thread_local std::vector<double> t, lo, up;
+        if ((int)t.size() < Nz + 1) { t.assign(Nz + 1, 0.0); lo.assign(Nz + 1, 0.0); up.assign(Nz + 1, 0.0); }
         for (int k = 0; k < Nz; k++) {
             // reference: -Δt * κ_Δz²  with  κ_Δz² = κ / Δzᶜ(k) / Δzᶠ(face)  (two successive divisions)
             up[k] = (k < Nz - 1) ? ((refar && (refbits & 1)) ? -dt * (Kface(k + 1) / dzc(k) / dzf(k + 1)) : -dt * Kface(k + 1) * rupz_[k]) : 0.0;
