@@ -11,6 +11,9 @@
 // inside the domain) and a general path with per-reconstruction order reduction and conditional operators.
 #include "ob_bc.cuh"
 #include "weno_gen.cuh"
+#ifndef TEND_LEITH
+#define TEND_LEITH 1   // 0: compile the QG-Leith stress out (instruction-count studies only)
+#endif
 
 // ---- TMA (cp.async.bulk.tensor) + mbarrier helpers: one elected thread fetches a whole (box_x, box_y, 1) tile of a
 // 3-D field into shared memory; completion is signalled on an mbarrier by transaction bytes.
@@ -107,6 +110,12 @@ __device__ __forceinline__ void load_metric_table(const Geom& G, double* smt, in
 #ifndef MOM_DB
 #define MOM_DB 0
 #endif
+// MOM_WSM = 1: the vertical velocity of the tile (levels k and k + 1) is staged in a two-slot shared-memory ring -- one global
+// load per thread and level (issued at the top of the derived-field phase, stored at its end) instead of eight with 64-bit
+// address arithmetic in the middle of the tendency phase.  Needs the end-of-level barrier (not combined with MOM_DB).
+#ifndef MOM_WSM
+#define MOM_WSM (MOM_DB ? 0 : 1)
+#endif
 // shared-memory tile geometry for the fast path (TX x TY cells per block)
 template <int TX, int TY>
 struct TileDims {
@@ -125,7 +134,9 @@ struct TileDims {
     static constexpr int NUP = (NU + 15) / 16 * 16;      // tile slot padded to 128 bytes (TMA destination alignment)
     static constexpr int NDER = 3 * NZ + 2 * ND + NK;     // derived fields of one level: zeta, I_y u, I_x v, dxU, dyV, K
     // doubles: u, v double-buffered (TMA) + derived fields (double-buffered when MOM_DB: ONE block barrier per level) + metrics
-    static constexpr int TOTAL = 4 * NUP + (MOM_DB ? 2 : 1) * NDER + MT_N * MT_ROWS;
+    // w at the cells [i0 - 1, i0 + TX - 1] x [j0 - 1, j0 + TY - 1], levels k and k + 1 (ring of two slots)
+    static constexpr int PW = TX + 1, NW = PW * (TY + 1);
+    static constexpr int TOTAL = 4 * NUP + (MOM_DB ? 2 : 1) * NDER + MT_N * MT_ROWS + (MOM_WSM ? 2 * NW : 0);
 };
 
 template <int TX, int TY>
@@ -296,7 +307,8 @@ __device__ __forceinline__ int order_from(const int* thr, int Nmax, int k) {
 // ================================================================================================
 template <bool GEN, class A>
 __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A& M, int i, int j, int k, int NV, int ND,
-                                         double time, const GenThr& T, const double* __restrict__ mrow) {
+                                         double time, const GenThr& T, const double* __restrict__ mrow,
+                                         const double u_below, const double u_above, const double* __restrict__ wk) {
     const long long c = idx3(G, i, j, k);
     // (1) vorticity flux
     const double dxcf0 = MET(mrow, DXCF, 0), dxcf1 = MET(mrow, DXCF, 1), rdxfc = MET(mrow, RDXFC, 0);
@@ -333,13 +345,13 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
         Phi = uh * d + uh * 0.5 * (M.dyV(i - 1, j, k) + M.dyV(i, j, k));
     }
     const double az = MET(mrow, AZCC, 0);
-    const int km = max(k - 1, 0), kp = min(k + 1, G.Nz - 1);
     double fl_lo, fl_hi;
     {
-        const double Wlo = 0.5 * (az * F.w[c - 1] + az * F.w[c]);
-        const double Whi = 0.5 * (az * F.w[c - 1 + G.sz] + az * F.w[c + G.sz]);
-        fl_lo = Wlo * 0.5 * (F.u[idx3(G, i, j, km)] + uh);
-        fl_hi = Whi * 0.5 * (uh + F.u[idx3(G, i, j, kp)]);
+        // wk: {w(i,j,k), w(i-1,j,k), w(i,j-1,k), w(i,j,k+1), w(i-1,j,k+1), w(i,j-1,k+1)}
+        const double Wlo = 0.5 * (az * wk[1] + az * wk[0]);
+        const double Whi = 0.5 * (az * wk[4] + az * wk[3]);
+        fl_lo = Wlo * 0.5 * (u_below + uh);    // u(k - 1), clamped at the bottom level
+        fl_hi = Whi * 0.5 * (uh + u_above);    // u(k + 1), clamped at the top level
         if (GEN) {
             // immersed-peripheral (f,c,f) faces carry no flux: the node below is peripheral but inside the domain
             if (k > 0 && k <= T.per_u) fl_lo = 0.0;
@@ -360,7 +372,7 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
     Gt += fbar * cor * rdxfc;
     Gt -= (F.p[c] - F.p[c - 1]) * rdxfc;
     // (6) QG-Leith stress divergence
-    if (G.qgleith) {
+    if (TEND_LEITH && G.qgleith) {
         const MomG Mg{G, F.u, F.v};
         const double ax = G.dy * G.dzc[k];
         auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * Mg.divxy(a, b, k) : 0.0; };
@@ -401,7 +413,8 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
 
 template <bool GEN, class A>
 __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A& M, int i, int j, int k, int NV, int ND,
-                                         double time, const GenThr& T, const double* __restrict__ mrow) {
+                                         double time, const GenThr& T, const double* __restrict__ mrow,
+                                         const double v_below, const double v_above, const double* __restrict__ wk) {
     const long long c = idx3(G, i, j, k);
     const double dy = G.dy;
     const double q00 = dy * M.U(i, j - 1, k), q10 = dy * M.U(i + 1, j - 1, k);
@@ -435,12 +448,11 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
         }
         Phi = vh * d + vh * 0.5 * (M.dxU(i, j - 1, k) + M.dxU(i, j, k));
     }
-    const int km = max(k - 1, 0), kp = min(k + 1, G.Nz - 1);
     const double azm = MET(mrow, AZCC, -1), az0 = MET(mrow, AZCC, 0);
-    const double Wlo = 0.5 * (azm * F.w[c - G.pitch] + az0 * F.w[c]);
-    const double Whi = 0.5 * (azm * F.w[c - G.pitch + G.sz] + az0 * F.w[c + G.sz]);
-    double fl_lo = Wlo * 0.5 * (F.v[idx3(G, i, j, km)] + vh);
-    const double fl_hi = Whi * 0.5 * (vh + F.v[idx3(G, i, j, kp)]);
+    const double Wlo = 0.5 * (azm * wk[2] + az0 * wk[0]);
+    const double Whi = 0.5 * (azm * wk[5] + az0 * wk[3]);
+    double fl_lo = Wlo * 0.5 * (v_below + vh);
+    const double fl_hi = Whi * 0.5 * (vh + v_above);
     if (GEN) {
         if (k > 0 && k <= T.per_v) fl_lo = 0.0;
     }
@@ -457,7 +469,7 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
     const double cor = nact == 0 ? 0.0 : nact == 4 ? uavg : uavg / (0.25 * nact);
     Gt -= fbar * cor * G.rdy;
     Gt -= (F.p[c] - F.p[c - G.pitch]) * G.rdy;
-    if (G.qgleith) {
+    if (TEND_LEITH && G.qgleith) {
         const MomG Mg{G, F.u, F.v};
         const double ax = dy * G.dzc[k];
         auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * Mg.divxy(a, b, k) : 0.0; };
@@ -499,6 +511,9 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
 #ifndef MOM_MINB
 #define MOM_MINB (MOM_DB ? 3 : 4)
 #endif
+#ifndef MOM_KNBR
+#define MOM_KNBR 1   // own-column u, v at k - 1 / k + 1 from registers / the next TMA tile instead of global memory
+#endif
 #ifndef TRC_MINB
 #define TRC_MINB 4
 #endif
@@ -520,6 +535,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
     constexpr bool DB = MOM_DB && TMA;          // one barrier per level (derived fields double-buffered)
     double* der = sm + 4 * D::NUP;  // [u0 | v0 | u1 | v1] tile buffers first (128-byte aligned slots), then the derived fields
     double* smt = der + (MOM_DB ? 2 : 1) * D::NDER;       // metrics table [MT_N][MT_ROWS]
+    double* swr = smt + MT_N * MT_ROWS;                   // w ring [2][NW] (MOM_WSM)
     int tile, kf;
     int kskip = 0;   // masked tiles: levels below the shallowest sea floor of the tile are all solid -> G stays 0 (never written)
     if (GEN) { tile = slow_tiles[3 * blockIdx.x]; kf = slow_tiles[3 * blockIdx.x + 1]; kskip = slow_tiles[3 * blockIdx.x + 2]; }
@@ -589,6 +605,33 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
             zthr[r] = (kzx << 16) | kzy;
         }
     }
+    // own-column u, v one level below (clamped at the bottom): read once, then carried from level to level; the level above
+    // comes from the tile that TMA is already fetching for the next iteration (MOM_KNBR = 0: four global loads per cell)
+    const int own = (threadIdx.y + D::HU) * D::PU + (threadIdx.x + D::HUX);
+    double ub = 0.0, vb = 0.0;
+    if (MOM_KNBR && mine) {
+        const long long cb = idx3(G, i, j, max(k_begin - 1, 0));
+        ub = F.u[cb]; vb = F.v[cb];
+    }
+    // w ring: thread (tx, ty) stages w of its own cell at slot (tx + 1, ty + 1); the tx = 0 / ty = 0 threads add the column
+    // i0 - 1 / the row j0 - 1
+    const int wown = (threadIdx.y + 1) * D::PW + (threadIdx.x + 1);
+    auto stage_w_load = [&](int kk, double& a, double& b, double& c3) {
+        const long long cw = idx3(G, i, j, kk);
+        a = F.w[cw];
+        if (threadIdx.x == 0) b = F.w[cw - 1];
+        if (threadIdx.y == 0) c3 = F.w[cw - G.pitch];
+    };
+    auto stage_w_store = [&](double* dst, double a, double b, double c3) {
+        dst[wown] = a;
+        if (threadIdx.x == 0) dst[wown - 1] = b;
+        if (threadIdx.y == 0) dst[wown - D::PW] = c3;
+    };
+    if (MOM_WSM && mine) {   // level k_begin; made visible by the first mid-level barrier
+        double a = 0.0, b = 0.0, c3 = 0.0;
+        stage_w_load(k_begin, a, b, c3);
+        stage_w_store(swr, a, b, c3);
+    }
     int it = 0;
     for (int k = k_begin; k < k_end; k++, it++) {
         const int buf = TMA ? (it & 1) : 0;
@@ -621,6 +664,9 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
             if (k + 1 < k_end) prefetch(k + 1);
         }
         const double dzk = G.dzc[k];
+        // w(k + 1) of the tile: requested here, stored at the end of this phase into the slot w(k - 1) occupied
+        double wa = 0.0, wb = 0.0, wc = 0.0;
+        if (MOM_WSM && mine) stage_w_load(k + 1, wa, wb, wc);
         // zeta, I_y u, I_x v on [i0 - 4, i0 + TX + 4] x [j0 - 4, j0 + TY + 4]
 #pragma unroll
         for (int r = 0; r < NRYZ; r++)
@@ -665,6 +711,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
                     sK[e] = (0.5 * (ua * ua + ub * ub) + 0.5 * (va * va + vb * vb)) / 2.0;
                 }
             }
+        if (MOM_WSM && mine) stage_w_store(swr + ((it + 1) & 1) * D::NW, wa, wb, wc);
         __syncthreads();
         if (DB && tid == 0 && it >= 1 && k + 1 < k_end) {
             // every warp is past the compute phase of level k - 1, the last reader of the other tile buffer: refill it
@@ -676,17 +723,39 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
         }
         if (mine) {
             const long long c = idx3(G, i, j, k);
+            double ua, va;
+            if (MOM_KNBR && TMA && k + 1 < k_end) {
+                // the next level's tiles were requested at the top of this iteration: by now they have normally landed
+                mbar_wait(&bar[buf ^ 1], ((it + 1) >> 1) & 1);
+                const double* nu = sm + (buf ^ 1) * 2 * D::NUP;
+                ua = nu[own]; va = nu[D::NUP + own];
+            } else {
+                const long long ca = idx3(G, i, j, min(k + 1, G.Nz - 1));
+                ua = F.u[ca]; va = F.v[ca];
+            }
+            if (!MOM_KNBR) { const long long cb = idx3(G, i, j, max(k - 1, 0)); ub = F.u[cb]; vb = F.v[cb]; }
+            double wk[6];
+            if (MOM_WSM) {
+                const double* w0 = swr + (it & 1) * D::NW + wown;
+                const double* w1 = swr + ((it + 1) & 1) * D::NW + wown;
+                wk[0] = w0[0]; wk[1] = w0[-1]; wk[2] = w0[-D::PW];
+                wk[3] = w1[0]; wk[4] = w1[-1]; wk[5] = w1[-D::PW];
+            } else {
+                wk[0] = F.w[c]; wk[1] = F.w[c - 1]; wk[2] = F.w[c - G.pitch];
+                wk[3] = F.w[c + G.sz]; wk[4] = F.w[c - 1 + G.sz]; wk[5] = F.w[c - G.pitch + G.sz];
+            }
             if (!GEN) {
-                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time, T, mrow);
-                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time, T, mrow);
+                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, ub, ua, wk);
+                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, vb, va, wk);
             } else if (k >= T.kfast) {
                 // most cells of a masked tile are still far from any boundary: full-order, check-free path
-                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time, T, mrow);
-                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time, T, mrow);
+                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, ub, ua, wk);
+                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, vb, va, wk);
             } else {
-                F.Gu[c] = k < T.per_u ? 0.0 : tend_u<true>(G, F, M, i, j, k, NV, ND, time, T, mrow);
-                F.Gv[c] = k < T.per_v ? 0.0 : tend_v<true>(G, F, M, i, j, k, NV, ND, time, T, mrow);
+                F.Gu[c] = k < T.per_u ? 0.0 : tend_u<true>(G, F, M, i, j, k, NV, ND, time, T, mrow, ub, ua, wk);
+                F.Gv[c] = k < T.per_v ? 0.0 : tend_v<true>(G, F, M, i, j, k, NV, ND, time, T, mrow, vb, va, wk);
             }
+            if (MOM_KNBR) { ub = su[own]; vb = sv[own]; }
         }
         if (!DB) __syncthreads();
     }
@@ -697,6 +766,13 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
 // ================================================================================================
 // ---- fast path: T and S tiles in shared memory, every face flux computed ONCE (the reference computes each
 // face twice, once per adjacent cell), upwind side only, then each thread differences the fluxes of its cell.
+// TRC_PIPE = 1 (TMA instantiations): fluxes and face velocities alternate between two shared-memory slots, so the barrier that
+// ended a level goes away (two block barriers per level instead of three); the own-column values of the vertical flux come
+// from registers (k - 1: the centre value of the previous level; w(k): the previous level's w(k + 1)) and from the tile TMA is
+// already fetching for the next level (k + 1) -- one global load per cell and level instead of six.
+#ifndef TRC_PIPE
+#define TRC_PIPE 0   // measured at C3 on one B200: 12.76 ms against 11.93 ms without (the carried values spill at 64 registers)
+#endif
 template <int TX, int TY>
 struct TracerTile {
     static constexpr int HC = 4;                                   // WENO-7 halo
@@ -704,7 +780,7 @@ struct TracerTile {
     static constexpr int NC = PC * RC;
     static constexpr int NCP = (NC + 15) / 16 * 16;                // tile slot padded to 128 bytes
     static constexpr int NFX = (TX + 1) * TY, NFY = TX * (TY + 1); // faces per tracer
-    static constexpr int TOTAL = 4 * NCP + 3 * (NFX + NFY);  // T, S tiles double-buffered + fluxes + face velocities
+    static constexpr int TOTAL = 4 * NCP + (TRC_PIPE ? 2 : 1) * 3 * (NFX + NFY);  // T, S tiles double-buffered + fluxes + face velocities
 };
 
 template <int TX, int TY, bool GEN, bool TMA>
@@ -719,8 +795,9 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
     constexpr int RV = (NFV + NT - 1) / NT;
     extern __shared__ __align__(128) double sm[];
     __shared__ unsigned long long bar[2];
-    double* sfx = sm + 4 * D::NCP;         // after the [T0 | S0 | T1 | S1] tile buffers: [2][(TX+1)*TY x-faces | TX*(TY+1) y-faces]
-    double* svel = sfx + 2 * NFV;          // [NFX + NFY] face velocities u (x-faces) then v (y-faces)
+    constexpr bool PIPE = TRC_PIPE && TMA;
+    double* sfx0 = sm + 4 * D::NCP;        // after the [T0 | S0 | T1 | S1] tile buffers: slots of [2 tracers][(TX+1)*TY x-faces | TX*(TY+1) y-faces]
+    double* svel0 = sfx0 + (TRC_PIPE ? 2 : 1) * 2 * NFV;   // slots of [NFX + NFY] face velocities u (x-faces) then v (y-faces)
     int tile, kf;
     int kskip = 0;   // masked tiles: levels below the shallowest sea floor of the tile are all solid -> G stays 0 (never written)
     if (GEN) { tile = slow_tiles[3 * blockIdx.x]; kf = slow_tiles[3 * blockIdx.x + 1]; kskip = slow_tiles[3 * blockIdx.x + 2]; }
@@ -802,12 +879,22 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
             fthr[2 * r + 1] = (thr[4] << 16) | thr[3];
         }
     }
+    // PIPE: own-column values carried from level to level
+    const int qown = (threadIdx.y + D::HC) * D::PC + (threadIdx.x + D::HC);
+    double wlo_c = 0.0, Tm_c = 0.0, Sm_c = 0.0;
+    if (PIPE && mine) {
+        const long long cm = cbase + (long long)max(k_begin - 1, 0) * G.sz;
+        wlo_c = F.w[cbase + (long long)k_begin * G.sz]; Tm_c = F.T[cm]; Sm_c = F.S[cm];
+    }
     int it = 0;
     for (int k = k_begin; k < k_end; k++, it++) {
         const int buf = TMA ? (it & 1) : 0;
         double* sc = sm + buf * 2 * D::NCP;   // T tile, then S tile at + NCP
+        double* sfx = sfx0 + (PIPE ? buf : 0) * 2 * NFV;
+        double* svel = svel0 + (PIPE ? buf : 0) * NFV;
         if (TMA && tid == 0 && k + 1 < k_end) {
-            // the other buffer was last read in the previous iteration, which ended with a block barrier
+            // the other buffer was last read before the second barrier of the previous iteration (PIPE: the centre values are
+            // taken in the flux phase), otherwise the previous iteration ended with a block barrier
             fence_proxy_async();
             double* nx = sm + (buf ^ 1) * 2 * D::NCP;
             mbar_expect_tx(&bar[buf ^ 1], 2 * TILE_BYTES);
@@ -829,12 +916,16 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
         if (k + 1 < k_end) prefetch(k + 1);
         // own-column values for the vertical flux, requested now, consumed after the flux phase
         const int km = max(k - 1, 0), kp = min(k + 1, G.Nz - 1);
-        double wlo = 0, whi = 0, Tm = 0, Tp = 0, Sm = 0, Sp = 0;
+        double wlo = 0, whi = 0, Tm = 0, Tp = 0, Sm = 0, Sp = 0, ckT = 0, ckS = 0;
         if (mine) {
             const long long c = cbase + (long long)k * G.sz;
-            wlo = F.w[c]; whi = F.w[c + G.sz];
-            Tm = F.T[cbase + (long long)km * G.sz]; Tp = F.T[cbase + (long long)kp * G.sz];
-            Sm = F.S[cbase + (long long)km * G.sz]; Sp = F.S[cbase + (long long)kp * G.sz];
+            whi = F.w[c + G.sz];
+            if (PIPE) { wlo = wlo_c; Tm = Tm_c; Sm = Sm_c; ckT = sc[qown]; ckS = sc[D::NCP + qown]; }
+            else {
+                wlo = F.w[c];
+                Tm = F.T[cbase + (long long)km * G.sz]; Tp = F.T[cbase + (long long)kp * G.sz];
+                Sm = F.S[cbase + (long long)km * G.sz]; Sp = F.S[cbase + (long long)kp * G.sz];
+            }
         }
         const double dzk = G.dzc[k], rdzk = G.rdzc[k];
         if (!GEN) {
@@ -916,10 +1007,20 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
         if (mine) {
             const long long c = cbase + (long long)k * G.sz;
             const int fxi = threadIdx.y * (TX + 1) + threadIdx.x, fyi = threadIdx.y * TX + threadIdx.x;
-            const int q = (threadIdx.y + D::HC) * D::PC + (threadIdx.x + D::HC);
+            const int q = qown;
+            if (PIPE) {
+                if (k + 1 < k_end) {   // the next level's tiles, requested at the top of this iteration
+                    mbar_wait(&bar[buf ^ 1], ((it + 1) >> 1) & 1);
+                    const double* nx = sm + (buf ^ 1) * 2 * D::NCP;
+                    Tp = nx[q]; Sp = nx[D::NCP + q];
+                } else {
+                    Tp = F.T[cbase + (long long)kp * G.sz]; Sp = F.S[cbase + (long long)kp * G.sz];
+                }
+                wlo_c = whi; Tm_c = ckT; Sm_c = ckS;
+            }
 #pragma unroll
             for (int tr = 0; tr < 2; tr++) {
-                const double ck = sc[tr * D::NCP + q];
+                const double ck = PIPE ? (tr == 0 ? ckT : ckS) : sc[tr * D::NCP + q];
                 const double cm = tr == 0 ? Tm : Sm, cp = tr == 0 ? Tp : Sp;
                 double fzl = az * wlo * 0.5 * (cm + ck);
                 const double fzh = az * whi * 0.5 * (ck + cp);
@@ -935,7 +1036,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
                 (tr == 0 ? F.GT : F.GS)[c] = Gt;
             }
         }
-        __syncthreads();
+        if (!PIPE) __syncthreads();
     }
 }
 
