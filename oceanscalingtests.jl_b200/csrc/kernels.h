@@ -9,29 +9,29 @@ extern long long ob_launch_count;   // kernels launched by this library (bench.p
 
 struct Fields {
     // 3-D (Nz+1 planes)
-    double *u, *v, *w, *T, *S, *p, *kc, *ku, *Ri, *scratch, *scratch2;
-    double *Gu, *Gv, *GT, *GS, *Gu0, *Gv0, *GT0, *GS0;
-    double *nuL, *qx, *qy;
+    real *u, *v, *w, *T, *S, *p, *kc, *ku, *Ri, *scratch, *scratch2;
+    real *Gu, *Gv, *GT, *GS, *Gu0, *Gv0, *GT0, *GS0;
+    real *nuL, *qx, *qy;
     // 2-D
-    double *eta, *U, *V, *etab, *Ub, *Vb, *GU, *GV, *Hfc, *Hcf, *Ld;
-    double *Usum, *Vsum;   // sum_k dz u, sum_k dz v of the freshly solved u, v (barotropic layout), produced by the implicit solve
+    real *eta, *U, *V, *etab, *Ub, *Vb, *GU, *GV, *Hfc, *Hcf, *Ld;
+    real *Usum, *Vsum;   // sum_k dz u, sum_k dz v of the freshly solved u, v (barotropic layout), produced by the implicit solve
     // RealisticOcean forcing (Nx x Ny(+1) x 6, compact), may be null
-    double* forcing[6];
+    real* forcing[6];
 };
 
 // kernels_halo.cu
 void launch_fill_halos(const Geom& G, const Fields& F, bool periodic_x, cudaStream_t st);
 void launch_mask_fields(const Geom& G, const Fields& F, cudaStream_t st);
 // layout: 0 = 3-D field, 1 = 2-D in the 3-D plane layout (Ld), 2 = 2-D barotropic layout
-void launch_copy_field(const Geom& G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, int layout,
+void launch_copy_field(const Geom& G, real* field, real* buf, int ny, int nz, int hx, int hy, int hz, int layout,
                        bool to_field, int ex, cudaStream_t st);
 // exchange groups of the 7-column x-halos: u, v, eta (final after the corrector) | T, S (final after their implicit solve)
 #define OB_XG_UVETA 0
 #define OB_XG_TS 1
-void launch_pack_x(const Geom& G, const Fields& F, double* sendW, double* sendE, int group, cudaStream_t st);
-void launch_unpack_x(const Geom& G, const Fields& F, const double* recvW, const double* recvE, int group, cudaStream_t st);
+void launch_pack_x(const Geom& G, const Fields& F, real* sendW, real* sendE, int group, cudaStream_t st);
+void launch_unpack_x(const Geom& G, const Fields& F, const real* recvW, const real* recvE, int group, cudaStream_t st);
 size_t pack_x_count(const Geom& G, int group);
-void launch_diagnostics(const Geom& G, const Fields& F, double* out8, cudaStream_t st);
+void launch_diagnostics(const Geom& G, const Fields& F, double* out8, cudaStream_t st); /*f64*/
 
 // kernels_column.cu
 void launch_w_p(const Geom& G, const Fields& F, cudaStream_t st);                       // all columns [-2, Nx + 2)
@@ -39,35 +39,35 @@ void launch_ri_kappa(const Geom& G, const Fields& F, double time, cudaStream_t s
 // the same sweeps on the columns [a0, a0 + n0) U [a1, a1 + n1)
 void launch_w_p(const Geom& G, const Fields& F, int a0, int n0, int a1, int n1, cudaStream_t st);
 void launch_ri_kappa(const Geom& G, const Fields& F, double time, int a0, int n0, int a1, int n1, cudaStream_t st);
-void launch_barotropic_forcing(const Geom& G, const Fields& F, double chi, cudaStream_t st);
+void launch_barotropic_forcing(const Geom& G, const Fields& F, real chi, cudaStream_t st);
 // momentum (u, v: also G^U, G^V) and tracer (T, S) solves can run on different streams (separate scratch arrays)
 // `onchip`: eliminated coefficients and forward values in shared memory (every array crosses HBM once); needs
 // ab2_onchip_fits(G), otherwise the variant with an HBM scratch array.  Same arithmetic, same bits.
 bool ab2_onchip_fits(const Geom& G);
-void launch_ab2_implicit_uv(const Geom& G, const Fields& F, double dt, double chi, bool onchip, cudaStream_t st);
-void launch_ab2_implicit_ts(const Geom& G, const Fields& F, double dt, double chi, bool onchip, cudaStream_t st);
+void launch_ab2_implicit_uv(const Geom& G, const Fields& F, real dt, real chi, bool onchip, cudaStream_t st);
+void launch_ab2_implicit_ts(const Geom& G, const Fields& F, real dt, real chi, bool onchip, cudaStream_t st);
 void launch_correct(const Geom& G, const Fields& F, cudaStream_t st);
 
 // kernels_baro.cu
 // `ex` = columns beyond the interior computed on each side (0 on one GPU, Wb - 1 on x-slabs)
 void launch_baro_init(const Geom& G, const Fields& F, bool periodic_x, int ex, cudaStream_t st);
-void launch_baro_eta(const Geom& G, const Fields& F, double dtau, bool periodic_x, int ex, cudaStream_t st);
-void launch_baro_vel(const Geom& G, const Fields& F, double dtau, double wgt, bool periodic_x, int ex, cudaStream_t st);
+void launch_baro_eta(const Geom& G, const Fields& F, real dtau, bool periodic_x, int ex, cudaStream_t st);
+void launch_baro_vel(const Geom& G, const Fields& F, real dtau, real wgt, bool periodic_x, int ex, cudaStream_t st);
 void launch_baro_finish(const Geom& G, const Fields& F, cudaStream_t st);
 // per-substep slab exchange: interior columns only; edge columns through contiguous buffers of Ny doubles (kernels_baro.cu)
-void launch_baro_eta_edge(const Geom& G, const Fields& F, double dtau, double* send_eta, const double* recv_eta, double* send_U,
-                          const double* recv_U, cudaStream_t st);
-void launch_baro_vel_edge(const Geom& G, const Fields& F, double dtau, double wgt, double* send_eta, const double* recv_eta,
-                          double* send_U, const double* recv_U, cudaStream_t st);
-void launch_baro_edge_first(const Geom& G, const Fields& F, double* send_U, cudaStream_t st);
-int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const double* weights_dev, int M, bool periodic_x,
+void launch_baro_eta_edge(const Geom& G, const Fields& F, real dtau, real* send_eta, const real* recv_eta, real* send_U,
+                          const real* recv_U, cudaStream_t st);
+void launch_baro_vel_edge(const Geom& G, const Fields& F, real dtau, real wgt, real* send_eta, const real* recv_eta,
+                          real* send_U, const real* recv_U, cudaStream_t st);
+void launch_baro_edge_first(const Geom& G, const Fields& F, real* send_U, cudaStream_t st);
+int launch_baro_persistent(const Geom& G, const Fields& F, real dtau, const real* weights_dev, int M, bool periodic_x,
                            int ex, cudaStream_t st);
 // persistent ON-CHIP variant: eta, U, V resident in shared memory for all M substeps (returns -2 when the slab does not fit)
 bool baro_onchip_fits(const Geom& G, int ex);
-int launch_baro_onchip(const Geom& G, const Fields& F, double dtau, const double* weights_dev, int M, bool periodic_x, int ex,
+int launch_baro_onchip(const Geom& G, const Fields& F, real dtau, const real* weights_dev, int M, bool periodic_x, int ex,
                        cudaStream_t st);
 size_t pack_baro_count(const Geom& G, int W);
-void launch_pack_baro(const Geom& G, const Fields& F, double* bufW, double* bufE, int W, bool unpack, cudaStream_t st);
+void launch_pack_baro(const Geom& G, const Fields& F, real* bufW, real* bufE, int W, bool unpack, cudaStream_t st);
 
 // kernels_tend.cu
 // Per-tile plan of the momentum kernels: tile_kfast[t] = first level the shared-memory fast kernel may take for

@@ -20,33 +20,33 @@ __global__ void k_baro_init(Geom G, Fields F, bool periodic, int ex) {
     const int j = blockIdx.y;  // 0..Ny
     if (i >= G.Nx + ex) return;
     const int c = idx2b(G, i, j);
-    const double a = F.Ub[c], b = F.Vb[c];
+    const real a = F.Ub[c], b = F.Vb[c];
     F.U[c] = a;
     F.V[c] = b;
     if (periodic) {   // the first eta substep reads U at the east halo column
         if (i < OB_H) { F.U[c + G.Nx] = a; F.V[c + G.Nx] = b; }
         if (i >= G.Nx - OB_H) { F.U[c - G.Nx] = a; F.V[c - G.Nx] = b; }
     }
-    F.etab[c] = 0.0; F.Ub[c] = 0.0; F.Vb[c] = 0.0;
+    F.etab[c] = RL(0.0); F.Ub[c] = RL(0.0); F.Vb[c] = RL(0.0);
 }
 
 // Per-substep slab exchange (x-slabs narrower than the wide halo, and the microbenchmark of BASELINE configs[4]): the one
 // column a neighbour needs travels through contiguous edge buffers -- the producer writes its edge value there as well,
 // the consumer reads the neighbour's from there -- so there are no pack / unpack launches between the NCCL calls.
 struct BaroEdge {
-    double* send_eta;         // my eta(Nx - 1, j)      -> east neighbour's eta(-1, j)
-    const double* recv_eta;   // west neighbour's eta(Nx - 1, j)
-    double* send_U;           // my U(0, j)             -> west neighbour's U(Nx, j)
-    const double* recv_U;     // east neighbour's U(0, j)
+    real* send_eta;         // my eta(Nx - 1, j)      -> east neighbour's eta(-1, j)
+    const real* recv_eta;   // west neighbour's eta(Nx - 1, j)
+    real* send_U;           // my U(0, j)             -> west neighbour's U(Nx, j)
+    const real* recv_U;     // east neighbour's U(0, j)
 };
 
-__device__ __forceinline__ void eta_update(const Geom& G, const Fields& F, int i, int j, double dtau, bool periodic,
+__device__ __forceinline__ void eta_update(const Geom& G, const Fields& F, int i, int j, real dtau, bool periodic,
                                            const BaroEdge* E = nullptr) {
     const int c = idx2b(G, i, j);
-    const double Vn = (j + 1 == G.Ny) ? 0.0 : F.V[c + G.pitch2];
-    const double Vs = (j == 0) ? 0.0 : F.V[c];
-    const double Ue = (E && i == G.Nx - 1) ? E->recv_U[j] : F.U[c + 1];
-    const double e = F.eta[c] - dtau * ((G.dy * Ue - G.dy * F.U[c]) + (G.dxcf[j + 1] * Vn - G.dxcf[j] * Vs)) / G.azcc[j];
+    const real Vn = (j + 1 == G.Ny) ? RL(0.0) : F.V[c + G.pitch2];
+    const real Vs = (j == 0) ? RL(0.0) : F.V[c];
+    const real Ue = (E && i == G.Nx - 1) ? E->recv_U[j] : F.U[c + 1];
+    const real e = F.eta[c] - dtau * ((G.dy * Ue - G.dy * F.U[c]) + (G.dxcf[j + 1] * Vn - G.dxcf[j] * Vs)) / G.azcc[j];
     F.eta[c] = e;
     if (periodic) {
         if (i == G.Nx - 1) F.eta[c - G.Nx] = e;   // west halo column i = -1
@@ -55,15 +55,15 @@ __device__ __forceinline__ void eta_update(const Geom& G, const Fields& F, int i
     if (E && i == G.Nx - 1) E->send_eta[j] = e;
 }
 
-__device__ __forceinline__ void vel_update(const Geom& G, const Fields& F, int i, int j, double dtau, double wgt,
+__device__ __forceinline__ void vel_update(const Geom& G, const Fields& F, int i, int j, real dtau, real wgt,
                                            bool periodic, const BaroEdge* E = nullptr) {
     const int c = idx2b(G, i, j);
-    const double e = F.eta[c];
-    const double ew = (E && i == 0) ? E->recv_eta[j] : F.eta[c - 1];
-    const double detax = (e - ew) / G.dxfc[j];
-    const double detay = (j == 0) ? 0.0 : (e - F.eta[c - G.pitch2]) / G.dy;
-    const double Un = F.U[c] + dtau * (-G.g * F.Hfc[c] * detax + F.GU[c]);
-    const double Vn = F.V[c] + dtau * (-G.g * F.Hcf[c] * detay + F.GV[c]);
+    const real e = F.eta[c];
+    const real ew = (E && i == 0) ? E->recv_eta[j] : F.eta[c - 1];
+    const real detax = (e - ew) / G.dxfc[j];
+    const real detay = (j == 0) ? RL(0.0) : (e - F.eta[c - G.pitch2]) / G.dy;
+    const real Un = F.U[c] + dtau * (-G.g * F.Hfc[c] * detax + F.GU[c]);
+    const real Vn = F.V[c] + dtau * (-G.g * F.Hcf[c] * detay + F.GV[c]);
     F.U[c] = Un; F.V[c] = Vn;
     F.etab[c] += wgt * e;
     F.Ub[c] += wgt * Un;
@@ -75,22 +75,22 @@ __device__ __forceinline__ void vel_update(const Geom& G, const Fields& F, int i
     if (E && i == 0) E->send_U[j] = Un;
 }
 
-__global__ void __launch_bounds__(128) k_baro_eta(Geom G, Fields F, double dtau, bool periodic, int ex) {
+__global__ void __launch_bounds__(128) k_baro_eta(Geom G, Fields F, real dtau, bool periodic, int ex) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x - ex;
     if (i >= G.Nx + ex) return;
     eta_update(G, F, i, blockIdx.y, dtau, periodic);
 }
-__global__ void __launch_bounds__(128) k_baro_vel(Geom G, Fields F, double dtau, double wgt, bool periodic, int ex) {
+__global__ void __launch_bounds__(128) k_baro_vel(Geom G, Fields F, real dtau, real wgt, bool periodic, int ex) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x - ex;
     if (i >= G.Nx + ex) return;
     vel_update(G, F, i, blockIdx.y, dtau, wgt, periodic);
 }
-__global__ void __launch_bounds__(128) k_baro_eta_edge(Geom G, Fields F, double dtau, BaroEdge E) {
+__global__ void __launch_bounds__(128) k_baro_eta_edge(Geom G, Fields F, real dtau, BaroEdge E) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G.Nx) return;
     eta_update(G, F, i, blockIdx.y, dtau, false, &E);
 }
-__global__ void __launch_bounds__(128) k_baro_vel_edge(Geom G, Fields F, double dtau, double wgt, BaroEdge E) {
+__global__ void __launch_bounds__(128) k_baro_vel_edge(Geom G, Fields F, real dtau, real wgt, BaroEdge E) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G.Nx) return;
     vel_update(G, F, i, blockIdx.y, dtau, wgt, false, &E);
@@ -113,29 +113,29 @@ void launch_baro_init(const Geom& G, const Fields& F, bool periodic, int ex, cud
     k_baro_init<<<g, b, 0, st>>>(G, F, periodic, ex);
     OB_COUNT_LAUNCH(1);
 }
-void launch_baro_eta(const Geom& G, const Fields& F, double dtau, bool periodic, int ex, cudaStream_t st) {
+void launch_baro_eta(const Geom& G, const Fields& F, real dtau, bool periodic, int ex, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 2 * ex + 127) / 128, G.Ny);
     k_baro_eta<<<g, b, 0, st>>>(G, F, dtau, periodic, ex);
     OB_COUNT_LAUNCH(1);
 }
-void launch_baro_vel(const Geom& G, const Fields& F, double dtau, double wgt, bool periodic, int ex, cudaStream_t st) {
+void launch_baro_vel(const Geom& G, const Fields& F, real dtau, real wgt, bool periodic, int ex, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 2 * ex + 127) / 128, G.Ny);
     k_baro_vel<<<g, b, 0, st>>>(G, F, dtau, wgt, periodic, ex);
     OB_COUNT_LAUNCH(1);
 }
-void launch_baro_eta_edge(const Geom& G, const Fields& F, double dtau, double* send_eta, const double* recv_eta, double* send_U,
-                          const double* recv_U, cudaStream_t st) {
+void launch_baro_eta_edge(const Geom& G, const Fields& F, real dtau, real* send_eta, const real* recv_eta, real* send_U,
+                          const real* recv_U, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 127) / 128, G.Ny);
     k_baro_eta_edge<<<g, b, 0, st>>>(G, F, dtau, BaroEdge{send_eta, recv_eta, send_U, recv_U});
     OB_COUNT_LAUNCH(1);
 }
-void launch_baro_vel_edge(const Geom& G, const Fields& F, double dtau, double wgt, double* send_eta, const double* recv_eta,
-                          double* send_U, const double* recv_U, cudaStream_t st) {
+void launch_baro_vel_edge(const Geom& G, const Fields& F, real dtau, real wgt, real* send_eta, const real* recv_eta,
+                          real* send_U, const real* recv_U, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 127) / 128, G.Ny);
     k_baro_vel_edge<<<g, b, 0, st>>>(G, F, dtau, wgt, BaroEdge{send_eta, recv_eta, send_U, recv_U});
     OB_COUNT_LAUNCH(1);
 }
-void launch_baro_edge_first(const Geom& G, const Fields& F, double* send_U, cudaStream_t st) {
+void launch_baro_edge_first(const Geom& G, const Fields& F, real* send_U, cudaStream_t st) {
     k_baro_edge_first<<<(G.Ny + 127) / 128, 128, 0, st>>>(G, F, BaroEdge{nullptr, nullptr, send_U, nullptr});
     OB_COUNT_LAUNCH(1);
 }
@@ -146,7 +146,7 @@ void launch_baro_finish(const Geom& G, const Fields& F, cudaStream_t st) {
 }
 
 // ---- persistent variant: all substeps in one cooperative launch --------------------------------------
-__global__ void __launch_bounds__(256) k_baro_persistent(Geom G, Fields F, double dtau, const double* __restrict__ wts,
+__global__ void __launch_bounds__(256) k_baro_persistent(Geom G, Fields F, real dtau, const real* __restrict__ wts,
                                                           int M, bool periodic, int ex) {
     // rows are dealt to warps, columns to lanes: no integer division in the substep loop, coalesced rows
     cg::grid_group grid = cg::this_grid();
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) k_baro_persistent(Geom G, Fields F, doubl
             for (int i = i0 + lane; i < min(i0 + 256, G.Nx + ex); i += 32) eta_update(G, F, i, j, dtau, periodic);
         }
         grid.sync();
-        const double wgt = wts[m];
+        const real wgt = wts[m];
         for (int it = warp; it < nitems; it += nwarps) {
             const int j = it / xchunks, i0 = (it - j * xchunks) * 256 - ex;
             for (int i = i0 + lane; i < min(i0 + 256, G.Nx + ex); i += 32) vel_update(G, F, i, j, dtau, wgt, periodic);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) k_baro_persistent(Geom G, Fields F, doubl
     }
 }
 
-int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const double* wts, int M, bool periodic, int ex,
+int launch_baro_persistent(const Geom& G, const Fields& F, real dtau, const real* wts, int M, bool periodic, int ex,
                            cudaStream_t st) {
     static int nblk = 0;
     if (nblk == 0) {
@@ -188,19 +188,19 @@ int launch_baro_persistent(const Geom& G, const Fields& F, double dtau, const do
 }
 
 // ---- wide-halo exchange buffers: [Ubar | Vbar | eta | GU | GV] x (Ny + 1) rows x W columns --------------------
-__global__ void k_pack_baro(Geom G, Fields F, double* bufW, double* bufE, int W, bool unpack) {
+__global__ void k_pack_baro(Geom G, Fields F, real* bufW, real* bufE, int W, bool unpack) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y, q = blockIdx.z;
     if (h >= W) return;
-    double* fs[5] = {F.Ub, F.Vb, F.eta, F.GU, F.GV};
-    double* f = fs[q];
+    real* fs[5] = {F.Ub, F.Vb, F.eta, F.GU, F.GV};
+    real* f = fs[q];
     const size_t b = ((size_t)q * (G.Ny + 1) + j) * W + h;
     const int c = idx2b(G, 0, j);
     if (!unpack) { bufW[b] = f[c + h]; bufE[b] = f[c + G.Nx - W + h]; }
     else { f[c - W + h] = bufW[b]; f[c + G.Nx + h] = bufE[b]; }
 }
 size_t pack_baro_count(const Geom& G, int W) { return (size_t)5 * (G.Ny + 1) * W; }
-void launch_pack_baro(const Geom& G, const Fields& F, double* bufW, double* bufE, int W, bool unpack, cudaStream_t st) {
+void launch_pack_baro(const Geom& G, const Fields& F, real* bufW, real* bufE, int W, bool unpack, cudaStream_t st) {
     dim3 b(64), g((W + 63) / 64, G.Ny + 1, 5);
     k_pack_baro<<<g, b, 0, st>>>(G, F, bufW, bufE, W, unpack);
     OB_COUNT_LAUNCH(1);
@@ -218,7 +218,7 @@ void launch_pack_baro(const Geom& G, const Fields& F, double* bufW, double* bufE
 // the single-GPU grid (1.94 M columns x 24 B = 47 MB > 148 x 227 KB).  Same operations per column as k_baro_eta / _vel.
 // ==========================================================================================================
 __device__ __forceinline__ unsigned bsm_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bulk_row_load(double* dst, const double* src, unsigned bytes, unsigned long long* bar) {
+__device__ __forceinline__ void bulk_row_load(real* dst, const real* src, unsigned bytes, unsigned long long* bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bsm_u32(bar)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(bsm_u32(dst)), "l"(src), "r"(bytes), "r"(bsm_u32(bar)) : "memory");
@@ -236,18 +236,18 @@ __device__ __forceinline__ void bar_wait(unsigned long long* bar, unsigned parit
 }
 
 template <int MAXC>
-__global__ void __launch_bounds__(1024, 1) k_baro_onchip(Geom G, Fields F, double dtau, const double* __restrict__ wts, int M,
+__global__ void __launch_bounds__(1024, 1) k_baro_onchip(Geom G, Fields F, real dtau, const real* __restrict__ wts, int M,
                                                          bool periodic, int ex, int R, int Wp, int a0) {
     // Wp = padded row length in shared memory (even, covers array columns [a0, a0 + Wp) of a barotropic row: the slab's
     // columns [-ex - 1, Nx + ex] plus alignment padding, a0 even so that bulk copies are 16-byte aligned)
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ __align__(128) double bsm[];
+    extern __shared__ __align__(128) real bsm[];
     __shared__ unsigned long long bar[2];
     const int tid = threadIdx.x, NT = blockDim.x;
     const int j0 = blockIdx.x * R, j1 = min(j0 + R, G.Ny), nr = max(j1 - j0, 0);
-    double* sE = bsm;                       // (R + 1) rows: row 0 = eta(j0 - 1), row 1 + r = eta(j0 + r)
-    double* sU = sE + (size_t)(R + 1) * Wp;  // R rows
-    double* sV = sU + (size_t)R * Wp;        // (R + 1) rows: row r = V(j0 + r), row R(=nr) = V(j1) halo
+    real* sE = bsm;                       // (R + 1) rows: row 0 = eta(j0 - 1), row 1 + r = eta(j0 + r)
+    real* sU = sE + (size_t)(R + 1) * Wp;  // R rows
+    real* sV = sU + (size_t)R * Wp;        // (R + 1) rows: row r = V(j0 + r), row R(=nr) = V(j1) halo
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bsm_u32(&bar[0])) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bsm_u32(&bar[1])) : "memory");
@@ -260,21 +260,21 @@ __global__ void __launch_bounds__(1024, 1) k_baro_onchip(Geom G, Fields F, doubl
     for (int r = -1; r <= nr; r++) {
         const int j = j0 + r;
         if (j < 0 || j > G.Ny) continue;
-        const double* ge = F.eta + (size_t)(j + OB_H) * G.pitch2 + a0;
-        const double* gu = F.U + (size_t)(j + OB_H) * G.pitch2 + a0;
-        const double* gv = F.V + (size_t)(j + OB_H) * G.pitch2 + a0;
+        const real* ge = F.eta + (size_t)(j + OB_H) * G.pitch2 + a0;
+        const real* gu = F.U + (size_t)(j + OB_H) * G.pitch2 + a0;
+        const real* gv = F.V + (size_t)(j + OB_H) * G.pitch2 + a0;
         for (int x = tid; x < Wp; x += NT) {
             if (r < nr) sE[(size_t)(r + 1) * Wp + x] = ge[x];
             if (r >= 0 && r < nr) sU[(size_t)r * Wp + x] = gu[x];
             if (r >= 0) sV[(size_t)r * Wp + x] = gv[x];
         }
     }
-    double aE[MAXC], aU[MAXC], aV[MAXC];
+    real aE[MAXC], aU[MAXC], aV[MAXC];
 #pragma unroll
-    for (int c = 0; c < MAXC; c++) { aE[c] = 0.0; aU[c] = 0.0; aV[c] = 0.0; }
+    for (int c = 0; c < MAXC; c++) { aE[c] = RL(0.0); aU[c] = RL(0.0); aV[c] = RL(0.0); }
     __syncthreads();
     unsigned ph0 = 0, ph1 = 0;
-    const unsigned row_bytes = (unsigned)Wp * sizeof(double);
+    const unsigned row_bytes = (unsigned)Wp * sizeof(real);
     for (int m = 0; m < M; m++) {
         // ---- eta half step: eta -= dtau * div(U, V) / Az
 #pragma unroll
@@ -283,11 +283,11 @@ __global__ void __launch_bounds__(1024, 1) k_baro_onchip(Geom G, Fields F, doubl
             if (wi < nwork) {
                 const int r = wi / ncol, i = wi - r * ncol - ex, j = j0 + r;
                 const int x = xo + i;
-                const double Vn = (j + 1 == G.Ny) ? 0.0 : sV[(size_t)(r + 1) * Wp + x];
-                const double Vs = (j == 0) ? 0.0 : sV[(size_t)r * Wp + x];
-                const double* u = sU + (size_t)r * Wp + x;
-                double* e = sE + (size_t)(r + 1) * Wp + x;
-                const double en = e[0] - dtau * ((G.dy * u[1] - G.dy * u[0]) + (G.dxcf[j + 1] * Vn - G.dxcf[j] * Vs)) / G.azcc[j];
+                const real Vn = (j + 1 == G.Ny) ? RL(0.0) : sV[(size_t)(r + 1) * Wp + x];
+                const real Vs = (j == 0) ? RL(0.0) : sV[(size_t)r * Wp + x];
+                const real* u = sU + (size_t)r * Wp + x;
+                real* e = sE + (size_t)(r + 1) * Wp + x;
+                const real en = e[0] - dtau * ((G.dy * u[1] - G.dy * u[0]) + (G.dxcf[j + 1] * Vn - G.dxcf[j] * Vs)) / G.azcc[j];
                 e[0] = en;
                 if (periodic) {
                     if (i == G.Nx - 1) e[-G.Nx] = en;   // west halo column i = -1
@@ -298,8 +298,8 @@ __global__ void __launch_bounds__(1024, 1) k_baro_onchip(Geom G, Fields F, doubl
         __syncthreads();
         // publish my LAST row of eta for the block above, barrier, stage the row below my first
         if (nr > 0 && j1 < G.Ny) {
-            double* ge = F.eta + (size_t)(j1 - 1 + OB_H) * G.pitch2 + a0;
-            const double* se = sE + (size_t)nr * Wp;
+            real* ge = F.eta + (size_t)(j1 - 1 + OB_H) * G.pitch2 + a0;
+            const real* se = sE + (size_t)nr * Wp;
             for (int x = tid; x < Wp; x += NT) ge[x] = se[x];
         }
         grid.sync();
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(1024, 1) k_baro_onchip(Geom G, Fields F, doubl
             bar_wait(&bar[0], ph0); ph0 ^= 1;
         }
         // ---- velocity half step + averaging
-        const double wgt = wts[m];
+        const real wgt = wts[m];
 #pragma unroll
         for (int c = 0; c < MAXC; c++) {
             const int wi = tid + c * NT;
@@ -319,14 +319,14 @@ __global__ void __launch_bounds__(1024, 1) k_baro_onchip(Geom G, Fields F, doubl
                 const int r = wi / ncol, i = wi - r * ncol - ex, j = j0 + r;
                 const int x = xo + i;
                 const int cg2 = idx2b(G, i, j);
-                const double* e = sE + (size_t)(r + 1) * Wp + x;
-                const double en = e[0];
-                const double detax = (en - e[-1]) / G.dxfc[j];
-                const double detay = (j == 0) ? 0.0 : (en - e[-Wp]) / G.dy;
-                double* u = sU + (size_t)r * Wp + x;
-                double* v = sV + (size_t)r * Wp + x;
-                const double Un = u[0] + dtau * (-G.g * F.Hfc[cg2] * detax + F.GU[cg2]);
-                const double Vn = v[0] + dtau * (-G.g * F.Hcf[cg2] * detay + F.GV[cg2]);
+                const real* e = sE + (size_t)(r + 1) * Wp + x;
+                const real en = e[0];
+                const real detax = (en - e[-1]) / G.dxfc[j];
+                const real detay = (j == 0) ? RL(0.0) : (en - e[-Wp]) / G.dy;
+                real* u = sU + (size_t)r * Wp + x;
+                real* v = sV + (size_t)r * Wp + x;
+                const real Un = u[0] + dtau * (-G.g * F.Hfc[cg2] * detax + F.GU[cg2]);
+                const real Vn = v[0] + dtau * (-G.g * F.Hcf[cg2] * detay + F.GV[cg2]);
                 u[0] = Un; v[0] = Vn;
                 aE[c] += wgt * en; aU[c] += wgt * Un; aV[c] += wgt * Vn;
                 if (periodic) {
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(1024, 1) k_baro_onchip(Geom G, Fields F, doubl
         if (m + 1 < M) {
             // publish my FIRST row of V for the block below, barrier, stage the row above my last
             if (nr > 0 && j0 > 0) {
-                double* gv = F.V + (size_t)(j0 + OB_H) * G.pitch2 + a0;
+                real* gv = F.V + (size_t)(j0 + OB_H) * G.pitch2 + a0;
                 for (int x = tid; x < Wp; x += NT) gv[x] = sV[x];
             }
             grid.sync();
@@ -379,7 +379,7 @@ static bool onchip_plan(const Geom& G, int ex, int* R, int* Wp, int* a0, int* nb
     const int hi = G.X0b + G.Nx + ex + 1;           // one past the last (i = Nx + ex)
     *Wp = ((hi - *a0) + 1) & ~1;
     if (*a0 < 0 || *a0 + *Wp > G.pitch2) return false;
-    *smem = (size_t)(3 * *R + 2) * *Wp * sizeof(double);
+    *smem = (size_t)(3 * *R + 2) * *Wp * sizeof(real);
     const int per_thread = ((*R) * (G.Nx + 2 * ex) + 1023) / 1024;
     *maxc = per_thread <= 3 ? 3 : per_thread <= 6 ? 6 : per_thread <= 10 ? 10 : 0;
     return *smem <= 220 * 1024 && *maxc > 0;
@@ -388,7 +388,7 @@ bool baro_onchip_fits(const Geom& G, int ex) {
     int R, Wp, a0, nblk, maxc; size_t smem;
     return onchip_plan(G, ex, &R, &Wp, &a0, &nblk, &maxc, &smem);
 }
-int launch_baro_onchip(const Geom& G, const Fields& F, double dtau, const double* wts, int M, bool periodic, int ex, cudaStream_t st) {
+int launch_baro_onchip(const Geom& G, const Fields& F, real dtau, const real* wts, int M, bool periodic, int ex, cudaStream_t st) {
     int R, Wp, a0, nblk, maxc; size_t smem;
     if (!onchip_plan(G, ex, &R, &Wp, &a0, &nblk, &maxc, &smem)) return -2;
     void* kern = maxc == 3 ? (void*)k_baro_onchip<3> : maxc == 6 ? (void*)k_baro_onchip<6> : (void*)k_baro_onchip<10>;

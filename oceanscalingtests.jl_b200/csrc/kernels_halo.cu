@@ -7,12 +7,12 @@ __global__ void k_fill_x(Geom G, Fields F) {
     const int j = blockIdx.x * blockDim.y + threadIdx.y;   // 0..Ny (interior rows, plus the v wall row)
     const int k = blockIdx.y;
     if (h >= OB_H || j > G.Ny) return;
-    double* fs[4] = {F.u, F.v, F.T, F.S};
+    real* fs[4] = {F.u, F.v, F.T, F.S};
     const long long c = idx3(G, 0, j, k);
     if (k < G.Nz) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            double* f = fs[q];
+            real* f = fs[q];
             f[c - 1 - h] = f[c + G.Nx - 1 - h];
             f[c + G.Nx + h] = f[c + h];
         }
@@ -30,19 +30,19 @@ __global__ void k_fill_y(Geom G, Fields F) {
     const int k = blockIdx.y;
     if (i >= G.Nx + OB_H) return;
     if (k < G.Nz) {
-        double* fs[3] = {F.u, F.T, F.S};
+        real* fs[3] = {F.u, F.T, F.S};
         const long long s0 = idx3(G, i, 0, k), s1 = idx3(G, i, G.Ny - 1, k);
 #pragma unroll
         for (int q = 0; q < 3; q++) {
-            double* f = fs[q];
-            const double a = f[s0], b = f[s1];
+            real* f = fs[q];
+            const real a = f[s0], b = f[s1];
             for (int h = 1; h <= OB_H; h++) { f[s0 - (long long)h * G.pitch] = a; f[s1 + (long long)h * G.pitch] = b; }
         }
         const long long v0 = idx3(G, i, 0, k), v1 = idx3(G, i, G.Ny, k);
-        for (int h = 0; h <= OB_H; h++) { F.v[v0 - (long long)h * G.pitch] = 0.0; F.v[v1 + (long long)h * G.pitch] = 0.0; }
+        for (int h = 0; h <= OB_H; h++) { F.v[v0 - (long long)h * G.pitch] = RL(0.0); F.v[v1 + (long long)h * G.pitch] = RL(0.0); }
     } else {
         const int s0 = idx2b(G, i, 0), s1 = idx2b(G, i, G.Ny - 1);
-        const double a = F.eta[s0], b = F.eta[s1];
+        const real a = F.eta[s0], b = F.eta[s1];
         for (int h = 1; h <= OB_H; h++) { F.eta[s0 - h * G.pitch2] = a; F.eta[s1 + h * G.pitch2] = b; }
     }
 }
@@ -66,11 +66,11 @@ __global__ void k_mask(Geom G, Fields F) {
     if (i >= G.Nx) return;
     const long long c = idx3(G, i, j, k);
     if (j < G.Ny) {
-        if (peripheral_fcc(G, i, j, k)) F.u[c] = 0.0;
-        if (!active(G, i, j, k)) { F.T[c] = 0.0; F.S[c] = 0.0; }
-        if (k == G.Nz - 1 && !active(G, i, j, k)) F.eta[idx2b(G, i, j)] = 0.0;
+        if (peripheral_fcc(G, i, j, k)) F.u[c] = RL(0.0);
+        if (!active(G, i, j, k)) { F.T[c] = RL(0.0); F.S[c] = RL(0.0); }
+        if (k == G.Nz - 1 && !active(G, i, j, k)) F.eta[idx2b(G, i, j)] = RL(0.0);
     }
-    if (peripheral_cfc(G, i, j, k)) F.v[c] = 0.0;
+    if (peripheral_cfc(G, i, j, k)) F.v[c] = RL(0.0);
 }
 void launch_mask_fields(const Geom& G, const Fields& F, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 127) / 128, G.Ny + 1, G.Nz);
@@ -79,7 +79,7 @@ void launch_mask_fields(const Geom& G, const Fields& F, cudaStream_t st) {
 }
 
 // interior <-> user buffer laid out like an Oceananigans parent array with halos (hx, hy, hz)
-__global__ void k_copy_field(Geom G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, int layout,
+__global__ void k_copy_field(Geom G, real* field, real* buf, int ny, int nz, int hx, int hy, int hz, int layout,
                              bool to_field, int ex) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x - ex;   // ex x-halo columns travel too (option transfer_x_halo)
     const int j = blockIdx.y, k = blockIdx.z;
@@ -89,7 +89,7 @@ __global__ void k_copy_field(Geom G, double* field, double* buf, int ny, int nz,
     const long long c = layout == 0 ? idx3(G, i, j, k) : layout == 1 ? (long long)idx2(G, i, j) : (long long)idx2b(G, i, j);
     if (to_field) field[c] = buf[b]; else buf[b] = field[c];
 }
-void launch_copy_field(const Geom& G, double* field, double* buf, int ny, int nz, int hx, int hy, int hz, int layout,
+void launch_copy_field(const Geom& G, real* field, real* buf, int ny, int nz, int hx, int hy, int hz, int layout,
                        bool to_field, int ex, cudaStream_t st) {
     dim3 b(128), g((G.Nx + 2 * ex + 127) / 128, ny, nz);
     k_copy_field<<<g, b, 0, st>>>(G, field, buf, ny, nz, hx, hy, hz, layout, to_field, ex);
@@ -103,7 +103,7 @@ size_t pack_x_count(const Geom& G, int group) {
     return (size_t)OB_H * (G.Ny + 1) * (2 * (size_t)G.Nz + (group == OB_XG_UVETA ? 1 : 0));
 }
 
-__global__ void k_pack_x(Geom G, Fields F, double* sendW, double* sendE, bool unpack, int group) {
+__global__ void k_pack_x(Geom G, Fields F, real* sendW, real* sendE, bool unpack, int group) {
     const int h = threadIdx.x;
     const int j = blockIdx.x * blockDim.y + threadIdx.y;
     const int k = blockIdx.y;   // 0..Nz (Nz = eta, group u, v, eta only)
@@ -111,7 +111,7 @@ __global__ void k_pack_x(Geom G, Fields F, double* sendW, double* sendE, bool un
     const size_t per = (size_t)OB_H * (G.Ny + 1);
     const size_t o = (size_t)j * OB_H + h;
     if (k < G.Nz) {
-        double* fs[2] = {group == OB_XG_UVETA ? F.u : F.T, group == OB_XG_UVETA ? F.v : F.S};
+        real* fs[2] = {group == OB_XG_UVETA ? F.u : F.T, group == OB_XG_UVETA ? F.v : F.S};
         const long long c = idx3(G, 0, j, k);
 #pragma unroll
         for (int q = 0; q < 2; q++) {
@@ -126,36 +126,36 @@ __global__ void k_pack_x(Geom G, Fields F, double* sendW, double* sendE, bool un
         else { F.eta[c - OB_H + h] = sendW[b]; F.eta[c + G.Nx + h] = sendE[b]; }
     }
 }
-void launch_pack_x(const Geom& G, const Fields& F, double* sendW, double* sendE, int group, cudaStream_t st) {
+void launch_pack_x(const Geom& G, const Fields& F, real* sendW, real* sendE, int group, cudaStream_t st) {
     dim3 b(8, 16), g((G.Ny + 1 + 15) / 16, G.Nz + (group == OB_XG_UVETA ? 1 : 0));
     k_pack_x<<<g, b, 0, st>>>(G, F, sendW, sendE, false, group);
     OB_COUNT_LAUNCH(1);
 }
 // recvW = data for the west halo (from the west neighbour's east edge), recvE likewise
-void launch_unpack_x(const Geom& G, const Fields& F, const double* recvW, const double* recvE, int group, cudaStream_t st) {
+void launch_unpack_x(const Geom& G, const Fields& F, const real* recvW, const real* recvE, int group, cudaStream_t st) {
     dim3 b(8, 16), g((G.Ny + 1 + 15) / 16, G.Nz + (group == OB_XG_UVETA ? 1 : 0));
-    k_pack_x<<<g, b, 0, st>>>(G, F, const_cast<double*>(recvW), const_cast<double*>(recvE), true, group);
+    k_pack_x<<<g, b, 0, st>>>(G, F, const_cast<real*>(recvW), const_cast<real*>(recvE), true, group);
     OB_COUNT_LAUNCH(1);
 }
 
 // ---- diagnostics: max |u|,|v|,|w|,|eta|,|T|,|S| and the advective CFL time scale (TimeStepWizard) ----------
-__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {   // v >= 0 or the canonical (positive) NaN,
-    atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));   // whose bit pattern tops every finite one
+__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {   // v >= 0 or the canonical (positive) NaN, /*f64*/
+    atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));   // whose bit pattern tops every finite one /*f64*/
 }
 // max that PROPAGATES NaN like Julia's `maximum(abs, u)` (fmax drops it): after a blow-up the progress line and the wizard
 // must see NaN, not the maximum over the cells that are still finite
-__device__ __forceinline__ double max_nan(double a, double b) { return (a != a || b != b) ? nan("") : fmax(a, b); }
-__global__ void __launch_bounds__(256) k_diag(Geom G, Fields F, double* out) {
+__device__ __forceinline__ real max_nan(real a, real b) { return (a != a || b != b) ? nan("") : fmax(a, b); }
+__global__ void __launch_bounds__(256) k_diag(Geom G, Fields F, double* out) { /*f64*/
     // one block per (row j, level-chunk): threads stride over i and 8 levels, then one atomic per block and quantity
-    __shared__ double red[7][8];
+    __shared__ real red[7][8];
     const int j = blockIdx.y, k0 = blockIdx.z * 8;
-    double m[7] = {0, 0, 0, 0, 0, 0, 0};
+    real m[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int k = k0; k < min(k0 + 8, G.Nz); k++)
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < G.Nx; i += gridDim.x * blockDim.x) {
             const long long c = idx3(G, i, j, k);
-            const double au = fabs(F.u[c]), av = fabs(F.v[c]), aw = fabs(F.w[c]);
+            const real au = fabs(F.u[c]), av = fabs(F.v[c]), aw = fabs(F.w[c]);
             m[0] = max_nan(m[0], au); m[1] = max_nan(m[1], av);
-            m[2] = max_nan(m[2], max_nan(aw, k == G.Nz - 1 ? fabs(F.w[c + G.sz]) : 0.0));
+            m[2] = max_nan(m[2], max_nan(aw, k == G.Nz - 1 ? fabs(F.w[c + G.sz]) : RL(0.0)));
             if (k == 0) m[3] = max_nan(m[3], fabs(F.eta[idx2b(G, i, j)]));
             m[4] = max_nan(m[4], fabs(F.T[c])); m[5] = max_nan(m[5], fabs(F.S[c]));
             // 1 / cell advection time scale: |u|/dx + |v|/dy + |w|/dz
@@ -163,19 +163,19 @@ __global__ void __launch_bounds__(256) k_diag(Geom G, Fields F, double* out) {
         }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int q = 0; q < 7; q++) {
-        double v = m[q];
+        real v = m[q];
         for (int o = 16; o > 0; o >>= 1) v = max_nan(v, __shfl_xor_sync(0xffffffffu, v, o));
         if (lane == 0) red[q][warp] = v;
     }
     __syncthreads();
     if (threadIdx.x < 7) {
-        double v = 0.0;
+        real v = RL(0.0);
         for (int w = 0; w < 8; w++) v = max_nan(v, red[threadIdx.x][w]);
-        if (v > 0.0 || v != v) atomic_max_pos(out + threadIdx.x, v);
+        if (v > RL(0.0) || v != v) atomic_max_pos(out + threadIdx.x, v);
     }
 }
-void launch_diagnostics(const Geom& G, const Fields& F, double* out8, cudaStream_t st) {
-    cudaMemsetAsync(out8, 0, 8 * sizeof(double), st);
+void launch_diagnostics(const Geom& G, const Fields& F, double* out8, cudaStream_t st) { /*f64*/
+    cudaMemsetAsync(out8, 0, 8 * sizeof(double), st); /*f64*/
     dim3 b(256), g(2, G.Ny, (G.Nz + 7) / 8);
     k_diag<<<g, b, 0, st>>>(G, F, out8);
     OB_COUNT_LAUNCH(1);

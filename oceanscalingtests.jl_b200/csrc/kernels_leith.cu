@@ -7,36 +7,36 @@
 
 #define LEITH_E 2   // columns/rows beyond the interior needed by the stress divergence
 
-__device__ __forceinline__ double jmin(double a, double b) { return (isnan(a) || isnan(b)) ? nan("") : fmin(a, b); }
-__device__ __forceinline__ double jmax(double a, double b) { return (isnan(a) || isnan(b)) ? nan("") : fmax(a, b); }
-__device__ __forceinline__ double f_ccc(const Geom& G, int j) { return 0.25 * (G.fff[j] + G.fff[j] + G.fff[j + 1] + G.fff[j + 1]); }
-__device__ __forceinline__ double b_at(const Geom& G, const Fields& F, int i, int j, int k) {
+__device__ __forceinline__ real jmin(real a, real b) { return (isnan(a) || isnan(b)) ? nan("") : fmin(a, b); }
+__device__ __forceinline__ real jmax(real a, real b) { return (isnan(a) || isnan(b)) ? nan("") : fmax(a, b); }
+__device__ __forceinline__ real f_ccc(const Geom& G, int j) { return RL(0.25) * (G.fff[j] + G.fff[j] + G.fff[j + 1] + G.fff[j + 1]); }
+__device__ __forceinline__ real b_at(const Geom& G, const Fields& F, int i, int j, int k) {
     const long long c = idx3(G, i, j, k);
     return buoyancy_of(G, F.T[c], F.S[c], k);
 }
-__device__ __forceinline__ double dzb(const Geom& G, const Fields& F, int i, int j, int k) {   // N^2, see n2_face
-    if (!active(G, i, j, k - 1) || !active(G, i, j, k)) return 0.0;
+__device__ __forceinline__ real dzb(const Geom& G, const Fields& F, int i, int j, int k) {   // N^2, see n2_face
+    if (!active(G, i, j, k - 1) || !active(G, i, j, k)) return RL(0.0);
     const long long c = idx3(G, i, j, k);
     return n2_face(G, F.T[c - G.sz], F.S[c - G.sz], F.T[c], F.S[c], k);
 }
-__device__ __forceinline__ double dxb(const Geom& G, const Fields& F, int i, int j, int k) {
-    if (!active(G, i - 1, j, k) || !active(G, i, j, k)) return 0.0;
+__device__ __forceinline__ real dxb(const Geom& G, const Fields& F, int i, int j, int k) {
+    if (!active(G, i - 1, j, k) || !active(G, i, j, k)) return RL(0.0);
     return (b_at(G, F, i, j, k) - b_at(G, F, i - 1, j, k)) / G.dxfc[j];
 }
-__device__ __forceinline__ double dyb(const Geom& G, const Fields& F, int i, int j, int k) {
-    if (!active(G, i, j - 1, k) || !active(G, i, j, k)) return 0.0;
+__device__ __forceinline__ real dyb(const Geom& G, const Fields& F, int i, int j, int k) {
+    if (!active(G, i, j - 1, k) || !active(G, i, j, k)) return RL(0.0);
     return (b_at(G, F, i, j, k) - b_at(G, F, i, j - 1, k)) / G.dy;
 }
-__device__ __forceinline__ double divxy(const Geom& G, const Fields& F, int i, int j, int k) {
+__device__ __forceinline__ real divxy(const Geom& G, const Fields& F, int i, int j, int k) {
     const long long c = idx3(G, i, j, k);
     return (G.dy * F.u[c + 1] - G.dy * F.u[c] + G.dxcf[j + 1] * F.v[c + G.pitch] - G.dxcf[j] * F.v[c]) * G.razcc[j];
 }
-__device__ __forceinline__ double zeta_c(const Geom& G, const Fields& F, int i, int j, int k) {
+__device__ __forceinline__ real zeta_c(const Geom& G, const Fields& F, int i, int j, int k) {
     const long long c = idx3(G, i, j, k);
-    double dxv = G.dy * F.v[c] - G.dy * F.v[c - 1];
-    double dyu = G.dxfc[j] * F.u[c] - G.dxfc[j - 1] * F.u[c - G.pitch];
-    if (inactive_cfc(G, i - 1, j, k) || inactive_cfc(G, i, j, k)) dxv = 0.0;
-    if (inactive_fcc(G, i, j - 1, k) || inactive_fcc(G, i, j, k)) dyu = 0.0;
+    real dxv = G.dy * F.v[c] - G.dy * F.v[c - 1];
+    real dyu = G.dxfc[j] * F.u[c] - G.dxfc[j - 1] * F.u[c - G.pitch];
+    if (inactive_cfc(G, i - 1, j, k) || inactive_cfc(G, i, j, k)) dxv = RL(0.0);
+    if (inactive_fcc(G, i, j - 1, k) || inactive_fcc(G, i, j, k)) dyu = RL(0.0);
     return (dxv - dyu) * G.razcf[j];
 }
 
@@ -44,18 +44,18 @@ __global__ void k_leith_ld(Geom G, Fields F) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x - LEITH_E;
     const int j = (int)blockIdx.y - LEITH_E;
     if (i >= G.Nx + LEITH_E) return;
-    double s = 0.0;
-    const double fc = fabs(f_ccc(G, j));
-    for (int k = 0; k < G.Nz; k++) s += G.dzf[k] * (sqrt(jmax(0.0, dzb(G, F, i, j, k))) / M_PI / fc);
+    real s = RL(0.0);
+    const real fc = fabs(f_ccc(G, j));
+    for (int k = 0; k < G.Nz; k++) s += G.dzf[k] * (sqrt(jmax(RL(0.0), dzb(G, F, i, j, k))) / M_PI / fc);
     F.Ld[idx2(G, i, j)] = s;
 }
 __global__ void k_leith_q(Geom G, Fields F) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x - LEITH_E;
     const int j = (int)blockIdx.y - LEITH_E, k = blockIdx.z;   // k = 0..Nz
     if (i >= G.Nx + LEITH_E) return;
-    const double coef = f_ccc(G, j) / jmax(G.leith_minN2, dzb(G, F, i, j, k));
-    const double bx = 0.25 * (dxb(G, F, i, j, k - 1) + dxb(G, F, i + 1, j, k - 1) + dxb(G, F, i, j, k) + dxb(G, F, i + 1, j, k));
-    const double by = 0.25 * (dyb(G, F, i, j, k - 1) + dyb(G, F, i, j + 1, k - 1) + dyb(G, F, i, j, k) + dyb(G, F, i, j + 1, k));
+    const real coef = f_ccc(G, j) / jmax(G.leith_minN2, dzb(G, F, i, j, k));
+    const real bx = RL(0.25) * (dxb(G, F, i, j, k - 1) + dxb(G, F, i + 1, j, k - 1) + dxb(G, F, i, j, k) + dxb(G, F, i + 1, j, k));
+    const real by = RL(0.25) * (dyb(G, F, i, j, k - 1) + dyb(G, F, i, j + 1, k - 1) + dyb(G, F, i, j, k) + dyb(G, F, i, j + 1, k));
     const long long c = idx3(G, i, j, k);
     F.qx[c] = coef * bx;
     F.qy[c] = coef * by;
@@ -67,35 +67,35 @@ __global__ void k_leith_nu(Geom G, Fields F) {
     const long long c = idx3(G, i, j, k);
     auto dxz = [&](int a, int b) { return (zeta_c(G, F, a + 1, b, k) - zeta_c(G, F, a, b, k)) / G.dxcf[b]; };
     auto dyz = [&](int a, int b) { return (zeta_c(G, F, a, b + 1, k) - zeta_c(G, F, a, b, k)) / G.dy; };
-    double dzx = 0.5 * (dxz(i, j) + dxz(i, j + 1));
-    double dzy = 0.5 * (dyz(i, j) + dyz(i + 1, j));
-    const double dfy = 0.5 * ((G.fff[j + 1] - G.fff[j]) / G.dy + (G.fff[j + 1] - G.fff[j]) / G.dy);
-    dzx += 0.0; dzy += dfy;
+    real dzx = RL(0.5) * (dxz(i, j) + dxz(i, j + 1));
+    real dzy = RL(0.5) * (dyz(i, j) + dyz(i + 1, j));
+    const real dfy = RL(0.5) * ((G.fff[j + 1] - G.fff[j]) / G.dy + (G.fff[j + 1] - G.fff[j]) / G.dy);
+    dzx += RL(0.0); dzy += dfy;
     const bool act = active(G, i, j, k);
-    const double dqx = act ? (F.qx[c + G.sz] - F.qx[c]) / G.dzc[k] : 0.0;
-    const double dqy = act ? (F.qy[c + G.sz] - F.qy[c]) / G.dzc[k] : 0.0;
+    const real dqx = act ? (F.qx[c + G.sz] - F.qx[c]) / G.dzc[k] : RL(0.0);
+    const real dqy = act ? (F.qy[c + G.sz] - F.qy[c]) / G.dzc[k] : RL(0.0);
     auto ddx = [&](int a, int b) {
-        if (!active(G, a - 1, b, k) || !active(G, a, b, k)) return 0.0;
+        if (!active(G, a - 1, b, k) || !active(G, a, b, k)) return RL(0.0);
         return (divxy(G, F, a, b, k) - divxy(G, F, a - 1, b, k)) / G.dxfc[b];
     };
     auto ddy = [&](int a, int b) {
-        if (!active(G, a, b - 1, k) || !active(G, a, b, k)) return 0.0;
+        if (!active(G, a, b - 1, k) || !active(G, a, b, k)) return RL(0.0);
         return (divxy(G, F, a, b, k) - divxy(G, F, a, b - 1, k)) / G.dy;
     };
-    const double ddx_ = 0.5 * (ddx(i, j) + ddx(i + 1, j)), ddy_ = 0.5 * (ddy(i, j) + ddy(i, j + 1));
-    const double dd2 = ddx_ * ddx_ + ddy_ * ddy_;
-    const double fc = f_ccc(G, j);
-    const double dz2 = dzx * dzx + dzy * dzy;
-    const double dq2 = (dqx + dzx) * (dqx + dzx) + (dqy + dzy) * (dqy + dzy);
-    const double A = 2.0 * (1.0 / (1.0 / (G.dxfc[j] * G.dxfc[j]) + 1.0 / (G.dy * G.dy)));
-    const double Ds = pow(A, 0.5);
-    const double ld = F.Ld[idx2(G, i, j)];
-    const double Bu = ld * ld / A;
-    const double Ro = G.leith_Vscale / (fc * Ds);
-    const double t1 = 1.0 + 1.0 / Bu, t2 = 1.0 + 1.0 / (Ro * Ro);
-    double dQ2 = jmin(dq2, dz2 * (t1 * t1));
+    const real ddx_ = RL(0.5) * (ddx(i, j) + ddx(i + 1, j)), ddy_ = RL(0.5) * (ddy(i, j) + ddy(i, j + 1));
+    const real dd2 = ddx_ * ddx_ + ddy_ * ddy_;
+    const real fc = f_ccc(G, j);
+    const real dz2 = dzx * dzx + dzy * dzy;
+    const real dq2 = (dqx + dzx) * (dqx + dzx) + (dqy + dzy) * (dqy + dzy);
+    const real A = RL(2.0) * (RL(1.0) / (RL(1.0) / (G.dxfc[j] * G.dxfc[j]) + RL(1.0) / (G.dy * G.dy)));
+    const real Ds = pow(A, RL(0.5));
+    const real ld = F.Ld[idx2(G, i, j)];
+    const real Bu = ld * ld / A;
+    const real Ro = G.leith_Vscale / (fc * Ds);
+    const real t1 = RL(1.0) + RL(1.0) / Bu, t2 = RL(1.0) + RL(1.0) / (Ro * Ro);
+    real dQ2 = jmin(dq2, dz2 * (t1 * t1));
     dQ2 = jmin(dQ2, dz2 * (t2 * t2));
-    F.nuL[c] = pow(G.leith_C * Ds / M_PI, 3.0) * sqrt(dQ2 + dd2);
+    F.nuL[c] = pow(G.leith_C * Ds / M_PI, RL(3.0)) * sqrt(dQ2 + dd2);
 }
 
 void launch_leith(const Geom& G, const Fields& F, cudaStream_t st) {

@@ -46,39 +46,39 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* tm, 
 // in which zeta, the tangential-velocity stencils, the divergence pieces and K were computed once (MomS).
 struct MomG {
     const Geom& G;
-    const double* __restrict__ u;
-    const double* __restrict__ v;
-    __device__ __forceinline__ double U(int i, int j, int k) const { return u[idx3(G, i, j, k)]; }
-    __device__ __forceinline__ double V(int i, int j, int k) const { return v[idx3(G, i, j, k)]; }
-    __device__ __forceinline__ double usm(int i, int j, int k) const { return 0.5 * (U(i, j - 1, k) + U(i, j, k)); }
-    __device__ __forceinline__ double vsm(int i, int j, int k) const { return 0.5 * (V(i - 1, j, k) + V(i, j, k)); }
+    const real* __restrict__ u;
+    const real* __restrict__ v;
+    __device__ __forceinline__ real U(int i, int j, int k) const { return u[idx3(G, i, j, k)]; }
+    __device__ __forceinline__ real V(int i, int j, int k) const { return v[idx3(G, i, j, k)]; }
+    __device__ __forceinline__ real usm(int i, int j, int k) const { return RL(0.5) * (U(i, j - 1, k) + U(i, j, k)); }
+    __device__ __forceinline__ real vsm(int i, int j, int k) const { return RL(0.5) * (V(i - 1, j, k) + V(i, j, k)); }
     // vertical vorticity at (f,f,c); GEN applies the immersed conditional differences
     template <bool GEN>
-    __device__ __forceinline__ double zeta(int i, int j, int k) const {
+    __device__ __forceinline__ real zeta(int i, int j, int k) const {
         const long long c = idx3(G, i, j, k);
-        double dxv = G.dy * v[c] - G.dy * v[c - 1];
-        double dyu = G.dxfc[j] * u[c] - G.dxfc[j - 1] * u[c - G.pitch];
+        real dxv = G.dy * v[c] - G.dy * v[c - 1];
+        real dyu = G.dxfc[j] * u[c] - G.dxfc[j - 1] * u[c - G.pitch];
         if (GEN) {
-            if (inactive_cfc(G, i - 1, j, k) || inactive_cfc(G, i, j, k)) dxv = 0.0;
-            if (inactive_fcc(G, i, j - 1, k) || inactive_fcc(G, i, j, k)) dyu = 0.0;
+            if (inactive_cfc(G, i - 1, j, k) || inactive_cfc(G, i, j, k)) dxv = RL(0.0);
+            if (inactive_fcc(G, i, j - 1, k) || inactive_fcc(G, i, j, k)) dyu = RL(0.0);
         }
         return (dxv - dyu) * G.razcf[j];
     }
-    __device__ __forceinline__ double dxU(int i, int j, int k) const {
+    __device__ __forceinline__ real dxU(int i, int j, int k) const {
         const long long c = idx3(G, i, j, k);
-        const double ax = G.dy * G.dzc[k];
+        const real ax = G.dy * G.dzc[k];
         return ax * u[c + 1] - ax * u[c];
     }
-    __device__ __forceinline__ double dyV(int i, int j, int k) const {
+    __device__ __forceinline__ real dyV(int i, int j, int k) const {
         const long long c = idx3(G, i, j, k);
         return G.dxcf[j + 1] * G.dzc[k] * v[c + G.pitch] - G.dxcf[j] * G.dzc[k] * v[c];
     }
-    __device__ __forceinline__ double Kh(int i, int j, int k) const {
+    __device__ __forceinline__ real Kh(int i, int j, int k) const {
         const long long c = idx3(G, i, j, k);
-        const double a = u[c], b = u[c + 1], cc = v[c], d = v[c + G.pitch];
-        return (0.5 * (a * a + b * b) + 0.5 * (cc * cc + d * d)) / 2.0;
+        const real a = u[c], b = u[c + 1], cc = v[c], d = v[c + G.pitch];
+        return (RL(0.5) * (a * a + b * b) + RL(0.5) * (cc * cc + d * d)) / RL(2.0);
     }
-    __device__ __forceinline__ double divxy(int i, int j, int k) const {   // horizontal divergence at ccc
+    __device__ __forceinline__ real divxy(int i, int j, int k) const {   // horizontal divergence at ccc
         const long long c = idx3(G, i, j, k);
         return (G.dy * u[c + 1] - G.dy * u[c] + G.dxcf[j + 1] * v[c + G.pitch] - G.dxcf[j] * v[c]) * G.razcc[j];
     }
@@ -89,12 +89,12 @@ struct MomG {
 enum { MT_DXFC = 0, MT_DXCF, MT_RAZCF, MT_RDXFC, MT_AZCC, MT_RAZCC, MT_FFF, MT_TAUX, MT_N };
 #define MT_ROWS 28
 #define MT_J0 6
-__device__ __forceinline__ void load_metric_table(const Geom& G, double* smt, int j0, int tid, int nt) {
-    const double* src[MT_N] = {G.dxfc, G.dxcf, G.razcf, G.rdxfc, G.azcc, G.razcc, G.fff, G.taux};
+__device__ __forceinline__ void load_metric_table(const Geom& G, real* smt, int j0, int tid, int nt) {
+    const real* src[MT_N] = {G.dxfc, G.dxcf, G.razcf, G.rdxfc, G.azcc, G.razcc, G.fff, G.taux};
     for (int e = tid; e < MT_N * MT_ROWS; e += nt) {
         const int m = e / MT_ROWS, r = e % MT_ROWS;
         const int j = min(j0 - MT_J0 + r, G.Ny + OB_H + 1);   // the arrays are indexable for j = -8 .. Ny + 8
-        double v = 0.0;
+        real v = RL(0.0);
 #pragma unroll
         for (int q = 0; q < MT_N; q++) if (q == m) v = src[q][j];
         smt[e] = v;
@@ -142,24 +142,24 @@ struct TileDims {
 template <int TX, int TY>
 struct MomS {
     using D = TileDims<TX, TY>;
-    const double *su, *sv, *sz, *sus, *svs, *sdx, *sdy, *sK;
+    const real *su, *sv, *sz, *sus, *svs, *sdx, *sdy, *sK;
     int i0, j0;
-    __device__ __forceinline__ double U(int i, int j, int) const { return su[(j - j0 + D::HU) * D::PU + (i - i0 + D::HUX)]; }
-    __device__ __forceinline__ double V(int i, int j, int) const { return sv[(j - j0 + D::HU) * D::PU + (i - i0 + D::HUX)]; }
-    __device__ __forceinline__ double usm(int i, int j, int) const { return sus[(j - j0 + D::HZ) * D::PZ + (i - i0 + D::HZ)]; }
-    __device__ __forceinline__ double vsm(int i, int j, int) const { return svs[(j - j0 + D::HZ) * D::PZ + (i - i0 + D::HZ)]; }
+    __device__ __forceinline__ real U(int i, int j, int) const { return su[(j - j0 + D::HU) * D::PU + (i - i0 + D::HUX)]; }
+    __device__ __forceinline__ real V(int i, int j, int) const { return sv[(j - j0 + D::HU) * D::PU + (i - i0 + D::HUX)]; }
+    __device__ __forceinline__ real usm(int i, int j, int) const { return sus[(j - j0 + D::HZ) * D::PZ + (i - i0 + D::HZ)]; }
+    __device__ __forceinline__ real vsm(int i, int j, int) const { return svs[(j - j0 + D::HZ) * D::PZ + (i - i0 + D::HZ)]; }
     template <bool GEN>
-    __device__ __forceinline__ double zeta(int i, int j, int) const { return sz[(j - j0 + D::HZ) * D::PZ + (i - i0 + D::HZ)]; }
-    __device__ __forceinline__ double dxU(int i, int j, int) const { return sdx[(j - j0 + D::HD) * D::PD + (i - i0 + D::HD)]; }
-    __device__ __forceinline__ double dyV(int i, int j, int) const { return sdy[(j - j0 + D::HD) * D::PD + (i - i0 + D::HD)]; }
-    __device__ __forceinline__ double Kh(int i, int j, int) const { return sK[(j - j0 + 1) * D::PK + (i - i0 + 1)]; }
+    __device__ __forceinline__ real zeta(int i, int j, int) const { return sz[(j - j0 + D::HZ) * D::PZ + (i - i0 + D::HZ)]; }
+    __device__ __forceinline__ real dxU(int i, int j, int) const { return sdx[(j - j0 + D::HD) * D::PD + (i - i0 + D::HD)]; }
+    __device__ __forceinline__ real dyV(int i, int j, int) const { return sdy[(j - j0 + D::HD) * D::PD + (i - i0 + D::HD)]; }
+    __device__ __forceinline__ real Kh(int i, int j, int) const { return sK[(j - j0 + 1) * D::PK + (i - i0 + 1)]; }
 };
 
 // ---- biased reconstructions along a line; `base + sgn*m` walks from the most upwind-ward point -------------
 template <int N, bool GEN, class A>
-__device__ __forceinline__ double recon_vort_y(const A& M, int i, int j, int k, bool left) {
+__device__ __forceinline__ real recon_vort_y(const A& M, int i, int j, int k, bool left) {
     const int base = left ? j - N + 1 : j + N, sgn = left ? 1 : -1;
-    double zq[2 * N - 1], us[2 * N - 1], vs[2 * N - 1];
+    real zq[2 * N - 1], us[2 * N - 1], vs[2 * N - 1];
 #pragma unroll
     for (int m = 0; m < 2 * N - 1; m++) {
         const int jj = base + sgn * m;
@@ -168,16 +168,16 @@ __device__ __forceinline__ double recon_vort_y(const A& M, int i, int j, int k, 
         vs[m] = M.vsm(i, jj, k);
     }
     if (N == 1) return zq[0];
-    double bu[N], bv[N];
+    real bu[N], bv[N];
     Weno<N>::beta2(us, vs, bu, bv);
 #pragma unroll
-    for (int s = 0; s < N; s++) bu[s] = 0.5 * (bu[s] + bv[s]);
+    for (int s = 0; s < N; s++) bu[s] = RL(0.5) * (bu[s] + bv[s]);
     return Weno<N>::combine(zq, bu);
 }
 template <int N, bool GEN, class A>
-__device__ __forceinline__ double recon_vort_x(const A& M, int i, int j, int k, bool left) {
+__device__ __forceinline__ real recon_vort_x(const A& M, int i, int j, int k, bool left) {
     const int base = left ? i - N + 1 : i + N, sgn = left ? 1 : -1;
-    double zq[2 * N - 1], us[2 * N - 1], vs[2 * N - 1];
+    real zq[2 * N - 1], us[2 * N - 1], vs[2 * N - 1];
 #pragma unroll
     for (int m = 0; m < 2 * N - 1; m++) {
         const int ii = base + sgn * m;
@@ -186,16 +186,16 @@ __device__ __forceinline__ double recon_vort_x(const A& M, int i, int j, int k, 
         vs[m] = M.vsm(ii, j, k);
     }
     if (N == 1) return zq[0];
-    double bu[N], bv[N];
+    real bu[N], bv[N];
     Weno<N>::beta2(us, vs, bu, bv);
 #pragma unroll
-    for (int s = 0; s < N; s++) bu[s] = 0.5 * (bu[s] + bv[s]);
+    for (int s = 0; s < N; s++) bu[s] = RL(0.5) * (bu[s] + bv[s]);
     return Weno<N>::combine(zq, bu);
 }
 template <int N, class A>
-__device__ __forceinline__ double recon_div_x(const A& M, int i, int j, int k, bool left) {
+__device__ __forceinline__ real recon_div_x(const A& M, int i, int j, int k, bool left) {
     const int base = left ? i - N : i + N - 1, sgn = left ? 1 : -1;
-    double q[2 * N - 1], s[2 * N - 1];
+    real q[2 * N - 1], s[2 * N - 1];
 #pragma unroll
     for (int m = 0; m < 2 * N - 1; m++) {
         const int ii = base + sgn * m;
@@ -203,14 +203,14 @@ __device__ __forceinline__ double recon_div_x(const A& M, int i, int j, int k, b
         s[m] = q[m] + M.dyV(ii, j, k);
     }
     if (N == 1) return q[0];
-    double b[N];
+    real b[N];
     Weno<N>::beta(s, b);
     return Weno<N>::combine(q, b);
 }
 template <int N, class A>
-__device__ __forceinline__ double recon_div_y(const A& M, int i, int j, int k, bool left) {
+__device__ __forceinline__ real recon_div_y(const A& M, int i, int j, int k, bool left) {
     const int base = left ? j - N : j + N - 1, sgn = left ? 1 : -1;
-    double q[2 * N - 1], s[2 * N - 1];
+    real q[2 * N - 1], s[2 * N - 1];
 #pragma unroll
     for (int m = 0; m < 2 * N - 1; m++) {
         const int jj = base + sgn * m;
@@ -218,17 +218,17 @@ __device__ __forceinline__ double recon_div_y(const A& M, int i, int j, int k, b
         s[m] = M.dxU(i, jj, k) + q[m];
     }
     if (N == 1) return q[0];
-    double b[N];
+    real b[N];
     Weno<N>::beta(s, b);
     return Weno<N>::combine(q, b);
 }
 template <int N>
-__device__ __forceinline__ double recon_cell(const double* __restrict__ c, long long base, long long stride) {
-    double q[2 * N - 1];
+__device__ __forceinline__ real recon_cell(const real* __restrict__ c, long long base, long long stride) {
+    real q[2 * N - 1];
 #pragma unroll
     for (int m = 0; m < 2 * N - 1; m++) q[m] = c[base + stride * m];
     if (N == 1) return q[0];
-    double b[N];
+    real b[N];
     Weno<N>::beta(q, b);
     return Weno<N>::combine(q, b);
 }
@@ -236,14 +236,14 @@ __device__ __forceinline__ double recon_cell(const double* __restrict__ c, long 
 // WENO-7 upwind-side reconstruction at the low face of tile cell q along a compile-time stride S: one 8-value
 // window (immediate LDS offsets) serves both upwind directions; the right-biased stencil is the mirror image.
 template <int S>
-__device__ __forceinline__ double recon7_window(const double* __restrict__ c, int q, bool left) {
-    double w[8];
+__device__ __forceinline__ real recon7_window(const real* __restrict__ c, int q, bool left) {
+    real w[8];
 #pragma unroll
     for (int m = 0; m < 8; m++) w[m] = c[q + (m - 4) * S];
-    double qq[7];
+    real qq[7];
 #pragma unroll
     for (int m = 0; m < 7; m++) qq[m] = left ? w[m] : w[7 - m];
-    double b[4];
+    real b[4];
     Weno<4>::beta(qq, b);
     return Weno<4>::combine(qq, b);
 }
@@ -306,20 +306,20 @@ __device__ __forceinline__ int order_from(const int* thr, int Nmax, int k) {
 // momentum tendencies
 // ================================================================================================
 template <bool GEN, class A>
-__device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A& M, int i, int j, int k, int NV, int ND,
-                                         double time, const GenThr& T, const double* __restrict__ mrow,
-                                         const double u_below, const double u_above, const double* __restrict__ wk) {
+__device__ __forceinline__ real tend_u(const Geom& G, const Fields& F, const A& M, int i, int j, int k, int NV, int ND,
+                                         double time, const GenThr& T, const real* __restrict__ mrow,
+                                         const real u_below, const real u_above, const real* __restrict__ wk) {
     const long long c = idx3(G, i, j, k);
     // (1) vorticity flux
-    const double dxcf0 = MET(mrow, DXCF, 0), dxcf1 = MET(mrow, DXCF, 1), rdxfc = MET(mrow, RDXFC, 0);
-    const double q00 = dxcf0 * M.V(i - 1, j, k), q01 = dxcf1 * M.V(i - 1, j + 1, k);
-    const double q10 = dxcf0 * M.V(i, j, k), q11 = dxcf1 * M.V(i, j + 1, k);
-    const double vavg = 0.5 * (0.5 * (q00 + q01) + 0.5 * (q10 + q11));
-    const double vhat = vavg * rdxfc;
-    double Gt = 0.0;
-    if (vhat != 0.0) {
-        const bool left = vhat > 0.0;
-        double z;
+    const real dxcf0 = MET(mrow, DXCF, 0), dxcf1 = MET(mrow, DXCF, 1), rdxfc = MET(mrow, RDXFC, 0);
+    const real q00 = dxcf0 * M.V(i - 1, j, k), q01 = dxcf1 * M.V(i - 1, j + 1, k);
+    const real q10 = dxcf0 * M.V(i, j, k), q11 = dxcf1 * M.V(i, j + 1, k);
+    const real vavg = RL(0.5) * (RL(0.5) * (q00 + q01) + RL(0.5) * (q10 + q11));
+    const real vhat = vavg * rdxfc;
+    real Gt = RL(0.0);
+    if (vhat != RL(0.0)) {
+        const bool left = vhat > RL(0.0);
+        real z;
         if (!GEN) z = recon_vort_y<5, false>(M, i, j, k, left);
         else {
             const int N = order_from(T.vy, 5, k);
@@ -330,11 +330,11 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
         Gt = vhat * z;
     }
     // (2) divergence flux + vertical advection
-    const double uh = M.U(i, j, k);
-    double Phi = 0.0;
-    if (uh != 0.0) {
-        const bool left = uh > 0.0;
-        double d;
+    const real uh = M.U(i, j, k);
+    real Phi = RL(0.0);
+    if (uh != RL(0.0)) {
+        const bool left = uh > RL(0.0);
+        real d;
         if (!GEN) d = recon_div_x<3>(M, i, j, k, left);
         else {
             const int N = order_from(T.dx, 3, k);
@@ -342,19 +342,19 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
                             (recon_div_x<3>(M, i, j, k, left)), (recon_div_x<3>(M, i, j, k, left)),
                             (recon_div_x<3>(M, i, j, k, left)));
         }
-        Phi = uh * d + uh * 0.5 * (M.dyV(i - 1, j, k) + M.dyV(i, j, k));
+        Phi = uh * d + uh * RL(0.5) * (M.dyV(i - 1, j, k) + M.dyV(i, j, k));
     }
-    const double az = MET(mrow, AZCC, 0);
-    double fl_lo, fl_hi;
+    const real az = MET(mrow, AZCC, 0);
+    real fl_lo, fl_hi;
     {
         // wk: {w(i,j,k), w(i-1,j,k), w(i,j-1,k), w(i,j,k+1), w(i-1,j,k+1), w(i,j-1,k+1)}
-        const double Wlo = 0.5 * (az * wk[1] + az * wk[0]);
-        const double Whi = 0.5 * (az * wk[4] + az * wk[3]);
-        fl_lo = Wlo * 0.5 * (u_below + uh);    // u(k - 1), clamped at the bottom level
-        fl_hi = Whi * 0.5 * (uh + u_above);    // u(k + 1), clamped at the top level
+        const real Wlo = RL(0.5) * (az * wk[1] + az * wk[0]);
+        const real Whi = RL(0.5) * (az * wk[4] + az * wk[3]);
+        fl_lo = Wlo * RL(0.5) * (u_below + uh);    // u(k - 1), clamped at the bottom level
+        fl_hi = Whi * RL(0.5) * (uh + u_above);    // u(k + 1), clamped at the top level
         if (GEN) {
             // immersed-peripheral (f,c,f) faces carry no flux: the node below is peripheral but inside the domain
-            if (k > 0 && k <= T.per_u) fl_lo = 0.0;
+            if (k > 0 && k <= T.per_u) fl_lo = RL(0.0);
             // (the node above an active node is active for a grid-fitted bottom; the top face is a domain boundary)
         }
     }
@@ -367,64 +367,64 @@ __device__ __forceinline__ double tend_u(const Geom& G, const Fields& F, const A
 #pragma unroll
         for (int n = 0; n < 4; n++) nact += k >= T.cu[n] ? 1 : 0;
     }
-    const double fbar = 0.5 * (MET(mrow, FFF, 0) + MET(mrow, FFF, 1));
-    const double cor = nact == 0 ? 0.0 : nact == 4 ? vavg : vavg / (0.25 * nact);
+    const real fbar = RL(0.5) * (MET(mrow, FFF, 0) + MET(mrow, FFF, 1));
+    const real cor = nact == 0 ? RL(0.0) : nact == 4 ? vavg : vavg / (RL(0.25) * nact);
     Gt += fbar * cor * rdxfc;
     Gt -= (F.p[c] - F.p[c - 1]) * rdxfc;
     // (6) QG-Leith stress divergence
     if (TEND_LEITH && G.qgleith) {
         const MomG Mg{G, F.u, F.v};
-        const double ax = G.dy * G.dzc[k];
-        auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * Mg.divxy(a, b, k) : 0.0; };
+        const real ax = G.dy * G.dzc[k];
+        auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * Mg.divxy(a, b, k) : RL(0.0); };
         auto fffc = [&](int a, int b) {
             const bool per = !active(G, a - 1, b - 1, k) || !active(G, a, b - 1, k) || !active(G, a - 1, b, k) || !active(G, a, b, k);
-            if (per && in_domain(G, b - 1, k) && in_domain(G, b, k)) return 0.0;
+            if (per && in_domain(G, b - 1, k) && in_domain(G, b, k)) return RL(0.0);
             const long long q = idx3(G, a, b, k);
-            const double nu = 0.25 * (F.nuL[q - 1 - G.pitch] + F.nuL[q - G.pitch] + F.nuL[q - 1] + F.nuL[q]);
+            const real nu = RL(0.25) * (F.nuL[q - 1 - G.pitch] + F.nuL[q - G.pitch] + F.nuL[q - 1] + F.nuL[q]);
             return nu * Mg.zeta<true>(a, b, k);
         };
-        const double t = ax * fccc(i, j) - ax * fccc(i - 1, j) +
+        const real t = ax * fccc(i, j) - ax * fccc(i - 1, j) +
                          (G.dxcf[j + 1] * G.dzc[k] * fffc(i, j + 1) - G.dxcf[j] * G.dzc[k] * fffc(i, j));
         Gt -= t / (az * G.dzc[k]);
     }
     // (7) flux boundary conditions
     if (k == G.Nz - 1) {
-        double J = 0.0;
+        real J = RL(0.0);
         if (G.bc_kind == OB200_BC_DOUBLEDRAKE) J = MET(mrow, TAUX, 0);
         else if (G.bc_kind == OB200_BC_REALISTIC) J = interp_flux(G, F.forcing[0], i, j, G.Ny, time, false);
         Gt -= J * G.rdzc[k];
     }
     if (k == 0) {
-        double J = 0.0;
+        real J = RL(0.0);
         if (G.bc_kind == OB200_BC_DOUBLEDRAKE) J = -G.mu_drag * uh;
         else if (G.bc_kind == OB200_BC_REALISTIC) {
-            const double v0 = M.V(i - 1, j, k), v1 = M.V(i - 1, j + 1, k), v2 = M.V(i, j, k), v3 = M.V(i, j + 1, k);
-            J = -G.mu_drag * uh * sqrt(uh * uh + 0.25 * (v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3));
+            const real v0 = M.V(i - 1, j, k), v1 = M.V(i - 1, j + 1, k), v2 = M.V(i, j, k), v3 = M.V(i, j + 1, k);
+            J = -G.mu_drag * uh * sqrt(uh * uh + RL(0.25) * (v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3));
         }
         Gt += J * G.rdzc[k];
     }
     // immersed quadratic bottom drag (RealisticOcean): first non-peripheral node above the sea floor
     if (GEN && G.bc_kind == OB200_BC_REALISTIC && k > 0 && k <= T.per_u) {
-        const double v0 = M.V(i - 1, j, k), v1 = M.V(i - 1, j + 1, k), v2 = M.V(i, j, k), v3 = M.V(i, j + 1, k);
-        Gt += -G.mu_drag * uh * sqrt(uh * uh + 0.25 * (v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3)) * G.rdzc[k];
+        const real v0 = M.V(i - 1, j, k), v1 = M.V(i - 1, j + 1, k), v2 = M.V(i, j, k), v3 = M.V(i, j + 1, k);
+        Gt += -G.mu_drag * uh * sqrt(uh * uh + RL(0.25) * (v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3)) * G.rdzc[k];
     }
     return Gt;
 }
 
 template <bool GEN, class A>
-__device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A& M, int i, int j, int k, int NV, int ND,
-                                         double time, const GenThr& T, const double* __restrict__ mrow,
-                                         const double v_below, const double v_above, const double* __restrict__ wk) {
+__device__ __forceinline__ real tend_v(const Geom& G, const Fields& F, const A& M, int i, int j, int k, int NV, int ND,
+                                         double time, const GenThr& T, const real* __restrict__ mrow,
+                                         const real v_below, const real v_above, const real* __restrict__ wk) {
     const long long c = idx3(G, i, j, k);
-    const double dy = G.dy;
-    const double q00 = dy * M.U(i, j - 1, k), q10 = dy * M.U(i + 1, j - 1, k);
-    const double q01 = dy * M.U(i, j, k), q11 = dy * M.U(i + 1, j, k);
-    const double uavg = 0.5 * (0.5 * (q00 + q10) + 0.5 * (q01 + q11));
-    const double uhat = uavg * G.rdy;
-    double Gt = 0.0;
-    if (uhat != 0.0) {
-        const bool left = uhat > 0.0;
-        double z;
+    const real dy = G.dy;
+    const real q00 = dy * M.U(i, j - 1, k), q10 = dy * M.U(i + 1, j - 1, k);
+    const real q01 = dy * M.U(i, j, k), q11 = dy * M.U(i + 1, j, k);
+    const real uavg = RL(0.5) * (RL(0.5) * (q00 + q10) + RL(0.5) * (q01 + q11));
+    const real uhat = uavg * G.rdy;
+    real Gt = RL(0.0);
+    if (uhat != RL(0.0)) {
+        const bool left = uhat > RL(0.0);
+        real z;
         if (!GEN) z = recon_vort_x<5, false>(M, i, j, k, left);
         else {
             const int N = order_from(T.vx, 5, k);
@@ -434,11 +434,11 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
         }
         Gt = -(uhat * z);
     }
-    const double vh = M.V(i, j, k);
-    double Phi = 0.0;
-    if (vh != 0.0) {
-        const bool left = vh > 0.0;
-        double d;
+    const real vh = M.V(i, j, k);
+    real Phi = RL(0.0);
+    if (vh != RL(0.0)) {
+        const bool left = vh > RL(0.0);
+        real d;
         if (!GEN) d = recon_div_y<3>(M, i, j, k, left);
         else {
             const int N = order_from(T.dy, 3, k);
@@ -446,15 +446,15 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
                             (recon_div_y<3>(M, i, j, k, left)), (recon_div_y<3>(M, i, j, k, left)),
                             (recon_div_y<3>(M, i, j, k, left)));
         }
-        Phi = vh * d + vh * 0.5 * (M.dxU(i, j - 1, k) + M.dxU(i, j, k));
+        Phi = vh * d + vh * RL(0.5) * (M.dxU(i, j - 1, k) + M.dxU(i, j, k));
     }
-    const double azm = MET(mrow, AZCC, -1), az0 = MET(mrow, AZCC, 0);
-    const double Wlo = 0.5 * (azm * wk[2] + az0 * wk[0]);
-    const double Whi = 0.5 * (azm * wk[5] + az0 * wk[3]);
-    double fl_lo = Wlo * 0.5 * (v_below + vh);
-    const double fl_hi = Whi * 0.5 * (vh + v_above);
+    const real azm = MET(mrow, AZCC, -1), az0 = MET(mrow, AZCC, 0);
+    const real Wlo = RL(0.5) * (azm * wk[2] + az0 * wk[0]);
+    const real Whi = RL(0.5) * (azm * wk[5] + az0 * wk[3]);
+    real fl_lo = Wlo * RL(0.5) * (v_below + vh);
+    const real fl_hi = Whi * RL(0.5) * (vh + v_above);
     if (GEN) {
-        if (k > 0 && k <= T.per_v) fl_lo = 0.0;
+        if (k > 0 && k <= T.per_v) fl_lo = RL(0.0);
     }
     Gt -= (Phi + fl_hi - fl_lo) * (MET(mrow, RAZCF, 0) * G.rdzc[k]);
     Gt -= (M.Kh(i, j, k) - M.Kh(i, j - 1, k)) * G.rdy;
@@ -464,39 +464,39 @@ __device__ __forceinline__ double tend_v(const Geom& G, const Fields& F, const A
 #pragma unroll
         for (int n = 0; n < 4; n++) nact += k >= T.cv[n] ? 1 : 0;
     }
-    const double f0 = MET(mrow, FFF, 0);
-    const double fbar = 0.5 * (f0 + f0);
-    const double cor = nact == 0 ? 0.0 : nact == 4 ? uavg : uavg / (0.25 * nact);
+    const real f0 = MET(mrow, FFF, 0);
+    const real fbar = RL(0.5) * (f0 + f0);
+    const real cor = nact == 0 ? RL(0.0) : nact == 4 ? uavg : uavg / (RL(0.25) * nact);
     Gt -= fbar * cor * G.rdy;
     Gt -= (F.p[c] - F.p[c - G.pitch]) * G.rdy;
     if (TEND_LEITH && G.qgleith) {
         const MomG Mg{G, F.u, F.v};
-        const double ax = dy * G.dzc[k];
-        auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * Mg.divxy(a, b, k) : 0.0; };
+        const real ax = dy * G.dzc[k];
+        auto fccc = [&](int a, int b) { return active(G, a, b, k) ? -F.nuL[idx3(G, a, b, k)] * Mg.divxy(a, b, k) : RL(0.0); };
         auto fffc = [&](int a, int b) {
             const bool per = !active(G, a - 1, b - 1, k) || !active(G, a, b - 1, k) || !active(G, a - 1, b, k) || !active(G, a, b, k);
-            if (per && in_domain(G, b - 1, k) && in_domain(G, b, k)) return 0.0;
+            if (per && in_domain(G, b - 1, k) && in_domain(G, b, k)) return RL(0.0);
             const long long q = idx3(G, a, b, k);
-            const double nu = 0.25 * (F.nuL[q - 1 - G.pitch] + F.nuL[q - G.pitch] + F.nuL[q - 1] + F.nuL[q]);
+            const real nu = RL(0.25) * (F.nuL[q - 1 - G.pitch] + F.nuL[q - G.pitch] + F.nuL[q - 1] + F.nuL[q]);
             return nu * Mg.zeta<true>(a, b, k);
         };
-        const double t = ax * (-fffc(i + 1, j)) - ax * (-fffc(i, j)) +
+        const real t = ax * (-fffc(i + 1, j)) - ax * (-fffc(i, j)) +
                          (G.dxfc[j] * G.dzc[k] * fccc(i, j) - G.dxfc[j - 1] * G.dzc[k] * fccc(i, j - 1));
         Gt -= t / (G.azcf[j] * G.dzc[k]);
     }
     if (k == G.Nz - 1 && G.bc_kind == OB200_BC_REALISTIC) Gt -= interp_flux(G, F.forcing[1], i, j, G.Ny + 1, time, false) * G.rdzc[k];
     if (k == 0) {
-        double J = 0.0;
+        real J = RL(0.0);
         if (G.bc_kind == OB200_BC_DOUBLEDRAKE) J = -G.mu_drag * vh;
         else if (G.bc_kind == OB200_BC_REALISTIC) {
-            const double u0 = M.U(i, j - 1, k), u1 = M.U(i + 1, j - 1, k), u2 = M.U(i, j, k), u3 = M.U(i + 1, j, k);
-            J = -G.mu_drag * vh * sqrt(vh * vh + 0.25 * (u0 * u0 + u2 * u2 + u1 * u1 + u3 * u3));
+            const real u0 = M.U(i, j - 1, k), u1 = M.U(i + 1, j - 1, k), u2 = M.U(i, j, k), u3 = M.U(i + 1, j, k);
+            J = -G.mu_drag * vh * sqrt(vh * vh + RL(0.25) * (u0 * u0 + u2 * u2 + u1 * u1 + u3 * u3));
         }
         Gt += J * G.rdzc[k];
     }
     if (GEN && G.bc_kind == OB200_BC_REALISTIC && k > 0 && k <= T.per_v) {
-        const double u0 = M.U(i, j - 1, k), u1 = M.U(i + 1, j - 1, k), u2 = M.U(i, j, k), u3 = M.U(i + 1, j, k);
-        Gt += -G.mu_drag * vh * sqrt(vh * vh + 0.25 * (u0 * u0 + u2 * u2 + u1 * u1 + u3 * u3)) * G.rdzc[k];
+        const real u0 = M.U(i, j - 1, k), u1 = M.U(i + 1, j - 1, k), u2 = M.U(i, j, k), u3 = M.U(i + 1, j, k);
+        Gt += -G.mu_drag * vh * sqrt(vh * vh + RL(0.25) * (u0 * u0 + u2 * u2 + u1 * u1 + u3 * u3)) * G.rdzc[k];
     }
     return Gt;
 }
@@ -530,12 +530,12 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
     using D = TileDims<TX, TY>;
     constexpr int NT = TX * TY;
     constexpr int RU = (D::NU + NT - 1) / NT;
-    extern __shared__ __align__(128) double sm[];
+    extern __shared__ __align__(128) real sm[];
     __shared__ unsigned long long bar[2];
     constexpr bool DB = MOM_DB && TMA;          // one barrier per level (derived fields double-buffered)
-    double* der = sm + 4 * D::NUP;  // [u0 | v0 | u1 | v1] tile buffers first (128-byte aligned slots), then the derived fields
-    double* smt = der + (MOM_DB ? 2 : 1) * D::NDER;       // metrics table [MT_N][MT_ROWS]
-    double* swr = smt + MT_N * MT_ROWS;                   // w ring [2][NW] (MOM_WSM)
+    real* der = sm + 4 * D::NUP;  // [u0 | v0 | u1 | v1] tile buffers first (128-byte aligned slots), then the derived fields
+    real* smt = der + (MOM_DB ? 2 : 1) * D::NDER;       // metrics table [MT_N][MT_ROWS]
+    real* swr = smt + MT_N * MT_ROWS;                   // w ring [2][NW] (MOM_WSM)
     int tile, kf;
     int kskip = 0;   // masked tiles: levels below the shallowest sea floor of the tile are all solid -> G stays 0 (never written)
     if (GEN) { tile = slow_tiles[3 * blockIdx.x]; kf = slow_tiles[3 * blockIdx.x + 1]; kskip = slow_tiles[3 * blockIdx.x + 2]; }
@@ -549,9 +549,9 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
     const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
     const bool mine = i < G.Nx && j < G.Ny;
     const int tx0 = i0 - D::HUX + OB_X0, ty0 = j0 - D::HU + OB_H;   // tile origin in array coordinates (even column)
-    constexpr unsigned TILE_BYTES = D::NU * sizeof(double);
+    constexpr unsigned TILE_BYTES = D::NU * sizeof(real);
     load_metric_table(G, smt, j0, tid, NT);
-    const double* mrow = smt + (threadIdx.y + MT_J0);               // this thread's row j: MET(mrow, X, dj) = X[j + dj]
+    const real* mrow = smt + (threadIdx.y + MT_J0);               // this thread's row j: MET(mrow, X, dj) = X[j + dj]
     // staging map: thread (tx, ty) stages the tile points (tx + TX p, ty + TY r) -- every smem offset below is this
     // thread's base plus a compile-time constant (no div / mod, no per-element index arithmetic in the level loop)
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
     constexpr int NRXD = (D::PD + TX - 1) / TX, NRYD = (D::RD + TY - 1) / TY;
     constexpr int NRXK = (D::PK + TX - 1) / TX, NRYK = (D::RK + TY - 1) / TY;
     int offu[TMA ? 1 : RU];
-    double ru[TMA ? 1 : RU], rv[TMA ? 1 : RU];
+    real ru[TMA ? 1 : RU], rv[TMA ? 1 : RU];
     auto prefetch = [&](int k) {
         const long long lev = (long long)k * G.sz;
 #pragma unroll
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
     // own-column u, v one level below (clamped at the bottom): read once, then carried from level to level; the level above
     // comes from the tile that TMA is already fetching for the next iteration (MOM_KNBR = 0: four global loads per cell)
     const int own = (threadIdx.y + D::HU) * D::PU + (threadIdx.x + D::HUX);
-    double ub = 0.0, vb = 0.0;
+    real ub = RL(0.0), vb = RL(0.0);
     if (MOM_KNBR && mine) {
         const long long cb = idx3(G, i, j, max(k_begin - 1, 0));
         ub = F.u[cb]; vb = F.v[cb];
@@ -616,39 +616,39 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
     // w ring: thread (tx, ty) stages w of its own cell at slot (tx + 1, ty + 1); the tx = 0 / ty = 0 threads add the column
     // i0 - 1 / the row j0 - 1
     const int wown = (threadIdx.y + 1) * D::PW + (threadIdx.x + 1);
-    auto stage_w_load = [&](int kk, double& a, double& b, double& c3) {
+    auto stage_w_load = [&](int kk, real& a, real& b, real& c3) {
         const long long cw = idx3(G, i, j, kk);
         a = F.w[cw];
         if (threadIdx.x == 0) b = F.w[cw - 1];
         if (threadIdx.y == 0) c3 = F.w[cw - G.pitch];
     };
-    auto stage_w_store = [&](double* dst, double a, double b, double c3) {
+    auto stage_w_store = [&](real* dst, real a, real b, real c3) {
         dst[wown] = a;
         if (threadIdx.x == 0) dst[wown - 1] = b;
         if (threadIdx.y == 0) dst[wown - D::PW] = c3;
     };
     if (MOM_WSM && mine) {   // level k_begin; made visible by the first mid-level barrier
-        double a = 0.0, b = 0.0, c3 = 0.0;
+        real a = RL(0.0), b = RL(0.0), c3 = RL(0.0);
         stage_w_load(k_begin, a, b, c3);
         stage_w_store(swr, a, b, c3);
     }
     int it = 0;
     for (int k = k_begin; k < k_end; k++, it++) {
         const int buf = TMA ? (it & 1) : 0;
-        double* su = sm + buf * 2 * D::NUP;
-        double* sv = su + D::NUP;
-        double* sz = der + (DB ? buf : 0) * D::NDER;
-        double* sus = sz + D::NZ;
-        double* svs = sus + D::NZ;
-        double* sdx = svs + D::NZ;
-        double* sdy = sdx + D::ND;
-        double* sK = sdy + D::ND;
+        real* su = sm + buf * 2 * D::NUP;
+        real* sv = su + D::NUP;
+        real* sz = der + (DB ? buf : 0) * D::NDER;
+        real* sus = sz + D::NZ;
+        real* svs = sus + D::NZ;
+        real* sdx = svs + D::NZ;
+        real* sdy = sdx + D::ND;
+        real* sK = sdy + D::ND;
         const MomS<TX, TY> M{su, sv, sz, sus, svs, sdx, sdy, sK, i0, j0};
         if (TMA) {
             // the other buffer was last read in the previous iteration, which ended with a block barrier
             if (!DB && tid == 0 && k + 1 < k_end) {
                 fence_proxy_async();
-                double* nu = sm + (buf ^ 1) * 2 * D::NUP;
+                real* nu = sm + (buf ^ 1) * 2 * D::NUP;
                 mbar_expect_tx(&bar[buf ^ 1], 2 * TILE_BYTES);
                 tma_load_tile(nu, &tmu, &bar[buf ^ 1], tx0, ty0, k + 1);
                 tma_load_tile(nu + D::NUP, &tmv, &bar[buf ^ 1], tx0, ty0, k + 1);
@@ -663,9 +663,9 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
             __syncthreads();
             if (k + 1 < k_end) prefetch(k + 1);
         }
-        const double dzk = G.dzc[k];
+        const real dzk = G.dzc[k];
         // w(k + 1) of the tile: requested here, stored at the end of this phase into the slot w(k - 1) occupied
-        double wa = 0.0, wb = 0.0, wc = 0.0;
+        real wa = RL(0.0), wb = RL(0.0), wc = RL(0.0);
         if (MOM_WSM && mine) stage_w_load(k + 1, wa, wb, wc);
         // zeta, I_y u, I_x v on [i0 - 4, i0 + TX + 4] x [j0 - 4, j0 + TY + 4]
 #pragma unroll
@@ -674,17 +674,17 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
             for (int p = 0; p < NRXZ; p++) {
                 if ((p == 0 || tx + TX * p < D::PZ) && (r == 0 || ty + TY * r < D::RZ)) {
                     const int e = ez0 + TX * p + TY * r * D::PZ, q = qz0 + TX * p + TY * r * D::PU;
-                    const double* mz = smt + (ty + TY * r + MT_J0 - D::HZ);     // row jj = j0 - HZ + b
-                    double dxv = G.dy * sv[q] - G.dy * sv[q - 1];
-                    double dyu = MET(mz, DXFC, 0) * su[q] - MET(mz, DXFC, -1) * su[q - D::PU];
+                    const real* mz = smt + (ty + TY * r + MT_J0 - D::HZ);     // row jj = j0 - HZ + b
+                    real dxv = G.dy * sv[q] - G.dy * sv[q - 1];
+                    real dyu = MET(mz, DXFC, 0) * su[q] - MET(mz, DXFC, -1) * su[q - D::PU];
                     if (GEN) {   // conditional differences: a difference that touches an inactive node is zero
                         const int th = zthr[r * NRXZ + p];
-                        if (k < (th >> 16)) dxv = 0.0;
-                        if (k < (th & 0xffff)) dyu = 0.0;
+                        if (k < (th >> 16)) dxv = RL(0.0);
+                        if (k < (th & 0xffff)) dyu = RL(0.0);
                     }
                     sz[e] = (dxv - dyu) * MET(mz, RAZCF, 0);
-                    sus[e] = 0.5 * (su[q - D::PU] + su[q]);
-                    svs[e] = 0.5 * (sv[q - 1] + sv[q]);
+                    sus[e] = RL(0.5) * (su[q - D::PU] + su[q]);
+                    svs[e] = RL(0.5) * (sv[q - 1] + sv[q]);
                 }
             }
         // dx(Ax u), dy(Ay v) on [i0 - 3, i0 + TX + 2] x [j0 - 3, j0 + TY + 2]
@@ -694,8 +694,8 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
             for (int p = 0; p < NRXD; p++) {
                 if ((p == 0 || tx + TX * p < D::PD) && (r == 0 || ty + TY * r < D::RD)) {
                     const int e = ed0 + TX * p + TY * r * D::PD, q = qd0 + TX * p + TY * r * D::PU;
-                    const double* md = smt + (ty + TY * r + MT_J0 - D::HD);     // row jj = j0 - HD + b
-                    const double ax = G.dy * dzk;
+                    const real* md = smt + (ty + TY * r + MT_J0 - D::HD);     // row jj = j0 - HD + b
+                    const real ax = G.dy * dzk;
                     sdx[e] = ax * su[q + 1] - ax * su[q];
                     sdy[e] = MET(md, DXCF, 1) * dzk * sv[q + D::PU] - MET(md, DXCF, 0) * dzk * sv[q];
                 }
@@ -707,8 +707,8 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
             for (int p = 0; p < NRXK; p++) {
                 if ((p == 0 || tx + TX * p < D::PK) && (r == 0 || ty + TY * r < D::RK)) {
                     const int e = ek0 + TX * p + TY * r * D::PK, q = qk0 + TX * p + TY * r * D::PU;
-                    const double ua = su[q], ub = su[q + 1], va = sv[q], vb = sv[q + D::PU];
-                    sK[e] = (0.5 * (ua * ua + ub * ub) + 0.5 * (va * va + vb * vb)) / 2.0;
+                    const real ua = su[q], ub = su[q + 1], va = sv[q], vb = sv[q + D::PU];
+                    sK[e] = (RL(0.5) * (ua * ua + ub * ub) + RL(0.5) * (va * va + vb * vb)) / RL(2.0);
                 }
             }
         if (MOM_WSM && mine) stage_w_store(swr + ((it + 1) & 1) * D::NW, wa, wb, wc);
@@ -716,28 +716,28 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
         if (DB && tid == 0 && it >= 1 && k + 1 < k_end) {
             // every warp is past the compute phase of level k - 1, the last reader of the other tile buffer: refill it
             fence_proxy_async();
-            double* nu = sm + (buf ^ 1) * 2 * D::NUP;
+            real* nu = sm + (buf ^ 1) * 2 * D::NUP;
             mbar_expect_tx(&bar[buf ^ 1], 2 * TILE_BYTES);
             tma_load_tile(nu, &tmu, &bar[buf ^ 1], tx0, ty0, k + 1);
             tma_load_tile(nu + D::NUP, &tmv, &bar[buf ^ 1], tx0, ty0, k + 1);
         }
         if (mine) {
             const long long c = idx3(G, i, j, k);
-            double ua, va;
+            real ua, va;
             if (MOM_KNBR && TMA && k + 1 < k_end) {
                 // the next level's tiles were requested at the top of this iteration: by now they have normally landed
                 mbar_wait(&bar[buf ^ 1], ((it + 1) >> 1) & 1);
-                const double* nu = sm + (buf ^ 1) * 2 * D::NUP;
+                const real* nu = sm + (buf ^ 1) * 2 * D::NUP;
                 ua = nu[own]; va = nu[D::NUP + own];
             } else {
                 const long long ca = idx3(G, i, j, min(k + 1, G.Nz - 1));
                 ua = F.u[ca]; va = F.v[ca];
             }
             if (!MOM_KNBR) { const long long cb = idx3(G, i, j, max(k - 1, 0)); ub = F.u[cb]; vb = F.v[cb]; }
-            double wk[6];
+            real wk[6];
             if (MOM_WSM) {
-                const double* w0 = swr + (it & 1) * D::NW + wown;
-                const double* w1 = swr + ((it + 1) & 1) * D::NW + wown;
+                const real* w0 = swr + (it & 1) * D::NW + wown;
+                const real* w1 = swr + ((it + 1) & 1) * D::NW + wown;
                 wk[0] = w0[0]; wk[1] = w0[-1]; wk[2] = w0[-D::PW];
                 wk[3] = w1[0]; wk[4] = w1[-1]; wk[5] = w1[-D::PW];
             } else {
@@ -752,8 +752,8 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
                 F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, ub, ua, wk);
                 F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, vb, va, wk);
             } else {
-                F.Gu[c] = k < T.per_u ? 0.0 : tend_u<true>(G, F, M, i, j, k, NV, ND, time, T, mrow, ub, ua, wk);
-                F.Gv[c] = k < T.per_v ? 0.0 : tend_v<true>(G, F, M, i, j, k, NV, ND, time, T, mrow, vb, va, wk);
+                F.Gu[c] = k < T.per_u ? RL(0.0) : tend_u<true>(G, F, M, i, j, k, NV, ND, time, T, mrow, ub, ua, wk);
+                F.Gv[c] = k < T.per_v ? RL(0.0) : tend_v<true>(G, F, M, i, j, k, NV, ND, time, T, mrow, vb, va, wk);
             }
             if (MOM_KNBR) { ub = su[own]; vb = sv[own]; }
         }
@@ -793,11 +793,11 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
     constexpr int RC = (D::NC + NT - 1) / NT;                 // tile elements per thread (per tracer)
     constexpr int NFV = D::NFX + D::NFY;                      // face velocities per level
     constexpr int RV = (NFV + NT - 1) / NT;
-    extern __shared__ __align__(128) double sm[];
+    extern __shared__ __align__(128) real sm[];
     __shared__ unsigned long long bar[2];
     constexpr bool PIPE = TRC_PIPE && TMA;
-    double* sfx0 = sm + 4 * D::NCP;        // after the [T0 | S0 | T1 | S1] tile buffers: slots of [2 tracers][(TX+1)*TY x-faces | TX*(TY+1) y-faces]
-    double* svel0 = sfx0 + (TRC_PIPE ? 2 : 1) * 2 * NFV;   // slots of [NFX + NFY] face velocities u (x-faces) then v (y-faces)
+    real* sfx0 = sm + 4 * D::NCP;        // after the [T0 | S0 | T1 | S1] tile buffers: slots of [2 tracers][(TX+1)*TY x-faces | TX*(TY+1) y-faces]
+    real* svel0 = sfx0 + (TRC_PIPE ? 2 : 1) * 2 * NFV;   // slots of [NFX + NFY] face velocities u (x-faces) then v (y-faces)
     int tile, kf;
     int kskip = 0;   // masked tiles: levels below the shallowest sea floor of the tile are all solid -> G stays 0 (never written)
     if (GEN) { tile = slow_tiles[3 * blockIdx.x]; kf = slow_tiles[3 * blockIdx.x + 1]; kskip = slow_tiles[3 * blockIdx.x + 2]; }
@@ -829,9 +829,9 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
             offv[r] = (int)idx3(G, min(i0 + a, G.Nx + OB_H - 1), min(j0 + b, G.Ny), 0);
         }
     }
-    double rT[TMA ? 1 : RC], rS[TMA ? 1 : RC], rV[RV];
+    real rT[TMA ? 1 : RC], rS[TMA ? 1 : RC], rV[RV];
     const int tx0 = i0 - D::HC + OB_X0, ty0 = j0 - D::HC + OB_H;   // tile origin in array coordinates
-    constexpr unsigned TILE_BYTES = D::NC * sizeof(double);
+    constexpr unsigned TILE_BYTES = D::NC * sizeof(real);
     auto prefetch = [&](int k) {   // issue the loads of level k; consumed one iteration later
         const long long lev = (long long)k * G.sz;
 #pragma unroll
@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
     }
     prefetch(k_begin);
     const long long cbase = mine ? idx3(G, i, j, 0) : 0;
-    const double az = G.azcc[min(j, G.Ny - 1)], raz = G.razcc[min(j, G.Ny - 1)];
+    const real az = G.azcc[min(j, G.Ny - 1)], raz = G.razcc[min(j, G.Ny - 1)];
     // masked tiles: per-face level thresholds of the reconstruction order (packed 16 bit), k independent
     constexpr int RFE = (NFV + NT - 1) / NT;
     int fthr[GEN ? 2 * RFE : 1];
@@ -881,7 +881,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
     }
     // PIPE: own-column values carried from level to level
     const int qown = (threadIdx.y + D::HC) * D::PC + (threadIdx.x + D::HC);
-    double wlo_c = 0.0, Tm_c = 0.0, Sm_c = 0.0;
+    real wlo_c = RL(0.0), Tm_c = RL(0.0), Sm_c = RL(0.0);
     if (PIPE && mine) {
         const long long cm = cbase + (long long)max(k_begin - 1, 0) * G.sz;
         wlo_c = F.w[cbase + (long long)k_begin * G.sz]; Tm_c = F.T[cm]; Sm_c = F.S[cm];
@@ -889,14 +889,14 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
     int it = 0;
     for (int k = k_begin; k < k_end; k++, it++) {
         const int buf = TMA ? (it & 1) : 0;
-        double* sc = sm + buf * 2 * D::NCP;   // T tile, then S tile at + NCP
-        double* sfx = sfx0 + (PIPE ? buf : 0) * 2 * NFV;
-        double* svel = svel0 + (PIPE ? buf : 0) * NFV;
+        real* sc = sm + buf * 2 * D::NCP;   // T tile, then S tile at + NCP
+        real* sfx = sfx0 + (PIPE ? buf : 0) * 2 * NFV;
+        real* svel = svel0 + (PIPE ? buf : 0) * NFV;
         if (TMA && tid == 0 && k + 1 < k_end) {
             // the other buffer was last read before the second barrier of the previous iteration (PIPE: the centre values are
             // taken in the flux phase), otherwise the previous iteration ended with a block barrier
             fence_proxy_async();
-            double* nx = sm + (buf ^ 1) * 2 * D::NCP;
+            real* nx = sm + (buf ^ 1) * 2 * D::NCP;
             mbar_expect_tx(&bar[buf ^ 1], 2 * TILE_BYTES);
             tma_load_tile(nx, &tmT, &bar[buf ^ 1], tx0, ty0, k + 1);
             tma_load_tile(nx + D::NCP, &tmS, &bar[buf ^ 1], tx0, ty0, k + 1);
@@ -916,7 +916,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
         if (k + 1 < k_end) prefetch(k + 1);
         // own-column values for the vertical flux, requested now, consumed after the flux phase
         const int km = max(k - 1, 0), kp = min(k + 1, G.Nz - 1);
-        double wlo = 0, whi = 0, Tm = 0, Tp = 0, Sm = 0, Sp = 0, ckT = 0, ckS = 0;
+        real wlo = 0, whi = 0, Tm = 0, Tp = 0, Sm = 0, Sp = 0, ckT = 0, ckS = 0;
         if (mine) {
             const long long c = cbase + (long long)k * G.sz;
             whi = F.w[c + G.sz];
@@ -927,20 +927,20 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
                 Sm = F.S[cbase + (long long)km * G.sz]; Sp = F.S[cbase + (long long)kp * G.sz];
             }
         }
-        const double dzk = G.dzc[k], rdzk = G.rdzc[k];
+        const real dzk = G.dzc[k], rdzk = G.rdzc[k];
         if (!GEN) {
             // own cell: west face (x) and south face (y) of both tracers, compile-time strides
             {
                 const int q = (threadIdx.y + D::HC) * D::PC + (threadIdx.x + D::HC);
                 const int fx = threadIdx.y * (TX + 1) + threadIdx.x, fy = D::NFX + threadIdx.y * TX + threadIdx.x;
-                const double ux = svel[fx], vy = svel[fy];
-                const double mx = G.dy * dzk, my = G.dxcf[min(j, G.Ny)] * dzk;
+                const real ux = svel[fx], vy = svel[fy];
+                const real mx = G.dy * dzk, my = G.dxcf[min(j, G.Ny)] * dzk;
 #pragma unroll
                 for (int tr = 0; tr < 2; tr++) {
-                    const double* cc = sc + tr * D::NCP;
-                    double flx = 0.0, fly = 0.0;
-                    if (ux != 0.0) flx = G.dy * dzk * (ux * recon7_window<1>(cc, q, ux > 0.0));
-                    if (vy != 0.0) fly = G.dxcf[min(j, G.Ny)] * dzk * (vy * recon7_window<D::PC>(cc, q, vy > 0.0));
+                    const real* cc = sc + tr * D::NCP;
+                    real flx = RL(0.0), fly = RL(0.0);
+                    if (ux != RL(0.0)) flx = G.dy * dzk * (ux * recon7_window<1>(cc, q, ux > RL(0.0)));
+                    if (vy != RL(0.0)) fly = G.dxcf[min(j, G.Ny)] * dzk * (vy * recon7_window<D::PC>(cc, q, vy > RL(0.0)));
                     sfx[tr * NFV + fx] = flx;
                     sfx[tr * NFV + fy] = fly;
                 }
@@ -949,15 +949,15 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
             // the tile's east column of x-faces and north row of y-faces: (TY + TX) faces x 2 tracers
             if (tid < 2 * (TX + TY)) {
                 const int tr = tid / (TX + TY), g = tid - tr * (TX + TY);
-                const double* cc = sc + tr * D::NCP;
+                const real* cc = sc + tr * D::NCP;
                 const bool isx = g < TY;
                 const int a = isx ? TX : g - TY, b = isx ? g : TY;
                 const int f = isx ? b * (TX + 1) + a : D::NFX + b * TX + a;
                 const int q = (b + D::HC) * D::PC + (a + D::HC);
-                const double vel = svel[f];
-                double flux = 0.0;
-                if (vel != 0.0) {
-                    const double r = isx ? recon7_window<1>(cc, q, vel > 0.0) : recon7_window<D::PC>(cc, q, vel > 0.0);
+                const real vel = svel[f];
+                real flux = RL(0.0);
+                if (vel != RL(0.0)) {
+                    const real r = isx ? recon7_window<1>(cc, q, vel > RL(0.0)) : recon7_window<D::PC>(cc, q, vel > RL(0.0));
                     flux = (isx ? G.dy : G.dxcf[min(j0 + b, G.Ny)]) * dzk * (vel * r);
                 }
                 sfx[tr * NFV + f] = flux;
@@ -970,7 +970,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
             for (int r = 0; r < RFE; r++) {
                 const int f = tid + r * NT;
                 if (f < NFV) {
-                    const double vel = svel[f];
+                    const real vel = svel[f];
                     const bool isx = f < D::NFX;
                     const int g = isx ? f : f - D::NFX;
                     const int w = isx ? TX + 1 : TX;
@@ -982,18 +982,18 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
                     if (k >= (t12 >> 16)) N = 2;
                     if (k >= (t34 & 0xffff)) N = 3;
                     if (k >= (t34 >> 16)) N = 4;
-                    double flux[2] = {0.0, 0.0};
-                    if (vel != 0.0 && N > 0) {
-                        const bool left = vel > 0.0;
+                    real flux[2] = {RL(0.0), RL(0.0)};
+                    if (vel != RL(0.0) && N > 0) {
+                        const bool left = vel > RL(0.0);
                         const int q = (b + D::HC) * D::PC + (a + D::HC);   // the cell on the high side of the face
                         const int jj = min(j0 + b, isx ? G.Ny - 1 : G.Ny);
-                        const double metric = isx ? G.dy : G.dxcf[jj];
+                        const real metric = isx ? G.dy : G.dxcf[jj];
                         const long long st = left ? stride : -stride;
                         const long long bq = left ? q - N * stride : q + (N - 1) * stride;
 #pragma unroll
                         for (int tr = 0; tr < 2; tr++) {
-                            const double* cc = sc + tr * D::NCP;
-                            const double rr = OB_DISPATCH(N, recon_cell<1>(cc, bq, st), recon_cell<2>(cc, bq, st),
+                            const real* cc = sc + tr * D::NCP;
+                            const real rr = OB_DISPATCH(N, recon_cell<1>(cc, bq, st), recon_cell<2>(cc, bq, st),
                                                           recon_cell<3>(cc, bq, st), recon_cell<4>(cc, bq, st), recon_cell<4>(cc, bq, st));
                             flux[tr] = metric * dzk * (vel * rr);
                         }
@@ -1011,7 +1011,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
             if (PIPE) {
                 if (k + 1 < k_end) {   // the next level's tiles, requested at the top of this iteration
                     mbar_wait(&bar[buf ^ 1], ((it + 1) >> 1) & 1);
-                    const double* nx = sm + (buf ^ 1) * 2 * D::NCP;
+                    const real* nx = sm + (buf ^ 1) * 2 * D::NCP;
                     Tp = nx[q]; Sp = nx[D::NCP + q];
                 } else {
                     Tp = F.T[cbase + (long long)kp * G.sz]; Sp = F.S[cbase + (long long)kp * G.sz];
@@ -1020,19 +1020,19 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
             }
 #pragma unroll
             for (int tr = 0; tr < 2; tr++) {
-                const double ck = PIPE ? (tr == 0 ? ckT : ckS) : sc[tr * D::NCP + q];
-                const double cm = tr == 0 ? Tm : Sm, cp = tr == 0 ? Tp : Sp;
-                double fzl = az * wlo * 0.5 * (cm + ck);
-                const double fzh = az * whi * 0.5 * (ck + cp);
-                if (GEN && k > 0 && k <= kb_own) fzl = 0.0;   // immersed-peripheral bottom face
-                const double fxw = sfx[tr * NFV + fxi], fxe = sfx[tr * NFV + fxi + 1];
-                const double fys = sfx[tr * NFV + D::NFX + fyi], fyn = sfx[tr * NFV + D::NFX + fyi + TX];
-                double Gt = -((fxe - fxw) + (fyn - fys) + (fzh - fzl)) * (raz * rdzk);
+                const real ck = PIPE ? (tr == 0 ? ckT : ckS) : sc[tr * D::NCP + q];
+                const real cm = tr == 0 ? Tm : Sm, cp = tr == 0 ? Tp : Sp;
+                real fzl = az * wlo * RL(0.5) * (cm + ck);
+                const real fzh = az * whi * RL(0.5) * (ck + cp);
+                if (GEN && k > 0 && k <= kb_own) fzl = RL(0.0);   // immersed-peripheral bottom face
+                const real fxw = sfx[tr * NFV + fxi], fxe = sfx[tr * NFV + fxi + 1];
+                const real fys = sfx[tr * NFV + D::NFX + fyi], fyn = sfx[tr * NFV + D::NFX + fyi + TX];
+                real Gt = -((fxe - fxw) + (fyn - fys) + (fzh - fzl)) * (raz * rdzk);
                 if (k == G.Nz - 1) {
-                    const double J = tr == 0 ? top_flux_T(G, F, i, j, ck, time) : top_flux_S(G, F, i, j, ck, time);
+                    const real J = tr == 0 ? top_flux_T(G, F, i, j, ck, time) : top_flux_S(G, F, i, j, ck, time);
                     Gt -= J * rdzk;
                 }
-                if (GEN && k < kb_own) Gt = 0.0;
+                if (GEN && k < kb_own) Gt = RL(0.0);
                 (tr == 0 ? F.GT : F.GS)[c] = Gt;
             }
         }
@@ -1058,7 +1058,7 @@ static void launch_momentum_t(const Geom& G, const Fields& F, const MomPlan& P, 
     static bool attr_set[64] = {};   // the opt-in to > 48 KB of dynamic shared memory is per device
     int dev = 0;
     cudaGetDevice(&dev);
-    const size_t smem = D::TOTAL * sizeof(double);
+    const size_t smem = D::TOTAL * sizeof(real);
     if (!attr_set[dev & 63]) {
         cudaFuncSetAttribute(k_momentum_tiled<MOM_TX, MOM_TY, false, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_momentum_tiled<MOM_TX, MOM_TY, true, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1092,7 +1092,7 @@ static void launch_tracers_t(const Geom& G, const Fields& F, const MomPlan& P, i
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const size_t smem = D::TOTAL * sizeof(double);
+    const size_t smem = D::TOTAL * sizeof(real);
     if (!attr_set[dev & 63]) {
         cudaFuncSetAttribute(k_tracers_tiled<MOM_TX, MOM_TY, false, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_tracers_tiled<MOM_TX, MOM_TY, true, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,5 +1,5 @@
 // Shared device-side definitions of libocean_b200: geometry, indexing, node predicates,
-// equation of state, WENO wrappers.  sm_100a only; Float64 throughout.
+// equation of state, WENO wrappers.  sm_100a only; `real` = Float64 (default build) or Float32 (-DOB200_F32).
 //
 // HBM layout (DESIGN.md "Data layout"): every 3-D field is one array of (Nz+1) planes x NyP rows x
 // `pitch` doubles, i (longitude) contiguous.  Interior column 0 sits at element X0 = 16 of a row (128-byte
@@ -12,6 +12,16 @@
 
 #include "../../include/ocean_b200.h"
 
+// Arithmetic type of the library (the reference's PRECISION, experiments/run.jl:38): Float64, or Float32 when built with
+// -DOB200_F32 (libocean_b200_f32.so).  Every floating literal of the device code is written RL(x) so that the Float32
+// build has no Float64 arithmetic; the model clock (`time`) and the diagnostics stay Float64 in both.
+#ifdef OB200_F32
+typedef float real;
+#else
+typedef double real;
+#endif
+#define RL(x) ((real)(x))
+
 #define OB_H 7     // horizontal halo used by stencils
 #define OB_X0 16   // element offset of interior column 0 inside a row
 
@@ -21,23 +31,23 @@ struct Geom {
     int pitch2, X0b, Wb;     // barotropic 2-D arrays: own pitch / origin so that they can carry a halo of Wb columns
     long long sz;            // plane stride = pitch * NyP
     // per-latitude metrics, indexable for j = -OB_H-1 .. Ny+OB_H+1 (pointers pre-offset so [j] works)
-    const double *dxfc, *dxcf, *azcc, *azcf, *fff, *taux, *sflux, *tref;
-    const double *rdxfc, *razcc, *razcf;   // reciprocals used by the tendency kernels (DESIGN.md spec decision 8)
+    const real *dxfc, *dxcf, *azcc, *azcf, *fff, *taux, *sflux, *tref;
+    const real *rdxfc, *razcc, *razcf;   // reciprocals used by the tendency kernels (DESIGN.md spec decision 8)
     // vertical metrics: dzc[k], zc[k] for k = -1..Nz (pre-offset), dzf[k] for k = 0..Nz
-    const double *dzc, *dzf, *zc, *rdzc, *rdzf, *rupz, *rloz;   // rupz[k] = 1/(dzc[k] dzf[k+1]), rloz[k] = 1/(dzc[k] dzf[k])
-    const double* zfa;       // z of the (c,c,f) faces, k = 0..Nz (the caller's z_faces)
+    const real *dzc, *dzf, *zc, *rdzc, *rdzf, *rupz, *rloz;   // rupz[k] = 1/(dzc[k] dzf[k+1]), rloz[k] = 1/(dzc[k] dzf[k])
+    const real* zfa;       // z of the (c,c,f) faces, k = 0..Nz (the caller's z_faces)
     const int* kb;           // first active level per column (2-D, field layout); Nz = no active cell
     const int* kfast;        // level from which the full-order, mask-free stencils are valid (2-D)
-    double dy, rdy;
-    double g, alpha, beta_s, rho0;
+    real dy, rdy;
+    real g, alpha, beta_s, rho0;
     int eos;
-    double nu_z, kappa_z;
+    real nu_z, kappa_z;
     int ri_enabled;
-    double ri_nu0, ri_kappa0, ri_kappa_ca, ri_Cen, ri_Cav, ri_Ri0, ri_Ridelta, r1cav, rRidelta;
+    real ri_nu0, ri_kappa0, ri_kappa_ca, ri_Cen, ri_Cav, ri_Ri0, ri_Ridelta, r1cav, rRidelta;
     int bc_kind;
-    double lambda_T, mu_drag;
+    real lambda_T, mu_drag;
     int qgleith;
-    double leith_C, leith_minN2, leith_Vscale;
+    real leith_C, leith_minN2, leith_Vscale;
 };
 
 __device__ __forceinline__ long long idx3(const Geom& G, int i, int j, int k) {
@@ -68,42 +78,42 @@ __device__ __forceinline__ bool peripheral_cff(const Geom& G, int i, int j, int 
 
 // ---- TEOS-10 55-term polynomial (Roquet et al. 2015; SeawaterPolynomials 0.3.2) [OCN-recall coefficients].
 // Stored as R[k][j][i] (powers of zeta, tau, s); evaluated by nested Horner over the triangular support.
-static __device__ __constant__ double TEOS_R[4][7][7] = {
-    {{8.0189615746e+02, 8.6672408165e+02, -1.7864682637e+03, 2.0375295546e+03, -1.2849161071e+03, 4.3227585684e+02, -6.0579916612e+01},
-     {2.6010145068e+01, -6.5281885265e+01, 8.1770425108e+01, -5.6888046321e+01, 1.7681814114e+01, -1.9193502195e+00, 0},
-     {-3.7074170417e+01, 6.1548258127e+01, -6.0362551501e+01, 2.9130021253e+01, -5.4723692739e+00, 0, 0},
-     {2.1661789529e+01, -3.3449108469e+01, 1.9717078466e+01, -3.1742946532e+00, 0, 0, 0},
-     {-8.3627885467e+00, 1.1311538584e+01, -5.3563304045e+00, 0, 0, 0, 0},
-     {5.4048723791e-01, 4.8169980163e-01, 0, 0, 0, 0, 0},
-     {-1.9083568888e-01, 0, 0, 0, 0, 0, 0}},
-    {{1.9681925209e+01, -4.2549998214e+01, 5.0774768218e+01, -3.0938076334e+01, 6.6051753097e+00, 0, 0},
-     {-1.3336301113e+01, -4.4870114575e+00, 5.0042598061e+00, -6.5399043664e-01, 0, 0, 0},
-     {6.7080479603e+00, 3.5063081279e+00, -1.8795372996e+00, 0, 0, 0, 0},
-     {-2.4649669534e+00, -5.5077101279e-01, 0, 0, 0, 0, 0},
-     {5.5927935970e-01, 0, 0, 0, 0, 0, 0},
+static __device__ __constant__ real TEOS_R[4][7][7] = {
+    {{RL(8.0189615746e+02), RL(8.6672408165e+02), -RL(1.7864682637e+03), RL(2.0375295546e+03), -RL(1.2849161071e+03), RL(4.3227585684e+02), -RL(6.0579916612e+01)},
+     {RL(2.6010145068e+01), -RL(6.5281885265e+01), RL(8.1770425108e+01), -RL(5.6888046321e+01), RL(1.7681814114e+01), -RL(1.9193502195e+00), 0},
+     {-RL(3.7074170417e+01), RL(6.1548258127e+01), -RL(6.0362551501e+01), RL(2.9130021253e+01), -RL(5.4723692739e+00), 0, 0},
+     {RL(2.1661789529e+01), -RL(3.3449108469e+01), RL(1.9717078466e+01), -RL(3.1742946532e+00), 0, 0, 0},
+     {-RL(8.3627885467e+00), RL(1.1311538584e+01), -RL(5.3563304045e+00), 0, 0, 0, 0},
+     {RL(5.4048723791e-01), RL(4.8169980163e-01), 0, 0, 0, 0, 0},
+     {-RL(1.9083568888e-01), 0, 0, 0, 0, 0, 0}},
+    {{RL(1.9681925209e+01), -RL(4.2549998214e+01), RL(5.0774768218e+01), -RL(3.0938076334e+01), RL(6.6051753097e+00), 0, 0},
+     {-RL(1.3336301113e+01), -RL(4.4870114575e+00), RL(5.0042598061e+00), -RL(6.5399043664e-01), 0, 0, 0},
+     {RL(6.7080479603e+00), RL(3.5063081279e+00), -RL(1.8795372996e+00), 0, 0, 0, 0},
+     {-RL(2.4649669534e+00), -RL(5.5077101279e-01), 0, 0, 0, 0, 0},
+     {RL(5.5927935970e-01), 0, 0, 0, 0, 0, 0},
      {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}},
-    {{2.0660924175e+00, -4.9527603989e+00, 2.5019633244e+00, 0, 0, 0, 0},
-     {2.0564311499e+00, -2.1311365518e-01, 0, 0, 0, 0, 0},
-     {-1.2419983026e+00, 0, 0, 0, 0, 0, 0},
+    {{RL(2.0660924175e+00), -RL(4.9527603989e+00), RL(2.5019633244e+00), 0, 0, 0, 0},
+     {RL(2.0564311499e+00), -RL(2.1311365518e-01), 0, 0, 0, 0, 0},
+     {-RL(1.2419983026e+00), 0, 0, 0, 0, 0, 0},
      {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}},
-    {{-2.3342758797e-02, -1.8507636718e-02, 0, 0, 0, 0, 0},
-     {3.7969820455e-01, 0, 0, 0, 0, 0, 0},
+    {{-RL(2.3342758797e-02), -RL(1.8507636718e-02), 0, 0, 0, 0, 0},
+     {RL(3.7969820455e-01), 0, 0, 0, 0, 0, 0},
      {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}}};
 
 // r'(tau, s, zeta) and optionally its derivatives w.r.t. Theta and S_A
 template <bool DERIV>
-__device__ __forceinline__ double teos_rprime(double Th, double SA, double Z, double* dTh, double* dSA) {
-    const double Sau = 40.0 * 35.16504 / 35.0, Thu = 40.0, Zu = 1e4, dS = 32.0;
-    const double tau = Th / Thu, s = sqrt((SA + dS) / Sau), ze = -Z / Zu;
+__device__ __forceinline__ real teos_rprime(real Th, real SA, real Z, real* dTh, real* dSA) {
+    const real Sau = RL(40.0) * RL(35.16504) / RL(35.0), Thu = RL(40.0), Zu = RL(1e4), dS = RL(32.0);
+    const real tau = Th / Thu, s = sqrt((SA + dS) / Sau), ze = -Z / Zu;
     const int deg[4] = {6, 4, 2, 1};
-    double r = 0.0, rt = 0.0, rs = 0.0;
+    real r = RL(0.0), rt = RL(0.0), rs = RL(0.0);
 #pragma unroll
     for (int k = 3; k >= 0; k--) {
-        double pj = 0.0, pjt = 0.0, pjs = 0.0;
+        real pj = RL(0.0), pjt = RL(0.0), pjs = RL(0.0);
 #pragma unroll
         for (int j = 6; j >= 0; j--) {
             if (j > deg[k]) continue;
-            double pi = 0.0, pis = 0.0;
+            real pi = RL(0.0), pis = RL(0.0);
 #pragma unroll
             for (int i = 6; i >= 0; i--) {
                 if (i + j > deg[k]) continue;
@@ -116,18 +126,18 @@ __device__ __forceinline__ double teos_rprime(double Th, double SA, double Z, do
         r = r * ze + pj;
         if (DERIV) { rt = rt * ze + pjt; rs = rs * ze + pjs; }
     }
-    if (DERIV) { *dTh = rt / Thu; *dSA = rs / (2.0 * s * Sau); }
+    if (DERIV) { *dTh = rt / Thu; *dSA = rs / (RL(2.0) * s * Sau); }
     return r;
 }
 
 // compile-time equation of state (the column sweeps are instantiated per EOS: the TEOS-10 polynomial costs registers the
 // linear instance does not have under its 32-register occupancy bound)
 template <bool TEOS>
-__device__ __forceinline__ double buoyancy_t(const Geom& G, double T, double S, int k) {
+__device__ __forceinline__ real buoyancy_t(const Geom& G, real T, real S, int k) {
     if (!TEOS) return G.g * (G.alpha * T - G.beta_s * S);
     return -G.g * teos_rprime<false>(T, S, G.zc[k], nullptr, nullptr) / G.rho0;
 }
-__device__ __forceinline__ double buoyancy_of(const Geom& G, double T, double S, int k) {
+__device__ __forceinline__ real buoyancy_of(const Geom& G, real T, real S, int k) {
     return G.eos == OB200_EOS_LINEAR ? buoyancy_t<false>(G, T, S, k) : buoyancy_t<true>(G, T, S, k);
 }
 
@@ -136,44 +146,44 @@ __device__ __forceinline__ double buoyancy_of(const Geom& G, double T, double S,
 // -- not a difference of in-situ buoyancies, which for TEOS-10 would add the compressibility term ∂rho'/∂z at fixed T, S.
 // The caller applies the immersed conditional (zero when either cell is inactive).
 template <bool TEOS>
-__device__ __forceinline__ double n2_face_t(const Geom& G, double Tm, double Sm, double Tk, double Sk, int kf) {
-    double al = G.alpha, be = G.beta_s;
+__device__ __forceinline__ real n2_face_t(const Geom& G, real Tm, real Sm, real Tk, real Sk, int kf) {
+    real al = G.alpha, be = G.beta_s;
     if (TEOS) {
-        double dTh, dSA;
-        teos_rprime<true>(0.5 * (Tm + Tk), 0.5 * (Sm + Sk), G.zfa[kf], &dTh, &dSA);
+        real dTh, dSA;
+        teos_rprime<true>(RL(0.5) * (Tm + Tk), RL(0.5) * (Sm + Sk), G.zfa[kf], &dTh, &dSA);
         al = -dTh / G.rho0; be = dSA / G.rho0;
     }
-    const double rdzf = G.rdzf[kf];
+    const real rdzf = G.rdzf[kf];
     return G.g * (al * ((Tk - Tm) * rdzf) - be * ((Sk - Sm) * rdzf));
 }
-__device__ __forceinline__ double n2_face(const Geom& G, double Tm, double Sm, double Tk, double Sk, int kf) {
+__device__ __forceinline__ real n2_face(const Geom& G, real Tm, real Sm, real Tk, real Sk, int kf) {
     return G.eos == OB200_EOS_LINEAR ? n2_face_t<false>(G, Tm, Sm, Tk, Sk, kf) : n2_face_t<true>(G, Tm, Sm, Tk, Sk, kf);
 }
 
 // Deterministic tanh from +,-,*,/ only (the library is compiled with -fmad=false): the same operation
 // sequence as the CPU oracle, so kappa agrees bit for bit; |error| < 3e-16 absolute.
-__device__ __forceinline__ double det_exp_neg(double y) {   // exp(y), y <= 0
-    const double LOG2E = 1.4426950408889634, LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
-    const double n = rint(y * LOG2E);
-    const double r = (y - n * LN2_HI) - n * LN2_LO;
-    double p = 1.0 / 6227020800.0;
-    const double inv_fact[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
-                                 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+__device__ __forceinline__ real det_exp_neg(real y) {   // exp(y), y <= 0
+    const real LOG2E = RL(1.4426950408889634), LN2_HI = RL(6.93147180369123816490e-01), LN2_LO = RL(1.90821492927058770002e-10);
+    const real n = rint(y * LOG2E);
+    const real r = (y - n * LN2_HI) - n * LN2_LO;
+    real p = RL(1.0) / RL(6227020800.0);
+    const real inv_fact[13] = {RL(1.0) / RL(479001600.0), RL(1.0) / RL(39916800.0), RL(1.0) / RL(3628800.0), RL(1.0) / RL(362880.0), RL(1.0) / RL(40320.0),
+                                 RL(1.0) / RL(5040.0), RL(1.0) / RL(720.0), RL(1.0) / RL(120.0), RL(1.0) / RL(24.0), RL(1.0) / RL(6.0), RL(0.5), RL(1.0), RL(1.0)};
 #pragma unroll
     for (int m = 0; m < 13; m++) p = p * r + inv_fact[m];
     return ldexp(p, (int)n);
 }
-__device__ __forceinline__ double det_tanh(double x) {
-    const double a = fabs(x);
-    if (a > 20.0) return x > 0 ? 1.0 : -1.0;
-    const double t = det_exp_neg(-2.0 * a);
-    const double r = (1.0 - t) / (1.0 + t);
+__device__ __forceinline__ real det_tanh(real x) {
+    const real a = fabs(x);
+    if (a > RL(20.0)) return x > 0 ? RL(1.0) : -RL(1.0);
+    const real t = det_exp_neg(-RL(2.0) * a);
+    const real r = (RL(1.0) - t) / (RL(1.0) + t);
     return x < 0 ? -r : r;
 }
 
-__device__ __forceinline__ double upwind_flux(double vel, double L, double R) {
-    const double a = fabs(vel);
-    return 0.5 * ((vel + a) * L + (vel - a) * R);
+__device__ __forceinline__ real upwind_flux(real vel, real L, real R) {
+    const real a = fabs(vel);
+    return RL(0.5) * ((vel + a) * L + (vel - a) * R);
 }
 
 #define OB_CUDA_CHECK(h, expr)                                                         \

@@ -101,7 +101,11 @@ def metrics(path, workload, n_gpus, git, fp64_peak='37.2'):
         gen = ', 1, 1>' in name.replace('(bool)', '').replace('(int)', '') or '<16, 16, 1,' in name
         a = agg.setdefault(key, {'dram_bytes': 0.0, 'fp64_flops': 0.0, 'ms': 0.0, 'launches': 0, 'fp64_pipe_frac': None})
         a['dram_bytes'] += (val(row, 'dram__bytes_read.sum') or 0.0) + (val(row, 'dram__bytes_write.sum') or 0.0)
-        f = [val(row, f'smsp__sass_thread_inst_executed_op_{op}_pred_on.sum') or 0.0 for op in ('dfma', 'dmul', 'dadd')]
+        # thread-level op counts: the .sum counter when the capture has it, else (sum over SMSPs per cycle) x elapsed cycles
+        cyc = val(row, 'smsp__cycles_elapsed.avg') or 0.0
+        f = [val(row, f'smsp__sass_thread_inst_executed_op_{op}_pred_on.sum')
+             or (val(row, f'smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed') or 0.0) * cyc
+             for op in ('dfma', 'dmul', 'dadd')]
         a['fp64_flops'] += 2 * f[0] + f[1] + f[2]
         a['ms'] += val(row, 'gpu__time_duration.sum') or 0.0
         a['launches'] += 1
