@@ -271,6 +271,9 @@ def main():
     ap.add_argument("--balance", default=os.environ.get("OB200_BALANCE", "equal"), choices=["equal", "cost", "wet"],
                     help="x-slab widths: equal (reference default for DoubleDrake), balanced by kernel cost, or by wet-cell count "
                          "(the reference's LOADBALANCE=1 for RealisticOcean, grid_load_balance.jl:35-75)")
+    ap.add_argument("--precision", default=os.environ.get("PRECISION", "Float64"), choices=["Float64", "Float32"],
+                    help="the reference's PRECISION (experiments/run.jl:38): Float64 is the metric's configuration; Float32 runs "
+                         "libocean_b200_f32.so (launch_strong_scaling.sh:7) and is reported with dtype f32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--persistent-barotropic", type=int, default=int(os.environ.get("OB200_PERSISTENT_BARO", "0")))
@@ -307,7 +310,11 @@ def main():
     else:
         bcs = pkg.set_boundary_conditions("DoubleDrake", grid)
     model = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=fs, eos=pkg.equation_of_state(case.experiment),
-                                            boundary_conditions=bcs, device=local_rank, comm=pkg.Comm())
+                                            boundary_conditions=bcs, device=local_rank, comm=pkg.Comm(), precision=args.precision)
+    f32 = args.precision == "Float32"
+    np_real, torch_real, real_bytes = (np.float32, torch.float32, 4) if f32 else (np.float64, torch.float64, 8)
+    if f32:
+        args.no_cpu_baseline = True      # the CPU oracle is Float64
     if args.persistent_barotropic:
         model.backend.set_option("persistent_barotropic", 1)
     if os.environ.get("OB200_BARO_GRAPH", "1") == "0":
@@ -325,14 +332,14 @@ def main():
 
         def upload():      # one field at a time from pageable memory
             for k in ("T", "S", "U", "V", "ETA"):
-                a = np.ascontiguousarray(realistic_field(pkg, grid, k), dtype=np.float64)
+                a = np.ascontiguousarray(realistic_field(pkg, grid, k), dtype=np_real)
                 model.backend.lib.ob200_set_field(model.backend.h, pkg._abi.FIELD_ID[k], a.ctypes.data, 0, 0, 0, 0)
                 del a
             model.backend.update_state()
     else:
         state = initial_state(pkg, case, grid)
         # pinned host copies of the initial state (what a host application owns)
-        pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in state.items()}
+        pinned = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np_real)).pin_memory() for k, v in state.items()}
 
         def upload():
             for k, t in pinned.items():
@@ -340,7 +347,7 @@ def main():
             model.backend.update_state()
 
     out_names = ("U", "V", "W", "ETA", "T", "S")
-    out_pinned = {} if big else {k: torch.empty(pkg._abi.field_shape(k, *grid.size()), dtype=torch.float64).pin_memory() for k in out_names}
+    out_pinned = {} if big else {k: torch.empty(pkg._abi.field_shape(k, *grid.size()), dtype=torch_real).pin_memory() for k in out_names}
 
     def download():
         for k, t in out_pinned.items():
@@ -419,8 +426,8 @@ def main():
             t = torch.tensor([e2e_el], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_el = float(t.item())
-        h2d = sum(t.numel() * 8 for t in pinned.values())
-        d2h = sum(t.numel() * 8 for t in out_pinned.values())
+        h2d = sum(t.numel() * real_bytes for t in pinned.values())
+        d2h = sum(t.numel() * real_bytes for t in out_pinned.values())
         e2e = {"value": cells * args.steps / e2e_el, "unit": "cell-steps/s",
                "h2d_bytes_per_step": int(h2d * world / args.steps), "d2h_bytes_per_step": int(d2h * world / args.steps),
                "what": "pinned host initial state -> set! -> K x time_step! -> prognostic fields to pinned host; the copies happen "
@@ -436,14 +443,15 @@ def main():
     peak, peak_src = measured_peak()
     local_cells = grid.Nx * Ny * Nz
     mom_ms = groups[6] / args.steps
-    achieved = MOMENTUM_BYTES_PER_CELL * local_cells / (mom_ms * 1e-3) / 1e9 if mom_ms > 0 else None
-    prof = ncu_metrics(args.workload, world)     # committed ncu capture of THIS workload / GPU count, else None
+    bscale = real_bytes / 8.0        # algorithmic bytes per cell are counted in Float64 values: half in the Float32 build
+    achieved = bscale * MOMENTUM_BYTES_PER_CELL * local_cells / (mom_ms * 1e-3) / 1e9 if mom_ms > 0 else None
+    prof = None if f32 else ncu_metrics(args.workload, world)     # committed ncu capture of THIS workload / GPU count, else None
     roofline = {"bound": "hbm", "kernel": "k_momentum_tiled (fused Gu,Gv tendencies; full-order tiles)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the committed capture summary
                 "traffic": prof["momentum"]["dram_bytes"] if prof else None,
                 "traffic_source": (f"profiles/ncu_metrics.json (tree {prof.get('git', '?')}, {prof.get('source', '?')})" if prof else None),
-                "peak_source": peak_src, "algorithmic_bytes_per_cell": MOMENTUM_BYTES_PER_CELL,
+                "peak_source": peak_src, "algorithmic_bytes_per_cell": bscale * MOMENTUM_BYTES_PER_CELL,
                 "ms_per_launch": mom_ms, "note": "FP64-ALU-bound WENO stencil (SURVEY F10); HBM fraction reported as the contract asks"}
     if prof and mom_ms > 0 and "fp64_flops" in prof["momentum"]:
         # the roof that actually bounds this kernel: FP64 flops per launch counted by ncu (SASS op counters, DFMA = 2,
@@ -461,13 +469,13 @@ def main():
     kernel_rooflines = {}
     for name, g in zip(GROUP_NAMES, groups):
         if name in alg_bytes and g > 0:
-            gbs = alg_bytes[name] * local_cells / (g / args.steps * 1e-3) / 1e9
-            kernel_rooflines[name] = {"algorithmic_bytes_per_cell": alg_bytes[name], "GB/s": round(gbs, 1),
+            gbs = bscale * alg_bytes[name] * local_cells / (g / args.steps * 1e-3) / 1e9
+            kernel_rooflines[name] = {"algorithmic_bytes_per_cell": bscale * alg_bytes[name], "GB/s": round(gbs, 1),
                                       "frac_of_measured_hbm": round(gbs / peak, 3)}
     out = {"metric": "grid-cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": workload_config(pkg, args, world),
+           "vs_baseline": None, "dtype": "f32" if f32 else "f64", "data": "synthetic",
+           "config": dict(workload_config(pkg, args, world), **({"precision": "Float32 (libocean_b200_f32.so)"} if f32 else {})),
            "sypd": dt / (elapsed / args.steps) / 365.0,
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches1 - launches0),
            "stage_ms": {n: float(g / args.steps) for n, g in zip(GROUP_NAMES, groups)},

@@ -14,7 +14,11 @@
  *   - every entry point returns int: 0 = OB200_OK, negative = error; the message
  *     is retrievable with ob200_last_error(); nothing throws across the ABI.
  *   - one host thread per handle (the reference is 1 MPI rank : 1 GPU).
- *   - all arithmetic is Float64 (experiments/run.jl:38 PRECISION default).
+ *   - arithmetic and field buffers are Float64 in libocean_b200.so (experiments/run.jl:38 PRECISION default) and
+ *     Float32 in libocean_b200_f32.so (PRECISION="Float32", launch_strong_scaling.sh:7): the same sources built with
+ *     -DOB200_F32, the same entry points; `ob200_real` below is the element type of every FIELD buffer, and
+ *     ob200_real_bytes() tells a binding which of the two libraries it loaded.  Configuration values, the model
+ *     clock, dt and the diagnostics are double in both.
  *   - indices are 0-based here; face i lies between cells i-1 and i
  *     (Oceananigans' convention shifted by one).
  */
@@ -25,6 +29,12 @@
 
 #ifdef __cplusplus
 extern "C" {
+#endif
+
+#ifdef OB200_F32
+typedef float ob200_real;
+#else
+typedef double ob200_real;
 #endif
 
 #define OB200_OK            0
@@ -160,19 +170,20 @@ int  ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out);
 void ob200_destroy(ob200_handle* h);
 const char* ob200_last_error(const ob200_handle* h);   /* h may be NULL      */
 const char* ob200_version(void);
+int32_t ob200_real_bytes(void);                        /* 8 (libocean_b200.so) or 4 (libocean_b200_f32.so) */
 
 /* --- field transfer ------------------------------------------------------
  * `buf` is laid out like an Oceananigans parent array with halos (hx,hy,hz)
  * (0,0,0 = interior(field)); only the interior region is read / written.
  * Replaces set!(model, ...) (src/boundary_and_initial_conditions.jl:15) and
  * the reads done by the output writers (src/simulation_outputs.jl:14-37).   */
-int ob200_set_field(ob200_handle* h, int32_t field, const double* buf, int32_t buf_on_device,
+int ob200_set_field(ob200_handle* h, int32_t field, const ob200_real* buf, int32_t buf_on_device,
                     int32_t hx, int32_t hy, int32_t hz);
-int ob200_get_field(ob200_handle* h, int32_t field, double* buf, int32_t buf_on_device,
+int ob200_get_field(ob200_handle* h, int32_t field, ob200_real* buf, int32_t buf_on_device,
                     int32_t hx, int32_t hy, int32_t hz);
 /* One horizontal level k (0-based) of a 3-D field as a (ny + 2 hy) x (Nx + 2 hx) window: what the surface writer's
  * `Field(model.velocities.u; indices = (:, :, Nz))` views read (src/simulation_outputs.jl:17-25).                  */
-int ob200_get_level(ob200_handle* h, int32_t field, int32_t k, double* buf, int32_t buf_on_device,
+int ob200_get_level(ob200_handle* h, int32_t field, int32_t k, ob200_real* buf, int32_t buf_on_device,
                     int32_t hx, int32_t hy);
 /* --- borrowed arrays ("Julia owns, library borrows": SURVEY 8b) -------------------------------------------------
  * The reference's callbacks and writers read `model.velocities`, `model.tracers`, `model.free_surface.η` and
@@ -183,14 +194,14 @@ int ob200_get_level(ob200_handle* h, int32_t field, int32_t k, double* buf, int3
  * (one device-to-device pass per bound field: u, v, w, eta, T, S at 1/6 degree = 3.5 ms, so the Julia glue calls it on
  * the schedule of the callbacks, not every step); ob200_sync_inputs goes the other way (after `set!(model, ...)`) and
  * ends with update_state!.  Both are ordered on the handle's stream; ob200_sync_outputs returns after the copies are done. */
-int ob200_bind(ob200_handle* h, int32_t field, double* dev_ptr, int32_t hx, int32_t hy, int32_t hz);
+int ob200_bind(ob200_handle* h, int32_t field, ob200_real* dev_ptr, int32_t hx, int32_t hy, int32_t hz);
 int ob200_unbind(ob200_handle* h, int32_t field);
 int ob200_sync_outputs(ob200_handle* h);
 int ob200_sync_inputs(ob200_handle* h);
 
 /* RealisticOcean forcing arrays (src/boundary_and_initial_conditions.jl:90-105):
  * which = 0 taux, 1 tauy, 2 Qs, 3 Fs, 4 Tr, 5 Sr; Nx x Ny(+1 for tauy) x 6.   */
-int ob200_set_forcing(ob200_handle* h, int32_t which, const double* buf, int32_t buf_on_device);
+int ob200_set_forcing(ob200_handle* h, int32_t which, const ob200_real* buf, int32_t buf_on_device);
 
 /* --- the hot path --------------------------------------------------------- */
 /* update_state!(model) -- mask, halos, w, kappa, pHY', tendencies.           */

@@ -15,7 +15,10 @@ using Oceananigans: AbstractModel
 using CUDA
 import Oceananigans.TimeSteppers: time_step!
 
-const LIB = get(ENV, "OCEAN_B200_LIB", "libocean_b200.so")
+# The reference takes its precision from ENV["PRECISION"] (experiments/run.jl:38); so does the choice of the library: the
+# Float32 build has the same entry points and Float32 field buffers (include/ocean_b200.h `ob200_real`).
+const FT = get(ENV, "PRECISION", "Float64") == "Float32" ? Float32 : Float64
+const LIB = get(ENV, "OCEAN_B200_LIB", FT === Float32 ? "libocean_b200_f32.so" : "libocean_b200.so")
 const HALO = 7
 
 # include/ocean_b200.h :: ob200_config (field order and types must match the header)
@@ -84,6 +87,8 @@ progress every 100, near_global_simulation.jl:160-162); use 0 in profile mode an
 function attach(model; device = CUDA.deviceid(), bottom_height, bc_kind, wind_coeffs, salt_coeffs, λ, μ,
                 comm = nothing, MPI = nothing, sync_every = 10)
     grid = model.grid
+    eltype(grid) === FT || error("model precision $(eltype(grid)) but ENV[\"PRECISION\"] selected the $(FT) library ($LIB)")
+    ccall((:ob200_real_bytes, LIB), Int32, ()) == sizeof(FT) || error("$LIB is not the $(FT) build")
     arch = Oceananigans.architecture(grid)
     Nx, Ny, Nz = size(grid)
     fs = model.free_surface
@@ -121,7 +126,7 @@ end
 "ob200_bind: the library borrows the parent arrays for the lifetime of the handle (the model must outlive it)"
 function bind!(h::Handle, id, field)
     Hx, Hy, Hz = halo_size(field.grid)
-    check(h.ptr, ccall((:ob200_bind, LIB), Cint, (Ptr{Cvoid}, Int32, CuPtr{Float64}, Int32, Int32, Int32),
+    check(h.ptr, ccall((:ob200_bind, LIB), Cint, (Ptr{Cvoid}, Int32, CuPtr{FT}, Int32, Int32, Int32),
                        h.ptr, id, pointer(parent(field)), Hx, Hy, size(parent(field), 3) == 1 ? 0 : Hz))
 end
 function bind_model!(h::Handle, model)
@@ -146,12 +151,12 @@ sync_inputs!(model) = sync_inputs!(ATTACHED[model])
 function set_field!(h::Handle, id, field)
     Hx, Hy, Hz = halo_size(field.grid)
     CUDA.synchronize()
-    check(h.ptr, ccall((:ob200_set_field, LIB), Cint, (Ptr{Cvoid}, Int32, CuPtr{Float64}, Int32, Int32, Int32, Int32),
+    check(h.ptr, ccall((:ob200_set_field, LIB), Cint, (Ptr{Cvoid}, Int32, CuPtr{FT}, Int32, Int32, Int32, Int32),
                        h.ptr, id, pointer(parent(field)), 1, Hx, Hy, size(parent(field), 3) == 1 ? 0 : Hz))
 end
 function get_field!(field, h::Handle, id)
     Hx, Hy, Hz = halo_size(field.grid)
-    check(h.ptr, ccall((:ob200_get_field, LIB), Cint, (Ptr{Cvoid}, Int32, CuPtr{Float64}, Int32, Int32, Int32, Int32),
+    check(h.ptr, ccall((:ob200_get_field, LIB), Cint, (Ptr{Cvoid}, Int32, CuPtr{FT}, Int32, Int32, Int32, Int32),
                        h.ptr, id, pointer(parent(field)), 1, Hx, Hy, size(parent(field), 3) == 1 ? 0 : Hz))
 end
 
@@ -165,8 +170,8 @@ end
 
 "One horizontal level of a 3-D field into a Julia-owned 2-D device array (the surface writer's `indices = (:, :, Nz)` views,
 src/simulation_outputs.jl:17-25) without moving the whole field; `k` is 1-based like the reference's index."
-function get_level!(dst::CuArray{Float64, 2}, h::Handle, id, k; halo = (0, 0))
-    check(h.ptr, ccall((:ob200_get_level, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, CuPtr{Float64}, Int32, Int32, Int32),
+function get_level!(dst::CuArray{FT, 2}, h::Handle, id, k; halo = (0, 0))
+    check(h.ptr, ccall((:ob200_get_level, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, CuPtr{FT}, Int32, Int32, Int32),
                        h.ptr, id, k - 1, pointer(dst), 1, halo[1], halo[2]))
 end
 

@@ -13,6 +13,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OB200_LIB", os.path.join(HERE, "csrc", "libocean_b200.so"))   # OB200_LIB: tuning variants
+# the reference's PRECISION (experiments/run.jl:38): the Float32 build of the same sources, same entry points
+LIB_PATH_F32 = os.environ.get("OB200_LIB_F32", os.path.join(HERE, "csrc", "libocean_b200_f32.so"))
+PRECISIONS = {"Float64": (LIB_PATH, np.float64), "Float32": (LIB_PATH_F32, np.float32)}
 
 OB200_HALO = 7
 OB200_EOS_LINEAR, OB200_EOS_TEOS10 = 0, 1
@@ -89,21 +92,22 @@ EXPORTED_SYMBOLS = [
     "ob200_update_state", "ob200_time_step", "ob200_time_steps", "ob200_run_stage", "ob200_sync",
     "ob200_get_clock", "ob200_set_clock", "ob200_diagnostics", "ob200_get_timing", "ob200_set_stream",
     "ob200_set_option", "ob200_comm_unique_id", "ob200_comm_init",
-    "ob200_bind", "ob200_unbind", "ob200_sync_outputs", "ob200_sync_inputs",
+    "ob200_bind", "ob200_unbind", "ob200_sync_outputs", "ob200_sync_inputs", "ob200_real_bytes",
 ]
 
-_lib = None
+_libs = {}
 
 
-def load_library(path: str | None = None):
-    """dlopen libocean_b200.so and declare the prototypes.  Raises if the library is absent."""
-    global _lib
-    if _lib is not None and path is None:
-        return _lib
-    p = path or LIB_PATH
+def load_library(path: str | None = None, precision: str = "Float64"):
+    """dlopen libocean_b200.so (or its Float32 build) and declare the prototypes.  Raises if the library is absent."""
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)} (experiments/run.jl:38), got {precision!r}")
+    if path is None and precision in _libs:
+        return _libs[precision]
+    p = path or PRECISIONS[precision][0]
     if not os.path.exists(p):
         raise RuntimeError(
-            f"libocean_b200.so not found at {p}: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+            f"{os.path.basename(p)} not found at {p}: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
             " (there is no CPU fallback for the product path)")
     try:
         import torch  # noqa: F401  -- loads the bundled libnccl.so.2 / libcudart first so sonames resolve to them
@@ -120,6 +124,10 @@ def load_library(path: str | None = None):
     lib.ob200_last_error.restype = C.c_char_p
     lib.ob200_version.argtypes = []
     lib.ob200_version.restype = C.c_char_p
+    lib.ob200_real_bytes.argtypes = []
+    lib.ob200_real_bytes.restype = C.c_int32
+    if path is None and lib.ob200_real_bytes() != np.dtype(PRECISIONS[precision][1]).itemsize:
+        raise RuntimeError(f"{p} is not the {precision} build (ob200_real_bytes() = {lib.ob200_real_bytes()})")
     for f in (lib.ob200_set_field, lib.ob200_get_field):
         f.argtypes = [H, C.c_int32, dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         f.restype = C.c_int
@@ -162,5 +170,5 @@ def load_library(path: str | None = None):
     lib.ob200_comm_init.argtypes = [H, C.c_void_p]
     lib.ob200_comm_init.restype = C.c_int
     if path is None:
-        _lib = lib
+        _libs[precision] = lib
     return lib

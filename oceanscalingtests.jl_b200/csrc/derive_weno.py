@@ -22,6 +22,7 @@ Conventions:
     upwind-biased reconstruction.
 """
 import os
+import re
 import sys
 import sympy as sp
 
@@ -239,7 +240,23 @@ def emit_device_code(tables, path):
     out.append("};")
     out.append("")
     with open(path, "w") as f:
-        f.write("\n".join(out))
+        f.write(to_real("\n".join(out)))
+
+
+_LIT = re.compile(r'(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)(?![\w.])')
+
+
+def to_real(text):
+    """The device code is written against the library's `real` typedef (Float64, or Float32 with -DOB200_F32): `double`
+    becomes `real` and every floating literal x becomes RL(x) = ((real)(x)) -- same rule as tools/to_real.py."""
+    lines = []
+    for line in text.split("\n"):
+        i = line.find("//")
+        code, comment = (line, "") if i < 0 else (line[:i], line[i:])
+        code = re.sub(r"\bdouble\b", "real", code)
+        code = _LIT.sub(lambda m: "RL(%s)" % m.group(1), code)
+        lines.append(code + comment)
+    return "\n".join(lines)
 
 
 def main():

@@ -385,6 +385,9 @@ static bool onchip_plan(const Geom& G, int ex, int* R, int* Wp, int* a0, int* nb
     return *smem <= 220 * 1024 && *maxc > 0;
 }
 bool baro_onchip_fits(const Geom& G, int ex) {
+#ifdef OB200_F32
+    return false;   // the bulk row copies are laid out for 8-byte elements (16-byte granules): Float64 build only
+#endif
     int R, Wp, a0, nblk, maxc; size_t smem;
     return onchip_plan(G, ex, &R, &Wp, &a0, &nblk, &maxc, &smem);
 }

@@ -46,7 +46,7 @@ __global__ void k_leith_ld(Geom G, Fields F) {
     if (i >= G.Nx + LEITH_E) return;
     real s = RL(0.0);
     const real fc = fabs(f_ccc(G, j));
-    for (int k = 0; k < G.Nz; k++) s += G.dzf[k] * (sqrt(jmax(RL(0.0), dzb(G, F, i, j, k))) / M_PI / fc);
+    for (int k = 0; k < G.Nz; k++) s += G.dzf[k] * (sqrt(jmax(RL(0.0), dzb(G, F, i, j, k))) / RL(M_PI) / fc);
     F.Ld[idx2(G, i, j)] = s;
 }
 __global__ void k_leith_q(Geom G, Fields F) {
@@ -95,7 +95,7 @@ __global__ void k_leith_nu(Geom G, Fields F) {
     const real t1 = RL(1.0) + RL(1.0) / Bu, t2 = RL(1.0) + RL(1.0) / (Ro * Ro);
     real dQ2 = jmin(dq2, dz2 * (t1 * t1));
     dQ2 = jmin(dQ2, dz2 * (t2 * t2));
-    F.nuL[c] = pow(G.leith_C * Ds / M_PI, RL(3.0)) * sqrt(dQ2 + dd2);
+    F.nuL[c] = pow(G.leith_C * Ds / RL(M_PI), RL(3.0)) * sqrt(dQ2 + dd2);
 }
 
 void launch_leith(const Geom& G, const Fields& F, cudaStream_t st) {

@@ -15,6 +15,12 @@
 
 #include "kernels.h"
 
+#ifdef OB200_F32
+#define OB_NCCL_REAL ncclFloat
+#else
+#define OB_NCCL_REAL ncclDouble
+#endif
+
 static thread_local std::string g_last_error;
 long long ob_launch_count = 0;
 
@@ -24,11 +30,11 @@ struct ob200_handle {
     Geom G;
     Fields F;
     MomPlan mom_plan;
-    double *F_Hfc = nullptr, *F_Hcf = nullptr;
-    double *bsendW = nullptr, *bsendE = nullptr, *brecvW = nullptr, *brecvE = nullptr;
+    real *F_Hfc = nullptr, *F_Hcf = nullptr;
+    real *bsendW = nullptr, *bsendE = nullptr, *brecvW = nullptr, *brecvE = nullptr;
     size_t bcount = 0;
     bool substep_exchange = false;   // x-slabs: one-column eta / U exchanges every half substep instead of the wide halo
-    double *e_send_eta = nullptr, *e_recv_eta = nullptr, *e_send_U = nullptr, *e_recv_U = nullptr;   // Ny doubles each
+    real *e_send_eta = nullptr, *e_recv_eta = nullptr, *e_send_U = nullptr, *e_recv_U = nullptr;   // Ny doubles each
     bool periodic_local = true;
     bool own_stream = true;
     cudaStream_t stream = nullptr;
@@ -46,10 +52,10 @@ struct ob200_handle {
     cudaEvent_t ev2[4];                        // timing events on stream2
     int n_timed = 0;
     std::vector<void*> allocs;
-    struct Bound { double* ptr = nullptr; int hx = 0, hy = 0, hz = 0; };
+    struct Bound { real* ptr = nullptr; int hx = 0, hy = 0, hz = 0; };
     Bound bound[OB200_F_COUNT];   // caller-owned device parent arrays (ob200_bind)
     std::vector<double> weights;
-    double* d_weights = nullptr;
+    real* d_weights = nullptr;
     double* d_diag = nullptr;
     // clock
     double time = 0.0, last_dt = INFINITY;
@@ -57,7 +63,7 @@ struct ob200_handle {
     bool fields_dirty = true;   // set_field since the last mask
     // NCCL ring
     ncclComm_t comm = nullptr;
-    double *sendW[2] = {nullptr, nullptr}, *sendE[2] = {nullptr, nullptr}, *recvW[2] = {nullptr, nullptr}, *recvE[2] = {nullptr, nullptr};
+    real *sendW[2] = {nullptr, nullptr}, *sendE[2] = {nullptr, nullptr}, *recvW[2] = {nullptr, nullptr}, *recvE[2] = {nullptr, nullptr};
     size_t xcount[2] = {0, 0};      // per exchange group (OB_XG_UVETA, OB_XG_TS)
     bool early_ts_exchange = true;  // option "early_ts_exchange": T, S halos travel right after their solve, on stream2
     cudaEvent_t ev_ts[2] = {nullptr, nullptr};   // T, S solved (fork) / their halos unpacked (join)
@@ -83,6 +89,18 @@ int dev_alloc(ob200_handle* h, T** p, size_t n, bool zero = true) {
     if (zero) cudaMemset(q, 0, n * sizeof(T));
     h->allocs.push_back(q);
     *p = (T*)q;
+    return OB200_OK;
+}
+
+// host arrays are computed in Float64 and stored in the library's precision (identity copy in the Float64 build)
+int upload_real(ob200_handle* h, const double* src, size_t n, real** dst) {
+    if (int rc = dev_alloc(h, dst, n, false)) return rc;
+#ifdef OB200_F32
+    std::vector<real> t(src, src + n);
+    cudaMemcpy(*dst, t.data(), n * sizeof(real), cudaMemcpyHostToDevice);
+#else
+    cudaMemcpy(*dst, src, n * sizeof(real), cudaMemcpyHostToDevice);
+#endif
     return OB200_OK;
 }
 
@@ -112,7 +130,8 @@ int setup_geometry(ob200_handle* h) {
     const double dlam = (c.lon_east - c.lon_west) / c.Nx_global;
     const double dphi = (c.lat_north - c.lat_south) / c.Ny;
     const double dlam_rad = dlam * pi / 180.0;
-    G.dy = c.radius * (dphi * pi / 180.0);
+    const double dy = c.radius * (dphi * pi / 180.0);
+    G.dy = dy;
     // per-latitude metrics for j = -(H+1) .. Ny+H+1
     const int jo = OB_H + 1, nj = c.Ny + 2 * jo + 1;
     std::vector<double> m[11];
@@ -133,12 +152,11 @@ int setup_geometry(ob200_handle* h) {
         m[7][jj] = std::fmax(0.0, 30.0 * std::cos(1.2 * pi * pc(j) / 180.0));                // T_reference (:154)
         m[8][jj] = 1.0 / m[0][jj]; m[9][jj] = 1.0 / m[2][jj]; m[10][jj] = 1.0 / m[3][jj];
     }
-    G.rdy = 1.0 / G.dy;
-    const double** dst[11] = {&G.dxfc, &G.dxcf, &G.azcc, &G.azcf, &G.fff, &G.taux, &G.sflux, &G.tref, &G.rdxfc, &G.razcc, &G.razcf};
+    G.rdy = 1.0 / dy;
+    const real** dst[11] = {&G.dxfc, &G.dxcf, &G.azcc, &G.azcf, &G.fff, &G.taux, &G.sflux, &G.tref, &G.rdxfc, &G.razcc, &G.razcf};
     for (int q = 0; q < 11; q++) {
-        double* d = nullptr;
-        if (int rc = dev_alloc(h, &d, nj, false)) return rc;
-        cudaMemcpy(d, m[q].data(), nj * sizeof(double), cudaMemcpyHostToDevice);
+        real* d = nullptr;
+        if (int rc = upload_real(h, m[q].data(), nj, &d)) return rc;
         *dst[q] = d + jo;
     }
     // vertical metrics
@@ -148,35 +166,28 @@ int setup_geometry(ob200_handle* h) {
     dzc[0] = dzc[1]; dzc[Nz + 1] = dzc[Nz];
     zc[0] = c.z_faces[0] - 0.5 * dzc[0]; zc[Nz + 1] = c.z_faces[Nz] + 0.5 * dzc[Nz + 1];
     for (int k = 0; k <= Nz; k++) dzf[k] = zc[k + 1] - zc[k];
-    double *dzc_d, *zc_d, *dzf_d, *rdzc_d;
+    real *dzc_d, *zc_d, *dzf_d, *rdzc_d;
     std::vector<double> rdzc(Nz + 2);
     for (int k = 0; k < Nz + 2; k++) rdzc[k] = 1.0 / dzc[k];
-    if (int rc = dev_alloc(h, &rdzc_d, Nz + 2, false)) return rc;
-    cudaMemcpy(rdzc_d, rdzc.data(), (Nz + 2) * sizeof(double), cudaMemcpyHostToDevice);
+    if (int rc = upload_real(h, rdzc.data(), Nz + 2, &rdzc_d)) return rc;
     G.rdzc = rdzc_d + 1;
     {
         std::vector<double> rdzf(Nz + 1), rupz(Nz + 1, 0.0), rloz(Nz + 1, 0.0);
         for (int k = 0; k <= Nz; k++) rdzf[k] = 1.0 / dzf[k];
         for (int k = 0; k < Nz; k++) { rupz[k] = 1.0 / (dzc[k + 1] * dzf[k + 1]); rloz[k] = 1.0 / (dzc[k + 1] * dzf[k]); }
-        double* d[3];
+        real* d[3];
         const std::vector<double>* src[3] = {&rdzf, &rupz, &rloz};
-        for (int q = 0; q < 3; q++) {
-            if (int rc = dev_alloc(h, &d[q], Nz + 1, false)) return rc;
-            cudaMemcpy(d[q], src[q]->data(), (Nz + 1) * sizeof(double), cudaMemcpyHostToDevice);
-        }
+        for (int q = 0; q < 3; q++)
+            if (int rc = upload_real(h, src[q]->data(), Nz + 1, &d[q])) return rc;
         G.rdzf = d[0]; G.rupz = d[1]; G.rloz = d[2];
     }
-    if (int rc = dev_alloc(h, &dzc_d, Nz + 2, false)) return rc;
-    if (int rc = dev_alloc(h, &zc_d, Nz + 2, false)) return rc;
-    if (int rc = dev_alloc(h, &dzf_d, Nz + 1, false)) return rc;
-    cudaMemcpy(dzc_d, dzc.data(), (Nz + 2) * sizeof(double), cudaMemcpyHostToDevice);
-    cudaMemcpy(zc_d, zc.data(), (Nz + 2) * sizeof(double), cudaMemcpyHostToDevice);
-    cudaMemcpy(dzf_d, dzf.data(), (Nz + 1) * sizeof(double), cudaMemcpyHostToDevice);
+    if (int rc = upload_real(h, dzc.data(), Nz + 2, &dzc_d)) return rc;
+    if (int rc = upload_real(h, zc.data(), Nz + 2, &zc_d)) return rc;
+    if (int rc = upload_real(h, dzf.data(), Nz + 1, &dzf_d)) return rc;
     G.dzc = dzc_d + 1; G.zc = zc_d + 1; G.dzf = dzf_d;
     {
-        double* zfa_d;
-        if (int rc = dev_alloc(h, &zfa_d, Nz + 1, false)) return rc;
-        cudaMemcpy(zfa_d, c.z_faces, (Nz + 1) * sizeof(double), cudaMemcpyHostToDevice);
+        real* zfa_d;
+        if (int rc = upload_real(h, c.z_faces, Nz + 1, &zfa_d)) return rc;
         G.zfa = zfa_d;
     }
     // bathymetry -> first active level per column; rows outside the y-domain are fully inactive
@@ -209,10 +220,8 @@ int setup_geometry(ob200_handle* h) {
                 Hfc[(size_t)(j + OB_H) * G.pitch2 + (i + G.X0b)] = a;
                 Hcf[(size_t)(j + OB_H) * G.pitch2 + (i + G.X0b)] = b;
             }
-        if (int rc = dev_alloc(h, &h->F_Hfc, n2b, false)) return rc;
-        if (int rc = dev_alloc(h, &h->F_Hcf, n2b, false)) return rc;
-        cudaMemcpy(h->F_Hfc, Hfc.data(), n2b * sizeof(double), cudaMemcpyHostToDevice);
-        cudaMemcpy(h->F_Hcf, Hcf.data(), n2b * sizeof(double), cudaMemcpyHostToDevice);
+        if (int rc = upload_real(h, Hfc.data(), n2b, &h->F_Hfc)) return rc;
+        if (int rc = upload_real(h, Hcf.data(), n2b, &h->F_Hcf)) return rc;
     }
     // first level from which the mask-free full-order stencils are valid: every cell within 5 columns / rows
     // wet and in the domain; the level just above a neighbour's sea floor still needs the conditional
@@ -276,8 +285,8 @@ int setup_geometry(ob200_handle* h) {
     return OB200_OK;
 }
 
-// TMA descriptor of one 3-D field: dims (pitch, NyP, Nz+1) doubles, box (bx, by, 1); out-of-range elements read 0
-int encode_tile_map(ob200_handle* h, CUtensorMap* tm, double* base, int bx, int by) {
+// TMA descriptor of one 3-D field: dims (pitch, NyP, Nz+1) elements, box (bx, by, 1); out-of-range elements read 0
+int encode_tile_map(ob200_handle* h, CUtensorMap* tm, real* base, int bx, int by) {
     static PFN_cuTensorMapEncodeTiled encode = nullptr;
     if (!encode) {
         cudaDriverEntryPointQueryResult q;
@@ -288,10 +297,10 @@ int encode_tile_map(ob200_handle* h, CUtensorMap* tm, double* base, int bx, int 
     }
     const Geom& G = h->G;
     cuuint64_t dims[3] = {(cuuint64_t)G.pitch, (cuuint64_t)G.NyP, (cuuint64_t)(G.Nz + 1)};
-    cuuint64_t strides[2] = {(cuuint64_t)G.pitch * 8, (cuuint64_t)G.sz * 8};
+    cuuint64_t strides[2] = {(cuuint64_t)G.pitch * sizeof(real), (cuuint64_t)G.sz * sizeof(real)};
     cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = encode(tm, sizeof(real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return h->fail(OB200_ECUDA, "cuTensorMapEncodeTiled", "encode failed");
     return OB200_OK;
@@ -302,16 +311,16 @@ int alloc_fields(ob200_handle* h) {
     Fields& F = h->F;
     std::memset(&F, 0, sizeof(F));
     const size_t n3 = (size_t)G.sz * (G.Nz + 1), n2 = (size_t)G.sz;
-    double** f3[] = {&F.u, &F.v, &F.w, &F.T, &F.S, &F.p, &F.kc, &F.ku, &F.Ri, &F.scratch, &F.scratch2,
+    real** f3[] = {&F.u, &F.v, &F.w, &F.T, &F.S, &F.p, &F.kc, &F.ku, &F.Ri, &F.scratch, &F.scratch2,
                      &F.Gu, &F.Gv, &F.GT, &F.GS, &F.Gu0, &F.Gv0, &F.GT0, &F.GS0};
-    for (double** p : f3)
+    for (real** p : f3)
         if (int rc = dev_alloc(h, p, n3)) return rc;
     if (G.qgleith)
-        for (double** p : {&F.nuL, &F.qx, &F.qy})
+        for (real** p : {&F.nuL, &F.qx, &F.qy})
             if (int rc = dev_alloc(h, p, n3)) return rc;
     const size_t n2b = (size_t)G.pitch2 * G.NyP;
-    double** f2[] = {&F.eta, &F.U, &F.V, &F.etab, &F.Ub, &F.Vb, &F.GU, &F.GV, &F.Usum, &F.Vsum};
-    for (double** p : f2)
+    real** f2[] = {&F.eta, &F.U, &F.V, &F.etab, &F.Ub, &F.Vb, &F.GU, &F.GV, &F.Usum, &F.Vsum};
+    for (real** p : f2)
         if (int rc = dev_alloc(h, p, n2b)) return rc;
     F.Hfc = h->F_Hfc; F.Hcf = h->F_Hcf;
     if (int rc = dev_alloc(h, &F.Ld, n2)) return rc;
@@ -321,6 +330,9 @@ int alloc_fields(ob200_handle* h) {
         tend_tile_boxes(&mx, &my, &tx, &ty);
         const char* e = getenv("OB200_NO_TMA");
         P.use_tma = !(e && e[0] == '1');
+#ifdef OB200_F32
+        P.use_tma = false;   // the tile boxes (start column, row bytes) are laid out for 8-byte elements: register staging
+#endif
         if (P.use_tma) {
             if (int rc = encode_tile_map(h, &P.tm_u, F.u, mx, my)) return rc;
             if (int rc = encode_tile_map(h, &P.tm_v, F.v, mx, my)) return rc;
@@ -331,7 +343,7 @@ int alloc_fields(ob200_handle* h) {
     return OB200_OK;
 }
 
-struct FieldRef { double* p; int ny, nz; int layout; };   // layout: 0 = 3-D, 1 = 2-D plane layout, 2 = barotropic
+struct FieldRef { real* p; int ny, nz; int layout; };   // layout: 0 = 3-D, 1 = 2-D plane layout, 2 = barotropic
 FieldRef field_ref(ob200_handle* h, int id) {
     const Geom& G = h->G;
     Fields& F = h->F;
@@ -383,10 +395,10 @@ int exchange_halos(ob200_handle* h, cudaStream_t st = nullptr, int groups = 3) {
     ncclGroupStart();
     for (int g = 0; g < 2; g++)
         if (groups & (1 << g)) {
-            ncclSend(h->sendE[g], h->xcount[g], ncclDouble, east, h->comm, st);
-            ncclSend(h->sendW[g], h->xcount[g], ncclDouble, west, h->comm, st);
-            ncclRecv(h->recvW[g], h->xcount[g], ncclDouble, west, h->comm, st);
-            ncclRecv(h->recvE[g], h->xcount[g], ncclDouble, east, h->comm, st);
+            ncclSend(h->sendE[g], h->xcount[g], OB_NCCL_REAL, east, h->comm, st);
+            ncclSend(h->sendW[g], h->xcount[g], OB_NCCL_REAL, west, h->comm, st);
+            ncclRecv(h->recvW[g], h->xcount[g], OB_NCCL_REAL, west, h->comm, st);
+            ncclRecv(h->recvE[g], h->xcount[g], OB_NCCL_REAL, east, h->comm, st);
         }
     ncclResult_t rc = ncclGroupEnd();
     if (rc != ncclSuccess) return h->fail(OB200_ENCCL, "halo exchange", ncclGetErrorString(rc));
@@ -496,10 +508,10 @@ int barotropic_wide_exchange(ob200_handle* h) {
     const int west = (r + n - 1) % n, east = (r + 1) % n;
     launch_pack_baro(h->G, h->F, h->bsendW, h->bsendE, W, false, h->stream);
     ncclGroupStart();   // east-bound first: see exchange_halos
-    ncclSend(h->bsendE, h->bcount, ncclDouble, east, h->comm, h->stream);
-    ncclSend(h->bsendW, h->bcount, ncclDouble, west, h->comm, h->stream);
-    ncclRecv(h->brecvW, h->bcount, ncclDouble, west, h->comm, h->stream);
-    ncclRecv(h->brecvE, h->bcount, ncclDouble, east, h->comm, h->stream);
+    ncclSend(h->bsendE, h->bcount, OB_NCCL_REAL, east, h->comm, h->stream);
+    ncclSend(h->bsendW, h->bcount, OB_NCCL_REAL, west, h->comm, h->stream);
+    ncclRecv(h->brecvW, h->bcount, OB_NCCL_REAL, west, h->comm, h->stream);
+    ncclRecv(h->brecvE, h->bcount, OB_NCCL_REAL, east, h->comm, h->stream);
     ncclResult_t rc = ncclGroupEnd();
     if (rc != ncclSuccess) return h->fail(OB200_ENCCL, "barotropic halo exchange", ncclGetErrorString(rc));
     launch_pack_baro(h->G, h->F, h->brecvW, h->brecvE, W, true, h->stream);
@@ -507,10 +519,10 @@ int barotropic_wide_exchange(ob200_handle* h) {
 }
 
 // one-column ring exchange: my `send` goes to `to`, `recv` comes from the opposite neighbour
-int edge_exchange(ob200_handle* h, const double* send, double* recv, int to, int from) {
+int edge_exchange(ob200_handle* h, const real* send, real* recv, int to, int from) {
     ncclGroupStart();
-    ncclSend(send, h->G.Ny, ncclDouble, to, h->comm, h->stream);
-    ncclRecv(recv, h->G.Ny, ncclDouble, from, h->comm, h->stream);
+    ncclSend(send, h->G.Ny, OB_NCCL_REAL, to, h->comm, h->stream);
+    ncclRecv(recv, h->G.Ny, OB_NCCL_REAL, from, h->comm, h->stream);
     ncclResult_t rc = ncclGroupEnd();
     if (rc != ncclSuccess) return h->fail(OB200_ENCCL, "barotropic edge exchange", ncclGetErrorString(rc));
     return OB200_OK;
@@ -614,8 +626,8 @@ int step_body(ob200_handle* h, double dt, bool euler) {
     const Geom& G = h->G;
     cudaStream_t s1 = h->stream, s2 = h->stream2;
     if (euler) {
-        const size_t n3 = (size_t)G.sz * (G.Nz + 1) * sizeof(double);
-        for (double* g : {h->F.Gu0, h->F.Gv0, h->F.GT0, h->F.GS0}) cudaMemsetAsync(g, 0, n3, s1);
+        const size_t n3 = (size_t)G.sz * (G.Nz + 1) * sizeof(real);
+        for (real* g : {h->F.Gu0, h->F.Gv0, h->F.GT0, h->F.GS0}) cudaMemsetAsync(g, 0, n3, s1);
     }
     int e = 0;
     auto mark = [&]() { if (h->timing) cudaEventRecord(h->ev[e++], s1); };
@@ -660,8 +672,8 @@ int step_body_serial(ob200_handle* h, double dt, bool euler) {
     const Geom& G = h->G;
     cudaStream_t s1 = h->stream;
     if (euler) {
-        const size_t n3 = (size_t)G.sz * (G.Nz + 1) * sizeof(double);
-        for (double* g : {h->F.Gu0, h->F.Gv0, h->F.GT0, h->F.GS0}) cudaMemsetAsync(g, 0, n3, s1);
+        const size_t n3 = (size_t)G.sz * (G.Nz + 1) * sizeof(real);
+        for (real* g : {h->F.Gu0, h->F.Gv0, h->F.GT0, h->F.GS0}) cudaMemsetAsync(g, 0, n3, s1);
     }
     int e = 0;
     auto mark = [&]() { if (h->timing) cudaEventRecord(h->ev[e++], s1); };
@@ -694,7 +706,8 @@ int step_body_serial(ob200_handle* h, double dt, bool euler) {
 // ==========================================================================================================
 extern "C" {
 
-const char* ob200_version(void) { return "ocean_b200 0.1 (sm_100a, f64)"; }
+const char* ob200_version(void) { return sizeof(real) == 8 ? "ocean_b200 0.2 (sm_100a, f64)" : "ocean_b200 0.2 (sm_100a, f32)"; }
+int32_t ob200_real_bytes(void) { return (int32_t)sizeof(real); }
 const char* ob200_last_error(const ob200_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 
 int ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out) {
@@ -736,10 +749,9 @@ int ob200_create(const ob200_config* cfg, int32_t device, ob200_handle** out) {
     }
     int rc = setup_geometry(h);
     if (!rc) rc = alloc_fields(h);
-    if (!rc) rc = dev_alloc(h, &h->d_weights, cfg->n_substeps, false);
+    if (!rc) rc = upload_real(h, h->weights.data(), cfg->n_substeps, &h->d_weights);
     if (!rc) rc = dev_alloc(h, &h->d_diag, 8);
     if (rc) { g_last_error = h->err; ob200_destroy(h); return rc; }
-    cudaMemcpy(h->d_weights, h->weights.data(), cfg->n_substeps * sizeof(double), cudaMemcpyHostToDevice);
     h->cfg.z_faces = nullptr; h->cfg.bottom_height = nullptr; h->cfg.averaging_weights = nullptr;  // borrowed only during create
     {   // the shared-memory solve is an OPTION: measured slower than the HBM-scratch sweep
         const char* e = getenv("OB200_ONCHIP_SOLVE");
@@ -781,7 +793,7 @@ void ob200_destroy(ob200_handle* h) {
     delete h;
 }
 
-static int copy_common(ob200_handle* h, int32_t field, double* buf, int on_device, int hx, int hy, int hz, bool to_field,
+static int copy_common(ob200_handle* h, int32_t field, real* buf, int on_device, int hx, int hy, int hz, bool to_field,
                        int level = -1) {
     if (!h || !buf) return OB200_EINVAL;
     cudaSetDevice(h->device);
@@ -802,13 +814,13 @@ static int copy_common(ob200_handle* h, int32_t field, double* buf, int on_devic
         const int pitch = r.layout == 2 ? G.pitch2 : G.pitch, x0 = r.layout == 2 ? G.X0b : OB_X0;
         const size_t sx = (size_t)G.Nx + 2 * hx, sy = (size_t)r.ny + 2 * hy;
         cudaMemcpy3DParms p = {};
-        const cudaPitchedPtr host = make_cudaPitchedPtr(buf, sx * sizeof(double), sx, sy);
-        const cudaPitchedPtr dev = make_cudaPitchedPtr(r.p, (size_t)pitch * sizeof(double), pitch, G.NyP);
-        const cudaPos hpos = make_cudaPos((size_t)(hx - ex) * sizeof(double), hy, r.layout == 0 ? hz : 0);
-        const cudaPos dpos = make_cudaPos((size_t)(x0 - ex) * sizeof(double), OB_H, 0);
+        const cudaPitchedPtr host = make_cudaPitchedPtr(buf, sx * sizeof(real), sx, sy);
+        const cudaPitchedPtr dev = make_cudaPitchedPtr(r.p, (size_t)pitch * sizeof(real), pitch, G.NyP);
+        const cudaPos hpos = make_cudaPos((size_t)(hx - ex) * sizeof(real), hy, r.layout == 0 ? hz : 0);
+        const cudaPos dpos = make_cudaPos((size_t)(x0 - ex) * sizeof(real), OB_H, 0);
         p.srcPtr = to_field ? host : dev; p.srcPos = to_field ? hpos : dpos;
         p.dstPtr = to_field ? dev : host; p.dstPos = to_field ? dpos : hpos;
-        p.extent = make_cudaExtent((size_t)(G.Nx + 2 * ex) * sizeof(double), r.ny, r.nz);
+        p.extent = make_cudaExtent((size_t)(G.Nx + 2 * ex) * sizeof(real), r.ny, r.nz);
         p.kind = to_field ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
         OB_CUDA_CHECK(h, cudaMemcpy3DAsync(&p, h->stream));
         OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
@@ -817,14 +829,14 @@ static int copy_common(ob200_handle* h, int32_t field, double* buf, int on_devic
     if (to_field) h->fields_dirty = true;
     return OB200_OK;
 }
-int ob200_set_field(ob200_handle* h, int32_t field, const double* buf, int32_t on_device, int32_t hx, int32_t hy, int32_t hz) {
-    return copy_common(h, field, const_cast<double*>(buf), on_device, hx, hy, hz, true);
+int ob200_set_field(ob200_handle* h, int32_t field, const ob200_real* buf, int32_t on_device, int32_t hx, int32_t hy, int32_t hz) {
+    return copy_common(h, field, const_cast<real*>(buf), on_device, hx, hy, hz, true);
 }
-int ob200_get_field(ob200_handle* h, int32_t field, double* buf, int32_t on_device, int32_t hx, int32_t hy, int32_t hz) {
+int ob200_get_field(ob200_handle* h, int32_t field, ob200_real* buf, int32_t on_device, int32_t hx, int32_t hy, int32_t hz) {
     return copy_common(h, field, buf, on_device, hx, hy, hz, false);
 }
 
-int ob200_bind(ob200_handle* h, int32_t field, double* dev_ptr, int32_t hx, int32_t hy, int32_t hz) {
+int ob200_bind(ob200_handle* h, int32_t field, ob200_real* dev_ptr, int32_t hx, int32_t hy, int32_t hz) {
     if (!h) return OB200_EINVAL;
     if (field < 0 || field >= OB200_F_COUNT || !field_ref(h, field).p) return h->fail(OB200_EINVAL, "bind", "unknown or unallocated field id");
     if (!dev_ptr || hx < 0 || hy < 0 || hz < 0) return h->fail(OB200_EINVAL, "bind", "null pointer or negative halo");
@@ -860,17 +872,17 @@ int ob200_sync_inputs(ob200_handle* h) {
     return any ? ob200_update_state(h) : OB200_OK;
 }
 
-int ob200_get_level(ob200_handle* h, int32_t field, int32_t k, double* buf, int32_t on_device, int32_t hx, int32_t hy) {
+int ob200_get_level(ob200_handle* h, int32_t field, int32_t k, ob200_real* buf, int32_t on_device, int32_t hx, int32_t hy) {
     return copy_common(h, field, buf, on_device, hx, hy, 0, false, k);
 }
 
-int ob200_set_forcing(ob200_handle* h, int32_t which, const double* buf, int32_t on_device) {
+int ob200_set_forcing(ob200_handle* h, int32_t which, const ob200_real* buf, int32_t on_device) {
     if (!h || !buf || which < 0 || which > 5) return OB200_EINVAL;
     cudaSetDevice(h->device);
     const size_t n = (size_t)h->G.Nx * (which == 1 ? h->G.Ny + 1 : h->G.Ny) * 6;
     if (!h->F.forcing[which])
         if (int rc = dev_alloc(h, &h->F.forcing[which], n, false)) return rc;
-    OB_CUDA_CHECK(h, cudaMemcpyAsync(h->F.forcing[which], buf, n * sizeof(double),
+    OB_CUDA_CHECK(h, cudaMemcpyAsync(h->F.forcing[which], buf, n * sizeof(real),
                                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
@@ -1039,13 +1051,13 @@ int ob200_comm_init(ob200_handle* h, const void* id128) {
     if (rc != ncclSuccess) return h->fail(OB200_ENCCL, "ncclCommInitRank", ncclGetErrorString(rc));
     for (int g = 0; g < 2; g++) {
         h->xcount[g] = pack_x_count(h->G, g);
-        for (double** p : {&h->sendW[g], &h->sendE[g], &h->recvW[g], &h->recvE[g]})
+        for (real** p : {&h->sendW[g], &h->sendE[g], &h->recvW[g], &h->recvE[g]})
             if (int r2 = dev_alloc(h, p, h->xcount[g])) return r2;
     }
     h->bcount = pack_baro_count(h->G, h->G.Wb);
-    for (double** p : {&h->bsendW, &h->bsendE, &h->brecvW, &h->brecvE})
+    for (real** p : {&h->bsendW, &h->bsendE, &h->brecvW, &h->brecvE})
         if (int r2 = dev_alloc(h, p, h->bcount)) return r2;
-    for (double** p : {&h->e_send_eta, &h->e_recv_eta, &h->e_send_U, &h->e_recv_U})
+    for (real** p : {&h->e_send_eta, &h->e_recv_eta, &h->e_send_U, &h->e_recv_U})
         if (int r2 = dev_alloc(h, p, (size_t)h->G.Ny + 1)) return r2;
     return OB200_OK;
 }

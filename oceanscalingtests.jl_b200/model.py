@@ -189,8 +189,10 @@ class B200Backend:
     """libocean_b200.so through ctypes (the Julia glue does the same with ccall)."""
     name = "b200"
 
-    def __init__(self, cfg, device: int = 0):
-        self.lib = _abi.load_library()
+    def __init__(self, cfg, device: int = 0, precision: str = "Float64"):
+        self.lib = _abi.load_library(precision=precision)
+        self.precision = precision
+        self.dtype = np.float64 if self.lib.ob200_real_bytes() == 8 else np.float32   # element type of every field buffer
         self.h = C.c_void_p()
         rc = self.lib.ob200_create(C.byref(cfg), device, C.byref(self.h))
         if rc != 0:
@@ -204,17 +206,17 @@ class B200Backend:
 
     def set_field(self, fid, arr: np.ndarray, halo=(0, 0, 0)):
         """`arr`: interior-shaped, or parent-shaped with `halo` = (hx, hy, hz) cells around the interior."""
-        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        arr = np.ascontiguousarray(arr, dtype=self.dtype)
         self._check(self.lib.ob200_set_field(self.h, fid, arr.ctypes.data, 0, *halo))
 
     def get_field(self, fid, shape, halo=(0, 0, 0)) -> np.ndarray:
-        out = np.zeros(shape, dtype=np.float64) if any(halo) else np.empty(shape, dtype=np.float64)   # halo cells are not written
+        out = np.zeros(shape, dtype=self.dtype) if any(halo) else np.empty(shape, dtype=self.dtype)   # halo cells are not written
         self._check(self.lib.ob200_get_field(self.h, fid, out.ctypes.data, 0, *halo))
         return out
 
     def get_level(self, fid, k: int, shape2d, halo=(0, 0)) -> np.ndarray:
         """One horizontal level of a 3-D field, (ny + 2 hy, Nx + 2 hx)."""
-        out = np.zeros(shape2d, dtype=np.float64) if any(halo) else np.empty(shape2d, dtype=np.float64)
+        out = np.zeros(shape2d, dtype=self.dtype) if any(halo) else np.empty(shape2d, dtype=self.dtype)
         self._check(self.lib.ob200_get_level(self.h, fid, int(k), out.ctypes.data, 0, *halo))
         return out
 
@@ -238,7 +240,7 @@ class B200Backend:
         self._check(self.lib.ob200_sync_inputs(self.h))
 
     def set_forcing(self, which, arr):
-        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        arr = np.ascontiguousarray(arr, dtype=self.dtype)
         self._check(self.lib.ob200_set_forcing(self.h, which, arr.ctypes.data, 0))
 
     def update_state(self):
@@ -314,7 +316,8 @@ class HydrostaticFreeSurfaceModel:
     def __init__(self, *, grid: LatitudeLongitudeGrid, free_surface: SplitExplicitFreeSurface, eos: str = "linear",
                  closure=(VerticalScalarDiffusivity(), RiBasedVerticalDiffusivity()),
                  boundary_conditions: Optional[BoundaryConditions] = None, advection_orders=(9, 5, 7),
-                 device: int = 0, backend_factory=None, comm=None, barotropic_exchange: str = "auto"):
+                 device: int = 0, backend_factory=None, comm=None, barotropic_exchange: str = "auto",
+                 precision: str = "Float64"):
         self.grid = grid
         self.free_surface = free_surface
         self.closure = tuple(closure)
@@ -324,7 +327,9 @@ class HydrostaticFreeSurfaceModel:
                                             boundary_conditions=self.boundary_conditions,
                                             advection_orders=advection_orders, barotropic_exchange=barotropic_exchange)
         factory = backend_factory or B200Backend
-        self.backend = factory(self.cfg, device) if factory is B200Backend else factory(self.cfg)
+        # `precision`: the reference's PRECISION (experiments/run.jl:38, near_global_simulation.jl:48): which build of the library
+        self.precision = precision
+        self.backend = factory(self.cfg, device, precision) if factory is B200Backend else factory(self.cfg)
         if grid.nranks > 1 and hasattr(self.backend, "comm_init"):
             # NCCL ring bootstrap (replaces MPI.Init + Distributed(...), experiments/run.jl:9-27): rank 0 creates the
             # unique id, `comm.bcast_bytes` (torch.distributed here, MPI.Bcast in Julia) hands it to every rank

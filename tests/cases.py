@@ -72,7 +72,7 @@ class Case:
         return pkg.LatitudeLongitudeGrid(self.Nx, self.Ny, self.Nz, zf, rank=rank, partition=part,
                                          bottom_height_global=bottom)
 
-    def make_model(self, pkg, backend_factory, rank=0, ranks=None, device=0, initialize=True, comm=None):
+    def make_model(self, pkg, backend_factory, rank=0, ranks=None, device=0, initialize=True, comm=None, precision="Float64"):
         grid = self.grid(pkg, rank, ranks)
         res = (self.sector_of or self.Nx) / 360.0
         max_dt = 3240.0 / res
@@ -90,7 +90,7 @@ class Case:
         eos = "linear" if self.experiment == "DoubleDrake" else "teos10"
         model = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=fs, eos=eos, closure=closure,
                                                 boundary_conditions=bcs, device=device,
-                                                backend_factory=backend_factory, comm=comm)
+                                                backend_factory=backend_factory, comm=comm, precision=precision)
         if initialize:
             self.initialize(pkg, model)
         return model

@@ -112,12 +112,14 @@ def test_abi_library_exports_every_declared_symbol(pkg):
     hdr = open(os.path.join(root, "include", "ocean_b200.h")).read()
     declared = sorted(set(re.findall(r"\b(ob200_[a-z_0-9]+)\s*\(", hdr)))
     assert declared == sorted(pkg._abi.EXPORTED_SYMBOLS)
-    lib = pkg._abi.LIB_PATH
-    assert os.path.exists(lib), "libocean_b200.so not built (run __graft_entry__.build())"
-    out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
-    exported = set(line.split()[-1] for line in out.splitlines() if line.strip())
-    missing = [s for s in declared if s not in exported]
-    assert not missing, missing
+    for precision, (lib, dtype) in pkg._abi.PRECISIONS.items():   # the Float64 library and its Float32 build: same entry points
+        assert os.path.exists(lib), f"{os.path.basename(lib)} not built (run __graft_entry__.build())"
+        out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+        exported = set(line.split()[-1] for line in out.splitlines() if line.strip())
+        missing = [s for s in declared if s not in exported]
+        assert not missing, (precision, missing)
+        # loads without a GPU, and says which element type its field buffers have
+        assert pkg._abi.load_library(precision=precision).ob200_real_bytes() == np.dtype(dtype).itemsize
     # the struct the host passes has the size the header's C compiler sees
     src = '#include "ocean_b200.h"\n#include <stdio.h>\nint main(){printf("%zu", sizeof(ob200_config));return 0;}\n'
     exe = "/tmp/ob200_sizeof"

@@ -499,3 +499,52 @@ def test_surface_writer_matches_oracle(pkg, orc, gpu_lib, tmp_path):
         if not err <= 1e-12 * max(float(np.max(np.abs(b))), 1e-300):
             bad.append(f"{k}: {err:.3e}")
     assert not bad, bad
+
+
+# ---- PRECISION = "Float32" (/root/reference/launch_strong_scaling.sh:7, experiments/run.jl:38) ------------------
+# libocean_b200_f32.so is the same source built with real = float.  Its checker is the Float64 oracle on the same inputs:
+# a Float32 run is not a bit pattern to reproduce but a floating-point approximation of the same step, so the bar is a
+# TOLERANCE, written here per field.  T and S carry a large mean (S ~ 35), hence one Float32 ulp is 1.2e-7 relative and
+# ten steps of round-off stay below 1e-5; u, v, eta are differences of O(1) pressure and Coriolis terms at amplitude
+# 1e-2 .. 1e-1 and w is a vertical sum of their horizontal differences, so their relative errors are larger.
+F32_TOL = {"T": 1e-5, "S": 1e-5, "U": 2e-3, "V": 2e-3, "ETA": 2e-3, "W": 2e-2}
+
+
+@pytest.mark.parametrize("name", ["dd_small", "realistic"])
+def test_float32_build_tracks_the_float64_oracle(pkg, orc, gpu_lib, name):
+    c = cases.build_case(name)
+    m32 = c.make_model(pkg, None, precision="Float32")
+    mo = c.make_model(pkg, orc.OracleBackend)
+    assert m32.backend.dtype == np.float32 and m32.get("T").dtype == np.float32
+    # the initial state is the Float64 one rounded to Float32
+    assert rel_linf(m32.get("T").astype(np.float64), mo.get("T")) <= 6e-8
+    for _ in range(10):
+        pkg.time_step(m32, c.dt)
+        pkg.time_step(mo, c.dt)
+    m32.backend.sync()
+    line, bad = [], []
+    for n in PROG:
+        a = m32.get(n).astype(np.float64)
+        assert np.all(np.isfinite(a)), n
+        e = rel_linf(a, mo.get(n))
+        line.append(f"{n} {e:.2e}")
+        if not e <= F32_TOL[n]:
+            bad.append(f"{n}: {e:.3e} > {F32_TOL[n]:g}")
+    print(f"\nFloat32 GPU vs Float64 oracle, {name}, 10 steps, rel Linf: " + "; ".join(line))
+    assert not bad, "; ".join(bad)
+
+
+def test_float32_quiescent_stays_at_rest_and_buffers_round_trip(pkg, gpu_lib):
+    c = cases.build_case("c1")
+    m = c.make_model(pkg, None, precision="Float32")
+    for _ in range(20):
+        pkg.time_step(m, c.dt)
+    for n in PROG:
+        assert np.max(np.abs(m.get(n))) == 0.0, n
+    # field buffers are Float32 end to end: what goes in comes out bit for bit (interior and parent-array layout)
+    rng = np.random.default_rng(7)
+    T = (10.0 + rng.random(m.get("T").shape)).astype(np.float32)
+    m.set("T", T)
+    assert m.get("T").dtype == np.float32 and np.array_equal(m.get("T"), T)
+    p = m.get_parent("T", halo=7)
+    assert p.dtype == np.float32 and np.array_equal(p[7:-7, 7:-7, 7:-7], T)
