@@ -212,6 +212,23 @@ def emit_device_code(tables, path):
         out.append("  }")
         out.append("  __device__ __forceinline__ static double combine(const double* __restrict__ q, const double* __restrict__ b) {")
         out.append("    const double tau = %s;" % taus[N])
+        # Float32 build: the reference's own form alpha_s = C_s (1 + (tau / (beta_s + eps))^2) -- the product of all
+        # (beta_s + eps) of the division-free form below underflows in Float32 ((1e-8)^N squared)
+        polys = []
+        for s_ in range(N):
+            off_ = N - 1 - s_
+            poly_ = None
+            for a_ in range(N):
+                cst_ = "WP%d[%d]" % (N, s_ * N + a_)
+                poly_ = "%s * q[%d]" % (cst_, off_ + a_) if poly_ is None else "fma(%s, q[%d], %s)" % (cst_, off_ + a_, poly_)
+            polys.append(poly_)
+        out.append("#ifdef OB200_F32")
+        out.append("    double asum = 0.0, r = 0.0;")
+        for s_ in range(N):
+            out.append("    { const double t = tau / (b[%d] + 1e-8); const double al = WO%d[%d] * fma(t, t, 1.0);" % (s_, N, s_))
+            out.append("      asum += al; r = fma(al, %s, r); }" % polys[s_])
+        out.append("    return r / asum;")
+        out.append("#else")
         # division-free Z-weights: alpha_s * P^2 = C_s * (P^2 + (tau * P_s)^2), P_s = prod_{r != s} d_r, d = beta + eps
         out.append("    double d[%d], L[%d], R[%d];" % (N, N, N))
         out.append("    " + " ".join("d[%d] = b[%d] + 1e-8;" % (s, s) for s in range(N)))
@@ -229,6 +246,7 @@ def emit_device_code(tables, path):
             out.append("    { const double t = tau * (L[%d] * R[%d]); const double al = WO%d[%d] * fma(t, t, PP);" % (s, s, N, s))
             out.append("      asum += al; r = fma(al, %s, r); }" % poly)
         out.append("    return r / asum;")
+        out.append("#endif")
         out.append("  }")
         out.append("};")
         out.append("")

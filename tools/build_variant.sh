@@ -12,5 +12,5 @@ objs=""
 for o in ocean_b200 kernels_column kernels_baro kernels_halo kernels_tend kernels_leith; do
   if [ "$o.cu" == "$src" ]; then objs="$objs /tmp/variant_$name.o"; else objs="$objs $o.o"; fi
 done
-$NVCC -shared $ARCH -o ../../gpurun_variants/lib_$name.so $objs -L/usr/lib/x86_64-linux-gnu -l:libnccl.so.2 -lcudart
+$NVCC -shared $ARCH -Xlinker -Bsymbolic -o ../../gpurun_variants/lib_$name.so $objs -L/usr/lib/x86_64-linux-gnu -l:libnccl.so.2 -lcudart
 echo built gpurun_variants/lib_$name.so
