@@ -11,6 +11,10 @@ struct Fields {
     // 3-D (Nz+1 planes)
     real *u, *v, *w, *T, *S, *p, *kc, *ku, *Ri, *scratch, *scratch2;
     real *Gu, *Gv, *GT, *GS, *Gu0, *Gv0, *GT0, *GS0;
+    // OPTION (OB200_AB2_COMBINED=1, measured slower overall): the AB2 combination (3/2 + chi) G^n - (1/2 + chi) G^- of u, v, T, S,
+    // written by the tendency kernels beside G^n so that the HBM-bound implicit solve reads ONE tendency array per field
+    // instead of two; null = not allocated
+    real *Gab[4];
     real *nuL, *qx, *qy;
     // 2-D
     real *eta, *U, *V, *etab, *Ub, *Vb, *GU, *GV, *Hfc, *Hcf, *Ld;
@@ -44,8 +48,9 @@ void launch_barotropic_forcing(const Geom& G, const Fields& F, real chi, cudaStr
 // `onchip`: eliminated coefficients and forward values in shared memory (every array crosses HBM once); needs
 // ab2_onchip_fits(G), otherwise the variant with an HBM scratch array.  Same arithmetic, same bits.
 bool ab2_onchip_fits(const Geom& G);
-void launch_ab2_implicit_uv(const Geom& G, const Fields& F, real dt, real chi, bool onchip, cudaStream_t st);
-void launch_ab2_implicit_ts(const Geom& G, const Fields& F, real dt, real chi, bool onchip, cudaStream_t st);
+// `gab`: F.Gab holds the AB2 combination of the current G^n, G^- for the configured chi (valid, regular AB2 step)
+void launch_ab2_implicit_uv(const Geom& G, const Fields& F, real dt, real chi, bool onchip, bool gab, cudaStream_t st);
+void launch_ab2_implicit_ts(const Geom& G, const Fields& F, real dt, real chi, bool onchip, bool gab, cudaStream_t st);
 void launch_correct(const Geom& G, const Fields& F, cudaStream_t st);
 
 // kernels_baro.cu

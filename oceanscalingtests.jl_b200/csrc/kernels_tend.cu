@@ -42,6 +42,17 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* tm, 
                  ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
+// G^n of field q (0 u, 1 v, 2 T, 3 S) and, when allocated, the AB2 combination the next regular step's implicit solve reads
+// instead of G^n and G^- (same expression, same operand order as k_ab2_implicit: bit-identical)
+__device__ __forceinline__ void store_tendency(const Geom& G, const Fields& F, int q, long long c, real g) {
+    real* Gn = q == 0 ? F.Gu : q == 1 ? F.Gv : q == 2 ? F.GT : F.GS;
+    Gn[c] = g;
+    if (F.Gab[q]) {
+        const real* G0 = q == 0 ? F.Gu0 : q == 1 ? F.Gv0 : q == 2 ? F.GT0 : F.GS0;
+        F.Gab[q][c] = G.ab2_ca * g - G.ab2_cb * G0[c];
+    }
+}
+
 // ---- accessors: the same operators read either straight from HBM/L1 (MomG) or from a shared-memory tile
 // in which zeta, the tangential-velocity stencils, the divergence pieces and K were computed once (MomS).
 struct MomG {
@@ -745,15 +756,15 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : MOM_MINB) k_momentum
                 wk[3] = F.w[c + G.sz]; wk[4] = F.w[c - 1 + G.sz]; wk[5] = F.w[c - G.pitch + G.sz];
             }
             if (!GEN) {
-                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, ub, ua, wk);
-                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, vb, va, wk);
+                store_tendency(G, F, 0, c, tend_u<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, ub, ua, wk));
+                store_tendency(G, F, 1, c, tend_v<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, vb, va, wk));
             } else if (k >= T.kfast) {
                 // most cells of a masked tile are still far from any boundary: full-order, check-free path
-                F.Gu[c] = tend_u<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, ub, ua, wk);
-                F.Gv[c] = tend_v<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, vb, va, wk);
+                store_tendency(G, F, 0, c, tend_u<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, ub, ua, wk));
+                store_tendency(G, F, 1, c, tend_v<false>(G, F, M, i, j, k, 5, 3, time, T, mrow, vb, va, wk));
             } else {
-                F.Gu[c] = k < T.per_u ? RL(0.0) : tend_u<true>(G, F, M, i, j, k, NV, ND, time, T, mrow, ub, ua, wk);
-                F.Gv[c] = k < T.per_v ? RL(0.0) : tend_v<true>(G, F, M, i, j, k, NV, ND, time, T, mrow, vb, va, wk);
+                store_tendency(G, F, 0, c, k < T.per_u ? RL(0.0) : tend_u<true>(G, F, M, i, j, k, NV, ND, time, T, mrow, ub, ua, wk));
+                store_tendency(G, F, 1, c, k < T.per_v ? RL(0.0) : tend_v<true>(G, F, M, i, j, k, NV, ND, time, T, mrow, vb, va, wk));
             }
             if (MOM_KNBR) { ub = su[own]; vb = sv[own]; }
         }
@@ -1033,7 +1044,7 @@ __global__ void __launch_bounds__(TX * TY, GEN ? GEN_MINB : TRC_MINB) k_tracers_
                     Gt -= J * rdzk;
                 }
                 if (GEN && k < kb_own) Gt = RL(0.0);
-                (tr == 0 ? F.GT : F.GS)[c] = Gt;
+                store_tendency(G, F, 2 + tr, c, Gt);
             }
         }
         if (!PIPE) __syncthreads();

@@ -39,6 +39,7 @@ struct Geom {
     const int* kb;           // first active level per column (2-D, field layout); Nz = no active cell
     const int* kfast;        // level from which the full-order, mask-free stencils are valid (2-D)
     real dy, rdy;
+    real ab2_ca, ab2_cb;     // 3/2 + chi, 1/2 + chi of the regular AB2 step (the tendency kernels write ca G^n - cb G^-)
     real g, alpha, beta_s, rho0;
     int eos;
     real nu_z, kappa_z;

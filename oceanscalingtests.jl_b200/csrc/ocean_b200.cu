@@ -61,6 +61,9 @@ struct ob200_handle {
     double time = 0.0, last_dt = INFINITY;
     int64_t iteration = 0;
     bool fields_dirty = true;   // set_field since the last mask
+    // F.Gab = ca G^n - cb G^- of the CURRENT G^n, G^- (written by the last tendencies launch, nothing touched G since): the next
+    // regular AB2 step's implicit solve reads it instead of G^n and G^-
+    bool gab_valid = false;
     // NCCL ring
     ncclComm_t comm = nullptr;
     real *sendW[2] = {nullptr, nullptr}, *sendE[2] = {nullptr, nullptr}, *recvW[2] = {nullptr, nullptr}, *recvE[2] = {nullptr, nullptr};
@@ -153,6 +156,7 @@ int setup_geometry(ob200_handle* h) {
         m[8][jj] = 1.0 / m[0][jj]; m[9][jj] = 1.0 / m[2][jj]; m[10][jj] = 1.0 / m[3][jj];
     }
     G.rdy = 1.0 / dy;
+    G.ab2_ca = (real)1.5 + (real)c.ab2_chi; G.ab2_cb = (real)0.5 + (real)c.ab2_chi;   // as k_ab2_implicit forms them
     const real** dst[11] = {&G.dxfc, &G.dxcf, &G.azcc, &G.azcf, &G.fff, &G.taux, &G.sflux, &G.tref, &G.rdxfc, &G.razcc, &G.razcf};
     for (int q = 0; q < 11; q++) {
         real* d = nullptr;
@@ -324,6 +328,15 @@ int alloc_fields(ob200_handle* h) {
         if (int rc = dev_alloc(h, p, n2b)) return rc;
     F.Hfc = h->F_Hfc; F.Hcf = h->F_Hcf;
     if (int rc = dev_alloc(h, &F.Ld, n2)) return rc;
+    {   // combined AB2 tendencies (kernels.h Fields::Gab): four more 3-D arrays, OPTION OB200_AB2_COMBINED=1.  Bit-identical
+        // (tests/test_parity_gpu.py with the variable set), measured at C3 on one B200: the implicit solve drops from 11.14
+        // to 9.94 ms (7.5 GB less DRAM traffic), but the tendency kernels pay 0.66 + 0.93 ms for the extra load and store
+        // (51.98 vs 51.60 ms per step) -- off by default
+        const char* e = getenv("OB200_AB2_COMBINED");
+        if (e && e[0] == '1')
+            for (int q = 0; q < 4; q++)
+                if (int rc = dev_alloc(h, &F.Gab[q], n3)) return rc;
+    }
     {   // TMA descriptors for the tile staging of the tendency kernels (OB200_NO_TMA=1 falls back to register staging)
         MomPlan& P = h->mom_plan;
         int mx, my, tx, ty;
@@ -450,6 +463,7 @@ void tendencies(ob200_handle* h, cudaEvent_t mid = nullptr, cudaEvent_t end = nu
     launch_momentum(G, h->F, P, h->cfg.order_vorticity, h->cfg.order_divergence, h->time, s1, fork ? 1 : 3);
     if (mid) cudaEventRecord(mid, s1);
     launch_tracers(G, h->F, P, h->cfg.order_tracer, h->time, s1, fork ? 1 : 3);
+    h->gab_valid = true;
     if (fork) cudaStreamWaitEvent(s1, h->ev_tend[1], 0);
     if (end) cudaEventRecord(end, s1);
 }
@@ -499,6 +513,7 @@ int update_state(ob200_handle* h) {
 void swap_tendencies(ob200_handle* h) {   // store_tendencies!: G^- <- G^n by pointer swap
     Fields& F = h->F;
     std::swap(F.Gu, F.Gu0); std::swap(F.Gv, F.Gv0); std::swap(F.GT, F.GT0); std::swap(F.GS, F.GS0);
+    h->gab_valid = false;   // until the next tendencies
 }
 
 int barotropic_wide_exchange(ob200_handle* h) {
@@ -633,12 +648,13 @@ int step_body(ob200_handle* h, double dt, bool euler) {
     auto mark = [&]() { if (h->timing) cudaEventRecord(h->ev[e++], s1); };
     auto mark2 = [&](int q) { if (h->timing) cudaEventRecord(h->ev2[q], s2); };
     mark();
-    launch_ab2_implicit_uv(G, h->F, dt, chi, h->onchip_solve, s1);   // also produces G^U, G^V (barotropic forcing)
+    const bool gab = !euler && h->gab_valid;
+    launch_ab2_implicit_uv(G, h->F, dt, chi, h->onchip_solve, gab, s1);   // also produces G^U, G^V (barotropic forcing)
     mark();
     // the T, S solve (HBM-bound) runs beside the barotropic substeps (launch-latency-bound, SMs mostly idle)
     cudaEventRecord(h->ev_join[0], s1); cudaStreamWaitEvent(s2, h->ev_join[0], 0);
     mark2(0);
-    launch_ab2_implicit_ts(G, h->F, dt, chi, h->onchip_solve, s2);
+    launch_ab2_implicit_ts(G, h->F, dt, chi, h->onchip_solve, gab, s2);
     mark2(1);
     const bool ts_early = !h->periodic_local && h->early_ts_exchange && !h->overlap_exchange && !h->fields_dirty;
     if (ts_early) {   // the T, S halos follow their solve on the same side stream
@@ -677,15 +693,16 @@ int step_body_serial(ob200_handle* h, double dt, bool euler) {
     }
     int e = 0;
     auto mark = [&]() { if (h->timing) cudaEventRecord(h->ev[e++], s1); };
+    const bool gab = !euler && h->gab_valid;
     if (h->timing) cudaEventRecord(h->ev2[0], s1);
-    launch_ab2_implicit_ts(G, h->F, dt, chi, h->onchip_solve, s1);
+    launch_ab2_implicit_ts(G, h->F, dt, chi, h->onchip_solve, gab, s1);
     if (h->timing) cudaEventRecord(h->ev2[1], s1);
     // set_field since the last step (fields_dirty): T, S still have to be masked before they travel -> regular exchange
     const bool ts_early = !h->periodic_local && h->early_ts_exchange && !h->overlap_exchange && !h->fields_dirty;
     if (ts_early)
         if (int rc = early_ts_exchange(h)) return rc;
     mark();
-    launch_ab2_implicit_uv(G, h->F, dt, chi, h->onchip_solve, s1);   // also produces G^U, G^V (barotropic forcing)
+    launch_ab2_implicit_uv(G, h->F, dt, chi, h->onchip_solve, gab, s1);   // also produces G^U, G^V (barotropic forcing)
     mark();
     if (int rc = barotropic_loop(h, dt)) return rc;
     mark();
@@ -826,7 +843,7 @@ static int copy_common(ob200_handle* h, int32_t field, real* buf, int on_device,
         OB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
     }
     OB_CUDA_CHECK(h, cudaGetLastError());
-    if (to_field) h->fields_dirty = true;
+    if (to_field) { h->fields_dirty = true; h->gab_valid = false; }   // the caller may have written G^n or G^-
     return OB200_OK;
 }
 int ob200_set_field(ob200_handle* h, int32_t field, const ob200_real* buf, int32_t on_device, int32_t hx, int32_t hy, int32_t hz) {
@@ -926,8 +943,8 @@ int ob200_run_stage(ob200_handle* h, int32_t stage, double dt, int32_t arg) {
     switch (stage) {
         case OB200_ST_BAROTROPIC_FORCING: launch_barotropic_forcing(h->G, h->F, chi, h->stream); break;
         case OB200_ST_AB2_IMPLICIT:
-            launch_ab2_implicit_uv(h->G, h->F, dt, chi, h->onchip_solve, h->stream);
-            launch_ab2_implicit_ts(h->G, h->F, dt, chi, h->onchip_solve, h->stream);
+            launch_ab2_implicit_uv(h->G, h->F, dt, chi, h->onchip_solve, dt == h->last_dt && h->gab_valid, h->stream);
+            launch_ab2_implicit_ts(h->G, h->F, dt, chi, h->onchip_solve, dt == h->last_dt && h->gab_valid, h->stream);
             break;
         case OB200_ST_BAROTROPIC_INIT: launch_baro_init(h->G, h->F, h->periodic_local, 0, h->stream); break;
         case OB200_ST_BAROTROPIC_ETA: launch_baro_eta(h->G, h->F, dtau, h->periodic_local, 0, h->stream); break;
