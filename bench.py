@@ -452,7 +452,8 @@ def main():
                 "traffic": prof["momentum"]["dram_bytes"] if prof else None,
                 "traffic_source": (f"profiles/ncu_metrics.json (tree {prof.get('git', '?')}, {prof.get('source', '?')})" if prof else None),
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": bscale * MOMENTUM_BYTES_PER_CELL,
-                "ms_per_launch": mom_ms, "note": "FP64-ALU-bound WENO stencil (SURVEY F10); HBM fraction reported as the contract asks"}
+                "ms_per_launch": mom_ms,
+                "note": ("FP32" if f32 else "FP64") + "-ALU-bound WENO stencil (SURVEY F10); HBM fraction reported as the contract asks"}
     if prof and mom_ms > 0 and "fp64_flops" in prof["momentum"]:
         # the roof that actually bounds this kernel: FP64 flops per launch counted by ncu (SASS op counters, DFMA = 2,
         # DMUL / DADD = 1) over the LIVE duration; peak measured with tools/fp64_peak.cu

@@ -213,7 +213,12 @@ def emit_device_code(tables, path):
         out.append("  __device__ __forceinline__ static double combine(const double* __restrict__ q, const double* __restrict__ b) {")
         out.append("    const double tau = %s;" % taus[N])
         # Float32 build: the reference's own form alpha_s = C_s (1 + (tau / (beta_s + eps))^2) -- the product of all
-        # (beta_s + eps) of the division-free form below underflows in Float32 ((1e-8)^N squared)
+        # (beta_s + eps) of the division-free form below underflows in Float32 ((1e-8)^N squared).  beta_s >= 0
+        # mathematically, but the expanded quadratic form rounds to values of either sign when the field is smooth, and in
+        # Float32 beta_s + eps is then EXACTLY zero about once per step at 3e7 cells (measured: isolated NaN tendencies after one
+        # step of a 270 x 900 x 120 grid).  The denominator is therefore kept at least 1e-12 away from zero, sign preserved
+        # (clamping beta_s at zero instead hands a stencil whose beta_s is rounding noise a weight 1e10 times the others':
+        # measured unstable within ten steps).
         polys = []
         for s_ in range(N):
             off_ = N - 1 - s_
@@ -225,7 +230,8 @@ def emit_device_code(tables, path):
         out.append("#ifdef OB200_F32")
         out.append("    double asum = 0.0, r = 0.0;")
         for s_ in range(N):
-            out.append("    { const double t = tau / (b[%d] + 1e-8); const double al = WO%d[%d] * fma(t, t, 1.0);" % (s_, N, s_))
+            out.append("    { const double d = b[%d] + 1e-8; const double t = tau / copysign(fmax(fabs(d), 1e-12), d);" % s_)
+            out.append("      const double al = WO%d[%d] * fma(t, t, 1.0);" % (N, s_))
             out.append("      asum += al; r = fma(al, %s, r); }" % polys[s_])
         out.append("    return r / asum;")
         out.append("#else")

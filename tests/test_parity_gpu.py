@@ -505,16 +505,18 @@ def test_surface_writer_matches_oracle(pkg, orc, gpu_lib, tmp_path):
 # libocean_b200_f32.so is the same source built with real = float.  Its checker is the Float64 oracle on the same inputs:
 # a Float32 run is not a bit pattern to reproduce but a floating-point approximation of the same step, so the bar is a
 # TOLERANCE, written here per field.  Measured on B200 after 10 steps (relative L-infinity against the Float64 oracle):
-#   dd_small   u 6.6e-5, v 4.2e-5, w 1.8e-3, eta 6.6e-5, T 2.4e-5, S 3.9e-6
-#   realistic  u 4.1e-3, v 3.1e-3, w 4.1e-2, eta 3.3e-3, T 1.4e-6, S 9.6e-7
-# T and S carry a large mean (one Float32 ulp is 1.2e-7 relative).  u, v, eta are driven by horizontal differences of the
-# hydrostatic pressure (O(1e3) m2/s2 on the 5 km deep RealisticOcean grid: one ulp of p is 6e-5, over a 100 km cell and a
-# 20 min step that is 1e-6 m/s of noise per step on velocities of 5e-2 m/s); w is a vertical sum of horizontal differences
-# of u, v and inherits their noise at a scale 30x smaller.  The bars below are 5x the measured values.
-F32_TOL = {"T": 1.2e-4, "S": 2e-5, "U": 2e-2, "V": 2e-2, "ETA": 2e-2, "W": 2e-1}
+#   dd_small  (96 x 48 x 12)            u 6.6e-5, v 4.2e-5, w 1.8e-3, eta 6.6e-5, T 2.4e-5, S 3.9e-6
+#   realistic (90 x 40 x 8, TEOS-10)    u 4.1e-3, v 3.1e-3, w 4.1e-2, eta 3.3e-3, T 1.4e-6, S 9.6e-7
+#   c3_sector (37 x 900 x 120, 1/6 deg) u 1.1e-2, v 5.0e-3, w 5.8e-3, eta 2.8e-4, T 5.8e-4, S 1.2e-4
+# T and S carry a large mean (one Float32 ulp is 1.2e-7 relative); at NZ = 120 the convective-adjustment switch (N^2 < 0)
+# of near-neutral thin surface layers flips on Float32 noise, which is where their 1e-4 comes from.  u, v, eta are driven
+# by horizontal differences of the hydrostatic pressure (O(1e3) m2/s2: one ulp of p is 6e-5; over a 20 km .. 100 km cell and
+# one step that is 1e-6 m/s of noise per step on velocities of 5e-2 .. 1e-1 m/s); w is a vertical sum of horizontal
+# differences of u, v.  The bars are 5x the largest measured value of each field.
+F32_TOL = {"T": 3e-3, "S": 6e-4, "U": 5e-2, "V": 2.5e-2, "ETA": 2e-2, "W": 2e-1}
 
 
-@pytest.mark.parametrize("name", ["dd_small", "realistic"])
+@pytest.mark.parametrize("name", ["dd_small", "realistic", "c3_sector"])
 def test_float32_build_tracks_the_float64_oracle(pkg, orc, gpu_lib, name):
     c = cases.build_case(name)
     m32 = c.make_model(pkg, None, precision="Float32")
