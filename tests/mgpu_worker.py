@@ -21,7 +21,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = ge.package()
     c = cases.build_case(case_name)
-    m = c.make_model(pkg, None, rank=rank, ranks=world, device=local, comm=pkg.Comm())
+    precision = os.environ.get("OB200_TEST_PRECISION", "Float64")     # Float32: libocean_b200_f32.so, ncclFloat exchanges
+    m = c.make_model(pkg, None, rank=rank, ranks=world, device=local, comm=pkg.Comm(), precision=precision)
     if os.environ.get("OB200_OVERLAP_EXCHANGE") == "1":
         # halo exchange on a second stream beside the interior columns of the auxiliary sweeps (option, same bits)
         m.backend.set_option("overlap_exchange", 1)
@@ -40,7 +41,7 @@ def main():
         d = tempfile.mkdtemp(prefix=f"ob200_ck_{rank}_")
         path = pkg.Checkpointer(d, f"DoubleDrake_checkpoint_{rank}", pkg.TimeInterval(86400.0)).write(m)
         m.backend.close()
-        m = c.make_model(pkg, None, rank=rank, ranks=world, device=local, comm=pkg.Comm(), initialize=False)
+        m = c.make_model(pkg, None, rank=rank, ranks=world, device=local, comm=pkg.Comm(), initialize=False, precision=precision)
         pkg.set_from_checkpoint(m, path)
         for _ in range(nsteps - half):
             pkg.time_step(m, c.dt)
@@ -56,12 +57,12 @@ def main():
         if rank == 0:
             full = np.concatenate(parts, axis=-1)
             if n == names[0]:
-                ref = c.make_model(pkg, None, device=local)
+                ref = c.make_model(pkg, None, device=local, precision=precision)
                 for _ in range(nsteps):
                     pkg.time_step(ref, c.dt)
             same = np.array_equal(full, ref.get(n))
             err = float(np.max(np.abs(full - ref.get(n))))
-            print(f"mgpu {case_name} x{world} {n}: identical={same} max|diff|={err:.3e}", flush=True)
+            print(f"mgpu {case_name} x{world} {precision} {n}: identical={same} max|diff|={err:.3e}", flush=True)
             ok = ok and same
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

@@ -9,8 +9,10 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("case_name", ["dd_mid", "bumpy"])
-def test_slabs_match_single_gpu(case_name):
+@pytest.mark.parametrize("case_name,precision", [("dd_mid", "Float64"), ("bumpy", "Float64"), ("dd_mid", "Float32")])
+def test_slabs_match_single_gpu(case_name, precision):
+    """Float32: the slab run of libocean_b200_f32.so (ncclFloat exchanges) against its own single-GPU run -- the same
+    operations in the same order, so also bit for bit."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -18,7 +20,7 @@ def test_slabs_match_single_gpu(case_name):
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(HERE, "mgpu_worker.py"), case_name, "6"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, OB200_TEST_PRECISION=precision))
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
