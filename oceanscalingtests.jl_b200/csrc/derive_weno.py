@@ -114,9 +114,11 @@ def emit(tables, path, cuda):
     guard = "OB200_WENO_TABLES_%s" % ("CUH" if cuda else "H")
     out = ["// GENERATED by oracle/derive_weno.py -- do not edit.",
            "// WENO-N tables, N = 2..5 (index [N][s][...], rows for N < 2 unused).",
+           "// `real` is the includer's arithmetic type (double, or float with -DOB200_F32); the literals are Float64 and",
+           "// are rounded once, exactly like RL(x) in the device code.",
            "#ifndef %s" % guard, "#define %s" % guard, ""]
     def arr3(name, key, width):
-        out.append("%s double %s[6][5][%d] = {" % (q, name, width))
+        out.append("%s real %s[6][5][%d] = {" % (q, name, width))
         for N in range(6):
             out.append("  {")
             for s in range(5):
@@ -129,7 +131,7 @@ def emit(tables, path, cuda):
             out.append("  },")
         out.append("};")
     arr3("WENO_COEFF", 0, 5)
-    out.append("%s double WENO_OPT[6][5] = {" % q)
+    out.append("%s real WENO_OPT[6][5] = {" % q)
     for N in range(6):
         vals = ["0.0"] * 5
         if N in tables:

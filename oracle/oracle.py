@@ -15,26 +15,28 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libocean_oracle.so")
+# the checker of libocean_b200_f32.so: the same restatement built with real = float (its C interface stays Float64)
+LIB_F32 = os.path.join(HERE, "libocean_oracle_f32.so")
 
 
 def build(force: bool = False) -> str:
     """Build the oracle if its .so is absent (the prebuilt .so travels to the GPU box; file times there are
     not meaningful, so staleness is only checked by `make` when forced, i.e. from __graft_entry__.build())."""
-    if force or not os.path.exists(LIB):
-        subprocess.check_call(["make", "-C", HERE, "libocean_oracle.so"], stdout=subprocess.DEVNULL)
+    if force or not os.path.exists(LIB) or not os.path.exists(LIB_F32):
+        subprocess.check_call(["make", "-C", HERE, "all"], stdout=subprocess.DEVNULL)
     return LIB
 
 
-_lib = None
+_libs = {}
 
 
-def load():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB):
+def load(precision: str = "Float64"):
+    if precision in _libs:
+        return _libs[precision]
+    path = {"Float64": LIB, "Float32": LIB_F32}[precision]
+    if not os.path.exists(path):
         build()
-    lib = C.CDLL(LIB)
+    lib = C.CDLL(path)
     H, dp = C.c_void_p, C.c_void_p
     lib.oracle_create.argtypes = [C.c_void_p]
     lib.oracle_create.restype = H
@@ -67,15 +69,18 @@ def load():
     lib.oracle_set_num_threads.restype = None
     lib.oracle_get_max_threads.restype = C.c_int
     lib.oracle_threads_in_parallel_region.restype = C.c_int
-    _lib = lib
+    lib.oracle_real_bytes.restype = C.c_int
+    assert lib.oracle_real_bytes() == (8 if precision == "Float64" else 4), path
+    _libs[precision] = lib
     return lib
 
 
 class OracleBackend:
     name = "oracle"
+    precision = "Float64"
 
     def __init__(self, cfg):
-        self.lib = load()
+        self.lib = load(self.precision)
         self.h = self.lib.oracle_create(C.byref(cfg))
         if not self.h:
             raise RuntimeError("oracle_create failed")
@@ -175,6 +180,12 @@ class OracleBackend:
             self.close()
         except Exception:
             pass
+
+
+class OracleBackendF32(OracleBackend):
+    """The Float32 build of the oracle.  Buffers at its interface are Float64 arrays holding Float32 values exactly."""
+    name = "oracle_f32"
+    precision = "Float32"
 
 
 def weno(N, q, sa=None, sb=None) -> float:

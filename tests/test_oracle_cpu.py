@@ -363,3 +363,38 @@ def test_compare_dump_tool_on_a_self_made_dump(pkg, orc, tmp_path):
     prod = compare_dump.run_case(pkg, orc.OracleBackend, steps, 600.0)
     d = compare_dump.distances(prod, np.load(path))
     assert 0.0 < max(d.values()) < 1e-11
+
+
+# ---- Float32 build of the oracle (the checker of libocean_b200_f32.so) --------------------------------------------------
+F32_TOL = {"T": 3e-3, "S": 6e-4, "U": 5e-2, "V": 2.5e-2, "ETA": 2e-2, "W": 2e-1}   # as in tests/test_parity_gpu.py
+
+
+@pytest.mark.parametrize("name", ["dd_small", "realistic"])
+def test_float32_oracle_tracks_the_float64_oracle(pkg, orc, name):
+    """libocean_oracle_f32.so is ocean_oracle.cpp compiled with real = float.  It starts from the Float64 initial state
+    rounded once, returns Float32 values exactly (its C interface is Float64), and after 10 steps sits inside the
+    per-field bars the GPU test holds the Float32 library to."""
+    c = cases.build_case(name)
+    m32, m64 = c.make_model(pkg, orc.OracleBackendF32), c.make_model(pkg, orc.OracleBackend)
+    for n in ("U", "V", "ETA", "T", "S"):
+        a = m32.get(n)
+        assert np.array_equal(a, a.astype(np.float32).astype(np.float64)), n      # Float32 values, held exactly
+        assert np.array_equal(a, m64.get(n).astype(np.float32).astype(np.float64)), n
+    for _ in range(10):
+        pkg.time_step(m32, c.dt)
+        pkg.time_step(m64, c.dt)
+    for n, tol in F32_TOL.items():
+        a, b = m32.get(n), m64.get(n)
+        assert np.all(np.isfinite(a)), n
+        assert np.array_equal(a, a.astype(np.float32).astype(np.float64)), n
+        e = float(np.max(np.abs(a - b))) / float(np.max(np.abs(b)))
+        assert 0.0 < e <= tol, (n, e)     # > 0: it really computes in Float32
+
+
+def test_float32_oracle_quiescent_stays_at_rest(pkg, orc):
+    c = cases.build_case("c1")
+    m = c.make_model(pkg, orc.OracleBackendF32)
+    for _ in range(5):
+        pkg.time_step(m, c.dt)
+    for n in ("U", "V", "W", "ETA", "T", "S"):
+        assert np.max(np.abs(m.get(n))) == 0.0, n

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """One-off source transform used to introduce the `real` typedef (Float32 build): in the CODE part of every line (not in
 // comments, not in string literals) `double` becomes `real` and every floating literal x becomes RL(x) = ((real)(x)).
-Lines carrying the marker /*f64*/ are left alone.  The Float64 build must come out bit-identical (SASS compared)."""
+Lines carrying the marker /*f64*/ and regions between /*f64-begin*/ and /*f64-end*/ are left alone.  The Float64 build must come out bit-identical (SASS compared)."""
 import re
 import sys
 
@@ -22,8 +22,15 @@ def conv_code(code):
 def conv(text):
     out = []
     in_block = False
+    keep = False      # between /*f64-begin*/ and /*f64-end*/ nothing is touched
     for line in text.split('\n'):
-        if '/*f64*/' in line or line.lstrip().startswith('#include'):
+        if '/*f64-begin*/' in line:
+            keep = True
+        if '/*f64-end*/' in line:
+            keep = False
+            out.append(line)
+            continue
+        if keep or '/*f64*/' in line or line.lstrip().startswith('#include'):
             out.append(line)
             continue
         if in_block:
