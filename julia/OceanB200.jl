@@ -93,14 +93,16 @@ function attach(model; device = CUDA.deviceid(), bottom_height, bc_kind, wind_co
     Nx, Ny, Nz = size(grid)
     fs = model.free_surface
     w = collect(Float64, fs.settings.substepping.averaging_weights)
-    zf = collect(Float64, Array(grid.underlying_grid.zᵃᵃᶠ[1:Nz+1]))
+    ug = hasproperty(grid, :underlying_grid) ? grid.underlying_grid : grid      # Quiescent has no immersed boundary
+    zf = collect(Float64, Array(ug.zᵃᵃᶠ[1:Nz+1]))
     Nx_global, i_offset, rank, nranks = slab_geometry(arch, Nx)
     hb = bottom_halo_columns(model)
     size(bottom_height) == (Nx + 2hb, Ny) || error("bottom_height must be (Nx + 2*$hb, Ny) = ($(Nx + 2hb), $Ny), got $(size(bottom_height))")
     cfg = Config(; Nx, Ny, Nz, Nx_global, i_offset, rank, nranks,
                  eos_kind = model.buoyancy.model.equation_of_state isa LinearEquationOfState ? 0 : 1,
                  n_substeps = length(w), frac_dtau = fs.settings.substepping.fractional_step_size,
-                 bc_kind, wind_coeffs, salt_coeffs, T_restoring_lambda = λ, drag_mu = μ, bottom_halo_columns = hb)
+                 bc_kind, wind_coeffs = NTuple{24, Float64}(Tuple(wind_coeffs)), salt_coeffs = NTuple{16, Float64}(Tuple(salt_coeffs)),
+                 T_restoring_lambda = λ, drag_mu = μ, bottom_halo_columns = hb)
     cfg.struct_bytes = sizeof(Config)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve w zf bottom_height begin
@@ -191,7 +193,7 @@ end
 function time_step!(h::Handle, model, Δt)
     check(h.ptr, ccall((:ob200_time_step, LIB), Cint, (Ptr{Cvoid}, Float64), h.ptr, Δt))
     Oceananigans.TimeSteppers.tick!(model.clock, Δt)
-    model.clock.last_Δt = Δt
+    hasproperty(model.clock, :last_Δt) && (model.clock.last_Δt = Δt)
     h.sync_every > 0 && model.clock.iteration % h.sync_every == 0 && sync_outputs!(h)
     return nothing
 end
