@@ -398,3 +398,205 @@ def test_float32_oracle_quiescent_stays_at_rest(pkg, orc):
         pkg.time_step(m, c.dt)
     for n in ("U", "V", "W", "ETA", "T", "S"):
         assert np.max(np.abs(m.get(n))) == 0.0, n
+
+
+# ---- single terms of the tendencies against closed forms (states built so that every other term vanishes) -----------------
+# Independent of the oracle's code structure: the expected values are written from the discrete formulas of SURVEY Appendix A
+# with numpy.  Grid metrics as Oceananigans defines them on a LatitudeLongitudeGrid: dx = R cos(phi) dlam, dy = R dphi,
+# Az(c,c) = R^2 dlam (sin phi_f[j+1] - sin phi_f[j]).
+EARTH_R, EARTH_OMEGA = 6371.0e3, 7.292115e-5
+
+
+def _metrics(g):
+    phic, phif = np.deg2rad(g.phi_c()), np.deg2rad(g.phi_f())
+    dlam, dphi = np.deg2rad(g.dlam), np.deg2rad(g.dphi)
+    return dict(phic=phic, phif=phif, dlam=dlam, dphi=dphi, dy=EARTH_R * dphi, dxfc=EARTH_R * np.cos(phic) * dlam,
+                Az=EARTH_R ** 2 * dlam * (np.sin(phif[1:]) - np.sin(phif[:-1])))
+
+
+def test_coriolis_term_alone(pkg, orc):
+    """u = 0, v uniform, T = S = 0 on a flat bottom: zeta = 0, dK/dx = 0, u-advection = 0, no pressure gradient, so
+    G^u = f-bar * (dx-weighted 4-point average of v) / dx(f,c)  (HydrostaticSphericalCoriolis, enstrophy-conserving form)."""
+    m = cases.build_case("quiescent").make_model(pkg, orc.OracleBackend)
+    M = _metrics(m.grid)
+    V0 = 0.1
+    pkg.set_model(m, v=lambda lam, phi, z: V0 + 0 * lam + 0 * phi + 0 * z)
+    f = 2 * EARTH_OMEGA * np.sin(M["phif"])
+    expect = 0.5 * (f[:-1] + f[1:]) * 0.5 * (np.cos(M["phif"][:-1]) + np.cos(M["phif"][1:])) / np.cos(M["phic"]) * V0
+    GU = m.get("GU")
+    inner = slice(8, -8)      # away from the walls, where v = 0 enters the stencils
+    assert np.max(np.abs(GU[:, inner, :] - expect[None, inner, None])) <= 1e-14 * np.max(np.abs(expect))
+
+
+def test_pressure_gradient_term_alone(pkg, orc):
+    """u = v = 0 with horizontally varying T, S (TEOS-10): G^u = -dx(pHY') / dx(f,c), G^v = -dy(pHY') / dy, nothing else."""
+    m = cases.build_case("quiescent").make_model(pkg, orc.OracleBackend)
+    M = _metrics(m.grid)
+    r = np.pi / 180
+    pkg.set_model(m, T=lambda lam, phi, z: 10 + 3 * np.sin(2 * lam * r) * np.cos(3 * phi * r) * np.exp(z / 800.0),
+                  S=lambda lam, phi, z: 35 + 0.3 * np.cos(lam * r) * np.sin(2 * phi * r) + 0 * z)
+    P, GU, GV = m.get("P"), m.get("GU"), m.get("GV")
+    eGU = -(P - np.roll(P, 1, axis=2)) / M["dxfc"][None, :, None]
+    eGV = -(P[:, 1:, :] - P[:, :-1, :]) / M["dy"]
+    assert np.max(np.abs(eGU)) > 1e-6
+    assert np.max(np.abs(GU - eGU)) <= 1e-14 * np.max(np.abs(eGU))
+    assert np.max(np.abs(GV[:, 1:-1, :] - eGV)) <= 1e-14 * np.max(np.abs(eGV))
+    assert np.max(np.abs(GV[:, 0, :])) == 0.0 and np.max(np.abs(GV[:, -1, :])) == 0.0      # walls
+
+
+@pytest.mark.parametrize("speed", [0.3, -0.2])
+def test_tracer_advection_of_a_linear_profile_is_exact(pkg, orc, speed):
+    """Non-divergent flows (zonal: u = U0 cos(phi); meridional: dx(c,f) v = const) advecting a tracer that is linear in the cell
+    index: every WENO candidate reproduces the face value exactly, so the flux-form tendency is -(A u) dT / V for either
+    upwind direction -- pins the flux form, the metrics (spherical Az in the volume) and the direction handling."""
+    m = cases.build_case("quiescent").make_model(pkg, orc.OracleBackend)
+    g, M = m.grid, _metrics(m.grid)
+    r, s = np.pi / 180, 0.01
+    lam0, phi0 = g.lam_c()[0], g.phi_c()[0]
+    away = slice(6, -6)      # away from the periodic wrap of the linear profile / from the walls
+    pkg.set_model(m, u=lambda lam, phi, z: speed * np.cos(phi * r) + 0 * lam + 0 * z,
+                  T=lambda lam, phi, z: 5 + s * (lam - lam0) / g.dlam + 0 * phi + 0 * z, S=35.0)
+    expect = -(speed * np.cos(M["phic"])) * s * M["dy"] / M["Az"]
+    assert np.max(np.abs(m.get("W"))) == 0.0
+    assert np.max(np.abs(m.get("GT")[:, :, away] - expect[None, :, None])) <= 1e-11 * np.max(np.abs(expect))
+    pkg.set_model(m, u=0.0, v=lambda lam, phi, z: speed / np.cos(phi * r) + 0 * lam + 0 * z,
+                  T=lambda lam, phi, z: 5 + s * (phi - phi0) / g.dphi + 0 * lam + 0 * z, S=35.0)
+    expect = -(speed * EARTH_R * M["dlam"]) * s / M["Az"]
+    assert np.max(np.abs(m.get("W")[:, away, :])) <= 1e-17
+    assert np.max(np.abs(m.get("GT")[:, away, :] - expect[None, away, None])) <= 1e-11 * np.max(np.abs(expect[away]))
+
+
+def test_surface_flux_boundary_conditions_alone(pkg, orc):
+    """DoubleDrake at rest with uniform T, S: the only tendencies are the top-level flux divergences -J / dz of the wind stress,
+    the salinity flux and the temperature restoring (src/bathymetry_and_forcings.jl:110-159,
+    src/boundary_and_initial_conditions.jl:58-81)."""
+    c = cases.build_case("dd_small")
+    m = c.make_model(pkg, orc.OracleBackend, initialize=False)
+    g = m.grid
+    T0, S0 = 10.0, 35.0
+    pkg.set_model(m, T=T0, S=S0)
+    dz_top = g.z_faces[-1] - g.z_faces[-2]
+    phi = g.phi_c()
+    L = 75.0
+    tau = np.array([pkg.wind_stress(p, pkg.wind_stress_coefficients(L)) for p in phi])
+    Fs = np.array([pkg.salinity_flux(p, pkg.salinity_flux_coefficients(L, 35.0)) for p in phi])
+    lam_T = 5.0 / (7 * 86400.0)
+    Qt = lam_T * (T0 - pkg.T_reference(phi))
+    GU, GV, GT, GS = (m.get(n) for n in ("GU", "GV", "GT", "GS"))
+    wet = ~g.immersed_cell_mask()[-1]                      # top level, (Ny, Nx)
+    wet_u = wet & np.roll(wet, 1, axis=1)
+    for G, J, w in ((GU, tau, wet_u), (GS, Fs, wet), (GT, Qt, wet)):
+        assert np.max(np.abs(G[:-1])) == 0.0                                   # nothing below the top level
+        e = np.where(w, -J[:, None] / dz_top, 0.0)
+        assert np.max(np.abs(G[-1] - e)) <= 1e-13 * np.max(np.abs(e))
+    assert np.max(np.abs(GV)) == 0.0
+
+
+def test_split_explicit_loop_and_corrector_against_a_numpy_restatement(pkg, orc):
+    """A free-surface bump over a resting, unstratified flat-bottom ocean: the 3-D tendencies vanish, so one time step is the
+    barotropic substep loop (eta first with U^m, then U, V with eta^(m+1); averages with the substep weights; eta <- average)
+    followed by the corrector u(k) = Ubar / H.  Restated here with whole-array numpy operations."""
+    c = cases.build_case("quiescent")
+    m = c.make_model(pkg, orc.OracleBackend)
+    g, fs = m.grid, m.free_surface
+    M = _metrics(g)
+    r = np.pi / 180
+    pkg.set_model(m, eta=lambda lam, phi: 0.1 * np.cos(phi * r) * np.sin(2 * lam * r))
+    eta = m.get("ETA").copy()
+    Ny, Nx = eta.shape
+    grav, H = 9.80665, g.Lz
+    dxcf = EARTH_R * np.cos(M["phif"]) * M["dlam"]
+    dtau = fs.fractional_step_size * c.dt
+    U, V = np.zeros((Ny, Nx)), np.zeros((Ny + 1, Nx))       # V = 0 on the two walls
+    etab, Ub, Vb = np.zeros_like(eta), np.zeros_like(U), np.zeros_like(V)
+    for w in fs.averaging_weights:
+        div = M["dy"] * (np.roll(U, -1, axis=1) - U) + dxcf[1:, None] * V[1:] - dxcf[:-1, None] * V[:-1]
+        eta = eta - dtau * div / M["Az"][:, None]
+        U = U + dtau * (-grav * H * (eta - np.roll(eta, 1, axis=1)) / M["dxfc"][:, None])
+        V[1:Ny] = V[1:Ny] + dtau * (-grav * H * (eta[1:] - eta[:-1]) / M["dy"])
+        etab += w * eta
+        Ub += w * U
+        Vb += w * V
+    pkg.time_step(m, c.dt)
+
+    def rel(a, b):
+        return np.max(np.abs(a - b)) / np.max(np.abs(b))
+    assert np.max(np.abs(Ub)) > 1.0      # the bump did set the ocean in motion (transport in m^2/s)
+    assert rel(m.get("ETA"), etab) <= 1e-13 and rel(m.get("UBAR"), Ub) <= 1e-13 and rel(m.get("VBAR"), Vb) <= 1e-13
+    u, v = m.get("U"), m.get("V")
+    assert rel(u, np.broadcast_to(Ub / H, u.shape)) <= 1e-13 and rel(v, np.broadcast_to(Vb / H, v.shape)) <= 1e-13
+
+
+@pytest.mark.parametrize("stable", [True, False])
+def test_ri_based_diffusivities_against_the_closed_form(pkg, orc, stable):
+    """Horizontally uniform u(z), T(z) on the flat part of DoubleDrake (linear EOS): Ri = N^2 / (du/dz)^2 on faces,
+    tau = (1 - tanh((Ri - Ri0) / Ri_delta)) / 2, kappa_c = kappa0 tau (+ kappa_ca where N^2 < 0), kappa_u = nu0 tau.  The
+    diffusivities are time filtered, so update_state! is repeated until the filter has forgotten its history."""
+    grav, alpha = 9.80665, 1.67e-4
+    m = cases.build_case("dd_small").make_model(pkg, orc.OracleBackend, initialize=False)
+    zc = m.grid.z_c()
+
+    def uf(z):
+        return 0.4 * np.exp(z / 150.0) + 0.3 * z / 3000.0
+
+    def Tf(z):
+        return 10 + 0.02 * np.exp(z / 200.0) + 1e-5 * z if stable else 10 - 8 * np.exp(z / 400.0)
+    pkg.set_model(m, u=lambda lam, phi, z: uf(z) + 0 * lam + 0 * phi, T=lambda lam, phi, z: Tf(z) + 0 * lam + 0 * phi, S=35.0)
+    for _ in range(80):          # the filter keeps 0.6 / 1.6 of its previous value per update: 0.375^80 ~ 1e-34
+        m.backend.update_state()
+    dzf = zc[1:] - zc[:-1]
+    N2 = grav * alpha * (Tf(zc)[1:] - Tf(zc)[:-1]) / dzf
+    S2 = ((uf(zc)[1:] - uf(zc)[:-1]) / dzf) ** 2
+    Ri = np.where(N2 <= 0, 0.0, N2 / S2)
+    tau = 0.5 * (1 - np.tanh((Ri - 0.1) / 0.4))
+    assert (np.all(N2 > 0) and Ri.min() < 0.1 < 1.0 < Ri.max()) if stable else np.all(N2 < 0)
+    ekc = 0.5 * tau + np.where(N2 < 0, 1.7, 0.0)
+    eku = 0.7 * tau
+    kc, ku = m.get("KAPPA_C"), m.get("KAPPA_U")
+    j, i = 20, 45                # far from the ridges and the walls
+    assert np.max(np.abs(kc[1:-1, j, i] / ekc - 1)) <= 1e-12 and np.max(np.abs(ku[1:-1, j, i] / eku - 1)) <= 1e-12
+    assert kc[0, j, i] == 0.0 and kc[-1, j, i] == 0.0
+
+
+def test_second_step_uses_the_quasi_adams_bashforth_combination(pkg, orc):
+    """After one (forward-Euler) step with the same dt, the next AB2 + implicit stage of S must be the backward-Euler solve of
+    S + dt ((3/2 + chi) G^n - (1/2 + chi) G^-) with chi = 0.1 (near_global_simulation.jl:105-113: QuasiAdamsBashforth2 default)."""
+    from scipy.linalg import solve_banded
+    c = cases.build_case("bumpy")
+    m = c.make_model(pkg, orc.OracleBackend)
+    g, dt, chi = m.grid, c.dt, 0.1
+    pkg.time_step(m, dt)
+    S0, Gn, G0, kc = m.get("S"), m.get("GS"), m.get("GS_PREV"), m.get("KAPPA_C")
+    assert np.max(np.abs(G0)) > 0 and np.max(np.abs(Gn - G0)) > 0
+    m.backend.run_stage(pkg._abi.STAGE_ID["AB2_IMPLICIT"], dt, 0)
+    S1 = m.get("S")
+    zf, zc = g.z_faces, g.z_c()
+    dzc = zf[1:] - zf[:-1]
+    dzf = np.full(g.Nz + 1, np.nan)
+    dzf[1:-1] = zc[1:] - zc[:-1]
+    solid = g.immersed_cell_mask()
+    worst, wrong = 0.0, 0.0
+    for j in range(2, g.Ny, 5):
+        for i in range(1, g.Nx, 7):
+            wet = ~solid[:, j, i]
+            if not wet.any():
+                continue
+            rhs = S0[:, j, i] + dt * ((1.5 + chi) * Gn[:, j, i] - (0.5 + chi) * G0[:, j, i])
+            euler = S0[:, j, i] + dt * Gn[:, j, i]
+            K = np.zeros(g.Nz + 1)
+            for kf in range(1, g.Nz):
+                if wet[kf - 1] and wet[kf]:
+                    K[kf] = 3e-5 + kc[kf, j, i]
+            ab = np.zeros((3, g.Nz))
+            for k in range(g.Nz):
+                up = -dt * K[k + 1] / (dzc[k] * dzf[k + 1]) if k < g.Nz - 1 else 0.0
+                lo = -dt * K[k] / (dzc[k] * dzf[k]) if k > 0 else 0.0
+                ab[1, k] = 1.0 - up - lo
+                if k < g.Nz - 1:
+                    ab[0, k + 1] = up
+                if k > 0:
+                    ab[2, k - 1] = lo
+            worst = max(worst, float(np.max(np.abs(solve_banded((1, 1), ab, rhs) - S1[:, j, i]))) / 35.0)
+            wrong = max(wrong, float(np.max(np.abs(solve_banded((1, 1), ab, euler) - S1[:, j, i]))) / 35.0)
+    assert worst < 1e-14, worst
+    assert wrong > 1e3 * worst       # the test can tell AB2 from forward Euler
