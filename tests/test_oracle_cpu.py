@@ -600,3 +600,159 @@ def test_second_step_uses_the_quasi_adams_bashforth_combination(pkg, orc):
             wrong = max(wrong, float(np.max(np.abs(solve_banded((1, 1), ab, euler) - S1[:, j, i]))) / 35.0)
     assert worst < 1e-14, worst
     assert wrong > 1e3 * worst       # the test can tell AB2 from forward Euler
+
+
+# ---- momentum tendencies: the whole assembly at sample points against an independent numpy restatement ------------------
+def _numpy_beta_and_candidates(N, vals):
+    """Per sub-stencil: the value at the face of the polynomial with the given cell averages, and its smoothness indicator
+    (sum over derivatives of the integral over the upwind cell), fitted numerically -- no coefficient tables."""
+    from numpy.polynomial import polynomial as P
+    scale = {2: 1.0, 3: 3.0, 4: 0.24, 5: 0.0504}[N]
+    cand, beta = [], []
+    for s in range(N):
+        cells = np.arange(-1 - s, -1 - s + N)
+        v = vals[N - 1 - s: 2 * N - 1 - s]
+        A = np.array([[((c + 1) ** (m + 1) - c ** (m + 1)) / (m + 1) for m in range(N)] for c in cells])
+        a = np.linalg.solve(A, v)
+        cand.append(a[0])
+        b = 0.0
+        for l in range(1, N):
+            d = P.polyder(a, l)
+            I = P.polyint(P.polymul(d, d))
+            b += P.polyval(0.0, I) - P.polyval(-1.0, I)
+        beta.append(scale * b)
+    return np.array(cand), np.array(beta)
+
+
+def numpy_weno_z(N, q, smooth):
+    """Z-weighted WENO of `q` (2N - 1 values, most upwind-ward first) with the smoothness measured on the fields in `smooth`
+    (their indicators averaged): VelocityStencil for the vorticity, the full divergence for the divergence flux."""
+    optimal = {2: [2 / 3, 1 / 3], 3: [3 / 10, 3 / 5, 1 / 10], 4: [4 / 35, 18 / 35, 12 / 35, 1 / 35],
+               5: [5 / 126, 20 / 63, 10 / 21, 10 / 63, 1 / 126]}[N]
+    tau_w = {2: [1, -1], 3: [1, 0, -1], 4: [1, 3, -3, -1], 5: [1, 2, -6, 2, 1]}[N]
+    cand, _ = _numpy_beta_and_candidates(N, np.asarray(q, dtype=np.float64))
+    beta = np.mean([_numpy_beta_and_candidates(N, np.asarray(f, dtype=np.float64))[1] for f in smooth], axis=0)
+    tau = abs(float(np.dot(tau_w, beta)))
+    alpha = np.array(optimal) * (1 + (tau / (beta + 1e-8)) ** 2)
+    return float(np.sum(alpha / alpha.sum() * cand))
+
+
+def test_momentum_tendencies_against_a_numpy_restatement_at_sample_points(pkg, orc):
+    """G^u, G^v of the vector-invariant form on a flat-bottom ocean with uniform T, S (no pressure gradient), assembled term by
+    term from SURVEY Appendix A with numpy: WENO-9 upwinded vorticity flux with velocity-stencil smoothness, WENO-5 upwinded
+    divergence flux with the full divergence as smoothness field, centred vertical advection, centred kinetic-energy gradient,
+    enstrophy-conserving Coriolis.  Points are at least 8 rows from the walls so that every stencil is full order."""
+    c = cases.build_case("quiescent")
+    m = c.make_model(pkg, orc.OracleBackend)
+    g = m.grid
+    M = _metrics(g)
+    r, D = np.pi / 180, g.Lz
+    pkg.set_model(m, u=lambda lam, phi, z: 0.1 * np.sin(2 * lam * r) * np.cos(phi * r) * (1.0 + z / D),
+                  v=lambda lam, phi, z: 0.05 * np.cos(3 * lam * r) * np.sin(2 * phi * r) * np.exp(z / 1000.0))
+    U, V, W, GU, GV = (m.get(n) for n in ("U", "V", "W", "GU", "GV"))
+    Nz, Ny, Nx = U.shape
+    dz = np.diff(g.z_faces)
+    dy, dxfc, Azc = M["dy"], M["dxfc"], M["Az"]                       # dx at (f,c) latitudes, Az at centre latitudes
+    dxcf = EARTH_R * np.cos(M["phif"]) * M["dlam"]                    # dx at face latitudes
+    Azf = np.full(Ny + 1, np.nan)
+    Azf[1:Ny] = EARTH_R ** 2 * M["dlam"] * (np.sin(M["phic"][1:]) - np.sin(M["phic"][:-1]))   # Az at face latitudes
+    f = 2 * EARTH_OMEGA * np.sin(M["phif"])
+    ix = lambda i: i % Nx
+
+    def u_(k, j, i): return U[k, j, ix(i)]
+    def v_(k, j, i): return V[k, j, ix(i)]
+    def w_(k, j, i): return W[k, j, ix(i)]
+    def zeta(k, j, i): return (dy * v_(k, j, i) - dy * v_(k, j, i - 1) - (dxfc[j] * u_(k, j, i) - dxfc[j - 1] * u_(k, j - 1, i))) / Azf[j]
+    def us(k, j, i): return 0.5 * (u_(k, j - 1, i) + u_(k, j, i))
+    def vs(k, j, i): return 0.5 * (v_(k, j, i - 1) + v_(k, j, i))
+    def dxU(k, j, i): return dy * dz[k] * (u_(k, j, i + 1) - u_(k, j, i))
+    def dyV(k, j, i): return dz[k] * (dxcf[j + 1] * v_(k, j + 1, i) - dxcf[j] * v_(k, j, i))
+    def K(k, j, i): return (0.5 * (u_(k, j, i) ** 2 + u_(k, j, i + 1) ** 2) + 0.5 * (v_(k, j, i) ** 2 + v_(k, j + 1, i) ** 2)) / 2
+
+    def Gu(k, j, i):
+        vavg = 0.25 * (dxcf[j] * v_(k, j, i - 1) + dxcf[j + 1] * v_(k, j + 1, i - 1) + dxcf[j] * v_(k, j, i) + dxcf[j + 1] * v_(k, j + 1, i))
+        vhat = vavg / dxfc[j]
+        js = range(j - 4, j + 5) if vhat > 0 else range(j + 5, j - 4, -1)       # zeta lives on face latitudes; the node sits between j and j + 1
+        zr = numpy_weno_z(5, [zeta(k, jj, i) for jj in js], [[us(k, jj, i) for jj in js], [vs(k, jj, i) for jj in js]])
+        uh = u_(k, j, i)
+        is_ = range(i - 3, i + 2) if uh > 0 else range(i + 2, i - 3, -1)        # divergence lives in cells; the node sits between i - 1 and i
+        dr = numpy_weno_z(3, [dxU(k, j, ii) for ii in is_], [[dxU(k, j, ii) + dyV(k, j, ii) for ii in is_]])
+        Phi = uh * dr + uh * 0.5 * (dyV(k, j, i - 1) + dyV(k, j, i))
+        ub, ua = u_(max(k - 1, 0), j, i), u_(min(k + 1, Nz - 1), j, i)
+        fl_lo = 0.5 * Azc[j] * (w_(k, j, i - 1) + w_(k, j, i)) * 0.5 * (ub + uh)
+        fl_hi = 0.5 * Azc[j] * (w_(k + 1, j, i - 1) + w_(k + 1, j, i)) * 0.5 * (uh + ua)
+        return (vhat * zr - (Phi + fl_hi - fl_lo) / (Azc[j] * dz[k]) - (K(k, j, i) - K(k, j, i - 1)) / dxfc[j]
+                + 0.5 * (f[j] + f[j + 1]) * vavg / dxfc[j])
+
+    def Gv(k, j, i):
+        uavg = 0.25 * (u_(k, j - 1, i) + u_(k, j - 1, i + 1) + u_(k, j, i) + u_(k, j, i + 1))
+        is_ = range(i - 4, i + 5) if uavg > 0 else range(i + 5, i - 4, -1)
+        zr = numpy_weno_z(5, [zeta(k, j, ii) for ii in is_], [[us(k, j, ii) for ii in is_], [vs(k, j, ii) for ii in is_]])
+        vh = v_(k, j, i)
+        js = range(j - 3, j + 2) if vh > 0 else range(j + 2, j - 3, -1)
+        dr = numpy_weno_z(3, [dyV(k, jj, i) for jj in js], [[dxU(k, jj, i) + dyV(k, jj, i) for jj in js]])
+        Phi = vh * dr + vh * 0.5 * (dxU(k, j - 1, i) + dxU(k, j, i))
+        vb, va = v_(max(k - 1, 0), j, i), v_(min(k + 1, Nz - 1), j, i)
+        fl_lo = 0.5 * (Azc[j - 1] * w_(k, j - 1, i) + Azc[j] * w_(k, j, i)) * 0.5 * (vb + vh)
+        fl_hi = 0.5 * (Azc[j - 1] * w_(k + 1, j - 1, i) + Azc[j] * w_(k + 1, j, i)) * 0.5 * (vh + va)
+        return (-uavg * zr - (Phi + fl_hi - fl_lo) / (Azf[j] * dz[k]) - (K(k, j, i) - K(k, j - 1, i)) / dy - f[j] * uavg)
+
+    su, sv = float(np.max(np.abs(GU))), float(np.max(np.abs(GV)))
+    worst_u = worst_v = 0.0
+    seen = set()
+    for k in (0, 3, Nz - 1):
+        for j in (9, 14, 20, 26, 30):
+            for i in (0, 1, 17, 44, 45, 71, Nx - 1):
+                worst_u = max(worst_u, abs(Gu(k, j, i) - GU[k, j, i]) / su)
+                worst_v = max(worst_v, abs(Gv(k, j, i) - GV[k, j, i]) / sv)
+                seen.add((V[k, j, i] > 0, U[k, j, i] > 0))
+    assert len(seen) == 4                       # both upwind directions of both components were exercised
+    assert worst_u <= 1e-12 and worst_v <= 1e-12, (worst_u, worst_v)
+
+
+def test_tracer_tendencies_against_a_numpy_restatement_at_sample_points(pkg, orc):
+    """G^T, G^S in flux form: WENO-7 upwinded reconstructions of the tracer at the x and y faces (smoothness on the tracer itself),
+    centred vertical flux, divided by the cell volume Az dz -- at sample points of a flat-bottom ocean, both upwind directions."""
+    c = cases.build_case("quiescent")
+    m = c.make_model(pkg, orc.OracleBackend)
+    g = m.grid
+    M = _metrics(g)
+    r, D = np.pi / 180, g.Lz
+    pkg.set_model(m, u=lambda lam, phi, z: 0.1 * np.sin(2 * lam * r) * np.cos(phi * r) * (1.0 + z / D),
+                  v=lambda lam, phi, z: 0.05 * np.cos(3 * lam * r) * np.sin(2 * phi * r) * np.exp(z / 1000.0),
+                  T=lambda lam, phi, z: 10 + 3 * np.sin(3 * lam * r) * np.cos(2 * phi * r) * np.exp(z / 500.0),
+                  S=lambda lam, phi, z: 35 + 0.2 * np.cos(2 * lam * r + 0.3) * np.sin(3 * phi * r) * np.exp(z / 800.0))
+    U, V, W = (m.get(n) for n in ("U", "V", "W"))
+    Nz, Ny, Nx = U.shape
+    dz = np.diff(g.z_faces)
+    dy, Azc = M["dy"], M["Az"]
+    dxcf = EARTH_R * np.cos(M["phif"]) * M["dlam"]
+    seen = set()
+    for name, gname in (("T", "GT"), ("S", "GS")):
+        C, G = m.get(name), m.get(gname)
+
+        def c_(k, j, i): return C[k, j, i % Nx]
+
+        def Fx(k, j, i):          # through the face between cells i - 1 and i
+            a = U[k, j, i % Nx]
+            cells = range(i - 4, i + 3) if a > 0 else range(i + 3, i - 4, -1)
+            q = [c_(k, j, ii) for ii in cells]
+            return dy * dz[k] * a * numpy_weno_z(4, q, [q])
+
+        def Fy(k, j, i):          # through the face between cells j - 1 and j
+            a = V[k, j, i % Nx]
+            cells = range(j - 4, j + 3) if a > 0 else range(j + 3, j - 4, -1)
+            q = [c_(k, jj, i) for jj in cells]
+            return dxcf[j] * dz[k] * a * numpy_weno_z(4, q, [q])
+
+        def Fz(k, j, i):          # through the face below level k; the face above the top level sees the top value on both sides
+            return Azc[j] * W[k, j, i % Nx] * 0.5 * (c_(max(k - 1, 0), j, i) + c_(min(k, Nz - 1), j, i))
+        scale, worst = float(np.max(np.abs(G))), 0.0
+        for k in (0, 3, Nz - 1):
+            for j in (9, 14, 21, 26, 30):
+                for i in (0, 1, 17, 44, 45, 71, Nx - 1):
+                    e = -((Fx(k, j, i + 1) - Fx(k, j, i)) + (Fy(k, j + 1, i) - Fy(k, j, i)) + (Fz(k + 1, j, i) - Fz(k, j, i))) / (Azc[j] * dz[k])
+                    worst = max(worst, abs(e - G[k, j, i]) / scale)
+                    seen.add((U[k, j, i] > 0, V[k, j, i] > 0))
+        assert worst <= 1e-11, (name, worst)
+    assert len(seen) == 4
