@@ -756,3 +756,56 @@ def test_tracer_tendencies_against_a_numpy_restatement_at_sample_points(pkg, orc
                     seen.add((U[k, j, i] > 0, V[k, j, i] > 0))
         assert worst <= 1e-11, (name, worst)
     assert len(seen) == 4
+
+
+def test_tracer_tendencies_next_to_immersed_boundaries_and_walls(pkg, orc):
+    """The same restatement on the k-dependent "bumpy" bathymetry, at wet cells that have a solid cell or a wall within four
+    cells: a face is reconstructed at the largest order N <= 4 whose 2N cells (i - N .. i + N - 1, the union of the two biased
+    stencils) are all wet and inside the domain, down to first-order upwind (DESIGN.md spec decision 1)."""
+    c = cases.build_case("bumpy")
+    m = c.make_model(pkg, orc.OracleBackend)
+    g = m.grid
+    M = _metrics(g)
+    U, V, W, C, G = (m.get(n) for n in ("U", "V", "W", "T", "GT"))
+    Nz, Ny, Nx = U.shape
+    solid = g.immersed_cell_mask()
+    dz = np.diff(g.z_faces)
+    dy, Azc = M["dy"], M["Az"]
+    dxcf = EARTH_R * np.cos(M["phif"]) * M["dlam"]
+
+    def wet(k, j, i): return 0 <= j < Ny and not solid[k, j, i % Nx]
+
+    def recon(values_at, ok_at, a):
+        """values_at(n) / ok_at(n): cell n relative to the face (n = -1 is the cell behind it, n = 0 the one ahead)"""
+        N = next((n for n in (4, 3, 2, 1) if all(ok_at(q) for q in range(-n, n))), 0)
+        if N == 0:
+            return 0.0          # a face between a wet and a solid cell: the velocity there is masked to zero
+        cells = range(-N, N - 1) if a > 0 else range(N - 1, -N, -1)
+        q = [values_at(n) for n in cells]
+        return q[0] if N == 1 else numpy_weno_z(N, q, [q])
+
+    def Fx(k, j, i):
+        a = U[k, j, i % Nx]
+        return dy * dz[k] * a * recon(lambda n: C[k, j, (i + n) % Nx], lambda n: wet(k, j, i + n), a)
+
+    def Fy(k, j, i):
+        a = V[k, j, i % Nx]
+        return dxcf[j] * dz[k] * a * recon(lambda n: C[k, j + n, i % Nx], lambda n: wet(k, j + n, i), a)
+
+    def Fz(k, j, i):
+        return Azc[j] * W[k, j, i % Nx] * 0.5 * (C[max(k - 1, 0), j, i % Nx] + C[min(k, Nz - 1), j, i % Nx])
+
+    near = [(k, j, i) for k in range(Nz) for j in range(Ny) for i in range(Nx)
+            if wet(k, j, i) and not all(wet(k, j + dj, i + di) for dj, di in
+                                        [(d, 0) for d in range(-4, 5)] + [(0, d) for d in range(-4, 5)])]
+    assert len(near) > 500
+    scale, worst, orders = float(np.max(np.abs(G))), 0.0, set()
+    for k, j, i in near[::max(1, len(near) // 150)]:
+        e = -((Fx(k, j, i + 1) - Fx(k, j, i)) + (Fy(k, j + 1, i) - Fy(k, j, i)) + (Fz(k + 1, j, i) - Fz(k, j, i))) / (Azc[j] * dz[k])
+        if k == Nz - 1:         # DoubleDrake restores the surface temperature (boundary_and_initial_conditions.jl:58-81)
+            e -= 5.0 / (7 * 86400.0) * (C[k, j, i] - pkg.T_reference(g.phi_c()[j])) / dz[k]
+        worst = max(worst, abs(e - G[k, j, i]) / scale)
+        orders.add(next((n for n in (4, 3, 2, 1) if all(wet(k, j, i + q) for q in range(-n, n))), 0))
+    assert orders >= {1, 2, 3}, orders          # reduced orders were really exercised
+    assert worst <= 1e-11, worst
+    assert np.max(np.abs(G[solid])) == 0.0      # tendencies are defined as zero in solid cells (spec decision 2)
