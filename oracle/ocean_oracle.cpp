@@ -1304,6 +1304,14 @@ static double weno_entry(int N, const double* q, const double* sa, const double*
 double oracle_weno(int N, const double* q, const double* sa, const double* sb) { return weno_entry(N, q, sa, sb, false); }
 double oracle_weno_ref(int N, const double* q, const double* sa, const double* sb) { return weno_entry(N, q, sa, sb, true); }
 double oracle_teos10_rprime(double Th, double SA, double Z) { static Teos t; return (double)t.rprime((real)Th, (real)SA, (real)Z); }
+// r' and its derivatives with respect to Conservative Temperature and Absolute Salinity (what N^2 at faces uses)
+double oracle_teos10_rprime_derivatives(double Th, double SA, double Z, double* dTh, double* dSA) {
+    static Teos t;
+    real a = RL(0.0), b = RL(0.0);
+    const real r = t.rprime((real)Th, (real)SA, (real)Z, &a, &b);
+    *dTh = (double)a; *dSA = (double)b;
+    return (double)r;
+}
 double oracle_det_tanh(double x) { return (double)det_tanh((real)x); }
 int oracle_real_bytes(void) { return (int)sizeof(real); }
 // OpenMP team size: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would silently turn the

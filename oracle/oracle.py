@@ -69,6 +69,8 @@ def load(precision: str = "Float64"):
     lib.oracle_set_num_threads.restype = None
     lib.oracle_get_max_threads.restype = C.c_int
     lib.oracle_threads_in_parallel_region.restype = C.c_int
+    lib.oracle_teos10_rprime_derivatives.argtypes = [C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.oracle_teos10_rprime_derivatives.restype = C.c_double
     lib.oracle_real_bytes.restype = C.c_int
     assert lib.oracle_real_bytes() == (8 if precision == "Float64" else 4), path
     _libs[precision] = lib

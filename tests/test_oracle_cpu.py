@@ -80,6 +80,21 @@ def test_deterministic_tanh_and_teos10_known_values(orc):
     assert err < 3e-16
     # TEOS-10 polynomial: fresh water at 0 C, 0 dbar -> 999.843 kg/m3 (known value); sea water is denser
     assert abs(lib.oracle_teos10_rprime(0.0, 0.0, 0.0) - 999.843) < 1e-3
+    # published known-answer value of the 55-term polynomial of Roquet et al. (2015) (polyTEOS10-bsq), quoted in NEMO's
+    # eosbn2.F90: "rho = 1028.21993233072 kg/m^3 for z = 3000 dbar, ct = 3 Celsius, sa = 35.5 g/kg" -- all 14 digits, which
+    # pins every one of the 52 non-zero coefficients recalled in oracle/ocean_oracle.cpp and csrc/ob_common.cuh
+    assert abs(lib.oracle_teos10_rprime(3.0, 35.5, -3000.0) - 1028.21993233072) < 5e-11
+    # the analytic derivatives N^2 is built from (alpha, beta at faces) against central differences of the polynomial
+    import ctypes as C
+    dT, dS = C.c_double(), C.c_double()
+    for Th, SA, Z in [(10.0, 35.16504, 0.0), (3.0, 35.5, -3000.0), (25.0, 34.0, -100.0), (-1.5, 33.0, -5000.0)]:
+        r = lib.oracle_teos10_rprime_derivatives(Th, SA, Z, C.byref(dT), C.byref(dS))
+        assert r == lib.oracle_teos10_rprime(Th, SA, Z)
+        h = 1e-4
+        fdT = (lib.oracle_teos10_rprime(Th + h, SA, Z) - lib.oracle_teos10_rprime(Th - h, SA, Z)) / (2 * h)
+        fdS = (lib.oracle_teos10_rprime(Th, SA + h, Z) - lib.oracle_teos10_rprime(Th, SA - h, Z)) / (2 * h)
+        assert abs(dT.value - fdT) < 2e-8 * abs(fdT) + 1e-9 and abs(dS.value - fdS) < 2e-8 * abs(fdS), (Th, SA, Z)
+        assert dS.value > 0 and (dT.value < 0 or Th < 0)      # saltier is denser; warmer is lighter (above ~0 C at depth)
     assert 1026.0 < lib.oracle_teos10_rprime(10.0, 35.0, 0.0) < 1028.0
     assert lib.oracle_teos10_rprime(10.0, 35.0, 0.0) > lib.oracle_teos10_rprime(20.0, 35.0, 0.0)
 
