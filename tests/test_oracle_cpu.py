@@ -824,3 +824,56 @@ def test_tracer_tendencies_next_to_immersed_boundaries_and_walls(pkg, orc):
     assert orders >= {1, 2, 3}, orders          # reduced orders were really exercised
     assert worst <= 1e-11, worst
     assert np.max(np.abs(G[solid])) == 0.0      # tendencies are defined as zero in solid cells (spec decision 2)
+
+
+# ---- consistency with the continuous equations (independent of any recollection of Oceananigans' source) -----------------
+def test_tendencies_converge_to_the_primitive_equations(pkg, orc):
+    """For a smooth analytic state on the sphere the discrete tendencies must converge to the tendencies of the hydrostatic
+    primitive equations in vector-invariant form,
+        G^u = (zeta + f) v - dK/dx - w du/dz - dp'/dx,  G^v = -(zeta + f) u - dK/dy - w dv/dz - dp'/dy,  G^T = -u . grad T,
+    with w from continuity and p' the hydrostatic integral of the (linear-EOS) buoyancy, all evaluated with sympy.  Signs,
+    metric factors (cos phi), the Coriolis parameter, the kinetic-energy and pressure gradients and the vertical advection are
+    checked against the PDE itself.  The top level is left out: the zero-gradient tracer / velocity value above the surface
+    makes the vertical advection of the top cell first-order with an O(1) coefficient (a property of the scheme, not an error)."""
+    import sympy as sp
+    a_, Om, grav, alpha, D = EARTH_R, EARTH_OMEGA, 9.80665, 1.67e-4, sp.Integer(3000)
+    lam, phi, z, zp = sp.symbols("lam phi z zp", real=True)
+    fu, fv, fT = 1 + z / D, sp.exp(z / 1000), sp.exp(z / 500)                   # vertical structure (integrated over z alone)
+    Uh, Vh, Th = sp.sin(2 * lam) * sp.cos(phi) / 10, sp.cos(3 * lam) * sp.sin(2 * phi) / 20, 3 * sp.sin(3 * lam) * sp.cos(2 * phi)
+    u, v, T = Uh * fu, Vh * fv, 10 + Th * fT
+    cosp = sp.cos(phi)
+    Iu, Iv = sp.integrate(fu.subs(z, zp), (zp, -D, z)), sp.integrate(fv.subs(z, zp), (zp, -D, z))
+    w = -(sp.diff(Uh, lam) * Iu + sp.diff(Vh * cosp, phi) * Iv) / (a_ * cosp)     # w(-D) = 0, dw/dz = -div_h(u, v)
+    zeta = (sp.diff(v, lam) - sp.diff(u * cosp, phi)) / (a_ * cosp)
+    K = (u ** 2 + v ** 2) / 2
+    p = -grav * alpha * (-10 * z + Th * sp.integrate(fT.subs(z, zp), (zp, z, 0)))   # dp'/dz = b = g alpha T, p'(0) = 0
+    f = 2 * Om * sp.sin(phi)
+    exprs = {"u": u, "v": v, "T": T, "W": w,
+             "GU": (zeta + f) * v - sp.diff(K, lam) / (a_ * cosp) - w * sp.diff(u, z) - sp.diff(p, lam) / (a_ * cosp),
+             "GV": -(zeta + f) * u - sp.diff(K, phi) / a_ - w * sp.diff(v, z) - sp.diff(p, phi) / a_,
+             "GT": -u * sp.diff(T, lam) / (a_ * cosp) - v * sp.diff(T, phi) / a_ - w * sp.diff(T, z)}
+    fn = {n: sp.lambdify((lam, phi, z), e, "numpy") for n, e in exprs.items()}
+    r = np.pi / 180
+
+    def errors(Nx, Ny, Nz):
+        grid = cases.Case("conv", Nx, Ny, Nz, experiment="Quiescent", perturb=False).grid(pkg)       # flat bottom, no forcing
+        m = pkg.HydrostaticFreeSurfaceModel(grid=grid, free_surface=pkg.SplitExplicitFreeSurface(substeps=30), eos="linear",
+                                            boundary_conditions=pkg.set_boundary_conditions("Quiescent", grid),
+                                            backend_factory=orc.OracleBackend)
+        pkg.set_model(m, u=lambda l, q, zz: fn["u"](l * r, q * r, zz), v=lambda l, q, zz: fn["v"](l * r, q * r, zz),
+                      T=lambda l, q, zz: fn["T"](l * r, q * r, zz), S=35.0)
+        g = m.grid
+        lc, lf, pc, pf, zc = g.lam_c() * r, (g.lam_c() - 0.5 * g.dlam) * r, g.phi_c() * r, g.phi_f() * r, g.z_c()
+        out = {}
+        for name, L, P, Z in (("GU", lf, pc, zc), ("GV", lc, pf, zc), ("GT", lc, pc, zc), ("W", lc, pc, g.z_faces)):
+            ZZ, PP, LL = np.meshgrid(Z, P, L, indexing="ij")
+            A = fn[name](LL, PP, ZZ)
+            sel = (np.abs(PP) < 50 * r) & ((ZZ < zc[-1]) | (name == "W"))      # away from the walls; below the top level
+            out[name] = float(np.max(np.abs(m.get(name) - A)[sel]) / np.max(np.abs(A[sel])))
+        return out
+    coarse, fine = errors(90, 40, 8), errors(180, 80, 16)
+    print("\nrelative L-infinity distance to the PDE tendencies, 90x40x8 -> 180x80x16:",
+          {n: (round(coarse[n], 5), round(fine[n], 5)) for n in coarse})
+    for n, bar in (("GU", 0.025), ("GV", 0.015), ("GT", 0.07), ("W", 0.01)):
+        assert coarse[n] < bar, (n, coarse[n])
+        assert fine[n] < 0.4 * coarse[n], (n, coarse[n], fine[n])
