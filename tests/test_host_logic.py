@@ -60,6 +60,19 @@ def test_barotropic_substeps_match_survey_appendix_b(pkg):
     assert pkg.barotropic_substeps(1.0, g) == 10
 
 
+def test_averaging_weights_are_normalised_and_centred_on_the_new_time_level(pkg):
+    """Split-explicit averaging (Shchepetkin & McWilliams 2005 shape function): the weights sum to one and their first moment
+    sum_m w_m m dtau sits at the new baroclinic time level (within the ~1 % the discrete truncation + renormalisation leaves),
+    for every substep count; a wrong shape constant would move the centroid by tens of per cent."""
+    for n in (10, 30, 38, 53, 80, 160):
+        fs = pkg.SplitExplicitFreeSurface(substeps=n)
+        w = np.asarray(fs.averaging_weights)
+        m = np.arange(1, len(w) + 1)
+        assert abs(w.sum() - 1.0) < 1e-14 and np.all(w[:-1] != 0.0)
+        assert abs((w * m).sum() * fs.fractional_step_size - 1.0) < 0.02, n
+        assert 1.3 < len(w) * fs.fractional_step_size < 1.5          # the substeps reach ~1.4 dt past the old time level
+
+
 def test_calculate_local_N_reference_algorithm(pkg):
     # uniform load: greedy `<=` advance takes one more column than the mean per rank (grid_load_balance.jl:102-109)
     load = np.full(100, 10)
