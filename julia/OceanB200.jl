@@ -114,6 +114,7 @@ function attach(model; device = CUDA.deviceid(), bottom_height, bc_kind, wind_co
     nranks > 1 && comm_init!(handle, comm, MPI)
     bind_model!(handle, model)
     sync_inputs!(handle)                 # the state `set!` / `initialize_model!` left in the Julia arrays, + update_state!
+    seed_barotropic_averages!(handle, model)
     ATTACHED[model] = handle
     return handle
 end
@@ -147,7 +148,19 @@ function sync_inputs!(h::Handle)
     CUDA.synchronize()
     check(h.ptr, ccall((:ob200_sync_inputs, LIB), Cint, (Ptr{Cvoid},), h.ptr))
 end
-sync_inputs!(model) = sync_inputs!(ATTACHED[model])
+function sync_inputs!(model)
+    h = ATTACHED[model]
+    sync_inputs!(h)
+    seed_barotropic_averages!(h, model)
+end
+
+"Every step starts its substeps from the previous step's averaged transports (U ← U̅, V ← V̅).  Whatever Oceananigans holds in
+`free_surface.state.U̅, V̅` -- zeros for a fresh model, `barotropic_mode!` of the velocities where its `initialize_free_surface!`
+ran -- seeds the library, so the first native step continues exactly where Oceananigans' own step would have."
+function seed_barotropic_averages!(h::Handle, model)
+    st = model.free_surface.state
+    set_field!(h, F_UBAR, st.U̅); set_field!(h, F_VBAR, st.V̅)
+end
 
 "Copy a Julia-owned field (parent array, any halo) into / out of the library: device-to-device."
 function set_field!(h::Handle, id, field)

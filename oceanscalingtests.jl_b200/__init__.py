@@ -16,7 +16,7 @@ from .grid_load_balance import (LatitudeLongitudeGrid, Partition, assess_x_load,
                                 kernel_cost_per_column, load_balanced_grid, redistribute_size_to_fulfill_memory_limitation)
 from .model import (B200Backend, BoundaryConditions, HydrostaticFreeSurfaceModel, QGLeith,
                     RiBasedVerticalDiffusivity, SplitExplicitFreeSurface, VerticalScalarDiffusivity,
-                    barotropic_substeps, build_config, set_model, substeps, time_step, weights_from_substeps)
+                    barotropic_substeps, build_config, initialize_free_surface, set_model, substeps, time_step, weights_from_substeps)
 from .near_global_simulation import (Callback, Comm, Simulation, aligned_time_step, equation_of_state, experiment_depth,
                                      initialize_simulation, profiled_time_steps, run, scaling_test_simulation,
                                      time_step_wizard)

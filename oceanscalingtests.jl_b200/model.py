@@ -432,6 +432,22 @@ def set_model(model: HydrostaticFreeSurfaceModel, **fields) -> None:
     model.backend.update_state()
 
 
+def initialize_free_surface(model: HydrostaticFreeSurfaceModel) -> None:
+    """Seed the averaged barotropic transports with the vertical integral of the current velocities,
+    U-bar, V-bar <- sum_k dz (u, v)  (Oceananigans' `barotropic_mode!`; [OCN-recall, low confidence] later Oceananigans versions
+    do this in `initialize_free_surface!` when `run!` initialises the model).
+
+    Every step starts its substeps from the PREVIOUS step's averages (U <- U-bar); a fresh model has U-bar = 0, so
+    without this call the barotropic part of an initial velocity field is dropped by the first step's corrector -- harmless for
+    the reference's runs, which start from rest (boundary_and_initial_conditions.jl:9-18) or in profile mode, and for this
+    repository's own checkpoints, which carry U-bar, V-bar (simulation_outputs.py `b200/*`).  NOT called by set_model or
+    time_step: the library and the oracle follow SURVEY A9 literally.  Velocities are zero on masked nodes, so the plain sum is
+    the sum over non-peripheral nodes."""
+    dz = np.diff(np.asarray(model.grid.z_faces))[:, None, None]
+    model.set("UBAR", (model.get("U") * dz).sum(axis=0))
+    model.set("VBAR", (model.get("V") * dz).sum(axis=0))
+
+
 def time_step(model: HydrostaticFreeSurfaceModel, dt: float) -> None:
     """time_step!(model, Δt) -- the hot path (near_global_simulation.jl:181,196)."""
     model.backend.time_step(dt)

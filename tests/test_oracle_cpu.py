@@ -877,3 +877,41 @@ def test_tendencies_converge_to_the_primitive_equations(pkg, orc):
     for n, bar in (("GU", 0.025), ("GV", 0.015), ("GT", 0.07), ("W", 0.01)):
         assert coarse[n] < bar, (n, coarse[n])
         assert fine[n] < 0.4 * coarse[n], (n, coarse[n], fine[n])
+
+
+def test_equatorial_kelvin_wave_travels_east_at_the_gravity_wave_speed(pkg, orc):
+    """Whole-model physics, independent of any recollection: an equatorially trapped free-surface bump with u = (g / c) eta, uniform
+    in depth, over a flat 3000 m ocean is an equatorial Kelvin wave; it must travel EASTWARD at c = sqrt(g H) = 171.5 m/s.
+    Thirty steps of 1200 s carry it 55.5 degrees of longitude (through the split-explicit solver, the barotropic corrector,
+    Coriolis and the beta effect of the spherical grid)."""
+    R, Om, grav = EARTH_R, EARTH_OMEGA, 9.80665
+    c = cases.build_case("quiescent")
+    m = c.make_model(pkg, orc.OracleBackend)
+    g = m.grid
+    cw = np.sqrt(grav * g.Lz)
+    trap = np.sqrt(cw / (2 * Om / R))                      # equatorial deformation radius sqrt(c / beta), 24.6 degrees
+    r = np.pi / 180
+
+    def eta0(lam, phi):
+        return 0.01 * np.exp(-((lam + 60.0) / 12.0) ** 2) * np.exp(-0.5 * (R * phi * r / trap) ** 2)
+    pkg.set_model(m, eta=eta0, u=lambda lam, phi, z: (grav / cw) * eta0(lam, phi) + 0 * z)
+    pkg.initialize_free_surface(m)        # the substeps start from U-bar: give them the barotropic part of the initial u
+
+    def peak(e):
+        row = 0.5 * (e[g.Ny // 2 - 1] + e[g.Ny // 2])      # the two rows next to the equator
+        i = int(np.argmax(row))
+        a, b, d = row[i - 1], row[i], row[(i + 1) % g.Nx]
+        return g.lam_c()[i] + 0.5 * (a - d) / (a - 2 * b + d) * g.dlam, float(b)
+    lam0, amp0 = peak(m.get("ETA"))
+    steps, dt = 30, 1200.0
+    for _ in range(steps):
+        pkg.time_step(m, dt)
+    lam1, amp1 = peak(m.get("ETA"))
+    expected = cw * steps * dt / (R * r)
+    assert abs(lam0 + 60.0) < 1e-9 and abs(expected - 55.53) < 0.01
+    assert abs((lam1 - lam0) - expected) < 0.03 * expected, (lam1 - lam0, expected)
+    assert amp1 > 0.8 * amp0
+    eta = m.get("ETA")
+    equatorial = np.abs(g.phi_c()) < 8.0
+    west = eta[equatorial][:, (g.lam_c() > -170) & (g.lam_c() < -80)]
+    assert np.max(np.abs(west)) < 0.25 * amp1             # along the equator nothing comparable went west
