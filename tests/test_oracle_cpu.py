@@ -915,3 +915,38 @@ def test_equatorial_kelvin_wave_travels_east_at_the_gravity_wave_speed(pkg, orc)
     equatorial = np.abs(g.phi_c()) < 8.0
     west = eta[equatorial][:, (g.lam_c() > -170) & (g.lam_c() < -80)]
     assert np.max(np.abs(west)) < 0.25 * amp1             # along the equator nothing comparable went west
+
+
+def test_teos10_pressure_gradient_converges_to_the_hydrostatic_integral(pkg, orc):
+    """Ocean at rest with horizontally varying T, S and the TEOS-10 equation of state: G^u must converge to -dp'/dx with
+    p'(z) = -int_z^0 b dz', b = -g rho'(T, S, z) / rho_0, evaluated here by Gauss-Legendre quadrature of the (known-answer-pinned)
+    polynomial -- sign of the buoyancy, reference density, depth convention and the pressure integral against the continuous
+    statement."""
+    R, grav, rho0 = EARTH_R, 9.80665, 1020.0
+    lib = orc.load()
+    r = np.pi / 180
+
+    def Tf(lam, phi, z): return 10 + 3 * np.sin(2 * lam * r) * np.cos(3 * phi * r) * np.exp(z / 800.0)
+    def Sf(lam, phi, z): return 35 + 0.3 * np.cos(lam * r) * np.sin(2 * phi * r) + 0 * z
+    xs, ws = np.polynomial.legendre.leggauss(24)
+
+    def pprime(lam, phi, z):
+        zz, wq = -0.5 * z * xs + 0.5 * z, -0.5 * z * ws
+        b = [-grav * lib.oracle_teos10_rprime(float(Tf(lam, phi, q)), float(Sf(lam, phi, q)), float(q)) / rho0 for q in zz]
+        return -float(np.sum(wq * np.array(b)))
+
+    def error(Nx, Ny, Nz):
+        m = cases.Case("t", Nx, Ny, Nz, experiment="Quiescent", perturb=False).make_model(pkg, orc.OracleBackend)
+        g = m.grid
+        pkg.set_model(m, T=Tf, S=Sf)
+        GU, zc, lamf, phic = m.get("GU"), g.z_c(), g.lam_c() - 0.5 * g.dlam, g.phi_c()
+        worst = scale = 0.0
+        d = 0.05       # degrees: centred difference of the quadrature
+        for k in range(0, Nz, Nz // 4):
+            for j in range(3, Ny - 3, Ny // 8):
+                for i in range(0, Nx, Nx // 9):
+                    e = -(pprime(lamf[i] + d, phic[j], zc[k]) - pprime(lamf[i] - d, phic[j], zc[k])) / (2 * d * r * R * np.cos(phic[j] * r))
+                    worst, scale = max(worst, abs(GU[k, j, i] - e)), max(scale, abs(e))
+        return worst / scale
+    coarse, fine = error(90, 40, 8), error(180, 80, 16)
+    assert coarse < 0.05 and fine < 0.4 * coarse, (coarse, fine)
