@@ -14,6 +14,9 @@ out, nsteps = ARGS[1], parse(Int, ARGS[2])
 sim = OceanScalingTests.scaling_test_simulation(1/5, (1, 1, 1), 10minutes, 365days;
                                                 child_arch = CPU(), Nz = 10, experiment = :DoubleDrake)
 m = sim.model
+# DESIGN.md spec decision 10: does this Oceananigans seed the averaged barotropic transports from u, v when a run is initialised?
+HFSM = Oceananigans.Models.HydrostaticFreeSurfaceModels
+@info "initialize_free_surface! defined in the pinned Oceananigans" isdefined(HFSM, :initialize_free_surface!)
 # tests/cases.py :: Case.initialize (angles in degrees -> radians with r = pi / 180; D = 3000 m)
 const D, r = 3000.0, π / 180
 const T_reference = OceanScalingTests.T_reference                   # src/bathymetry_and_forcings.jl:154
