@@ -190,6 +190,10 @@ struct Oracle {
     std::string err;
     bool refar = false;   // reference arithmetic (see the header)
     int refbits = 7;   // bisect mask: 1 metrics, 2 WENO, 4 tanh
+    // Timing runs only (bench.py's CPU legs): evaluate just the upwind-side reconstruction.  0.5 ((a + |a|) L + (a - |a|) R) is a L or
+    // a R exactly, so the fields are bit-identical (tests/test_oracle_cpu.py); the default evaluates both sides, as the reference does.
+    bool upwind1 = false;
+    inline bool skip_side(int side, real vel) const { return upwind1 && (side == 0 ? !(vel > RL(0.0)) : !(vel < RL(0.0))); }
     // x / metric: a true division (reference) or a multiplication by the correctly rounded reciprocal (product)
     inline real mdiv(real x, real m, real rm) const { return (refar && (refbits & 1)) ? x / m : x * rm; }
     // 1 / V = 1 / (Az dz): Oceananigans evaluates `1 / V * (...)`
@@ -716,6 +720,7 @@ struct Oracle {
         int N = order_faces_y(i, j, k, (c.order_vorticity + 1) / 2);
         real zq[9], us[9], vs[9], zL, zR;
         for (int side = 0; side < 2; side++) {
+            if (skip_side(side, vhat)) { (side == 0 ? zL : zR) = RL(0.0); continue; }
             for (int m = 0; m < 2 * N - 1; m++) {
                 int jj = side == 0 ? j - N + 1 + m : j + N - m;
                 zq[m] = zeta(i, jj, k);
@@ -729,6 +734,7 @@ struct Oracle {
         int Nd = order_cells_x(i, j, k, (c.order_divergence + 1) / 2);
         real dq[5], ds[5], dL, dR;
         for (int side = 0; side < 2; side++) {
+            if (skip_side(side, u(i, j, k))) { (side == 0 ? dL : dR) = RL(0.0); continue; }
             for (int m = 0; m < 2 * Nd - 1; m++) {
                 int ii = side == 0 ? i - Nd + m : i + Nd - 1 - m;
                 dq[m] = dxU(ii, j, k);
@@ -775,6 +781,7 @@ struct Oracle {
         int N = order_faces_x(i, j, k, (c.order_vorticity + 1) / 2);
         real zq[9], us[9], vs[9], zL, zR;
         for (int side = 0; side < 2; side++) {
+            if (skip_side(side, uhat)) { (side == 0 ? zL : zR) = RL(0.0); continue; }
             for (int m = 0; m < 2 * N - 1; m++) {
                 int ii = side == 0 ? i - N + 1 + m : i + N - m;
                 zq[m] = zeta(ii, j, k);
@@ -787,6 +794,7 @@ struct Oracle {
         int Nd = order_cells_y(i, j, k, (c.order_divergence + 1) / 2);
         real dq[5], ds[5], dL, dR;
         for (int side = 0; side < 2; side++) {
+            if (skip_side(side, v(i, j, k))) { (side == 0 ? dL : dR) = RL(0.0); continue; }
             for (int m = 0; m < 2 * Nd - 1; m++) {
                 int jj = side == 0 ? j - Nd + m : j + Nd - 1 - m;
                 dq[m] = dyV(i, jj, k);
@@ -852,22 +860,30 @@ struct Oracle {
             if (imm_peripheral_fcc(ii, j, k)) return RL(0.0);
             int N = order_cells_x(ii, j, k, Nt);
             if (N == 0) return RL(0.0);
-            real q[7], L, R;
-            for (int m = 0; m < 2 * N - 1; m++) q[m] = cfld(ii - N + m, j, k);
-            L = weno(N, q, q, nullptr, refar && (refbits & 2));
-            for (int m = 0; m < 2 * N - 1; m++) q[m] = cfld(ii + N - 1 - m, j, k);
-            R = weno(N, q, q, nullptr, refar && (refbits & 2));
+            real q[7], L = RL(0.0), R = RL(0.0);
+            if (!skip_side(0, u(ii, j, k))) {
+                for (int m = 0; m < 2 * N - 1; m++) q[m] = cfld(ii - N + m, j, k);
+                L = weno(N, q, q, nullptr, refar && (refbits & 2));
+            }
+            if (!skip_side(1, u(ii, j, k))) {
+                for (int m = 0; m < 2 * N - 1; m++) q[m] = cfld(ii + N - 1 - m, j, k);
+                R = weno(N, q, q, nullptr, refar && (refbits & 2));
+            }
             return dy * dzc(k) * upwind(u(ii, j, k), L, R);
         };
         auto flux_y = [&](int jj) {
             if (imm_peripheral_cfc(i, jj, k)) return RL(0.0);
             int N = order_cells_y(i, jj, k, Nt);
             if (N == 0) return RL(0.0);  // wall face: v = 0
-            real q[7], L, R;
-            for (int m = 0; m < 2 * N - 1; m++) q[m] = cfld(i, jj - N + m, k);
-            L = weno(N, q, q, nullptr, refar && (refbits & 2));
-            for (int m = 0; m < 2 * N - 1; m++) q[m] = cfld(i, jj + N - 1 - m, k);
-            R = weno(N, q, q, nullptr, refar && (refbits & 2));
+            real q[7], L = RL(0.0), R = RL(0.0);
+            if (!skip_side(0, v(i, jj, k))) {
+                for (int m = 0; m < 2 * N - 1; m++) q[m] = cfld(i, jj - N + m, k);
+                L = weno(N, q, q, nullptr, refar && (refbits & 2));
+            }
+            if (!skip_side(1, v(i, jj, k))) {
+                for (int m = 0; m < 2 * N - 1; m++) q[m] = cfld(i, jj + N - 1 - m, k);
+                R = weno(N, q, q, nullptr, refar && (refbits & 2));
+            }
             return dxcf(jj) * dzc(k) * upwind(v(i, jj, k), L, R);
         };
         auto flux_z = [&](int kf) {
@@ -1262,6 +1278,7 @@ int oracle_set_option(void* h, const char* name, int value) {
     if (!std::strcmp(name, "transfer_x_halo")) { ((Oracle*)h)->xfer_halo = value; return OB200_OK; }
     if (!std::strcmp(name, "reference_arithmetic")) { ((Oracle*)h)->refar = value != 0; return OB200_OK; }
     if (!std::strcmp(name, "reference_arithmetic_mask")) { ((Oracle*)h)->refbits = value; return OB200_OK; }
+    if (!std::strcmp(name, "upwind_side_only")) { ((Oracle*)h)->upwind1 = value != 0; return OB200_OK; }
     return OB200_EINVAL;
 }
 int oracle_get_strip(void* h, int id, double* buf, int side, int width, int interior_edge) {

@@ -950,3 +950,17 @@ def test_teos10_pressure_gradient_converges_to_the_hydrostatic_integral(pkg, orc
         return worst / scale
     coarse, fine = error(90, 40, 8), error(180, 80, 16)
     assert coarse < 0.05 and fine < 0.4 * coarse, (coarse, fine)
+
+
+@pytest.mark.parametrize("name", ["bumpy", "realistic", "dd_leith"])
+def test_upwind_side_only_timing_option_does_not_change_a_bit(pkg, orc, name):
+    """bench.py's CPU legs time the oracle with only the upwind-side reconstruction evaluated (0.5 ((a + |a|) L + (a - |a|) R)
+    is a L or a R exactly); the checker's default evaluates both sides.  Same bits."""
+    c = cases.build_case(name)
+    a, b = c.make_model(pkg, orc.OracleBackend), c.make_model(pkg, orc.OracleBackend)
+    b.backend.set_option("upwind_side_only", 1)
+    for _ in range(4):
+        pkg.time_step(a, c.dt)
+        pkg.time_step(b, c.dt)
+    for n in ("U", "V", "W", "ETA", "T", "S", "GU", "GV", "GT", "GS"):
+        assert np.array_equal(a.get(n), b.get(n)), n
