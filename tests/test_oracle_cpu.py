@@ -964,3 +964,135 @@ def test_upwind_side_only_timing_option_does_not_change_a_bit(pkg, orc, name):
         pkg.time_step(b, c.dt)
     for n in ("U", "V", "W", "ETA", "T", "S", "GU", "GV", "GT", "GS"):
         assert np.array_equal(a.get(n), b.get(n)), n
+
+
+def test_momentum_tendencies_next_to_immersed_boundaries_and_walls(pkg, orc):
+    """G^u, G^v on the k-dependent "bumpy" DoubleDrake bathymetry at nodes with a solid cell or a wall within five cells, restated
+    with numpy from the immersed-boundary rules of SURVEY Appendix A / DESIGN.md spec decisions 1-2:
+      * a node on a face is INACTIVE when both cells it separates are solid or outside the domain, PERIPHERAL when either is;
+      * the differences inside zeta are zero when they touch an inactive velocity node (conditional differences);
+      * the vorticity is reconstructed at the largest order N <= 5 whose face nodes j - N + 1 .. j + N ((c,f,c) nodes for G^u;
+        i - N + 1 .. i + N, (f,c,c) nodes for G^v) are all active; the divergence at the largest N <= 3 whose cells are all wet;
+      * vertical fluxes through immersed-peripheral faces vanish; Coriolis averages over the non-peripheral nodes only;
+      * tendencies are zero on peripheral nodes.
+    Plus the DoubleDrake boundary conditions (wind stress on u at the top, linear drag at the bottom level)."""
+    c = cases.build_case("bumpy")
+    m = c.make_model(pkg, orc.OracleBackend)
+    g = m.grid
+    M = _metrics(g)
+    U, V, W, P, GU, GV = (m.get(n) for n in ("U", "V", "W", "P", "GU", "GV"))
+    Nz, Ny, Nx = U.shape
+    solid = g.immersed_cell_mask()
+    dz = np.diff(g.z_faces)
+    dy, dxfc, Azc = M["dy"], M["dxfc"], M["Az"]
+    dxcf = EARTH_R * np.cos(M["phif"]) * M["dlam"]
+    Azf = np.full(Ny + 1, np.nan)
+    Azf[1:Ny] = EARTH_R ** 2 * M["dlam"] * (np.sin(M["phic"][1:]) - np.sin(M["phic"][:-1]))
+    f = 2 * EARTH_OMEGA * np.sin(M["phif"])
+    tau = [pkg.wind_stress(p, pkg.wind_stress_coefficients(75.0)) for p in g.phi_c()]
+    mu = 0.003
+
+    def wet(k, j, i): return 0 <= j < Ny and 0 <= k < Nz and not solid[k, j, i % Nx]
+    def u_(k, j, i): return U[k, j, i % Nx] if 0 <= j < Ny else 0.0
+    def v_(k, j, i): return V[k, j, i % Nx] if 0 <= j <= Ny else 0.0
+    def inactive_u(k, j, i): return not wet(k, j, i - 1) and not wet(k, j, i)          # (f,c,c)
+    def inactive_v(k, j, i): return not wet(k, j - 1, i) and not wet(k, j, i)          # (c,f,c)
+    def periph_u(k, j, i): return not wet(k, j, i - 1) or not wet(k, j, i)
+    def periph_v(k, j, i): return not wet(k, j - 1, i) or not wet(k, j, i)
+
+    def zeta(k, j, i):
+        dxv = 0.0 if inactive_v(k, j, i - 1) or inactive_v(k, j, i) else dy * v_(k, j, i) - dy * v_(k, j, i - 1)
+        dyu = 0.0 if inactive_u(k, j - 1, i) or inactive_u(k, j, i) else dxfc[j] * u_(k, j, i) - dxfc[j - 1] * u_(k, j - 1, i)
+        return (dxv - dyu) / Azf[j]
+    def us(k, j, i): return 0.5 * (u_(k, j - 1, i) + u_(k, j, i))
+    def vs(k, j, i): return 0.5 * (v_(k, j, i - 1) + v_(k, j, i))
+    def dxU(k, j, i): return dy * dz[k] * (u_(k, j, i + 1) - u_(k, j, i))
+    def dyV(k, j, i): return dz[k] * (dxcf[j + 1] * v_(k, j + 1, i) - dxcf[j] * v_(k, j, i))
+    def K(k, j, i): return (0.5 * (u_(k, j, i) ** 2 + u_(k, j, i + 1) ** 2) + 0.5 * (v_(k, j, i) ** 2 + v_(k, j + 1, i) ** 2)) / 2
+
+    def biased(N, a):        # offsets of the 2N - 1 points, most upwind-ward first, relative to the point just behind the node
+        return range(-N + 1, N) if a > 0 else range(N, -N + 1, -1)
+
+    orders = set()
+
+    def weno(N, q, smooth):
+        orders.add((len(smooth), N))          # (2 smoothness fields: vorticity; 1: divergence), order
+        return q[0] if N == 1 else numpy_weno_z(N, q, smooth)
+
+    def Gu(k, j, i):
+        if periph_u(k, j, i):
+            return 0.0
+        vavg = 0.25 * (dxcf[j] * v_(k, j, i - 1) + dxcf[j + 1] * v_(k, j + 1, i - 1) + dxcf[j] * v_(k, j, i) + dxcf[j + 1] * v_(k, j + 1, i))
+        vhat = vavg / dxfc[j]
+        G = 0.0
+        if vhat != 0.0:
+            N = next(n for n in (5, 4, 3, 2, 1) if not any(inactive_v(k, jj, i) for jj in range(j - n + 1, j + n + 1)))
+            js = [j + o for o in biased(N, vhat)]
+            G = vhat * weno(N, [zeta(k, jj, i) for jj in js], [[us(k, jj, i) for jj in js], [vs(k, jj, i) for jj in js]])
+        uh = u_(k, j, i)
+        Phi = 0.0
+        if uh != 0.0:
+            N = next(n for n in (3, 2, 1) if all(wet(k, j, ii) for ii in range(i - n, i + n)))
+            is_ = [i - 1 + o for o in biased(N, uh)]
+            Phi = uh * weno(N, [dxU(k, j, ii) for ii in is_], [[dxU(k, j, ii) + dyV(k, j, ii) for ii in is_]]) \
+                + uh * 0.5 * (dyV(k, j, i - 1) + dyV(k, j, i))
+        def wflux(kf):          # through the (f,c,f) face below level kf
+            if 0 < kf < Nz and (periph_u(kf - 1, j, i) or periph_u(kf, j, i)):
+                return 0.0
+            return 0.5 * Azc[j] * (W[kf, j, (i - 1) % Nx] + W[kf, j, i % Nx]) * 0.5 * (u_(max(kf - 1, 0), j, i) + u_(min(kf, Nz - 1), j, i))
+        G -= (Phi + wflux(k + 1) - wflux(k)) / (Azc[j] * dz[k])
+        G -= (K(k, j, i) - K(k, j, i - 1)) / dxfc[j]
+        nact = sum(not periph_v(k, j + b, i - 1 + a) for a in (0, 1) for b in (0, 1))
+        if nact:
+            G += 0.5 * (f[j] + f[j + 1]) * (vavg / (0.25 * nact)) / dxfc[j]
+        G -= (P[k, j, i % Nx] - P[k, j, (i - 1) % Nx]) / dxfc[j]
+        if k == Nz - 1:
+            G -= tau[j] / dz[k]
+        if k == 0:
+            G += -mu * uh / dz[k]
+        return G
+
+    def Gv(k, j, i):
+        if periph_v(k, j, i):
+            return 0.0
+        uavg = 0.25 * (u_(k, j - 1, i) + u_(k, j - 1, i + 1) + u_(k, j, i) + u_(k, j, i + 1))
+        G = 0.0
+        if uavg != 0.0:
+            N = next(n for n in (5, 4, 3, 2, 1) if not any(inactive_u(k, j, ii) for ii in range(i - n + 1, i + n + 1)))
+            is_ = [i + o for o in biased(N, uavg)]
+            G = -uavg * weno(N, [zeta(k, j, ii) for ii in is_], [[us(k, j, ii) for ii in is_], [vs(k, j, ii) for ii in is_]])
+        vh = v_(k, j, i)
+        Phi = 0.0
+        if vh != 0.0:
+            N = next(n for n in (3, 2, 1) if all(wet(k, jj, i) for jj in range(j - n, j + n)))
+            js = [j - 1 + o for o in biased(N, vh)]
+            Phi = vh * weno(N, [dyV(k, jj, i) for jj in js], [[dxU(k, jj, i) + dyV(k, jj, i) for jj in js]]) \
+                + vh * 0.5 * (dxU(k, j - 1, i) + dxU(k, j, i))
+        def wflux(kf):
+            if 0 < kf < Nz and (periph_v(kf - 1, j, i) or periph_v(kf, j, i)):
+                return 0.0
+            return 0.5 * (Azc[j - 1] * W[kf, j - 1, i % Nx] + Azc[j] * W[kf, j, i % Nx]) * 0.5 * (v_(max(kf - 1, 0), j, i) + v_(min(kf, Nz - 1), j, i))
+        G -= (Phi + wflux(k + 1) - wflux(k)) / (Azf[j] * dz[k])
+        G -= (K(k, j, i) - K(k, j - 1, i)) / dy
+        nact = sum(not periph_u(k, j - 1 + b, i + a) for a in (0, 1) for b in (0, 1))
+        if nact:
+            G -= f[j] * (uavg / (0.25 * nact))
+        G -= (P[k, j, i % Nx] - P[k, j - 1, i % Nx]) / dy
+        if k == 0:
+            G += -mu * vh / dz[k]
+        return G
+
+    def near_boundary(k, j, i):
+        return not all(wet(k, j + dj, i + di) for dj, di in [(d, 0) for d in range(-5, 6)] + [(0, d) for d in range(-5, 6)])
+    su, sv = float(np.max(np.abs(GU))), float(np.max(np.abs(GV)))
+    pts = [(k, j, i) for k in range(Nz) for j in range(Ny) for i in range(Nx) if wet(k, j, i) and near_boundary(k, j, i)]
+    assert len(pts) > 1000
+    worst_u = worst_v = 0.0
+    nper = 0
+    for k, j, i in pts[::max(1, len(pts) // 160)]:
+        worst_u = max(worst_u, abs(Gu(k, j, i) - GU[k, j, i]) / su)
+        worst_v = max(worst_v, abs(Gv(k, j, i) - GV[k, j, i]) / sv)
+        nper += periph_u(k, j, i) + periph_v(k, j, i)
+    assert nper > 10                               # peripheral nodes (zero tendency) were among the samples
+    assert {(2, n) for n in (1, 2, 3, 4, 5)} <= orders and {(1, n) for n in (1, 2, 3)} <= orders, orders   # every order was used
+    assert worst_u <= 1e-11 and worst_v <= 1e-11, (worst_u, worst_v)
