@@ -1096,3 +1096,44 @@ def test_momentum_tendencies_next_to_immersed_boundaries_and_walls(pkg, orc):
     assert nper > 10                               # peripheral nodes (zero tendency) were among the samples
     assert {(2, n) for n in (1, 2, 3, 4, 5)} <= orders and {(1, n) for n in (1, 2, 3)} <= orders, orders   # every order was used
     assert worst_u <= 1e-11 and worst_v <= 1e-11, (worst_u, worst_v)
+
+
+@pytest.mark.parametrize("day", [1.7, 4.2, 7.9, 13.1])
+def test_realistic_ocean_surface_fluxes_follow_the_reference_formulas(pkg, orc, day):
+    """RealisticOcean at rest: the top-level tendencies are -J / dz with the reference's own formulas
+    (src/bathymetry_and_forcings.jl:162-193): fluxes interpolated linearly between the daily slices n1 = floor(mod(t, 5)) + 1 and
+    n1 + 1; restoring values taken from slice mod(t, 15) div 3 + 1 WITHOUT interpolation (`÷` makes n an integer, so the weight of
+    slice n2 is zero -- a quirk of the reference that is kept); lambda = min dz / 30 days (T), / 60 days (S)."""
+    c = cases.build_case("realistic")
+    m = c.make_model(pkg, orc.OracleBackend, initialize=False)
+    g = m.grid
+    T0, S0 = pkg.synthetic.initial_T_S(g)
+    pkg.set_model(m, T=T0, S=S0)
+    m.backend.set_clock(day * 86400.0, 0, float("inf"))
+    m.backend.update_state()
+    F = pkg.synthetic.forcing_arrays(g)
+    n = day % 5.0
+    n1 = int(np.floor(n))
+    w2 = n - n1
+
+    def interp(a): return a[n1] * (1.0 - w2) + a[n1 + 1] * w2
+    nr = int((day % 15.0) // 3.0)
+    dz = np.diff(g.z_faces)
+    lamT, lamS = dz.min() / (30 * 86400.0), dz.min() / (60 * 86400.0)
+    solid = g.immersed_cell_mask()[-1]
+    wet_u = ~solid & ~np.roll(solid, 1, axis=1)
+    wet_v = np.zeros((g.Ny + 1, g.Nx), bool)
+    wet_v[1:-1] = ~solid[1:] & ~solid[:-1]
+    T, S = m.get("T")[-1], m.get("S")[-1]
+    expect = {"GU": np.where(wet_u, -interp(F["taux"]) / dz[-1], 0.0), "GV": np.where(wet_v, -interp(F["tauy"]) / dz[-1], 0.0),
+              "GT": np.where(~solid, -(interp(F["Qs"]) + lamT * (T - F["Tr"][nr])) / dz[-1], 0.0),
+              "GS": np.where(~solid, -(interp(F["Fs"]) + lamS * (S - F["Sr"][nr])) / dz[-1], 0.0)}
+    for name, e in expect.items():
+        G = m.get(name)[-1]
+        if name in ("GU", "GV"):      # the pressure gradient of the stratified state is there as well: compare what is left
+            P = m.get("P")[-1]
+            M = _metrics(g)
+            G = G + ((P - np.roll(P, 1, axis=1)) / M["dxfc"][:, None] if name == "GU"
+                     else np.vstack([np.zeros((1, g.Nx)), (P[1:] - P[:-1]) / M["dy"], np.zeros((1, g.Nx))]))
+            G = np.where(wet_u if name == "GU" else wet_v, G, 0.0)
+        assert np.max(np.abs(G - e)) <= 1e-12 * np.max(np.abs(e)) + 1e-22, (name, day)
